@@ -1,0 +1,344 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/* from the UNMODIFIED reference and pin the oracle.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+
+For every case it (1) runs the reference objects / apps through oracle/ref_harness.py, (2) asserts that
+oracle/efv_oracle.py reproduces them, (3) stores mesh + reference outputs as a compressed .npz fixture.
+The fixtures are what `tests/` use on machines without the reference (the GPU box).
+"""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+import scipy.sparse as sp
+
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+from oracle import ref_harness as R  # noqa: E402
+
+ns = R.load()
+P = ns["PyEFVLib"]
+
+
+def dump_shape_tables():
+    out = {}
+    for name in ("Triangle", "Quadrilateral", "Tetrahedron", "Hexahedron"):
+        c = getattr(P, name)
+        out[f"{name}_ifD"] = np.asarray(c.innerFaceShapeFunctionDerivatives, dtype=np.float64)
+        out[f"{name}_ifN"] = np.asarray(c.innerFaceShapeFunctionValues, dtype=np.float64)
+        out[f"{name}_ifNbr"] = np.asarray(c.innerFaceNeighborVertices, dtype=np.int64)
+        out[f"{name}_subD"] = np.asarray(c.subelementShapeFunctionDerivatives, dtype=np.float64)
+        out[f"{name}_subN"] = np.asarray(c.subelementShapeFunctionValues, dtype=np.float64)
+        out[f"{name}_subT"] = np.asarray(c.subelementTransformedVolumes, dtype=np.float64)
+        out[f"{name}_facetV"] = np.asarray(c.facetVerticesIndexes, dtype=np.int64)
+        out[f"{name}_ofN"] = np.asarray(c.outerFaceShapeFunctionValues, dtype=np.float64)
+    np.savez_compressed(os.path.join(GOLDEN, "shape_tables.npz"), **out)
+
+
+dump_shape_tables()
+from oracle import efv_oracle as O  # noqa: E402  (needs shape_tables.npz)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)) if a.size else 0.0
+
+
+def griddata_arrays(gd):
+    conn = gd.elementsConnectivities
+    bconn = gd.boundariesConnectivities
+    return dict(
+        dimension=np.int64(gd.dimension),
+        coords=np.asarray(gd.verticesCoordinates, dtype=np.float64),
+        conn_flat=np.concatenate([np.asarray(c, dtype=np.int64) for c in conn]),
+        conn_ptr=np.concatenate([[0], np.cumsum([len(c) for c in conn])]).astype(np.int64),
+        region_names=np.array(gd.regionsNames),
+        region_ptr=np.concatenate([[0], np.cumsum([len(r) for r in gd.regionsElementsIndexes])]).astype(np.int64),
+        region_elems=np.concatenate([np.asarray(r, dtype=np.int64) for r in gd.regionsElementsIndexes]),
+        boundary_names=np.array(gd.boundariesNames),
+        boundary_ptr=np.concatenate([[0], np.cumsum([len(r) for r in gd.boundariesIndexes])]).astype(np.int64),
+        boundary_facets=np.concatenate([np.asarray(r, dtype=np.int64) for r in gd.boundariesIndexes]),
+        bconn_flat=np.concatenate([np.asarray(c, dtype=np.int64) for c in bconn]),
+        bconn_ptr=np.concatenate([[0], np.cumsum([len(c) for c in bconn])]).astype(np.int64),
+    )
+
+
+def ref_geometry(grid):
+    """Flatten the reference object graph."""
+    G, S, vol = [], [], []
+    for e in grid.elements:
+        for f in e.innerFaces:
+            G.append(np.asarray(f.globalDerivatives).ravel())
+            S.append(f.area.getCoordinates())
+        vol.append(np.asarray(e.subelementVolumes, dtype=np.float64))
+    out = dict(G_flat=np.concatenate(G), S_flat=np.concatenate(S), vol_flat=np.concatenate(vol),
+               vertex_volume=np.array([v.volume for v in grid.vertices]))
+    for k, b in enumerate(grid.boundaries):
+        out[f"b{k}_vertices"] = np.array([v.handle for v in b.vertices], dtype=np.int64)
+        out[f"b{k}_facet_element"] = np.array([f.element.handle for f in b.facets], dtype=np.int64)
+        out[f"b{k}_facet_local"] = np.array([f.elementLocalIndex for f in b.facets], dtype=np.int64)
+        out[f"b{k}_facet_area"] = np.array([f.area.getCoordinates() for f in b.facets]).reshape(-1, 3)
+        out[f"b{k}_outer_vertex"] = np.array([of.vertex.handle for f in b.facets for of in f.outerFaces], dtype=np.int64)
+        out[f"b{k}_outer_area"] = np.array([of.area.getCoordinates() for f in b.facets for of in f.outerFaces]).reshape(-1, 3)
+    return out
+
+
+def check_geometry(og, ref):
+    G = _flat_by_element(og, "G")
+    S = _flat_by_element(og, "S")
+    vol = _flat_by_element(og, "vol")
+    errs = dict(G=rel(G, ref["G_flat"]), S=rel(S, ref["S_flat"]), vol=rel(vol, ref["vol_flat"]),
+                vv=rel(og.vertex_volume, ref["vertex_volume"]))
+    for k, b in enumerate(og.boundaries):
+        assert np.array_equal(b.vertices, ref[f"b{k}_vertices"]), "boundary vertex order"
+        assert np.array_equal(b.facet_element, ref[f"b{k}_facet_element"]), "facet element"
+        assert np.array_equal(b.facet_local, ref[f"b{k}_facet_local"]), "facet local"
+        assert np.array_equal(b.outer_vertex, ref[f"b{k}_outer_vertex"])
+        errs[f"fa{k}"] = rel(b.facet_area, ref[f"b{k}_facet_area"])
+        errs[f"oa{k}"] = rel(b.outer_area, ref[f"b{k}_outer_area"])
+    worst = max(errs.values())
+    assert worst < 1e-13, errs
+    return worst
+
+
+def _flat_by_element(og, what):
+    parts = [None] * og.numberOfElements
+    for g in og.groups:
+        arr = getattr(g, what)
+        for a, e in enumerate(g.ids):
+            parts[e] = arr[a].ravel()
+    return np.concatenate(parts)
+
+
+def bc_dict(spec, names, variable_names):
+    """spec: {var: {boundaryName: (kind, value)}} -> reference BoundaryConditions dict."""
+    out = {}
+    for var in variable_names:
+        d = {"InitialValue": 0.0}
+        for n in names:
+            kind, val = spec[var][n]
+            d[n] = {"condition": P.Dirichlet if kind == "dirichlet" else P.Neumann, "type": P.Constant, "value": val}
+        out[var] = d
+    return out
+
+
+def csr_parts(A):
+    A = sp.csr_matrix(A)
+    A.sum_duplicates()
+    A.sort_indices()
+    return A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
+
+
+def heat_case(mesh, props, bcs, tag, transient_steps=0, dt=0.01):
+    t0 = time.time()
+    path = R.mesh_path(mesh)
+    names = P.MSHReader(path).getData().boundariesNames
+    pd = P.ProblemData(
+        meshFilePath=path, outputFilePath="tmp/efv_golden",
+        numericalSettings=P.NumericalSettings(timeStep=dt, finalTime=None, tolerance=1e-6, maxNumberOfIterations=50),
+        propertyData=P.PropertyData(props),
+        boundaryConditions=P.BoundaryConditions(bc_dict({"temperature": bcs}, names, ["temperature"])))
+    ht = ns["heat_transfer"]
+    out = griddata_arrays(pd.grid.gridData)
+    ref = ref_geometry(pd.grid)
+    out.update(ref)
+    og = O.OracleGrid(O.read_msh(path))
+    gerr = check_geometry(og, ref)
+    # steady system
+    s = ht.HeatTransferSolver(pd, extension="csv", transient=False, verbosity=False)
+    s.settings(); s.init(); s.assembleMatrix(); s.addToIndependentVector(); s.solveLinearSystem()
+    ip, ix, dv = csr_parts(s.matrix)
+    out.update(heat_indptr=ip, heat_indices=ix, heat_data=dv, heat_rhs=s.independent.copy(), heat_T=s.temperatureField.copy())
+    A = O.heat_matrix(og, props, bcs)
+    b = O.heat_rhs(og, props, bcs)
+    D = sp.csr_matrix(A) - sp.csr_matrix(s.matrix)
+    merr = float(np.abs(D.data).max() / np.abs(dv).max()) if D.nnz else 0.0
+    berr = rel(b, s.independent)
+    terr = rel(O.solve_direct(A, b), s.temperatureField)
+    assert merr < 1e-13 and berr < 1e-13 and terr < 1e-10, (merr, berr, terr)
+    # interior pattern = union of element cliques with sorted columns
+    gptr, gcol = O.csr_pattern(og, 1)
+    out.update(pattern_indptr=gptr, pattern_indices=gcol.astype(np.int64), slot_map=O.slot_map(og, gptr, gcol))
+    if transient_steps:
+        s = ht.HeatTransferSolver(pd, extension="csv", transient=True, verbosity=False)
+        s.settings(); s.init(); s.assembleMatrix()
+        ip, ix, dv = csr_parts(s.matrix)
+        out.update(heatT_indptr=ip, heatT_indices=ix, heatT_data=dv, heatT_dt=np.float64(dt))
+        At = O.heat_matrix(og, props, bcs, transient=True, dt=dt)
+        D = sp.csr_matrix(At) - sp.csr_matrix(s.matrix)
+        assert (float(np.abs(D.data).max() / np.abs(dv).max()) if D.nnz else 0.0) < 1e-13
+        fields, rhss = [], []
+        Told = np.zeros(og.numberOfVertices)
+        for it in range(transient_steps):
+            s.addToIndependentVector(); s.solveLinearSystem()
+            rhss.append(s.independent.copy()); fields.append(s.temperatureField.copy())
+            bo = O.heat_rhs(og, props, bcs, transient=True, dt=dt, Told=Told)
+            assert rel(bo, s.independent) < 1e-13
+            Told = O.solve_direct(At, bo)
+            assert rel(Told, s.temperatureField) < 1e-10
+            s.prevTemperatureField = s.temperatureField
+        out.update(heatT_rhs=np.array(rhss), heatT_fields=np.array(fields))
+    np.savez_compressed(os.path.join(GOLDEN, f"heat_{tag}.npz"), **out)
+    print(f"heat_{tag}: nV={og.numberOfVertices} nE={og.numberOfElements} geom {gerr:.1e} A {merr:.1e} b {berr:.1e} T {terr:.1e}"
+          f"  trace={s.matrix.diagonal().sum() if not transient_steps else 0:.12e} ({time.time()-t0:.1f}s)")
+
+
+def stress_case(mesh, props, bcs, tag, gravity=False):
+    t0 = time.time()
+    path = R.mesh_path(mesh)
+    gd = P.MSHReader(path).getData()
+    variables = ["u", "v", "w"][:gd.dimension]
+    pd = P.ProblemData(meshFilePath=path, outputFilePath="tmp/efv_golden", propertyData=P.PropertyData(props),
+                       boundaryConditions=P.BoundaryConditions(bc_dict(bcs, gd.boundariesNames, variables)))
+    se = ns["stress_equilibrium"]
+    s = se.StressEquilibriumSolver(pd, extension="csv", gravity=gravity, verbosity=False)
+    s.settings(); s.init(); s.assembleLinearSystem(); s.solveLinearSystem()
+    out = griddata_arrays(pd.grid.gridData)
+    ip, ix, dv = csr_parts(s.matrix)
+    out.update(indptr=ip, indices=ix, data=dv, rhs=s.independent.copy(), x=np.asarray(s.displacements).copy())
+    og = O.OracleGrid(O.read_msh(path))
+    A, b = O.elasticity_system(og, props, bcs, gravity=gravity)
+    D = sp.csr_matrix(A) - sp.csr_matrix(s.matrix)
+    merr = float(np.abs(D.data).max() / np.abs(dv).max()) if D.nnz else 0.0
+    berr = rel(b, s.independent)
+    xe = O.solve_equilibrated(A, b)
+    xerr = rel(xe, s.displacements)
+    out.update(x_equilibrated=xe)
+    assert merr < 1e-13 and berr < 1e-13 and xerr < 1e-6, (merr, berr, xerr)
+    np.savez_compressed(os.path.join(GOLDEN, f"stress_{tag}.npz"), **out)
+    print(f"stress_{tag}: n={len(b)} A {merr:.1e} b {berr:.1e} x(vs ref inv) {xerr:.1e} ({time.time()-t0:.1f}s)")
+
+
+def biot_case(mesh, props, bcs, tag, dt=20.0, steps=2):
+    t0 = time.time()
+    path = R.mesh_path(mesh)
+    gd = P.MSHReader(path).getData()
+    d = gd.dimension
+    variables = ["u_x", "u_y", "u_z"][:d] + ["p"]
+    pd = P.ProblemData(meshFilePath=path, outputFilePath="tmp/efv_golden",
+                       numericalSettings=P.NumericalSettings(timeStep=dt, finalTime=1e30, tolerance=0.0, maxNumberOfIterations=steps),
+                       propertyData=P.PropertyData(props),
+                       boundaryConditions=P.BoundaryConditions(bc_dict(bcs, gd.boundariesNames, variables)))
+    geo = ns["geomechanics"]
+    captured = {"A": None, "b": [], "x": []}
+    real_inv, real_matmul = np.linalg.inv, np.matmul
+
+    def fake_inv(M):
+        if M.ndim == 2 and M.shape[0] == (d + 1) * pd.grid.numberOfVertices:
+            captured["A"] = M.copy()
+        return real_inv(M)
+
+    def fake_matmul(a, b, *args, **kw):
+        r = real_matmul(a, b, *args, **kw)
+        if getattr(a, "ndim", 0) == 2 and a.shape[0] == (d + 1) * pd.grid.numberOfVertices and getattr(b, "ndim", 0) == 1:
+            captured["b"].append(np.array(b)); captured["x"].append(np.array(r))
+        return r
+
+    class NoSaver:
+        def __init__(self, *a, **k):
+            pass
+
+        def save(self, *a, **k):
+            pass
+
+        def finalize(self, *a, **k):
+            pass
+    old = (P.CsvSaver, P.MeshioSaver)
+    P.CsvSaver = P.MeshioSaver = NoSaver
+    np.linalg.inv, np.matmul = fake_inv, fake_matmul
+    import io, contextlib
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            geo.geomechanics(pd)
+    finally:
+        np.linalg.inv, np.matmul = real_inv, real_matmul
+        P.CsvSaver, P.MeshioSaver = old
+    out = griddata_arrays(pd.grid.gridData)
+    ip, ix, dv = csr_parts(sp.csr_matrix(captured["A"]))
+    out.update(indptr=ip, indices=ix, data=dv, rhs=np.array(captured["b"]), x=np.array(captured["x"]), dt=np.float64(dt))
+    og = O.OracleGrid(O.read_msh(path))
+    nV = og.numberOfVertices
+    u_old, p_old = np.zeros(d * nV), np.zeros(nV)
+    xs = []
+    for it in range(len(captured["b"])):
+        A, b = O.biot_system(og, props, bcs, dt, u_old, p_old)
+        if it == 0:
+            D = sp.csr_matrix(A) - sp.csr_matrix(captured["A"])
+            D.eliminate_zeros()
+            # compare entry-wise relative to the row scale (u rows ~1e9, p rows ~1e-13)
+            scale = np.abs(captured["A"]).max(axis=1)
+            merr = float((np.abs(D).max(axis=1).toarray().ravel() / scale).max())
+            assert merr < 1e-13, merr
+        bscale = np.maximum(np.abs(captured["b"][it]), np.abs(sp.csr_matrix(captured["A"])) @ np.abs(captured["x"][it]))
+        berr = float((np.abs(b - captured["b"][it]) / np.maximum(bscale, 1e-300)).max())
+        assert berr < 1e-11, berr
+        x = O.solve_equilibrated(A, b)
+        xs.append(x)
+        # feed the REFERENCE's own fields forward so that RHS comparisons stay independent of solver error
+        u_old, p_old = captured["x"][it][:d * nV], captured["x"][it][d * nV:]
+    out.update(x_equilibrated=np.array(xs))
+    uerr = rel(xs[0][:d * nV], captured["x"][0][:d * nV]); perr = rel(xs[0][d * nV:], captured["x"][0][d * nV:])
+    np.savez_compressed(os.path.join(GOLDEN, f"biot_{tag}.npz"), **out)
+    print(f"biot_{tag}: n={len(b)} A {merr:.1e} b {berr:.1e} u {uerr:.1e} p {perr:.1e} ({time.time()-t0:.1f}s)")
+
+
+HEAT_PROPS = {"Body": {"HeatCapacity": 1.0, "Conductivity": 1.0, "Density": 1.0, "HeatGeneration": 100.0}}
+N0 = ("neumann", 0.0)
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    we = {"West": ("dirichlet", 300.0), "East": ("dirichlet", 400.0), "South": N0, "North": N0}
+    we3 = dict(we, Bottom=N0, Top=N0)
+    bc3d = {"West": ("dirichlet", 300.0), "East": ("dirichlet", 400.0), "Bottom": ("dirichlet", 500.0),
+            "Top": ("neumann", 1000.0), "South": N0, "North": N0}
+    heat_case("2D/Square.msh", HEAT_PROPS, we, "Square", transient_steps=2)
+    heat_case("2D/10x10.msh", HEAT_PROPS, we, "10x10")
+    two = {"WEST": {"HeatCapacity": 1.0, "Conductivity": 1.0, "Density": 1.0, "HeatGeneration": 100.0},
+           "EAST": {"HeatCapacity": 2.0, "Conductivity": 5.0, "Density": 3.0, "HeatGeneration": 10.0}}
+    heat_case("2D/test.msh", two, {"SW": N0, "W": ("dirichlet", 300.0), "NW": ("neumann", 50.0), "MW": N0, "SE": N0,
+                                   "E": ("dirichlet", 400.0), "NE": ("neumann", -20.0), "ME": N0}, "test_mixed", transient_steps=2)
+    heat_case("3D/Hexas3x3x3.msh", HEAT_PROPS, we3, "Hexas3x3x3_we")
+    heat_case("3D/Hexas3x3x3.msh", HEAT_PROPS, bc3d, "Hexas3x3x3_3d", transient_steps=2)
+    heat_case("3D/Hexas6x6x6.msh", HEAT_PROPS, we3, "Hexas6x6x6_we")
+    heat_case("3D/eight_sphere.msh", HEAT_PROPS, {"Outer": ("dirichlet", 300.0), "InnerZ": ("neumann", 10.0),
+                                                  "InnerY": ("dirichlet", 350.0), "InnerX": N0}, "eight_sphere", transient_steps=2)
+    heat_case("3D/Tetras.msh", HEAT_PROPS, we3, "Tetras_we")
+
+    sprops = {"Body": {"Density": 1800.0, "PoissonsRatio": 0.4, "ShearModulus": 6.0e6, "Gravity": 10.0}}
+    s2 = {"u": {"West": ("dirichlet", 0.0), "East": ("dirichlet", 0.0), "South": N0, "North": N0},
+          "v": {"West": N0, "East": N0, "South": ("dirichlet", 0.0), "North": ("neumann", -1e4)}}
+    stress_case("2D/Square.msh", sprops, s2, "Square")
+    stress_case("2D/10x10.msh", sprops, s2, "10x10_gravity", gravity=True)
+    s3 = {"u": dict(s2["u"], Bottom=N0, Top=N0), "v": dict(s2["v"], Bottom=N0, Top=N0),
+          "w": {"West": N0, "East": N0, "South": N0, "North": N0, "Bottom": ("dirichlet", 0.0), "Top": N0}}
+    stress_case("3D/Hexas4x4x4.msh", sprops, s3, "Hexas4x4x4")
+    stress_case("3D/eight_sphere.msh", sprops,
+                {"u": {"Outer": N0, "InnerZ": N0, "InnerY": N0, "InnerX": ("dirichlet", 0.0)},
+                 "v": {"Outer": N0, "InnerZ": N0, "InnerY": ("dirichlet", 0.0), "InnerX": N0},
+                 "w": {"Outer": ("neumann", 2e3), "InnerZ": ("dirichlet", 0.0), "InnerY": N0, "InnerX": N0}}, "eight_sphere")
+
+    bprops = {"Body": {"nu": 0.2, "G": 6.0e9, "cs": 0.0, "phi": 0.19, "k": 1.9e-15, "cf": 3.0303e-10, "mu": 1000.0,
+                       "rhos": 2700.0, "rhof": 1000.0}}
+    b2 = {"u_x": {"West": ("dirichlet", 0.0), "East": ("dirichlet", 0.0), "South": N0, "North": N0},
+          "u_y": {"West": N0, "East": N0, "South": ("dirichlet", 0.0), "North": ("neumann", 1e5)},
+          "p": {"West": N0, "East": N0, "South": N0, "North": ("dirichlet", 0.0)}}
+    biot_case("2D/Square.msh", bprops, b2, "Square")
+    b3 = {"u_x": dict(b2["u_x"], Bottom=N0, Top=N0), "u_y": dict(b2["u_y"], Bottom=N0, Top=N0),
+          "u_z": {"West": N0, "East": N0, "South": N0, "North": N0, "Bottom": ("dirichlet", 0.0), "Top": N0},
+          "p": dict(b2["p"], Bottom=N0, Top=N0)}
+    biot_case("3D/Hexas3x3x3.msh", bprops, b3, "Hexas3x3x3")
+    biot_case("3D/eight_sphere.msh", bprops,
+              {"u_x": {"Outer": N0, "InnerZ": N0, "InnerY": N0, "InnerX": ("dirichlet", 0.0)},
+               "u_y": {"Outer": N0, "InnerZ": N0, "InnerY": ("dirichlet", 0.0), "InnerX": N0},
+               "u_z": {"Outer": ("neumann", 1e5), "InnerZ": ("dirichlet", 0.0), "InnerY": N0, "InnerX": N0},
+               "p": {"Outer": ("dirichlet", 0.0), "InnerZ": N0, "InnerY": N0, "InnerX": N0}}, "eight_sphere", steps=1)
+
+
+if __name__ == "__main__":
+    main()

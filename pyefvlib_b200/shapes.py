@@ -1,0 +1,245 @@
+"""Reference-element tables of the EbFVM shapes, derived from first principles.
+
+The reference keeps these as literal class attributes (PyEFVLib/Shape.py:7-19 Triangle, :35-47
+Quadrilateral, :63-74 Tetrahedron, :98-109 Hexahedron).  Here they are *computed* with exact rational
+arithmetic from the definition of the element-based finite-volume sub-control volumes:
+
+* an inner face (sub-control surface) belongs to an element edge (b, f); in 3-D it is the bilinear patch
+  spanned by  edge midpoint -> centroid of one adjacent facet -> element centroid -> centroid of the other
+  adjacent facet; in 2-D it is the segment edge midpoint -> element centroid.  Its integration point is the
+  mean of those corners in parametric space (e.g. hexahedron face 0 sits at xi = (1/2, 1/4, 1/4)).
+* a sub-element (the part of the control volume of vertex k inside the element) is the quad / hexahedron
+  spanned by the vertex, the adjacent edge midpoints, (3-D) the adjacent facet centroids and the element
+  centroid; its integration point is the mean of those corners.
+* an outer face is the part of a boundary facet that belongs to one facet vertex; its integration point is
+  the sub-element point of the facet seen as a lower-dimensional element.
+
+`tests/test_shapes.py` checks every array against the constants dumped from the reference
+(`tests/golden/shape_tables.npz`) bit for bit, and `csrc/shape_tables.inc` (the CUDA copy) is generated
+from this module by `python -m pyefvlib_b200.shapes`.
+"""
+from fractions import Fraction as Fr
+from itertools import combinations
+
+import numpy as np
+
+# shape codes shared with the C-ABI (include/efv_b200.h: EFV_SHAPE_*)
+TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON = 0, 1, 2, 3
+SHAPE_NAMES = {TRIANGLE: "Triangle", QUADRILATERAL: "Quadrilateral", TETRAHEDRON: "Tetrahedron",
+               HEXAHEDRON: "Hexahedron"}
+
+
+def _N_simplex(xi):
+    return [1 - sum(xi)] + list(xi)
+
+
+def _dN_simplex(xi):
+    d = len(xi)
+    return [[Fr(-1)] * d] + [[Fr(int(i == j)) for j in range(d)] for i in range(d)]
+
+
+def _N_tensor(verts):
+    def N(xi):
+        out = []
+        for v in verts:
+            p = Fr(1)
+            for a, x in zip(v, xi):
+                p *= x if a == 1 else (1 - x)
+            out.append(p)
+        return out
+    return N
+
+
+def _dN_tensor(verts):
+    def dN(xi):
+        out = []
+        for v in verts:
+            row = []
+            for k in range(len(xi)):
+                p = Fr(1 if v[k] == 1 else -1)
+                for kk, (a, x) in enumerate(zip(v, xi)):
+                    if kk != k:
+                        p *= x if a == 1 else (1 - x)
+                row.append(p)
+            out.append(row)
+        return out
+    return dN
+
+
+def _mean(points):
+    n = len(points)
+    return [sum(p[k] for p in points) / n for k in range(len(points[0]))]
+
+
+class ShapeTable:
+    """Exact reference-element data of one shape.  Arrays mirror the reference attribute names."""
+
+    def __init__(self, code, dim, verts, edges, facets, N, dN, sub_volume):
+        self.code = code
+        self.name = SHAPE_NAMES[code]
+        self.dimension = dim
+        self.numberOfVertices = m = len(verts)
+        self.numberOfInnerFaces = len(edges)
+        self.numberOfFacets = len(facets)
+        self.vertices = [[Fr(c) for c in v] for v in verts]
+        self.facetVerticesIndexes = np.array(facets, dtype=np.int32)
+        centroid = _mean(self.vertices)
+
+        def midpoint(ids):
+            return _mean([self.vertices[i] for i in ids])
+
+        # ---- inner faces -----------------------------------------------------------------------
+        nbr, ipoints = [], []
+        for b, f in edges:
+            if dim == 2:
+                nbr.append([b, f])
+                ipoints.append(_mean([midpoint([b, f]), centroid]))
+                continue
+            adj = [list(fc) for fc in facets if b in fc and f in fc]
+            assert len(adj) == 2
+            # order the two adjacent facets so that the area vector
+            #   s = 1/2 [(p1-p0)x(p3-p0) + (p3-p2)x(p1-p2)]   (Shape.py:84-96, :119-139)
+            # points from b to f on the reference element
+            p0, p2 = centroid, midpoint([b, f])
+
+            def area(fa, fb):
+                p1, p3 = midpoint(fa), midpoint(fb)
+                u = [p1[k] - p0[k] for k in range(3)]
+                v = [p3[k] - p0[k] for k in range(3)]
+                w = [p3[k] - p2[k] for k in range(3)]
+                z = [p1[k] - p2[k] for k in range(3)]
+                cr = lambda a, c: [a[1] * c[2] - a[2] * c[1], a[2] * c[0] - a[0] * c[2], a[0] * c[1] - a[1] * c[0]]
+                c1, c2 = cr(u, v), cr(w, z)
+                return [(c1[k] + c2[k]) / 2 for k in range(3)]
+            e = [self.vertices[f][k] - self.vertices[b][k] for k in range(3)]
+            s = area(adj[0], adj[1])
+            if sum(s[k] * e[k] for k in range(3)) < 0:
+                adj = [adj[1], adj[0]]
+            others = [[v for v in fc if v not in (b, f)] for fc in adj]
+            nbr.append([b, f] + others[0] + others[1])
+            ipoints.append(_mean([midpoint([b, f]), midpoint(adj[0]), midpoint(adj[1]), centroid]))
+        self.innerFaceNeighborVertices = np.array(nbr, dtype=np.int32)
+        self.innerFacePoints = ipoints
+        self.innerFaceShapeFunctionValues = np.array([[float(x) for x in N(p)] for p in ipoints])
+        self.innerFaceShapeFunctionDerivatives = np.array([[[float(x) for x in r] for r in dN(p)] for p in ipoints])
+        if code == TETRAHEDRON:
+            # REFERENCE QUIRK, reproduced for parity: Shape.py:68 lists the shape-function VALUES of
+            # tetrahedron faces 4 and 5 in the order (edge 2-3, edge 1-3) while the neighbour table
+            # (Shape.py:70) has face 4 = edge 1-3 and face 5 = edge 2-3.  Derivatives are constant, so only
+            # users of the values (geomechanics.py:70,107) see it.
+            self.innerFaceShapeFunctionValues[[4, 5]] = self.innerFaceShapeFunctionValues[[5, 4]]
+
+        # ---- sub-elements ----------------------------------------------------------------------
+        spoints = []
+        for k in range(m):
+            corners = [self.vertices[k], centroid]
+            corners += [midpoint(e) for e in edges if k in e]
+            if dim == 3:
+                corners += [midpoint(fc) for fc in facets if k in fc]
+            spoints.append(_mean(corners))
+        self.subelementPoints = spoints
+        self.subelementShapeFunctionValues = np.array([[float(x) for x in N(p)] for p in spoints])
+        self.subelementShapeFunctionDerivatives = np.array([[[float(x) for x in r] for r in dN(p)] for p in spoints])
+        self.subelementTransformedVolumes = np.array([float(sub_volume)] * m)
+
+        # ---- outer faces (per facet, per facet vertex) -----------------------------------------
+        ofv = []
+        for fc in facets:
+            rows = []
+            fc = list(fc)
+            for k in fc:
+                if len(fc) == 2:       # line facet: 3/4 of the vertex, 1/4 of the other end
+                    pt = _mean([self.vertices[k], midpoint(fc)])
+                else:                  # sub-element point of the facet as a 2-D element
+                    n = len(fc)
+                    i = fc.index(k)
+                    ring = [midpoint([fc[i], fc[(i + 1) % n]]), midpoint([fc[i], fc[(i - 1) % n]])]
+                    pt = _mean([self.vertices[k], midpoint(fc)] + ring)
+                rows.append([float(x) for x in N(pt)])
+            ofv.append(rows)
+        self.outerFaceShapeFunctionValues = np.array(ofv)
+
+
+def _build():
+    tri_v = [(0, 0), (1, 0), (0, 1)]
+    quad_v = [(0, 0), (1, 0), (1, 1), (0, 1)]
+    tet_v = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
+    hex_v = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    return {
+        # edge (b, f) lists and facet vertex lists are topology; they follow Shape.py:13,17 / :41,45 /
+        # :69,73 / :104,108 so that per-face arrays line up with the reference's face numbering
+        TRIANGLE: ShapeTable(TRIANGLE, 2, tri_v, [(0, 1), (1, 2), (2, 0)], [(1, 0), (2, 1), (0, 2)],
+                             _N_simplex, _dN_simplex, Fr(1, 6)),
+        QUADRILATERAL: ShapeTable(QUADRILATERAL, 2, quad_v, [(0, 1), (1, 2), (2, 3), (3, 0)],
+                                  [(1, 0), (2, 1), (3, 2), (0, 3)], _N_tensor(quad_v), _dN_tensor(quad_v), Fr(1, 4)),
+        TETRAHEDRON: ShapeTable(TETRAHEDRON, 3, tet_v, [(0, 1), (1, 2), (2, 0), (0, 3), (1, 3), (2, 3)],
+                                [(0, 2, 1), (0, 3, 2), (0, 1, 3), (1, 2, 3)], _N_simplex, _dN_simplex, Fr(1, 24)),
+        HEXAHEDRON: ShapeTable(HEXAHEDRON, 3, hex_v,
+                               [(0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4),
+                                (4, 0), (5, 1), (6, 2), (7, 3)],
+                               [(0, 3, 2, 1), (0, 4, 7, 3), (0, 1, 5, 4), (4, 5, 6, 7), (1, 2, 6, 5), (2, 3, 7, 6)],
+                               _N_tensor(hex_v), _dN_tensor(hex_v), Fr(1, 8)),
+    }
+
+
+SHAPES = _build()
+BY_NAME = {t.name: t for t in SHAPES.values()}
+
+
+def shape_code_for(n_vertices, dimension):
+    """Shape of an element from its vertex count (Element.py:22-27 + Shape.py `_is`).  A 4-vertex element is
+    a quadrilateral in a 2-D grid and a tetrahedron in a 3-D grid (the reference decides by coplanarity,
+    Shape.py:4-5, which on valid meshes is the same thing)."""
+    if n_vertices == 3:
+        return TRIANGLE
+    if n_vertices == 4:
+        return QUADRILATERAL if dimension == 2 else TETRAHEDRON
+    if n_vertices == 8:
+        return HEXAHEDRON
+    raise Exception("This element has not been registered in Grid yet")   # Element.py:27
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CUDA table generator
+# ---------------------------------------------------------------------------------------------------------
+def _c_array(a, fmt):
+    a = np.asarray(a)
+    if a.ndim == 1:
+        return "{" + ", ".join(fmt(x) for x in a) + "}"
+    return "{" + ",\n ".join(_c_array(x, fmt) for x in a) + "}"
+
+
+def generate_cuda_tables():
+    """Text of csrc/shape_tables.inc: one struct of constexpr tables per shape."""
+    fd = lambda x: repr(float(x))
+    fi = lambda x: str(int(x))
+    out = ["// GENERATED by `python -m pyefvlib_b200.shapes` -- do not edit.",
+           "// Reference-element tables (see pyefvlib_b200/shapes.py for the derivation).", ""]
+    for code in (TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON):
+        t = SHAPES[code]
+        m, nf, d = t.numberOfVertices, t.numberOfInnerFaces, t.dimension
+        nfc, mf = t.facetVerticesIndexes.shape
+        nn = t.innerFaceNeighborVertices.shape[1]
+        out += [
+            f"struct {t.name}Tab {{",
+            f"  static constexpr int CODE = {code}, DIM = {d}, M = {m}, NF = {nf}, NFACETS = {nfc}, MF = {mf}, NNBR = {nn};",
+            f"  static constexpr double SUBVOL = {fd(t.subelementTransformedVolumes[0])};",
+            "};",
+            f"__device__ __constant__ double c_{t.name}_ifD[{nf}][{m}][{d}] =\n {_c_array(t.innerFaceShapeFunctionDerivatives, fd)};",
+            f"__device__ __constant__ double c_{t.name}_ifN[{nf}][{m}] =\n {_c_array(t.innerFaceShapeFunctionValues, fd)};",
+            f"__device__ __constant__ int c_{t.name}_ifNbr[{nf}][{nn}] =\n {_c_array(t.innerFaceNeighborVertices, fi)};",
+            f"__device__ __constant__ double c_{t.name}_subD[{m}][{m}][{d}] =\n {_c_array(t.subelementShapeFunctionDerivatives, fd)};",
+            f"__device__ __constant__ int c_{t.name}_facetV[{nfc}][{mf}] =\n {_c_array(t.facetVerticesIndexes, fi)};",
+            f"__device__ __constant__ double c_{t.name}_ofN[{nfc}][{mf}][{m}] =\n {_c_array(t.outerFaceShapeFunctionValues, fd)};",
+            "",
+        ]
+    return "\n".join(out) + "\n"
+
+
+if __name__ == "__main__":
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "shape_tables.inc")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as fh:
+        fh.write(generate_cuda_tables())
+    print("wrote", path)
