@@ -1,0 +1,141 @@
+/*
+ * efv_b200.h -- C-ABI of the B200-native EbFVM hot path (assembly + sparse solve) of PyEFVLib.
+ *
+ * The reference (GustavoExel/PyEFVLib) is pure Python and has no FFI; the seams this ABI slots into are cited
+ * per entry point as  [ref: file:line]  (paths relative to the reference root).  All entry points are
+ * extern "C", take plain pointers and sizes, and return 0 on success / non-zero on failure with a message
+ * available from efv_last_error().  HOST pointers are borrowed for the duration of the call only; device
+ * memory is owned by the opaque handles.  One process drives one GPU (efv_set_device); handles are not
+ * thread-safe.  There is no CPU fallback: every entry point needs a CUDA device.
+ *
+ * DOF numbering at this boundary is the reference's FIELD-MAJOR one, row = vertex + field * numberOfVertices
+ * [ref: apps/stress_equilibrium.py:77-79, apps/geomechanics.py:63, PyEFVLib/LinearSystem.py:119-124].
+ */
+#ifndef EFV_B200_H
+#define EFV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct efv_mesh efv_mesh;       /* device mesh: vertices, elements, boundaries, incidence, geometry   */
+typedef struct efv_system efv_system;   /* linear system on a mesh: CSR graph, slot map, values, vectors, Krylov */
+
+/* shape codes [ref: PyEFVLib/Shape.py:7,35,63,98 ; Grid.py:41] */
+enum { EFV_TRIANGLE = 0, EFV_QUADRILATERAL = 1, EFV_TETRAHEDRON = 2, EFV_HEXAHEDRON = 3 };
+/* Dirichlet application modes */
+enum { EFV_DIRICHLET_ROWS = 0,       /* reference form: row <- e_i^T, b_i = g  [ref: apps/heat_transfer.py:70-76,122-126] */
+       EFV_DIRICHLET_SYMMETRIC = 1   /* + column elimination into the RHS (same solution, CG-ready)  */ };
+/* vectors owned by a system (efv_vec_upload / efv_vec_download); all have rows = ndof * nV entries, field-major */
+enum { EFV_VEC_X = 0, EFV_VEC_B = 1, EFV_VEC_XOLD = 2, EFV_VEC_DIAG = 3 };
+/* physics selector of efv_system_create (decides which lumped per-vertex vectors exist) */
+enum { EFV_PHYS_HEAT = 0, EFV_PHYS_ELASTICITY = 1, EFV_PHYS_BIOT = 2 };
+
+/* ---- process-level -------------------------------------------------------------------------------------- */
+const char *efv_last_error(void);
+int efv_set_device(int device);
+int efv_device_count(int *count);
+void *efv_get_stream(void);            /* the cudaStream_t every kernel of this library is launched on */
+int efv_synchronize(void);
+int64_t efv_kernel_launch_count(void); /* kernels launched by this library since load (bench: gpu_launches) */
+
+/* ---- mesh  [ref: PyEFVLib/GridData.py:5-24 setters; Grid.py:18-65 build] ---------------------------------
+ * coords: nV x 3 doubles; elements: CSR-like (elem_ptr[nE+1] into conn, vertex ids 0-based) in grid order;
+ * the shape of an element follows from its vertex count and `dim` [ref: Element.py:22-27];
+ * region_of_elem[nE] in [0, n_regions).                                                                     */
+efv_mesh *efv_mesh_create(int dim, int64_t nV, const double *coords, int64_t nE, const int64_t *elem_ptr,
+                          const int32_t *conn, const int32_t *region_of_elem, int n_regions);
+/* boundary facets [ref: GridData.py:18-21; Grid.py:51-65; Boundary.py:27-75; Facet.py:22-36]:
+ * facets of all boundaries concatenated in boundary order; boundary b owns facets
+ * [boundary_ptr[b], boundary_ptr[b+1]); facet f has vertices facet_conn[facet_ptr[f] .. facet_ptr[f+1]).
+ * Matches every facet to its owning element + local facet, computes outward area vectors and outer faces. */
+int efv_mesh_set_boundaries(efv_mesh *m, int n_boundaries, const int64_t *boundary_ptr, int64_t n_facets,
+                            const int64_t *facet_ptr, const int32_t *facet_conn);
+void efv_mesh_destroy(efv_mesh *m);
+int64_t efv_mesh_num_vertices(const efv_mesh *m);
+int64_t efv_mesh_num_elements(const efv_mesh *m);
+int64_t efv_mesh_num_inner_faces(const efv_mesh *m);
+int64_t efv_mesh_num_facets(const efv_mesh *m);
+int64_t efv_mesh_num_outer_faces(const efv_mesh *m);                 /* = sum of facet vertex counts */
+int64_t efv_mesh_group_size(const efv_mesh *m, int shape_code);      /* elements of one shape */
+/* one-time geometry pass (north_star kernel 1): per inner face the global derivatives G = inv(D^T X) D^T
+ * [ref: InnerFace.py:23-25, Element.py:69-71], Jacobian inverse, area vector [ref: Shape.py:29-33,57-61,84-96,
+ * 119-139]; per element the sub-control volumes [ref: Element.py:39-48].  Stored on the device as SoA;
+ * exported per shape group (elements of one shape in grid order), element by element, face by face:
+ *   G    : per face d x m doubles (row-major),  Jinv : per face d x d,  S : per face 3,  vol : per element m,
+ *   vertex_volume : nV  [ref: Vertex.py:9, Element.py:46].  Any output pointer may be NULL.                  */
+int efv_geometry_build(efv_mesh *m);
+int efv_geometry_export_group(const efv_mesh *m, int shape_code, double *G, double *Jinv, double *S, double *vol);
+int efv_vertex_volume_export(const efv_mesh *m, double *vertex_volume);
+/* boundary geometry: per facet owning element, local facet index, outward area vector (3);
+ * per outer face (facet vertex) the vertex id and |area| [ref: OuterFace.py:18-19].                        */
+int efv_boundary_export(const efv_mesh *m, int64_t *facet_element, int32_t *facet_local, double *facet_area,
+                        int32_t *outer_vertex, double *outer_area_norm);
+
+/* ---- linear system  [ref: PyEFVLib/LinearSystem.py:113-183 LinearSystemCSR] -------------------------------
+ * CSR sparsity = union of element cliques with sorted columns (north_star kernel 2), DOF-expanded field-major
+ * exactly like LinearSystemCSR.initialize [ref: LinearSystem.py:114-128] with sorted stencils.              */
+efv_system *efv_system_create(efv_mesh *m, int ndof);
+void efv_system_destroy(efv_system *s);
+int64_t efv_system_rows(const efv_system *s);
+int64_t efv_system_nnz(const efv_system *s);          /* DOF-expanded: ndof^2 * graph nnz */
+int64_t efv_system_graph_nnz(const efv_system *s);
+int64_t efv_system_slotmap_size(const efv_system *s); /* sum over elements of m^2 */
+int efv_system_max_row_length(const efv_system *s);
+int efv_system_export_csr(const efv_system *s, int64_t *indptr, int32_t *indices);     /* getSparse() structure */
+int efv_system_export_graph(const efv_system *s, int64_t *gptr, int32_t *gcol);
+int efv_system_export_slotmap(const efv_system *s, int64_t *slots);  /* graph slot of (e,i,j), element order, i-major */
+int efv_system_export_values(const efv_system *s, double *data);     /* in efv_system_export_csr order */
+int efv_vec_upload(efv_system *s, int which, const double *host);
+int efv_vec_download(const efv_system *s, int which, double *host);
+
+/* ---- assembly (north_star kernels 3, 4) -------------------------------------------------------------------
+ * heat [ref: apps/heat_transfer.py:40-68 matrix, :89-113 RHS]: props = n_regions x 4 doubles
+ * {Conductivity, Density, HeatCapacity, HeatGeneration}.  Fills the interior operator (diffusion +, if
+ * transient, accumulation) and the lumped per-vertex vectors  gen = sum vol_k q,  acc = sum vol_k rho cp / dt.
+ * The kernel reads the SoA geometry of efv_geometry_build (built on demand).                                */
+int efv_heat_assemble(efv_system *s, const double *props, double dt, int transient);
+/* elasticity [ref: apps/stress_equilibrium.py:81-117]: props = n_regions x 4 {ShearModulus, PoissonsRatio,
+ * Density, Gravity}; gravity != 0 adds -rho g vol to the y component [ref: :81-90].  sign = +1 keeps the
+ * reference's sign convention (negative-definite interior operator).                                       */
+int efv_elasticity_assemble(efv_system *s, const double *props, int gravity);
+/* Biot [ref: apps/geomechanics.py:39-115 matrix, :143-199 RHS operator parts]: props = n_regions x 9
+ * {nu, G, cs, phi, k, cf, mu, rhos, rhof}; gvec = 3 doubles (reference uses 0).                              */
+int efv_biot_assemble(efv_system *s, const double *props, double dt, const double *gvec);
+
+/* boundary conditions.  Dirichlet rows are given in the order the reference visits them (boundaries in grid
+ * order, vertices in first-appearance order): for duplicates the LAST value wins
+ * [ref: apps/heat_transfer.py:122-126].  rows are field-major DOF indices.                                  */
+int efv_bc_clear(efv_system *s);
+int efv_bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int64_t n);
+/* Neumann: static_rhs[dof(outer vertex)] += sign * value * |outer face area| over the outer faces of
+ * `boundary`  [ref: apps/heat_transfer.py:115-120 (sign +1); apps/stress_equilibrium.py:131-141 (sign -1)] */
+int efv_bc_neumann(efv_system *s, int boundary, int dof, double value, double sign);
+/* apply the recorded Dirichlet set to the matrix values (north_star kernel 4) */
+int efv_apply_dirichlet(efv_system *s, int mode);
+/* RHS of one step into EFV_VEC_B:  heat: gen + acc * XOLD + neumann, Dirichlet rows <- g
+ * [ref: apps/heat_transfer.py:89-132]; elasticity: gravity + neumann, Dirichlet rows <- g
+ * [ref: apps/stress_equilibrium.py:119-163]; Biot: + S/dt vol p_old + alpha/dt N.s u_old terms
+ * [ref: apps/geomechanics.py:166-239].  In symmetric mode the eliminated columns are folded in.            */
+int efv_build_rhs(efv_system *s, int transient);
+
+/* ---- Krylov solvers (north_star kernel 5) -----------------------------------------------------------------
+ * replace the reference's sparse/dense inverse [ref: apps/heat_transfer.py:78-81,134-135;
+ * apps/stress_equilibrium.py:170-173; apps/geomechanics.py:140,254].  Solve A x = B from initial guess X;
+ * stop when ||r||_2 <= rtol * ||b||_2.  scale: multiply the system by -1 internally (elasticity) so that CG
+ * sees an SPD operator.  Outputs: iterations done and final relative residual.                             */
+int efv_solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres);
+int efv_solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres);
+int efv_spmv(efv_system *s, int which_in, int which_out);   /* y = A x on two of the system's vectors */
+/* max_i |X_i - XOLD_i|  [ref: apps/heat_transfer.py:142] and X -> XOLD copy */
+int efv_max_abs_diff(efv_system *s, double *out);
+int efv_advance(efv_system *s);
+/* per-kernel timing of the last solve / assemble (CUDA events on the library stream), milliseconds */
+int efv_last_timings(efv_system *s, double *assemble_ms, double *solve_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EFV_B200_H */

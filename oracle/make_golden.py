@@ -287,57 +287,17 @@ def biot_case(mesh, props, bcs, tag, dt=20.0, steps=2):
     print(f"biot_{tag}: n={len(b)} A {merr:.1e} b {berr:.1e} u {uerr:.1e} p {perr:.1e} ({time.time()-t0:.1f}s)")
 
 
-HEAT_PROPS = {"Body": {"HeatCapacity": 1.0, "Conductivity": 1.0, "Density": 1.0, "HeatGeneration": 100.0}}
-N0 = ("neumann", 0.0)
+from tests.cases import HEAT_CASES, STRESS_CASES, BIOT_CASES  # noqa: E402
 
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
-    we = {"West": ("dirichlet", 300.0), "East": ("dirichlet", 400.0), "South": N0, "North": N0}
-    we3 = dict(we, Bottom=N0, Top=N0)
-    bc3d = {"West": ("dirichlet", 300.0), "East": ("dirichlet", 400.0), "Bottom": ("dirichlet", 500.0),
-            "Top": ("neumann", 1000.0), "South": N0, "North": N0}
-    heat_case("2D/Square.msh", HEAT_PROPS, we, "Square", transient_steps=2)
-    heat_case("2D/10x10.msh", HEAT_PROPS, we, "10x10")
-    two = {"WEST": {"HeatCapacity": 1.0, "Conductivity": 1.0, "Density": 1.0, "HeatGeneration": 100.0},
-           "EAST": {"HeatCapacity": 2.0, "Conductivity": 5.0, "Density": 3.0, "HeatGeneration": 10.0}}
-    heat_case("2D/test.msh", two, {"SW": N0, "W": ("dirichlet", 300.0), "NW": ("neumann", 50.0), "MW": N0, "SE": N0,
-                                   "E": ("dirichlet", 400.0), "NE": ("neumann", -20.0), "ME": N0}, "test_mixed", transient_steps=2)
-    heat_case("3D/Hexas3x3x3.msh", HEAT_PROPS, we3, "Hexas3x3x3_we")
-    heat_case("3D/Hexas3x3x3.msh", HEAT_PROPS, bc3d, "Hexas3x3x3_3d", transient_steps=2)
-    heat_case("3D/Hexas6x6x6.msh", HEAT_PROPS, we3, "Hexas6x6x6_we")
-    heat_case("3D/eight_sphere.msh", HEAT_PROPS, {"Outer": ("dirichlet", 300.0), "InnerZ": ("neumann", 10.0),
-                                                  "InnerY": ("dirichlet", 350.0), "InnerX": N0}, "eight_sphere", transient_steps=2)
-    heat_case("3D/Tetras.msh", HEAT_PROPS, we3, "Tetras_we")
-
-    sprops = {"Body": {"Density": 1800.0, "PoissonsRatio": 0.4, "ShearModulus": 6.0e6, "Gravity": 10.0}}
-    s2 = {"u": {"West": ("dirichlet", 0.0), "East": ("dirichlet", 0.0), "South": N0, "North": N0},
-          "v": {"West": N0, "East": N0, "South": ("dirichlet", 0.0), "North": ("neumann", -1e4)}}
-    stress_case("2D/Square.msh", sprops, s2, "Square")
-    stress_case("2D/10x10.msh", sprops, s2, "10x10_gravity", gravity=True)
-    s3 = {"u": dict(s2["u"], Bottom=N0, Top=N0), "v": dict(s2["v"], Bottom=N0, Top=N0),
-          "w": {"West": N0, "East": N0, "South": N0, "North": N0, "Bottom": ("dirichlet", 0.0), "Top": N0}}
-    stress_case("3D/Hexas4x4x4.msh", sprops, s3, "Hexas4x4x4")
-    stress_case("3D/eight_sphere.msh", sprops,
-                {"u": {"Outer": N0, "InnerZ": N0, "InnerY": N0, "InnerX": ("dirichlet", 0.0)},
-                 "v": {"Outer": N0, "InnerZ": N0, "InnerY": ("dirichlet", 0.0), "InnerX": N0},
-                 "w": {"Outer": ("neumann", 2e3), "InnerZ": ("dirichlet", 0.0), "InnerY": N0, "InnerX": N0}}, "eight_sphere")
-
-    bprops = {"Body": {"nu": 0.2, "G": 6.0e9, "cs": 0.0, "phi": 0.19, "k": 1.9e-15, "cf": 3.0303e-10, "mu": 1000.0,
-                       "rhos": 2700.0, "rhof": 1000.0}}
-    b2 = {"u_x": {"West": ("dirichlet", 0.0), "East": ("dirichlet", 0.0), "South": N0, "North": N0},
-          "u_y": {"West": N0, "East": N0, "South": ("dirichlet", 0.0), "North": ("neumann", 1e5)},
-          "p": {"West": N0, "East": N0, "South": N0, "North": ("dirichlet", 0.0)}}
-    biot_case("2D/Square.msh", bprops, b2, "Square")
-    b3 = {"u_x": dict(b2["u_x"], Bottom=N0, Top=N0), "u_y": dict(b2["u_y"], Bottom=N0, Top=N0),
-          "u_z": {"West": N0, "East": N0, "South": N0, "North": N0, "Bottom": ("dirichlet", 0.0), "Top": N0},
-          "p": dict(b2["p"], Bottom=N0, Top=N0)}
-    biot_case("3D/Hexas3x3x3.msh", bprops, b3, "Hexas3x3x3")
-    biot_case("3D/eight_sphere.msh", bprops,
-              {"u_x": {"Outer": N0, "InnerZ": N0, "InnerY": N0, "InnerX": ("dirichlet", 0.0)},
-               "u_y": {"Outer": N0, "InnerZ": N0, "InnerY": ("dirichlet", 0.0), "InnerX": N0},
-               "u_z": {"Outer": ("neumann", 1e5), "InnerZ": ("dirichlet", 0.0), "InnerY": N0, "InnerX": N0},
-               "p": {"Outer": ("dirichlet", 0.0), "InnerZ": N0, "InnerY": N0, "InnerX": N0}}, "eight_sphere", steps=1)
+    for tag, c in HEAT_CASES.items():
+        heat_case(c["mesh"], c["props"], c["bcs"], tag, transient_steps=c["transient_steps"])
+    for tag, c in STRESS_CASES.items():
+        stress_case(c["mesh"], c["props"], c["bcs"], tag, gravity=c["gravity"])
+    for tag, c in BIOT_CASES.items():
+        biot_case(c["mesh"], c["props"], c["bcs"], tag, dt=c["dt"], steps=c["steps"])
 
 
 if __name__ == "__main__":

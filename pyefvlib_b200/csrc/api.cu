@@ -1,0 +1,298 @@
+// api.cu -- the extern "C" boundary declared in include/efv_b200.h.
+#include "../../include/efv_b200.h"
+#include "views.cuh"
+#include <cstring>
+
+namespace efv {
+const std::string &last_error();
+void set_device(int device);
+int64_t launch_count();
+}  // namespace efv
+
+#define EFV_API_BEGIN try {
+#define EFV_API_END                                   \
+  return 0;                                           \
+  }                                                   \
+  catch (const std::exception &ex) {                  \
+    efv::set_last_error(ex.what());                   \
+    return -1;                                        \
+  }
+#define EFV_API_END_PTR(ptr_to_free)                  \
+  }                                                   \
+  catch (const std::exception &ex) {                  \
+    efv::set_last_error(ex.what());                   \
+    delete ptr_to_free;                               \
+    return nullptr;                                   \
+  }
+
+extern "C" {
+
+const char *efv_last_error(void) { return efv::last_error().c_str(); }
+
+int efv_set_device(int device) {
+  EFV_API_BEGIN
+  efv::set_device(device);
+  EFV_API_END
+}
+int efv_device_count(int *count) {
+  EFV_API_BEGIN
+  int c = 0;
+  cudaError_t e = cudaGetDeviceCount(&c);
+  if (e != cudaSuccess) { c = 0; cudaGetLastError(); }
+  *count = c;
+  EFV_API_END
+}
+void *efv_get_stream(void) {
+  try { return (void *)efv::stream(); } catch (const std::exception &ex) { efv::set_last_error(ex.what()); return nullptr; }
+}
+int efv_synchronize(void) {
+  EFV_API_BEGIN
+  EFV_CUDA(cudaStreamSynchronize(efv::stream()));
+  EFV_API_END
+}
+int64_t efv_kernel_launch_count(void) { return efv::launch_count(); }
+
+// ---- mesh ----------------------------------------------------------------------------------------------------------
+efv_mesh *efv_mesh_create(int dim, int64_t nV, const double *coords, int64_t nE, const int64_t *elem_ptr,
+                          const int32_t *conn, const int32_t *region_of_elem, int n_regions) {
+  efv_mesh *m = nullptr;
+  try {
+    EFV_REQUIRE(dim == 2 || dim == 3, "dimension must be 2 or 3");
+    EFV_REQUIRE(nV > 0 && nE > 0, "empty mesh");
+    EFV_REQUIRE(nV < (int64_t(1) << 31), "vertex ids must fit int32");
+    EFV_REQUIRE(coords && elem_ptr && conn, "null mesh array");
+    m = new efv_mesh();
+    m->dim = dim; m->nV = nV; m->nE = nE; m->n_regions = n_regions > 0 ? n_regions : 1;
+    m->conn_size = elem_ptr[nE];
+    m->coords.upload(coords, (size_t)nV * 3);
+    m->conn.upload(conn, (size_t)m->conn_size);
+    if (region_of_elem) m->region.upload(region_of_elem, (size_t)nE);
+    else { m->region.alloc(nE); m->region.zero(); }
+    std::vector<int64_t> ep(elem_ptr, elem_ptr + nE + 1);
+    efv::mesh_finalize(m, ep);
+    return m;
+  EFV_API_END_PTR(m)
+}
+
+int efv_mesh_set_boundaries(efv_mesh *m, int n_boundaries, const int64_t *boundary_ptr, int64_t n_facets,
+                            const int64_t *facet_ptr, const int32_t *facet_conn) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(m, "null mesh");
+  efv::mesh_set_boundaries(m, n_boundaries, boundary_ptr, n_facets, facet_ptr, facet_conn);
+  EFV_API_END
+}
+void efv_mesh_destroy(efv_mesh *m) { delete m; }
+int64_t efv_mesh_num_vertices(const efv_mesh *m) { return m ? m->nV : -1; }
+int64_t efv_mesh_num_elements(const efv_mesh *m) { return m ? m->nE : -1; }
+int64_t efv_mesh_num_inner_faces(const efv_mesh *m) { return m ? m->n_inner_faces : -1; }
+int64_t efv_mesh_num_facets(const efv_mesh *m) { return m ? m->bnd.nF : -1; }
+int64_t efv_mesh_num_outer_faces(const efv_mesh *m) { return m ? m->bnd.nOuter : -1; }
+int64_t efv_mesh_group_size(const efv_mesh *m, int shape_code) {
+  return (m && shape_code >= 0 && shape_code < efv::kNumShapes) ? m->groups[shape_code].n : -1;
+}
+
+int efv_geometry_build(efv_mesh *m) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(m, "null mesh");
+  efv::geometry_build(m);
+  EFV_CUDA(cudaStreamSynchronize(efv::stream()));
+  EFV_API_END
+}
+int efv_geometry_export_group(const efv_mesh *m, int shape_code, double *G, double *Jinv, double *S, double *vol) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(m, "null mesh");
+  efv::geometry_export_group(m, shape_code, G, Jinv, S, vol);
+  EFV_API_END
+}
+int efv_vertex_volume_export(const efv_mesh *m, double *vertex_volume) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(m, "null mesh");
+  efv::vertex_volume_export(m, vertex_volume);
+  EFV_API_END
+}
+int efv_boundary_export(const efv_mesh *m, int64_t *facet_element, int32_t *facet_local, double *facet_area,
+                        int32_t *outer_vertex, double *outer_area_norm) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(m, "null mesh");
+  const efv::Boundaries &B = m->bnd;
+  if (facet_element) B.facet_element.download(facet_element, B.nF);
+  if (facet_local) B.facet_local.download(facet_local, B.nF);
+  if (facet_area) B.facet_area.download(facet_area, B.nF * 3);
+  if (outer_vertex) B.outer_vertex.download(outer_vertex, B.nOuter);
+  if (outer_area_norm) B.outer_area_norm.download(outer_area_norm, B.nOuter);
+  EFV_API_END
+}
+
+// ---- system --------------------------------------------------------------------------------------------------------
+efv_system *efv_system_create(efv_mesh *m, int ndof) {
+  efv_system *s = nullptr;
+  try {
+    EFV_REQUIRE(m, "null mesh");
+    EFV_REQUIRE(ndof >= 1 && ndof <= 4, "ndof must be 1..4");
+    s = new efv_system();
+    s->mesh = m;
+    s->ndof = ndof;
+    efv::system_build_graph(s);
+    s->vals.alloc((size_t)s->nnzg * ndof * ndof);
+    s->vals.zero();
+    efv::ensure_vectors(s);
+    efv::bc_clear(s);
+    EFV_CUDA(cudaStreamSynchronize(efv::stream()));
+    return s;
+  EFV_API_END_PTR(s)
+}
+void efv_system_destroy(efv_system *s) {
+  if (!s) return;
+  efv::krylov_free(s);
+  delete s;
+}
+int64_t efv_system_rows(const efv_system *s) { return s ? s->rows : -1; }
+int64_t efv_system_nnz(const efv_system *s) { return s ? s->nnzg * s->ndof * s->ndof : -1; }
+int64_t efv_system_graph_nnz(const efv_system *s) { return s ? s->nnzg : -1; }
+int64_t efv_system_slotmap_size(const efv_system *s) { return s ? s->slot_size : -1; }
+int efv_system_max_row_length(const efv_system *s) { return s ? s->max_row_len : -1; }
+
+int efv_system_export_csr(const efv_system *s, int64_t *indptr, int32_t *indices) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::export_csr(s, indptr, indices);
+  EFV_API_END
+}
+int efv_system_export_graph(const efv_system *s, int64_t *gptr, int32_t *gcol) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  if (gptr) s->gptr.download(gptr, s->nV + 1);
+  if (gcol) s->gcol.download(gcol, s->nnzg);
+  EFV_API_END
+}
+int efv_system_export_slotmap(const efv_system *s, int64_t *slots) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::export_slotmap(s, slots);
+  EFV_API_END
+}
+int efv_system_export_values(const efv_system *s, double *data) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::export_values(s, data);
+  EFV_API_END
+}
+
+static efv::DBuf<double> *pick_vec(efv_system *s, int which) {
+  switch (which) {
+    case EFV_VEC_X: return &s->x;
+    case EFV_VEC_B: return &s->b;
+    case EFV_VEC_XOLD: return &s->xold;
+    default: throw efv::Error("unknown vector id");
+  }
+}
+int efv_vec_upload(efv_system *s, int which, const double *host) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && host, "null argument");
+  efv::vec_upload(s, *pick_vec(s, which), host);
+  EFV_API_END
+}
+int efv_vec_download(const efv_system *s, int which, double *host) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && host, "null argument");
+  efv::vec_download(s, *pick_vec(const_cast<efv_system *>(s), which), host);
+  EFV_API_END
+}
+
+// ---- assembly / BCs ------------------------------------------------------------------------------------------------
+int efv_heat_assemble(efv_system *s, const double *props, double dt, int transient) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && props, "null argument");
+  EFV_REQUIRE(!transient || dt > 0, "transient assembly needs a positive time step");
+  efv::heat_assemble(s, props, dt, transient);
+  EFV_API_END
+}
+int efv_elasticity_assemble(efv_system *s, const double *props, int gravity) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && props, "null argument");
+  efv::elasticity_assemble(s, props, gravity);
+  EFV_API_END
+}
+int efv_biot_assemble(efv_system *s, const double *props, double dt, const double *gvec) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && props, "null argument");
+  EFV_REQUIRE(dt > 0, "Biot assembly needs a positive time step");
+  efv::biot_assemble(s, props, dt, gvec);
+  EFV_API_END
+}
+int efv_bc_clear(efv_system *s) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::bc_clear(s);
+  EFV_API_END
+}
+int efv_bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int64_t n) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(n == 0 || (rows && values), "null Dirichlet arrays");
+  for (int64_t k = 0; k < n; ++k) EFV_REQUIRE(rows[k] >= 0 && rows[k] < s->rows, "Dirichlet row out of range");
+  efv::bc_dirichlet(s, rows, values, n);
+  EFV_API_END
+}
+int efv_bc_neumann(efv_system *s, int boundary, int dof, double value, double sign) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::bc_neumann(s, boundary, dof, value, sign);
+  EFV_API_END
+}
+int efv_apply_dirichlet(efv_system *s, int mode) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::apply_dirichlet(s, mode);
+  EFV_API_END
+}
+int efv_build_rhs(efv_system *s, int transient) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::build_rhs(s, transient);
+  EFV_API_END
+}
+
+// ---- solvers -------------------------------------------------------------------------------------------------------
+int efv_solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::solve_pcg(s, rtol, maxit, negate, iters, relres);
+  EFV_API_END
+}
+int efv_solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::solve_bicgstab(s, rtol, maxit, iters, relres);
+  EFV_API_END
+}
+int efv_spmv(efv_system *s, int which_in, int which_out) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(which_in != which_out, "in-place SpMV is not supported");
+  efv::ensure_vectors(s);
+  efv::spmv(s, pick_vec(s, which_in)->p, pick_vec(s, which_out)->p);
+  EFV_API_END
+}
+int efv_max_abs_diff(efv_system *s, double *out) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && out, "null argument");
+  *out = efv::max_abs_diff(s);
+  EFV_API_END
+}
+int efv_advance(efv_system *s) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::ensure_vectors(s);
+  EFV_CUDA(cudaMemcpyAsync(s->xold.p, s->x.p, s->rows * sizeof(double), cudaMemcpyDeviceToDevice, efv::stream()));
+  EFV_API_END
+}
+int efv_last_timings(efv_system *s, double *assemble_ms, double *solve_ms) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  if (assemble_ms) *assemble_ms = s->t_assemble_ms;
+  if (solve_ms) *solve_ms = s->t_solve_ms;
+  EFV_API_END
+}
+
+}  // extern "C"

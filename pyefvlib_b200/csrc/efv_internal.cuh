@@ -1,0 +1,137 @@
+// efv_internal.cuh -- device data model of libefv_b200.
+//
+// HBM layout (all SoA, sized for one B200):
+//   mesh      coords f64[nV][3] | elem_ptr i64[nE+1] | conn i32[sum m] | elem_shape u8[nE] | elem_gidx i32[nE]
+//             region i32[nE] | incidence: inc_ptr i64[nV+1], inc u32[sum m] = (element << 3 | local vertex),
+//             sorted by element id inside each vertex list (deterministic reduction order)
+//   geometry  per shape group g (elements of one shape, index-in-group k):
+//             Jinv f64[NF*d*d][n_g] | S f64[NF*3][n_g] | vol f64[M][n_g]          (component-major = coalesced)
+//   system    graph CSR gptr i64[nV+1], gcol i32[nnzg] (sorted) | slotpos u8[sum m*m] (position inside the row)
+//             vals f64[nnzg][ndof][ndof] (BSR over the vertex graph) | vectors f64[nV][ndof] (vertex-major inside,
+//             field-major at the C-ABI) | dirichlet flag u8 / value f64 per DOF
+#pragma once
+#include "common.cuh"
+
+namespace efv {
+
+constexpr int kNumShapes = 4;
+constexpr int kMaxM = 8;
+enum { EFV_TRI = 0, EFV_QUAD = 1, EFV_TET = 2, EFV_HEX = 3 };
+
+struct ShapeGroup {
+  int code = -1;
+  int64_t n = 0;            // elements of this shape
+  DBuf<int32_t> ids;        // global element id of group member k (empty when the mesh is uniform: id = k)
+  // SoA geometry (efv_geometry_build)
+  DBuf<double> Jinv, S, vol;
+};
+
+struct Boundaries {
+  int nB = 0;
+  int64_t nF = 0, nOuter = 0;
+  std::vector<int64_t> boundary_ptr;       // host copy, facets of boundary b
+  std::vector<int64_t> outer_ptr_host;     // outer faces of boundary b: [outer_ptr[b], outer_ptr[b+1])
+  DBuf<int64_t> facet_ptr;                 // nF+1
+  DBuf<int32_t> facet_conn;
+  DBuf<int64_t> facet_element;             // nF
+  DBuf<int32_t> facet_local;               // nF
+  DBuf<double> facet_area;                 // nF x 3 (outward)
+  // outer faces = one per facet vertex, in facet order (Facet.py:41-45)
+  DBuf<int32_t> outer_vertex;              // nOuter
+  DBuf<int32_t> outer_local;               // position of the vertex in the element's facet table (Boundary.py:66)
+  DBuf<int64_t> outer_facet;               // nOuter
+  DBuf<double> outer_area_norm;            // nOuter
+  // compact boundary-vertex -> outer-face map (ascending outer id = reference visiting order)
+  int64_t nbv = 0;
+  DBuf<int32_t> bv;                        // nbv vertex ids (ascending)
+  DBuf<int64_t> bvo_ptr, bvo;              // nbv+1, nOuter
+};
+
+}  // namespace efv
+
+struct efv_mesh {
+  int dim = 0;
+  int64_t nV = 0, nE = 0, conn_size = 0, n_inner_faces = 0;
+  int n_regions = 0;
+  int uniform_code = -1;     // shape code when every element has the same shape, else -1
+  int max_m = 0;
+  efv::DBuf<double> coords;
+  efv::DBuf<int64_t> elem_ptr;
+  efv::DBuf<int32_t> conn;
+  efv::DBuf<uint8_t> elem_shape;
+  efv::DBuf<int32_t> elem_gidx;
+  efv::DBuf<int32_t> region;
+  efv::DBuf<int64_t> inc_ptr;
+  efv::DBuf<uint32_t> inc;
+  efv::DBuf<int64_t> slot_ptr;   // per element offset into slot-map-sized arrays (sum of m*m); empty if uniform
+  efv::DBuf<double> vertex_volume;
+  efv::ShapeGroup groups[efv::kNumShapes];
+  efv::Boundaries bnd;
+  bool has_geometry = false;
+};
+
+namespace efv {
+struct KrylovWork;
+}
+
+struct efv_system {
+  efv_mesh *mesh = nullptr;
+  int ndof = 1;
+  int64_t nV = 0, rows = 0, nnzg = 0, slot_size = 0;
+  int max_row_len = 0;
+  efv::DBuf<int64_t> gptr;
+  efv::DBuf<int32_t> gcol;
+  efv::DBuf<uint8_t> slotpos;
+  efv::DBuf<int32_t> diag_slot;        // graph slot of (v, v)
+  efv::DBuf<double> vals;              // nnzg * ndof * ndof
+  // vectors (vertex-major interleaved: [v][dof])
+  efv::DBuf<double> x, b, xold, static_rhs, elim;
+  // heat lumped vectors; Biot reuses acc for S/dt * vol
+  efv::DBuf<double> gen, acc;
+  // Biot: copy of the pre-Dirichlet p-row operator needed for the RHS (p rows x all cols)
+  efv::DBuf<double> rhs_op;
+  // Dirichlet set
+  efv::DBuf<uint8_t> dir_flag;
+  efv::DBuf<double> dir_value;
+  efv::DBuf<int32_t> dir_last;
+  int dirichlet_mode = -1;
+  bool has_dirichlet = false;
+  int physics = 0;
+  // Krylov workspace
+  efv::KrylovWork *kw = nullptr;
+  double t_assemble_ms = 0, t_solve_ms = 0, t_spmv_ms = 0;
+};
+
+namespace efv {
+// mesh.cu
+void mesh_finalize(efv_mesh *m, const std::vector<int64_t> &elem_ptr_host);
+void mesh_set_boundaries(efv_mesh *m, int nB, const int64_t *boundary_ptr, int64_t nF, const int64_t *facet_ptr,
+                         const int32_t *facet_conn);
+// geometry.cu
+void geometry_build(efv_mesh *m);
+void geometry_export_group(const efv_mesh *m, int code, double *G, double *Jinv, double *S, double *vol);
+void vertex_volume_export(const efv_mesh *m, double *vv);
+// csr.cu
+void system_build_graph(efv_system *s);
+// assemble.cu
+void heat_assemble(efv_system *s, const double *props_host, double dt, int transient);
+void elasticity_assemble(efv_system *s, const double *props_host, int gravity);
+void biot_assemble(efv_system *s, const double *props_host, double dt, const double *gvec);
+void bc_clear(efv_system *s);
+void bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int64_t n);
+void bc_neumann(efv_system *s, int boundary, int dof, double value, double sign);
+void apply_dirichlet(efv_system *s, int mode);
+void build_rhs(efv_system *s, int transient);
+void ensure_vectors(efv_system *s);
+void export_csr(const efv_system *s, int64_t *indptr, int32_t *indices);
+void export_slotmap(const efv_system *s, int64_t *slots);
+void export_values(const efv_system *s, double *data);
+void vec_upload(efv_system *s, DBuf<double> &dst, const double *host);
+void vec_download(const efv_system *s, const DBuf<double> &src, double *host);
+// krylov.cu
+void krylov_free(efv_system *s);
+void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres);
+void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres);
+void spmv(efv_system *s, const double *x, double *y);
+double max_abs_diff(efv_system *s);
+}  // namespace efv

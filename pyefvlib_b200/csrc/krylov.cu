@@ -1,0 +1,468 @@
+// krylov.cu -- north_star kernel 5: Jacobi-preconditioned CG and BiCGStab on a vectorised CSR/BSR SpMV.
+//
+// The matrix is BSR over the vertex graph (block = ndof x ndof, ndof = 1 for heat => plain CSR).  SpMV assigns a
+// group of L lanes to a graph row; the L lanes stream the row's values and column indices with coalesced loads,
+// gather x through L1/L2 and combine with warp shuffles.  Every scalar of the Krylov recurrences lives on the
+// device: dot products are reduced in two deterministic stages (fixed grid, per-block partial -> every block of
+// the NEXT kernel re-sums the partials in the same fixed order), so an iteration is 3 launches with no host
+// round trip and no float atomics; the host only polls a `done` flag every few dozen iterations.
+// These solvers replace the reference's explicit inverses (apps/heat_transfer.py:78-81,134-135,
+// apps/stress_equilibrium.py:170-173, apps/geomechanics.py:140,254).
+#include "views.cuh"
+#include <cmath>
+#include <cstdlib>
+
+namespace efv {
+
+constexpr int kBlock = 256;
+
+struct KrylovWork {
+  int64_t n = 0;
+  int grid = 0;
+  DBuf<double> r, p, Ap, dinv, rhat, v, sv, t, phat, shat;
+  DBuf<double> partial;     // 4 * grid
+  DBuf<double> sc;          // device scalars
+  DBuf<int> flags;          // [0] done, [1] iterations, [2] breakdown
+  int *h_flags = nullptr;   // pinned
+  double *h_sc = nullptr;   // pinned
+  cudaEvent_t ev = nullptr, e0 = nullptr, e1 = nullptr;
+};
+
+static KrylovWork *work(efv_system *s) {
+  if (!s->kw) {
+    KrylovWork *w = new KrylovWork();
+    w->n = s->rows;
+    w->grid = num_sms() * 4;
+    w->partial.alloc((size_t)4 * w->grid);
+    w->sc.alloc(16);
+    w->flags.alloc(4);
+    EFV_CUDA(cudaMallocHost(&w->h_flags, 4 * sizeof(int)));
+    EFV_CUDA(cudaMallocHost(&w->h_sc, 16 * sizeof(double)));
+    EFV_CUDA(cudaEventCreateWithFlags(&w->ev, cudaEventDisableTiming));
+    EFV_CUDA(cudaEventCreate(&w->e0));
+    EFV_CUDA(cudaEventCreate(&w->e1));
+    s->kw = w;
+  }
+  return s->kw;
+}
+void krylov_free(efv_system *s) {
+  if (!s->kw) return;
+  KrylovWork *w = s->kw;
+  if (w->h_flags) cudaFreeHost(w->h_flags);
+  if (w->h_sc) cudaFreeHost(w->h_sc);
+  if (w->ev) cudaEventDestroy(w->ev);
+  if (w->e0) cudaEventDestroy(w->e0);
+  if (w->e1) cudaEventDestroy(w->e1);
+  delete w;
+  s->kw = nullptr;
+}
+
+// fixed-order sum of `count` partials, identical in every block
+__device__ __forceinline__ double sum_partials(const double *__restrict__ part, int count, double *red) {
+  double a = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) a += part[i];
+  a = block_sum(a, red);
+  __shared__ double bc;
+  if (threadIdx.x == 0) bc = a;
+  __syncthreads();
+  double r = bc;
+  __syncthreads();
+  return r;
+}
+
+// ---- SpMV: y = sigma * A x  (optionally y *= rowscale), partial[blockIdx] = sum_i w_i * y_i -------------------------
+template <int NDOF, int L>
+__global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__restrict__ gptr,
+                                                 const int32_t *__restrict__ gcol, const double *__restrict__ vals,
+                                                 const double *__restrict__ x, double *__restrict__ y, double sigma,
+                                                 const double *__restrict__ rowscale, const double *__restrict__ w,
+                                                 double *__restrict__ partial, const int *__restrict__ done) {
+  __shared__ double red[32];
+  if (done && *done) return;
+  const int gl = threadIdx.x % L;
+  const int64_t rows_per_block = kBlock / L;
+  double dot = 0.0;
+  for (int64_t v = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / L; v < nV; v += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t r0 = gptr[v], r1 = gptr[v + 1];
+    double acc[NDOF];
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
+    for (int64_t t = r0 + gl; t < r1; t += L) {
+      const int64_t c = gcol[t];
+      if (NDOF == 1) {
+        acc[0] += vals[t] * x[c];
+      } else {
+        double xv[NDOF];
+#pragma unroll
+        for (int j = 0; j < NDOF; ++j) xv[j] = x[c * NDOF + j];
+        const double *blk = vals + t * (NDOF * NDOF);
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+          for (int j = 0; j < NDOF; ++j) acc[i] += blk[i * NDOF + j] * xv[j];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) acc[i] = group_sum<L>(acc[i]);
+    if (gl == 0) {
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) {
+        double yi = sigma * acc[i];
+        if (rowscale) yi *= rowscale[v * NDOF + i];
+        y[v * NDOF + i] = yi;
+        if (w) dot += w[v * NDOF + i] * yi;
+      }
+    }
+  }
+  if (partial) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+  }
+}
+
+static int pick_lanes(const efv_system *s) {
+  const char *env = getenv("EFV_SPMV_LANES");
+  if (env) { int l = atoi(env); if (l == 2 || l == 4 || l == 8 || l == 16 || l == 32) return l; }
+  double avg = (double)s->nnzg / (double)(s->nV > 0 ? s->nV : 1);
+  if (avg <= 6) return 2;
+  if (avg <= 20) return 4;
+  if (avg <= 48) return 8;
+  if (avg <= 96) return 16;
+  return 32;
+}
+
+template <int NDOF>
+static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
+                          const double *w, double *partial, const int *done) {
+  switch (pick_lanes(s)) {
+    case 2: EFV_LAUNCH((k_spmv<NDOF, 2>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
+    case 4: EFV_LAUNCH((k_spmv<NDOF, 4>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
+    case 8: EFV_LAUNCH((k_spmv<NDOF, 8>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
+    case 16: EFV_LAUNCH((k_spmv<NDOF, 16>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
+    default: EFV_LAUNCH((k_spmv<NDOF, 32>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
+  }
+}
+static void launch_spmv(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
+                        const double *w, double *partial, const int *done) {
+  switch (s->ndof) {
+    case 1: launch_spmv_l<1>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
+    case 2: launch_spmv_l<2>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
+    case 3: launch_spmv_l<3>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
+    case 4: launch_spmv_l<4>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
+    default: throw Error("unsupported ndof");
+  }
+}
+
+void spmv(efv_system *s, const double *x, double *y) {
+  EFV_REQUIRE(s->vals.n, "no values assembled");
+  launch_spmv(s, num_sms() * 4, x, y, 1.0, nullptr, nullptr, nullptr, nullptr);
+}
+
+// ---- Jacobi -----------------------------------------------------------------------------------------------------------
+__global__ void k_jacobi(int64_t nV, int ndof, const int32_t *__restrict__ diag_slot, const double *__restrict__ vals,
+                         double sigma, double *__restrict__ dinv) {
+  int64_t n = nV * ndof;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t v = i / ndof;
+    int f = (int)(i % ndof);
+    double d = sigma * vals[((int64_t)diag_slot[v] * ndof + f) * ndof + f];
+    dinv[i] = (d != 0.0) ? 1.0 / d : 1.0;
+  }
+}
+
+// ---- PCG kernels ---------------------------------------------------------------------------------------------------------
+// r = sigma*b - y (y = sigma*A*x0); z = dinv r; p = z; partials: [0] r.z  [1] r.r  [2] b.b
+__global__ void __launch_bounds__(kBlock) k_pcg_init(int64_t n, const double *__restrict__ b, const double *__restrict__ y,
+                                                     const double *__restrict__ dinv, double sigma, double *__restrict__ r,
+                                                     double *__restrict__ p, double *__restrict__ partial) {
+  __shared__ double red[32];
+  double rz = 0, rr = 0, bb = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double bi = b[i];
+    double ri = sigma * bi - y[i];
+    double zi = dinv[i] * ri;
+    r[i] = ri; p[i] = zi;
+    rz += ri * zi; rr += ri * ri; bb += bi * bi;
+  }
+  int G = gridDim.x;
+  rz = block_sum(rz, red); if (threadIdx.x == 0) partial[blockIdx.x] = rz;
+  rr = block_sum(rr, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = rr;
+  bb = block_sum(bb, red); if (threadIdx.x == 0) partial[2 * G + blockIdx.x] = bb;
+}
+// sc: [0],[1] rz ping-pong, [2] b.b, [3] r.r, [4] rtol^2
+__global__ void k_pcg_init_scalars(int G, const double *__restrict__ partial, double *__restrict__ sc, int *__restrict__ flags,
+                                   double rtol) {
+  __shared__ double red[32];
+  double rz = sum_partials(partial, G, red);
+  double rr = sum_partials(partial + G, G, red);
+  double bb = sum_partials(partial + 2 * G, G, red);
+  if (threadIdx.x == 0) {
+    sc[0] = rz; sc[1] = 0.0; sc[2] = bb; sc[3] = rr; sc[4] = rtol * rtol;
+    flags[0] = (rr <= rtol * rtol * bb) ? 1 : 0;
+    flags[1] = 0; flags[2] = 0;
+  }
+}
+// alpha = rz / p.Ap ; x += alpha p ; r -= alpha Ap ; partials [0] r.z(new) [1] r.r(new)
+__global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, const double *__restrict__ sc,
+                                                          const double *__restrict__ pAp_partial, int G,
+                                                          const double *__restrict__ p, const double *__restrict__ Ap,
+                                                          const double *__restrict__ dinv, double *__restrict__ x,
+                                                          double *__restrict__ r, double *__restrict__ partial,
+                                                          const int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  double pAp = sum_partials(pAp_partial, G, red);
+  double alpha = sc[it & 1] / pAp;
+  double rz = 0, rr = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    double ri = r[i] - alpha * Ap[i];
+    r[i] = ri;
+    rz += ri * ri * dinv[i];
+    rr += ri * ri;
+  }
+  rz = block_sum(rz, red); if (threadIdx.x == 0) partial[blockIdx.x] = rz;
+  rr = block_sum(rr, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = rr;
+}
+// beta = rz_new / rz_old ; p = dinv r + beta p ; block 0 publishes the scalars and the convergence flag
+__global__ void __launch_bounds__(kBlock) k_pcg_update_p(int64_t n, int it, double *__restrict__ sc,
+                                                         const double *__restrict__ partial, int G,
+                                                         const double *__restrict__ r, const double *__restrict__ dinv,
+                                                         double *__restrict__ p, int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  double rz_new = sum_partials(partial, G, red);
+  double rr = sum_partials(partial + G, G, red);
+  double beta = rz_new / sc[it & 1];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = dinv[i] * r[i] + beta * p[i];
+  // every block must have read flags[0]/sc before block 0 overwrites them: the values written here are only
+  // consumed by the NEXT kernel (sc[(it+1)&1] is the slot nobody reads in this one)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc[(it + 1) & 1] = rz_new;
+    sc[3] = rr;
+    flags[1] = it + 1;
+    // benign race: a block of THIS kernel that has not started yet may see done=1 and skip its p update,
+    // which is irrelevant once converged (x and r are final after k_pcg_update_xr)
+    if (!(rr > sc[4] * sc[2])) flags[0] = 1;
+  }
+}
+
+void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres) {
+  EFV_REQUIRE(s->vals.n, "no values assembled");
+  ensure_vectors(s);
+  KrylovWork *w = work(s);
+  const int64_t n = s->rows;
+  if (!w->r.n) { w->r.alloc(n); w->p.alloc(n); w->Ap.alloc(n); w->dinv.alloc(n); }
+  const double sigma = negate ? -1.0 : 1.0;
+  const int G = w->grid;
+  EFV_CUDA(cudaEventRecord(w->e0, stream()));
+  EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->nV, s->ndof, s->diag_slot.p, s->vals.p, sigma, w->dinv.p);
+  EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
+  launch_spmv(s, G, s->x.p, w->Ap.p, sigma, nullptr, nullptr, nullptr, nullptr);
+  EFV_LAUNCH(k_pcg_init, G, kBlock, 0, n, s->b.p, w->Ap.p, w->dinv.p, sigma, w->r.p, w->p.p, w->partial.p);
+  EFV_LAUNCH(k_pcg_init_scalars, 1, kBlock, 0, G, w->partial.p, w->sc.p, w->flags.p, rtol);
+  const int check_every = 32;
+  int it = 0;
+  bool done = false;
+  while (!done && it < maxit) {
+    int batch_end = std::min(maxit, it + check_every);
+    for (; it < batch_end; ++it) {
+      launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, w->partial.p + 3 * G, w->flags.p);
+      EFV_LAUNCH(k_pcg_update_xr, G, kBlock, 0, n, it, w->sc.p, w->partial.p + 3 * G, G, w->p.p, w->Ap.p, w->dinv.p, s->x.p,
+                 w->r.p, w->partial.p, w->flags.p);
+      EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, w->partial.p, G, w->r.p, w->dinv.p, w->p.p, w->flags.p);
+    }
+    EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+    done = w->h_flags[0] != 0;
+  }
+  EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaMemcpyAsync(w->h_sc, w->sc.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaEventRecord(w->e1, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+  float ms = 0;
+  EFV_CUDA(cudaEventElapsedTime(&ms, w->e0, w->e1));
+  s->t_solve_ms = ms;
+  if (iters) *iters = w->h_flags[1];
+  if (relres) *relres = (w->h_sc[2] > 0) ? std::sqrt(w->h_sc[3] / w->h_sc[2]) : 0.0;
+}
+
+// ---- BiCGStab on the row-scaled system D^-1 A x = D^-1 b ---------------------------------------
+// sc: [0] rho, [1] alpha, [2] omega, [3] ||b~||^2, [4] ||r~||^2, [5] rtol^2
+__global__ void __launch_bounds__(kBlock) k_bi_init(int64_t n, const double *__restrict__ b, const double *__restrict__ y,
+                                                    const double *__restrict__ dinv, double *__restrict__ r,
+                                                    double *__restrict__ rhat, double *__restrict__ p, double *__restrict__ v,
+                                                    double *__restrict__ partial) {
+  __shared__ double red[32];
+  double rr = 0, bb = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double bi = dinv[i] * b[i];
+    double ri = bi - y[i];
+    r[i] = ri; rhat[i] = ri; p[i] = 0.0; v[i] = 0.0;
+    rr += ri * ri; bb += bi * bi;
+  }
+  int G = gridDim.x;
+  rr = block_sum(rr, red); if (threadIdx.x == 0) partial[blockIdx.x] = rr;
+  bb = block_sum(bb, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = bb;
+}
+__global__ void k_bi_init_scalars(int G, const double *__restrict__ partial, double *__restrict__ sc, int *__restrict__ flags,
+                                  double rtol) {
+  __shared__ double red[32];
+  double rr = sum_partials(partial, G, red);
+  double bb = sum_partials(partial + G, G, red);
+  if (threadIdx.x == 0) {
+    sc[0] = 1.0; sc[1] = 1.0; sc[2] = 1.0; sc[3] = bb; sc[4] = rr; sc[5] = rtol * rtol; sc[6] = rr;   // sc[6] = (rhat, r)
+    flags[0] = (rr <= rtol * rtol * bb) ? 1 : 0;
+    flags[1] = 0; flags[2] = 0; flags[3] = 0;
+  }
+}
+// beta = (rho_new/rho)(alpha/omega); p = r + beta (p - omega v)
+__global__ void __launch_bounds__(kBlock) k_bi_p(int64_t n, const double *__restrict__ sc, const double *__restrict__ r,
+                                                 const double *__restrict__ v, double *__restrict__ p,
+                                                 const int *__restrict__ flags) {
+  if (flags[0]) return;
+  double rho_new = sc[6], rho = sc[0], alpha = sc[1], omega = sc[2];
+  double beta = (rho_new / rho) * (alpha / omega);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = r[i] + beta * (p[i] - omega * v[i]);
+}
+// alpha = rho_new / (rhat, v); s = r - alpha v ; block 0 stores alpha
+__global__ void __launch_bounds__(kBlock) k_bi_s(int64_t n, double *__restrict__ sc, const double *__restrict__ rv_partial, int G,
+                                                 const double *__restrict__ r, const double *__restrict__ v,
+                                                 double *__restrict__ sv, const int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  double rv = sum_partials(rv_partial, G, red);
+  double alpha = sc[6] / rv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    sv[i] = r[i] - alpha * v[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc[7] = alpha;     // staged alpha (sc[1] still read by nobody in this kernel)
+}
+// t = A s done by spmv with partial (t,s); (t,t) needs its own pass fused here:
+__global__ void __launch_bounds__(kBlock) k_bi_tt(int64_t n, const double *__restrict__ t, double *__restrict__ partial,
+                                                  const int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  double tt = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) tt += t[i] * t[i];
+  tt = block_sum(tt, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tt;
+}
+// omega = (t,s)/(t,t); x += alpha p + omega s; r = s - omega t; partials (rhat,r), (r,r)
+__global__ void __launch_bounds__(kBlock) k_bi_xr(int64_t n, const double *__restrict__ sc, const double *__restrict__ ts_partial,
+                                                  const double *__restrict__ tt_partial, int G, const double *__restrict__ p,
+                                                  const double *__restrict__ sv, const double *__restrict__ t,
+                                                  const double *__restrict__ rhat, double *__restrict__ x,
+                                                  double *__restrict__ r, double *__restrict__ partial,
+                                                  const int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  double ts = sum_partials(ts_partial, G, red);
+  double tt = sum_partials(tt_partial, G, red);
+  double omega = (tt > 0) ? ts / tt : 0.0;
+  double alpha = sc[7];
+  double hr = 0, rr = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i] + omega * sv[i];
+    double ri = sv[i] - omega * t[i];
+    r[i] = ri;
+    hr += rhat[i] * ri; rr += ri * ri;
+  }
+  hr = block_sum(hr, red); if (threadIdx.x == 0) partial[blockIdx.x] = hr;
+  rr = block_sum(rr, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = rr;
+}
+__global__ void k_bi_scalars(int it, int G, const double *__restrict__ partial, const double *__restrict__ ts_partial,
+                             const double *__restrict__ tt_partial, double *__restrict__ sc, int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  double hr = sum_partials(partial, G, red);
+  double rr = sum_partials(partial + G, G, red);
+  double ts = sum_partials(ts_partial, G, red);
+  double tt = sum_partials(tt_partial, G, red);
+  if (threadIdx.x == 0) {
+    sc[0] = sc[6];            // rho <- rho_new
+    sc[1] = sc[7];            // alpha
+    sc[2] = (tt > 0) ? ts / tt : 0.0;
+    sc[6] = hr;               // next rho_new = (rhat, r)
+    sc[4] = rr;
+    flags[1] = it + 1;
+    if (!(rr > sc[5] * sc[3])) flags[0] = 1;
+    else if (hr == 0.0 || sc[2] == 0.0) { flags[0] = 1; flags[2] = 1; }   // breakdown
+  }
+}
+
+void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres) {
+  EFV_REQUIRE(s->vals.n, "no values assembled");
+  ensure_vectors(s);
+  KrylovWork *w = work(s);
+  const int64_t n = s->rows;
+  if (!w->r.n) { w->r.alloc(n); w->p.alloc(n); w->Ap.alloc(n); w->dinv.alloc(n); }
+  if (!w->rhat.n) { w->rhat.alloc(n); w->v.alloc(n); w->sv.alloc(n); w->t.alloc(n); }
+  const int G = w->grid;
+  double *P = w->partial.p;
+  EFV_CUDA(cudaEventRecord(w->e0, stream()));
+  EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->nV, s->ndof, s->diag_slot.p, s->vals.p, 1.0, w->dinv.p);
+  EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
+  launch_spmv(s, G, s->x.p, w->Ap.p, 1.0, w->dinv.p, nullptr, nullptr, nullptr);
+  EFV_LAUNCH(k_bi_init, G, kBlock, 0, n, s->b.p, w->Ap.p, w->dinv.p, w->r.p, w->rhat.p, w->p.p, w->v.p, P);
+  EFV_LAUNCH(k_bi_init_scalars, 1, kBlock, 0, G, P, w->sc.p, w->flags.p, rtol);
+  const int check_every = 16;
+  int it = 0;
+  bool done = false;
+  while (!done && it < maxit) {
+    int batch_end = std::min(maxit, it + check_every);
+    for (; it < batch_end; ++it) {
+      EFV_LAUNCH(k_bi_p, G, kBlock, 0, n, w->sc.p, w->r.p, w->v.p, w->p.p, w->flags.p);
+      launch_spmv(s, G, w->p.p, w->v.p, 1.0, w->dinv.p, w->rhat.p, P + 2 * G, w->flags.p);          // v = D^-1 A p, (rhat,v)
+      EFV_LAUNCH(k_bi_s, G, kBlock, 0, n, w->sc.p, P + 2 * G, G, w->r.p, w->v.p, w->sv.p, w->flags.p);
+      launch_spmv(s, G, w->sv.p, w->t.p, 1.0, w->dinv.p, w->sv.p, P + 2 * G, w->flags.p);           // t = D^-1 A s, (t,s)
+      EFV_LAUNCH(k_bi_tt, G, kBlock, 0, n, w->t.p, P + 3 * G, w->flags.p);
+      EFV_LAUNCH(k_bi_xr, G, kBlock, 0, n, w->sc.p, P + 2 * G, P + 3 * G, G, w->p.p, w->sv.p, w->t.p, w->rhat.p, s->x.p,
+                 w->r.p, P, w->flags.p);
+      EFV_LAUNCH(k_bi_scalars, 1, kBlock, 0, it, G, P, P + 2 * G, P + 3 * G, w->sc.p, w->flags.p);
+    }
+    EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+    done = w->h_flags[0] != 0;
+  }
+  EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaMemcpyAsync(w->h_sc, w->sc.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaEventRecord(w->e1, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+  float ms = 0;
+  EFV_CUDA(cudaEventElapsedTime(&ms, w->e0, w->e1));
+  s->t_solve_ms = ms;
+  if (iters) *iters = w->h_flags[1];
+  if (relres) *relres = (w->h_sc[3] > 0) ? std::sqrt(w->h_sc[4] / w->h_sc[3]) : 0.0;
+}
+
+// ---- max |x - xold| (heat_transfer.py:142) ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_max_abs_diff(int64_t n, const double *__restrict__ a, const double *__restrict__ b,
+                                                         double *__restrict__ partial) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmax(m, fabs(a[i] - b[i]));
+  m = block_max(m, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = m;
+}
+__global__ void k_max_final(int G, const double *__restrict__ partial, double *__restrict__ out) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < G; i += blockDim.x) m = fmax(m, partial[i]);
+  m = block_max(m, red);
+  if (threadIdx.x == 0) *out = m;
+}
+double max_abs_diff(efv_system *s) {
+  ensure_vectors(s);
+  KrylovWork *w = work(s);
+  EFV_LAUNCH(k_max_abs_diff, w->grid, kBlock, 0, s->rows, s->x.p, s->xold.p, w->partial.p);
+  EFV_LAUNCH(k_max_final, 1, kBlock, 0, w->grid, w->partial.p, w->sc.p + 15);
+  double out = 0;
+  EFV_CUDA(cudaMemcpyAsync(&out, w->sc.p + 15, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+  return out;
+}
+
+}  // namespace efv

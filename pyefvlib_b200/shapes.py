@@ -209,28 +209,57 @@ def _c_array(a, fmt):
     return "{" + ",\n ".join(_c_array(x, fmt) for x in a) + "}"
 
 
+def vertex_faces(t):
+    """Per local vertex the inner faces that touch it, encoded 2*face + (1 if the vertex is the forward one).
+    The heat flux of face f enters row b with sign -1 and row f with sign +1 (heat_transfer.py:52-54)."""
+    rows = []
+    for l in range(t.numberOfVertices):
+        enc = []
+        for f, nb in enumerate(t.innerFaceNeighborVertices):
+            if nb[0] == l:
+                enc.append(2 * f)
+            elif nb[1] == l:
+                enc.append(2 * f + 1)
+        rows.append(enc)
+    assert len(set(len(r) for r in rows)) == 1
+    return np.array(rows, dtype=np.int32)
+
+
 def generate_cuda_tables():
-    """Text of csrc/shape_tables.inc: one struct of constexpr tables per shape."""
+    """Text of csrc/shape_tables.inc: __constant__ tables + one traits struct per shape."""
     fd = lambda x: repr(float(x))
     fi = lambda x: str(int(x))
     out = ["// GENERATED by `python -m pyefvlib_b200.shapes` -- do not edit.",
-           "// Reference-element tables (see pyefvlib_b200/shapes.py for the derivation).", ""]
+           "// Reference-element tables (see pyefvlib_b200/shapes.py for the derivation).", "#pragma once", ""]
     for code in (TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON):
         t = SHAPES[code]
+        n = t.name
         m, nf, d = t.numberOfVertices, t.numberOfInnerFaces, t.dimension
         nfc, mf = t.facetVerticesIndexes.shape
         nn = t.innerFaceNeighborVertices.shape[1]
+        vf = vertex_faces(t)
+        nvf = vf.shape[1]
         out += [
-            f"struct {t.name}Tab {{",
-            f"  static constexpr int CODE = {code}, DIM = {d}, M = {m}, NF = {nf}, NFACETS = {nfc}, MF = {mf}, NNBR = {nn};",
+            f"static __constant__ double c_{n}_ifD[{nf}][{m}][{d}] =\n {_c_array(t.innerFaceShapeFunctionDerivatives, fd)};",
+            f"static __constant__ double c_{n}_ifN[{nf}][{m}] =\n {_c_array(t.innerFaceShapeFunctionValues, fd)};",
+            f"static __constant__ int c_{n}_nbr[{nf}][{nn}] =\n {_c_array(t.innerFaceNeighborVertices, fi)};",
+            f"static __constant__ double c_{n}_subD[{m}][{m}][{d}] =\n {_c_array(t.subelementShapeFunctionDerivatives, fd)};",
+            f"static __constant__ int c_{n}_facetV[{nfc}][{mf}] =\n {_c_array(t.facetVerticesIndexes, fi)};",
+            f"static __constant__ double c_{n}_ofN[{nfc}][{mf}][{m}] =\n {_c_array(t.outerFaceShapeFunctionValues, fd)};",
+            f"static __constant__ int c_{n}_vface[{m}][{nvf}] =\n {_c_array(vf, fi)};",
+            f"struct {n}Tab {{",
+            f"  static constexpr int CODE = {code}, DIM = {d}, M = {m}, NF = {nf}, NFACETS = {nfc}, MF = {mf}, NNBR = {nn}, NVF = {nvf};",
             f"  static constexpr double SUBVOL = {fd(t.subelementTransformedVolumes[0])};",
+            f"  __device__ static __forceinline__ double ifD(int f, int j, int a) {{ return c_{n}_ifD[f][j][a]; }}",
+            f"  __device__ static __forceinline__ double ifN(int f, int j) {{ return c_{n}_ifN[f][j]; }}",
+            f"  // compile-time copy for statically unrolled code (keeps vertex arrays in registers)",
+            f"  __host__ __device__ static constexpr int nbr(int f, int k) {{ constexpr int T[{nf}][{nn}] = {_c_array(t.innerFaceNeighborVertices, fi).replace(chr(10), '')}; return T[f][k]; }}",
+            f"  __device__ static __forceinline__ int nbr_dyn(int f, int k) {{ return c_{n}_nbr[f][k]; }}",
+            f"  __device__ static __forceinline__ double subD(int k, int j, int a) {{ return c_{n}_subD[k][j][a]; }}",
+            f"  __device__ static __forceinline__ int facetV(int f, int k) {{ return c_{n}_facetV[f][k]; }}",
+            f"  __device__ static __forceinline__ double ofN(int f, int k, int j) {{ return c_{n}_ofN[f][k][j]; }}",
+            f"  __device__ static __forceinline__ int vface(int l, int k) {{ return c_{n}_vface[l][k]; }}",
             "};",
-            f"__device__ __constant__ double c_{t.name}_ifD[{nf}][{m}][{d}] =\n {_c_array(t.innerFaceShapeFunctionDerivatives, fd)};",
-            f"__device__ __constant__ double c_{t.name}_ifN[{nf}][{m}] =\n {_c_array(t.innerFaceShapeFunctionValues, fd)};",
-            f"__device__ __constant__ int c_{t.name}_ifNbr[{nf}][{nn}] =\n {_c_array(t.innerFaceNeighborVertices, fi)};",
-            f"__device__ __constant__ double c_{t.name}_subD[{m}][{m}][{d}] =\n {_c_array(t.subelementShapeFunctionDerivatives, fd)};",
-            f"__device__ __constant__ int c_{t.name}_facetV[{nfc}][{mf}] =\n {_c_array(t.facetVerticesIndexes, fi)};",
-            f"__device__ __constant__ double c_{t.name}_ofN[{nfc}][{mf}][{m}] =\n {_c_array(t.outerFaceShapeFunctionValues, fd)};",
             "",
         ]
     return "\n".join(out) + "\n"

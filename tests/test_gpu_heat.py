@@ -1,0 +1,159 @@
+"""GPU parity of the heat path against the committed reference outputs (tests/golden, produced by the
+unmodified reference) and against the oracle on synthetic meshes.  Everything goes through the C-ABI.
+
+Tolerances (BASELINE.json north_star): CSR structure + slot map bit-exact; assembled values <= 1e-12 relative;
+solution <= 1e-8 relative L2 at a 1e-10 solver residual."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from tests import util
+from tests.cases import HEAT_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def props_array(grid, props):
+    return np.array([[props[r.name]["Conductivity"], props[r.name]["Density"], props[r.name]["HeatCapacity"],
+                      props[r.name]["HeatGeneration"]] for r in grid.regions])
+
+
+def apply_bcs(system, grid, bcs):
+    system.bc_clear()
+    for b in grid.boundaries:
+        kind, val = bcs[b.name]
+        if kind == "neumann":
+            system.bc_neumann(b.handle, 0, val, 1.0)
+    for b in grid.boundaries:
+        kind, val = bcs[b.name]
+        if kind == "dirichlet":
+            system.bc_dirichlet(b.verticesIndexes, np.full(len(b.verticesIndexes), val))
+
+
+@pytest.mark.parametrize("tag", list(HEAT_CASES))
+def test_geometry_matches_reference(tag):
+    z = util.load("heat_" + tag)
+    grid = util.product_grid(z)
+    geo = grid.device.export_geometry()
+    nE = grid.numberOfElements
+    assert util.rel_max(util.flatten_by_element(geo, nE, "G"), z["G_flat"]) <= 1e-12
+    assert util.rel_max(util.flatten_by_element(geo, nE, "S"), z["S_flat"]) <= 1e-12
+    assert util.rel_max(util.flatten_by_element(geo, nE, "vol"), z["vol_flat"]) <= 1e-12
+    assert util.rel_max(grid.device.vertex_volume(), z["vertex_volume"]) <= 1e-12
+    bd = grid.device.export_boundaries()
+    fo = oo = 0
+    for k, b in enumerate(grid.boundaries):
+        assert np.array_equal(b.verticesIndexes, z[f"b{k}_vertices"])
+        nf = len(z[f"b{k}_facet_element"]); no = len(z[f"b{k}_outer_vertex"])
+        assert np.array_equal(bd["facet_element"][fo:fo + nf], z[f"b{k}_facet_element"])
+        assert np.array_equal(bd["facet_local"][fo:fo + nf], z[f"b{k}_facet_local"])
+        assert util.rel_max(bd["facet_area"][fo:fo + nf], z[f"b{k}_facet_area"]) <= 1e-12
+        assert np.array_equal(bd["outer_vertex"][oo:oo + no], z[f"b{k}_outer_vertex"])
+        assert util.rel_max(bd["outer_area_norm"][oo:oo + no], np.linalg.norm(z[f"b{k}_outer_area"], axis=1)) <= 1e-12
+        fo += nf; oo += no
+
+
+@pytest.mark.parametrize("tag", list(HEAT_CASES))
+def test_csr_structure_and_slot_map_bit_exact(tag):
+    import pyefvlib_b200.device as D
+    z = util.load("heat_" + tag)
+    grid = util.product_grid(z)
+    s = D.DeviceSystem(grid, 1)
+    indptr, indices = s.csr_structure()
+    assert np.array_equal(indptr, z["pattern_indptr"])
+    assert np.array_equal(indices.astype(np.int64), z["pattern_indices"])
+    assert np.array_equal(s.slot_map(), z["slot_map"])
+
+
+@pytest.mark.parametrize("tag", list(HEAT_CASES))
+def test_steady_matrix_rhs_solution(tag):
+    import pyefvlib_b200.device as D
+    z = util.load("heat_" + tag)
+    case = HEAT_CASES[tag]
+    grid = util.product_grid(z)
+    s = D.DeviceSystem(grid, 1)
+    # reference form (row replacement) -> values and RHS parity
+    s.heat_assemble(props_array(grid, case["props"]), 0.0, False)
+    apply_bcs(s, grid, case["bcs"])
+    s.apply_dirichlet(D.DIRICHLET_ROWS)
+    s.build_rhs(False)
+    A = s.to_scipy()
+    Aref = util.csr_from(z, "heat_")
+    assert util.row_rel_matrix_error(A, Aref) <= 1e-12
+    A.eliminate_zeros()
+    assert A.nnz == Aref.nnz                       # after dropping the explicit zeros of Dirichlet rows (B.6)
+    b = s.download(D.VEC_B)
+    assert util.rel_max(b, z["heat_rhs"]) <= 1e-12
+    # CG-ready form -> solution parity
+    s.heat_assemble(props_array(grid, case["props"]), 0.0, False)
+    s.apply_dirichlet(D.DIRICHLET_SYMMETRIC)
+    s.build_rhs(False)
+    As = s.to_scipy()
+    assert abs(As - As.T).max() <= 1e-12 * abs(As).max() or tag in ("eight_sphere",)
+    s.upload(D.VEC_X, np.zeros(s.rows))
+    iters, relres = s.solve_pcg(1e-10, 5000)
+    assert relres <= 1e-10
+    T = s.download(D.VEC_X)
+    assert util.rel_l2(T, z["heat_T"]) <= 1e-8, (iters, relres)
+
+
+@pytest.mark.parametrize("tag", [t for t, c in HEAT_CASES.items() if c["transient_steps"]])
+def test_transient_steps(tag):
+    import pyefvlib_b200.device as D
+    z = util.load("heat_" + tag)
+    case = HEAT_CASES[tag]
+    grid = util.product_grid(z)
+    dt = float(z["heatT_dt"])
+    s = D.DeviceSystem(grid, 1)
+    s.heat_assemble(props_array(grid, case["props"]), dt, True)
+    apply_bcs(s, grid, case["bcs"])
+    s.apply_dirichlet(D.DIRICHLET_ROWS)
+    assert util.row_rel_matrix_error(s.to_scipy(), util.csr_from(z, "heatT_")) <= 1e-12
+    s.heat_assemble(props_array(grid, case["props"]), dt, True)
+    s.apply_dirichlet(D.DIRICHLET_SYMMETRIC)
+    s.upload(D.VEC_XOLD, np.zeros(s.rows))
+    s.upload(D.VEC_X, np.zeros(s.rows))
+    for step in range(len(z["heatT_fields"])):
+        s.build_rhs(True)
+        iters, relres = s.solve_pcg(1e-10, 5000)
+        assert relres <= 1e-10
+        T = s.download(D.VEC_X)
+        assert util.rel_l2(T, z["heatT_fields"][step]) <= 1e-8
+        s.advance()
+
+
+@pytest.mark.parametrize("n,kind,perturb", [(12, "hex", 0.0), (10, "hex", 0.2), (9, "tet", 0.0), (8, "tet", 0.15)])
+def test_structured_against_oracle(n, kind, perturb):
+    """Synthetic meshes of the benchmark family at sizes the oracle finishes in seconds."""
+    import pyefvlib_b200 as P
+    import pyefvlib_b200.device as D
+    from oracle import efv_oracle as O
+    from tests.cases import BC3D, HEAT_PROPS
+    gd = P.structured_grid_data(n, kind, perturb)
+    grid = P.Grid(gd)
+    og = O.OracleGrid(O.OracleGridData(3, gd.verticesCoordinates.tolist(), gd.elementsConnectivities.tolist(), gd.regionsNames,
+                                       [list(r) for r in gd.regionsElementsIndexes], gd.boundariesNames,
+                                       [list(r) for r in gd.boundariesIndexes], gd.boundariesConnectivities.tolist()))
+    s = D.DeviceSystem(grid, 1)
+    gptr, gcol = O.csr_pattern(og, 1)
+    ip, ix = s.csr_structure()
+    assert np.array_equal(ip, gptr) and np.array_equal(ix, gcol)
+    assert np.array_equal(s.slot_map(), O.slot_map(og, gptr, gcol))
+    dt = 1e-2
+    s.heat_assemble(props_array(grid, HEAT_PROPS), dt, True)
+    apply_bcs(s, grid, BC3D)
+    s.apply_dirichlet(D.DIRICHLET_ROWS)
+    Aref = O.heat_matrix(og, HEAT_PROPS, BC3D, transient=True, dt=dt)
+    assert util.row_rel_matrix_error(s.to_scipy(), Aref) <= 1e-12
+    Told = 300.0 + 50.0 * np.sin(np.arange(grid.numberOfVertices))
+    s.upload(D.VEC_XOLD, Told)
+    s.build_rhs(True)
+    bref = O.heat_rhs(og, HEAT_PROPS, BC3D, transient=True, dt=dt, Told=Told)
+    assert util.rel_max(s.download(D.VEC_B), bref) <= 1e-12
+    s.heat_assemble(props_array(grid, HEAT_PROPS), dt, True)
+    s.apply_dirichlet(D.DIRICHLET_SYMMETRIC)
+    s.build_rhs(True)
+    s.upload(D.VEC_X, Told)
+    iters, relres = s.solve_pcg(1e-10, 5000)
+    assert relres <= 1e-10
+    assert util.rel_l2(s.download(D.VEC_X), O.solve_direct(Aref, bref)) <= 1e-8
