@@ -280,13 +280,15 @@ __global__ void __launch_bounds__(256) k_apply_dirichlet(SysView s, const uint8_
                                                          double *__restrict__ elim) {
   constexpr int GROUP = 8;
   int gl = threadIdx.x % GROUP;
-  for (int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / GROUP; v < s.nV;
-       v += (int64_t)gridDim.x * blockDim.x / GROUP) {
-    int64_t r0 = s.gptr[v];
-    int len = (int)(s.gptr[v + 1] - r0);
+  const int64_t rows_per_block = blockDim.x / GROUP;
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_block; base < s.nV; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t v = base + threadIdx.x / GROUP;      // block-uniform loop: all lanes take part in the shuffles
+    const bool valid = v < s.nV;
+    int64_t r0 = valid ? s.gptr[v] : 0;
+    int len = valid ? (int)(s.gptr[v + 1] - r0) : 0;
     bool rowd[NDOF];
 #pragma unroll
-    for (int i = 0; i < NDOF; ++i) rowd[i] = flag[v * NDOF + i];
+    for (int i = 0; i < NDOF; ++i) rowd[i] = valid ? flag[v * NDOF + i] : false;
     double el[NDOF];
 #pragma unroll
     for (int i = 0; i < NDOF; ++i) el[i] = 0.0;
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(256) k_apply_dirichlet(SysView s, const uint8_
 #pragma unroll
       for (int i = 0; i < NDOF; ++i) {
         double tot = group_sum<GROUP>(el[i]);
-        if (gl == 0) elim[v * NDOF + i] = rowd[i] ? 0.0 : tot;
+        if (valid && gl == 0) elim[v * NDOF + i] = rowd[i] ? 0.0 : tot;
       }
     }
   }

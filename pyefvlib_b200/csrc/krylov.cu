@@ -82,8 +82,11 @@ __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__re
   const int gl = threadIdx.x % L;
   const int64_t rows_per_block = kBlock / L;
   double dot = 0.0;
-  for (int64_t v = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / L; v < nV; v += (int64_t)gridDim.x * rows_per_block) {
-    const int64_t r0 = gptr[v], r1 = gptr[v + 1];
+  // block-uniform trip count: every lane executes the same shuffles (sub-warp groups share a warp)
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_block; base < nV; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t v = base + threadIdx.x / L;
+    const bool valid = v < nV;
+    const int64_t r0 = valid ? gptr[v] : 0, r1 = valid ? gptr[v + 1] : 0;
     double acc[NDOF];
 #pragma unroll
     for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__re
     }
 #pragma unroll
     for (int i = 0; i < NDOF; ++i) acc[i] = group_sum<L>(acc[i]);
-    if (gl == 0) {
+    if (valid && gl == 0) {
 #pragma unroll
       for (int i = 0; i < NDOF; ++i) {
         double yi = sigma * acc[i];
