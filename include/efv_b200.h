@@ -67,6 +67,7 @@ int64_t efv_mesh_group_size(const efv_mesh *m, int shape_code);      /* elements
  *   G    : per face d x m doubles (row-major),  Jinv : per face d x d,  S : per face 3,  vol : per element m,
  *   vertex_volume : nV  [ref: Vertex.py:9, Element.py:46].  Any output pointer may be NULL.                  */
 int efv_geometry_build(efv_mesh *m);
+int efv_geometry_release(efv_mesh *m);   /* frees the SoA (it is rebuilt on demand) */
 int efv_geometry_export_group(const efv_mesh *m, int shape_code, double *G, double *Jinv, double *S, double *vol);
 int efv_vertex_volume_export(const efv_mesh *m, double *vertex_volume);
 /* boundary geometry: per facet owning element, local facet index, outward area vector (3);
@@ -113,6 +114,9 @@ int efv_bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, i
 /* Neumann: static_rhs[dof(outer vertex)] += sign * value * |outer face area| over the outer faces of
  * `boundary`  [ref: apps/heat_transfer.py:115-120 (sign +1); apps/stress_equilibrium.py:131-141 (sign -1)] */
 int efv_bc_neumann(efv_system *s, int boundary, int dof, double value, double sign);
+/* how the next assembly call treats the recorded Dirichlet set: -1 leave the interior operator (apply later with
+ * efv_apply_dirichlet), EFV_DIRICHLET_ROWS or EFV_DIRICHLET_SYMMETRIC applied inside the assembly kernel.          */
+int efv_assemble_dirichlet_mode(efv_system *s, int mode);
 /* apply the recorded Dirichlet set to the matrix values (north_star kernel 4) */
 int efv_apply_dirichlet(efv_system *s, int mode);
 /* RHS of one step into EFV_VEC_B:  heat: gen + acc * XOLD + neumann, Dirichlet rows <- g

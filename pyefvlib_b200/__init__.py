@@ -8,7 +8,6 @@ kernels (pyefvlib_b200/csrc) through the C-ABI of include/efv_b200.h; there is n
 from .grid import GridData, MSHReader, Grid, Region, Boundary, read, structured_grid, structured_grid_data  # noqa: F401
 from .shapes import SHAPES, TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON  # noqa: F401
 
-Neumann = "NEUMANN_BOUNDARY_CONDITION"          # PyEFVLib/__init__.py:28-31
-Dirichlet = "DIRICHLET_BOUNDARY_CONDITION"
-Constant = "BOUNDARY_CONDITION_CONSTANT_VALUE"
-Variable = "BOUNDARY_CONDITION_VARIABLE_VALUE"
+from .problem import (ProblemData, NumericalSettings, PropertyData, BoundaryConditions, DirichletBoundaryCondition,  # noqa: F401
+                      NeumannBoundaryCondition, Neumann, Dirichlet, Constant, Variable)
+from .solver import Solver, Saver, CsvSaver, NullSaver  # noqa: F401

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "efv_mesh_num_outer_faces": (C.c_int64, [C.c_void_p]),
     "efv_mesh_group_size": (C.c_int64, [C.c_void_p, C.c_int]),
     "efv_geometry_build": (C.c_int, [C.c_void_p]),
+    "efv_geometry_release": (C.c_int, [C.c_void_p]),
     "efv_geometry_export_group": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_f64p, c_f64p, c_f64p]),
     "efv_vertex_volume_export": (C.c_int, [C.c_void_p, c_f64p]),
     "efv_boundary_export": (C.c_int, [C.c_void_p, c_i64p, c_i32p, c_f64p, c_i32p, c_f64p]),
@@ -57,6 +58,7 @@ PROTOTYPES = {
     "efv_bc_clear": (C.c_int, [C.c_void_p]),
     "efv_bc_dirichlet": (C.c_int, [C.c_void_p, c_i64p, c_f64p, C.c_int64]),
     "efv_bc_neumann": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "efv_assemble_dirichlet_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_apply_dirichlet": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_build_rhs": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_solve_pcg": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, c_intp, c_f64p]),

@@ -1,0 +1,132 @@
+"""HeatTransferSolver on the GPU: same class, hooks and result attributes as apps/heat_transfer.py:10-158.
+
+What changes is where the work happens: the element loops of assembleMatrix / addToIndependentVector are CUDA
+kernels (efv_heat_assemble, efv_bc_*, efv_build_rhs) and the sparse inverse + dense mat-vec of
+invertMatrix / solveLinearSystem (heat_transfer.py:78-81,134-135) is a Jacobi-PCG (or BiCGStab on
+non-symmetric operators) on the device; fields stay in HBM between time steps."""
+import numpy as np
+
+from ..device import DeviceSystem, DIRICHLET_ROWS, DIRICHLET_SYMMETRIC, VEC_X, VEC_B, VEC_XOLD
+from ..solver import Solver
+
+PROPERTY_NAMES = ["Conductivity", "Density", "HeatCapacity", "HeatGeneration"]
+
+
+class HeatTransferSolver(Solver):
+    def __init__(self, workspaceDirectory, rtol=1e-10, maxLinearIterations=20000, linearSolver="auto", **kwargs):
+        Solver.__init__(self, workspaceDirectory, **kwargs)
+        self.rtol, self.maxLinearIterations, self.linearSolver = rtol, maxLinearIterations, linearSolver
+        self.linearIterations = []
+
+    def init(self):
+        self.system = DeviceSystem(self.grid, 1)
+        self.temperatureField = np.repeat(0.0, self.grid.numberOfVertices)
+        self.prevTemperatureField = np.asarray(self.problemData.initialValues["temperature"], dtype=np.float64)
+        self.system.upload(VEC_XOLD, self.prevTemperatureField)
+        self.system.upload(VEC_X, self.prevTemperatureField)          # initial guess of the first solve
+        self.saver.save("temperature", self.prevTemperatureField, self.currentTime)
+        self.difference = 0.0
+        self._matrix_mode = None
+
+    def mainloop(self):
+        self.assembleMatrix()
+        while not self.converged:
+            self.addToIndependentVector()
+            self.solveLinearSystem()
+            self.printIterationData()
+            self.currentTime += self.timeStep
+            self.saveIterationResults()
+            self.checkConvergence()
+            self.prevTemperatureField = self.temperatureField
+            self.system.advance()
+            self.iteration += 1
+
+    # -- boundary conditions in the reference's visiting order ----------------------------------------------------
+    def _send_boundary_conditions(self):
+        s = self.system
+        s.bc_clear()
+        for bc in self.problemData.neumannBoundaries["temperature"]:         # heat_transfer.py:115-120
+            if bc.expression:
+                raise Exception("Variable Neumann conditions are not supported on the GPU backend "
+                                "(the reference evaluates them with an outer-face handle, heat_transfer.py:120)")
+            s.bc_neumann(bc.boundary.handle, 0, bc.value, 1.0)
+        for bc in self.problemData.dirichletBoundaries["temperature"]:       # heat_transfer.py:70-76, 122-126
+            s.bc_dirichlet(bc.boundary.verticesIndexes, bc.values_on_vertices(self.currentTime))
+
+    def assembleMatrix(self, mode=DIRICHLET_SYMMETRIC):
+        props = self.propertyData.table(PROPERTY_NAMES)
+        self._send_boundary_conditions()
+        self.system.assemble_dirichlet_mode(mode)          # Dirichlet rows/columns handled inside the assembly kernel
+        self.system.heat_assemble(props, self.timeStep, self.transient)
+        self._matrix_mode = mode
+
+    @property
+    def matrix(self):
+        """The reference's `solver.matrix` (row-replaced Dirichlet form, heat_transfer.py:70-80) as scipy CSR,
+        re-assembled on demand into a second system so that the solver's symmetric form stays intact."""
+        tmp = DeviceSystem(self.grid, 1)
+        tmp.heat_assemble(self.propertyData.table(PROPERTY_NAMES), self.timeStep, self.transient)
+        for bc in self.problemData.dirichletBoundaries["temperature"]:
+            tmp.bc_dirichlet(bc.boundary.verticesIndexes, bc.values_on_vertices(self.currentTime))
+        tmp.apply_dirichlet(DIRICHLET_ROWS)
+        A = tmp.to_scipy()
+        A.eliminate_zeros()
+        return A
+
+    def addToIndependentVector(self):
+        self.system.build_rhs(self.transient)
+
+    @property
+    def independent(self):
+        """RHS of the reference's system (heat_transfer.py:89-132): in symmetric mode the eliminated-column term is
+        removed again so that the vector matches `solver.independent` of the reference."""
+        if self._matrix_mode == DIRICHLET_ROWS:
+            return self.system.download(VEC_B)
+        tmp = DeviceSystem(self.grid, 1)
+        tmp.heat_assemble(self.propertyData.table(PROPERTY_NAMES), self.timeStep, self.transient)
+        for bc in self.problemData.neumannBoundaries["temperature"]:
+            tmp.bc_neumann(bc.boundary.handle, 0, bc.value, 1.0)
+        for bc in self.problemData.dirichletBoundaries["temperature"]:
+            tmp.bc_dirichlet(bc.boundary.verticesIndexes, bc.values_on_vertices(self.currentTime))
+        tmp.apply_dirichlet(DIRICHLET_ROWS)
+        tmp.upload(VEC_XOLD, self.prevTemperatureField)
+        tmp.build_rhs(self.transient)
+        return tmp.download(VEC_B)
+
+    def solveLinearSystem(self):
+        solver = self.linearSolver
+        if solver == "auto":
+            solver = "pcg" if self._matrix_mode == DIRICHLET_SYMMETRIC else "bicgstab"
+        if solver == "pcg":
+            iters, relres = self.system.solve_pcg(self.rtol, self.maxLinearIterations)
+            if not relres <= self.rtol:          # non-symmetric operator (general quads/hexes): fall over to BiCGStab
+                iters2, relres = self.system.solve_bicgstab(self.rtol, self.maxLinearIterations)
+                iters += iters2
+        else:
+            iters, relres = self.system.solve_bicgstab(self.rtol, self.maxLinearIterations)
+        self.linearIterations.append(iters)
+        self.linearResidual = relres
+        self.temperatureField = self.system.download(VEC_X)
+
+    def saveIterationResults(self):
+        self.saver.save("temperature", self.temperatureField, self.currentTime)
+
+    def checkConvergence(self):
+        self.converged = False
+        self.difference = self.system.max_abs_diff()                               # heat_transfer.py:142
+        if self.problemData.finalTime is not None and self.currentTime > self.problemData.finalTime:
+            self.converged = True
+            return
+        if self.iteration > 0 and self.tolerance is not None and self.difference < self.tolerance:
+            self.converged = True
+            return
+        if self.problemData.maxNumberOfIterations and self.iteration >= self.problemData.maxNumberOfIterations:
+            self.converged = True
+            return
+
+
+def heatTransfer(problemData, solve=True, extension="csv", saverType="default", transient=True, verbosity=True, **kwargs):
+    solver = HeatTransferSolver(problemData, extension=extension, saverType=saverType, transient=transient, verbosity=verbosity, **kwargs)
+    if solve:
+        solver.solve()
+    return solver

@@ -98,6 +98,14 @@ int efv_geometry_build(efv_mesh *m) {
   EFV_CUDA(cudaStreamSynchronize(efv::stream()));
   EFV_API_END
 }
+int efv_geometry_release(efv_mesh *m) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(m, "null mesh");
+  for (int c = 0; c < efv::kNumShapes; ++c) { m->groups[c].Jinv.release(); m->groups[c].S.release(); m->groups[c].vol.release(); m->groups[c].St.release(); }
+  m->vertex_volume.release();
+  m->has_geometry = false;
+  EFV_API_END
+}
 int efv_geometry_export_group(const efv_mesh *m, int shape_code, double *G, double *Jinv, double *S, double *vol) {
   EFV_API_BEGIN
   EFV_REQUIRE(m, "null mesh");
@@ -144,6 +152,8 @@ efv_system *efv_system_create(efv_mesh *m, int ndof) {
 void efv_system_destroy(efv_system *s) {
   if (!s) return;
   efv::krylov_free(s);
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
 }
 int64_t efv_system_rows(const efv_system *s) { return s ? s->rows : -1; }
@@ -240,6 +250,13 @@ int efv_bc_neumann(efv_system *s, int boundary, int dof, double value, double si
   efv::bc_neumann(s, boundary, dof, value, sign);
   EFV_API_END
 }
+int efv_assemble_dirichlet_mode(efv_system *s, int mode) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(mode >= -1 && mode <= 1, "bad Dirichlet mode");
+  s->fuse_mode = mode;
+  EFV_API_END
+}
 int efv_apply_dirichlet(efv_system *s, int mode) {
   EFV_API_BEGIN
   EFV_REQUIRE(s, "null system");
@@ -290,6 +307,13 @@ int efv_advance(efv_system *s) {
 int efv_last_timings(efv_system *s, double *assemble_ms, double *solve_ms) {
   EFV_API_BEGIN
   EFV_REQUIRE(s, "null system");
+  if (s->assemble_timed) {
+    EFV_CUDA(cudaEventSynchronize(s->ev1));
+    float ms = 0;
+    EFV_CUDA(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->t_assemble_ms = ms;
+    s->assemble_timed = false;
+  }
   if (assemble_ms) *assemble_ms = s->t_assemble_ms;
   if (solve_ms) *solve_ms = s->t_solve_ms;
   EFV_API_END

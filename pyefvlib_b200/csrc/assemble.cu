@@ -60,94 +60,154 @@ __device__ __forceinline__ double tab_ifD(const SmemTables &T, int code, int f, 
   }
 }
 
-// t[a] = sum_b Jinv[b][a] s[b]  so that  (G^T s)_j = sum_a D[j][a] t[a]   (InnerFace.py:25 + heat_transfer.py:47)
-template <int D>
-__device__ __forceinline__ void face_t(const double *__restrict__ Jinv, const double *__restrict__ S, int f, int64_t n,
-                                       int64_t gi, double (&t)[3]) {
-  double R[D][D], s[D];
-#pragma unroll
-  for (int b = 0; b < D; ++b) {
-    s[b] = S[(int64_t)(f * 3 + b) * n + gi];
-#pragma unroll
-    for (int a = 0; a < D; ++a) R[b][a] = Jinv[(int64_t)(f * D * D + b * D + a) * n + gi];
-  }
-#pragma unroll
-  for (int a = 0; a < D; ++a) {
-    double acc = 0.0;
-#pragma unroll
-    for (int b = 0; b < D; ++b) acc += R[b][a] * s[b];
-    t[a] = acc;
-  }
-  if (D == 2) t[2] = 0.0;
-}
-
+// ---- heat ---------------------------------------------------------------------------------------------------------
+// One group of 8 lanes per graph row.  The incidence list of the row is processed in chunks of 8 (element,
+// local vertex) pairs:
+//   load phase   : lane q fetches everything pair q needs -- the 3 (2 in 2-D) face vectors  J^-T s  that touch the
+//                  local vertex (pre-multiplied by +-k), the byte slot positions of the m columns, the sub-control
+//                  volume -- and parks it in shared memory.  All loads of a chunk are independent => deep MLP.
+//   reduce phase : pairs are consumed in ascending element order; lane j turns the face vectors into the
+//                  coefficient of column conn[e][j] (3 FMAs per face against the shape table) and adds it to the
+//                  shared-memory row at slotpos[e][l][j].  Fixed order, one owner per entry: deterministic.
+// Epilogue: accumulation term on the diagonal, optional Dirichlet treatment, coalesced store of the row.
 // props per region: [0] conductivity, [1] rho*cp/dt (0 when steady), [2] heat generation
-template <int GROUP>
+constexpr int kAsmGroup = 8;
+constexpr int kAsmRows = 256 / kAsmGroup;
+
+template <int UCODE>
 __global__ void __launch_bounds__(256) k_heat_rows(MeshView m, GeomView g, SysView s, const double *__restrict__ props,
-                                                   int transient, int max_row_len, double *__restrict__ gen_out,
-                                                   double *__restrict__ acc_out) {
+                                                   int transient, int max_row_len, int dir_mode,
+                                                   const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
+                                                   double *__restrict__ gen_out, double *__restrict__ acc_out,
+                                                   double *__restrict__ elim_out) {
   extern __shared__ double smem_dyn[];
   __shared__ SmemTables T;
+  __shared__ double tbuf[kAsmRows][kAsmGroup][9];
+  __shared__ double volq[kAsmRows][kAsmGroup][2];
+  __shared__ unsigned long long posb[kAsmRows][kAsmGroup];
+  __shared__ int meta[kAsmRows][kAsmGroup];
   load_tables(T);
-  constexpr int ROWS = 256 / GROUP;
-  int grp = threadIdx.x / GROUP, gl = threadIdx.x % GROUP;
+  const int grp = threadIdx.x / kAsmGroup, gl = threadIdx.x % kAsmGroup;
   double *row = smem_dyn + (size_t)grp * max_row_len;
-  unsigned gmask = (GROUP == 32) ? 0xffffffffu : (((1u << GROUP) - 1u) << ((threadIdx.x & 31) / GROUP * GROUP));
-  for (int64_t v0 = (int64_t)blockIdx.x * ROWS; v0 < m.nV; v0 += (int64_t)gridDim.x * ROWS) {
-    int64_t v = v0 + grp;
-    if (v < m.nV) {
-      int64_t r0 = s.gptr[v];
-      int len = (int)(s.gptr[v + 1] - r0);
-      for (int t = gl; t < len; t += GROUP) row[t] = 0.0;
-      __syncwarp(gmask);
-      double gen = 0.0, accv = 0.0;
-      for (int64_t p = m.inc_ptr[v]; p < m.inc_ptr[v + 1]; ++p) {
-        uint32_t pk = m.inc[p];
-        int64_t e = pk >> 3;
-        int l = pk & 7;
-        int code = m.code(e);
-        int mm = shape_m(code), nvf = shape_nvf(code);
-        int64_t gi = m.group_index(e), n = g.n[code];
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) / kAsmGroup * kAsmGroup);
+  for (int64_t v0 = (int64_t)blockIdx.x * kAsmRows; v0 < m.nV; v0 += (int64_t)gridDim.x * kAsmRows) {
+    const int64_t v = v0 + grp;
+    if (v >= m.nV) continue;               // whole groups drop out together; syncs below are group-scoped
+    const int64_t r0 = s.gptr[v];
+    const int len = (int)(s.gptr[v + 1] - r0);
+    for (int t = gl; t < len; t += kAsmGroup) row[t] = 0.0;
+    double gen = 0.0, accv = 0.0;
+    const int64_t p0 = m.inc_ptr[v], p1 = m.inc_ptr[v + 1];
+    for (int64_t pc = p0; pc < p1; pc += kAsmGroup) {
+      // ---- load phase ------------------------------------------------------------------------------------------
+      const int64_t p = pc + gl;
+      if (p < p1) {
+        const uint32_t pk = m.inc[p];
+        const int64_t e = pk >> 3;
+        const int l = pk & 7;
+        const int code = (UCODE >= 0) ? UCODE : m.code(e);
+        const int mm = shape_m(code), nvf = shape_nvf(code), d = shape_dim(code);
+        const int64_t gi = (UCODE >= 0) ? e : m.group_index(e);
+        const int64_t n = g.n[code];
         const double *pr = props + 3 * m.region[e];
-        double cond = pr[0];
-        double sum = 0.0;
-        for (int q = 0; q < nvf; ++q) {
-          int enc = tab_vface(T, code, l, q);
-          int f = enc >> 1;
-          double t[3];
-          if (code < 2) face_t<2>(g.Jinv[code], g.S[code], f, n, gi, t);
-          else face_t<3>(g.Jinv[code], g.S[code], f, n, gi, t);
-          if (gl < mm) {
-            double w = tab_ifD(T, code, f, gl, 0) * t[0] + tab_ifD(T, code, f, gl, 1) * t[1];
-            if (code >= 2) w += tab_ifD(T, code, f, gl, 2) * t[2];
-            w *= cond;
-            sum += (enc & 1) ? w : -w;          // forward vertex row gets +flux, backward -flux (heat_transfer.py:52-54)
+        const double cond = pr[0];
+        const double *St = g.St[code];
+        int mt = 1 | (code << 1);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (q < nvf) {
+            const int enc = tab_vface(T, code, l, q);
+            const int f = enc >> 1;
+            const double sg = (enc & 1) ? cond : -cond;     // forward vertex +flux, backward -flux (heat_transfer.py:52-54)
+            mt |= f << (3 + 4 * q);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) tbuf[grp][gl][q * 3 + a] = (a < d) ? sg * St[(int64_t)(f * d + a) * n + gi] : 0.0;
           }
         }
-        if (gl < mm) row[s.slotpos[m.slot_begin(e) + (int64_t)l * mm + gl]] += sum;
-        if (gl == 0) {
-          double vol = g.vol[code][(int64_t)l * n + gi];
-          gen += vol * pr[2];
-          accv += vol * pr[1];
+        meta[grp][gl] = mt;
+        const uint8_t *sp = s.slotpos + ((UCODE >= 0) ? e * (int64_t)(mm * mm) : m.slot_begin(e)) + l * mm;
+        unsigned long long pb;
+        if (UCODE >= 0 && mm == 8) pb = *reinterpret_cast<const unsigned long long *>(sp);      // aligned: e*64 + l*8
+        else if (UCODE >= 0 && mm == 4) pb = *reinterpret_cast<const unsigned int *>(sp);       // aligned: e*16 + l*4
+        else {
+          pb = 0;
+          for (int j = 0; j < mm; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
         }
-        __syncwarp(gmask);
-      }
-      if (gl == 0) {
-        if (transient) row[s.diag_slot[v] - r0] += accv;       // heat_transfer.py:62-67
-        gen_out[v] = gen;
-        acc_out[v] = accv;
+        posb[grp][gl] = pb;
+        const double vol = g.vol[code][(int64_t)l * n + gi];
+        volq[grp][gl][0] = vol * pr[2];
+        volq[grp][gl][1] = vol * pr[1];
       }
       __syncwarp(gmask);
-      for (int t = gl; t < len; t += GROUP) s.vals[r0 + t] = row[t];
+      // ---- reduce phase (ascending element order) ------------------------------------------------------------------
+      const int cnt = (int)((p1 - pc < kAsmGroup) ? (p1 - pc) : kAsmGroup);
+      for (int q = 0; q < cnt; ++q) {
+        const int mt = meta[grp][q];
+        const int code = (UCODE >= 0) ? UCODE : ((mt >> 1) & 3);
+        const int mm = shape_m(code), nvf = shape_nvf(code);
+        if (gl < mm) {
+          double w = 0.0;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (k < nvf) {
+              const int f = (mt >> (3 + 4 * k)) & 15;
+              w += tab_ifD(T, code, f, gl, 0) * tbuf[grp][q][k * 3] + tab_ifD(T, code, f, gl, 1) * tbuf[grp][q][k * 3 + 1];
+              if (code >= 2) w += tab_ifD(T, code, f, gl, 2) * tbuf[grp][q][k * 3 + 2];
+            }
+          }
+          const int pos = (int)((posb[grp][q] >> (8 * gl)) & 0xff);
+          row[pos] += w;
+        }
+        if (gl == 0) { gen += volq[grp][q][0]; accv += volq[grp][q][1]; }
+      }
       __syncwarp(gmask);
     }
+    // ---- epilogue ------------------------------------------------------------------------------------------------
+    if (gl == 0) {
+      if (transient) row[s.diag_slot[v] - r0] += accv;       // heat_transfer.py:62-67
+      gen_out[v] = gen;
+      acc_out[v] = accv;
+    }
+    __syncwarp(gmask);
+    if (dir_mode < 0) {
+      for (int t = gl; t < len; t += kAsmGroup) s.vals[r0 + t] = row[t];
+    } else {
+      const bool rowd = dflag[v];
+      double el = 0.0;
+      for (int t = gl; t < len; t += kAsmGroup) {
+        const int c = s.gcol[r0 + t];
+        double a = row[t];
+        if (rowd) a = (c == v) ? 1.0 : 0.0;                    // heat_transfer.py:70-76
+        else if (dir_mode == 1 && dflag[c]) { el -= a * dval[c]; a = 0.0; }
+        s.vals[r0 + t] = a;
+      }
+      if (dir_mode == 1) {
+#pragma unroll
+        for (int o = kAsmGroup / 2; o > 0; o >>= 1) el += __shfl_xor_sync(gmask, el, o);
+        if (gl == 0) elim_out[v] = rowd ? 0.0 : el;
+      }
+    }
+    __syncwarp(gmask);
   }
+}
+
+template <int UCODE>
+static void launch_heat_rows(efv_system *s, const double *dprops, int transient) {
+  efv_mesh *m = s->mesh;
+  MeshView mv = view_of(m);
+  GeomView gv = geom_of(m);
+  SysView sv = sys_view(s);
+  size_t smem = (size_t)kAsmRows * s->max_row_len * sizeof(double);
+  EFV_CUDA(cudaFuncSetAttribute(k_heat_rows<UCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EFV_LAUNCH(k_heat_rows<UCODE>, grid_for(s->nV * kAsmGroup, 256, 6), 256, smem, mv, gv, sv, dprops, transient,
+             s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
 }
 
 void heat_assemble(efv_system *s, const double *props_host, double dt, int transient) {
   efv_mesh *m = s->mesh;
   EFV_REQUIRE(s->ndof == 1, "heat needs a 1-DOF system");
   geometry_build(m);
+  if (!s->dir_flag.n) bc_clear(s);
   std::vector<double> pr(3 * m->n_regions);
   for (int r = 0; r < m->n_regions; ++r) {
     const double *p = props_host + 4 * r;   // Conductivity, Density, HeatCapacity, HeatGeneration
@@ -155,33 +215,21 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
     pr[3 * r + 1] = transient ? p[1] * p[2] / dt : 0.0;    // heat_transfer.py:61
     pr[3 * r + 2] = p[3];
   }
-  DBuf<double> dprops;
-  dprops.upload(pr.data(), pr.size());
+  if (s->props_dev.n < pr.size()) s->props_dev.alloc(pr.size());
+  s->props_dev.upload(pr.data(), pr.size());
   if (!s->gen.n) { s->gen.alloc(s->nV); s->acc.alloc(s->nV); }
-  cudaEvent_t e0, e1;
-  EFV_CUDA(cudaEventCreate(&e0)); EFV_CUDA(cudaEventCreate(&e1));
-  EFV_CUDA(cudaEventRecord(e0, stream()));
-  MeshView mv = view_of(m);
-  GeomView gv = geom_of(m);
-  SysView sv = sys_view(s);
-  if (m->max_m <= 4) {
-    constexpr int GROUP = 4;
-    size_t smem = (size_t)(256 / GROUP) * s->max_row_len * sizeof(double);
-    EFV_CUDA(cudaFuncSetAttribute(k_heat_rows<GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EFV_LAUNCH(k_heat_rows<GROUP>, grid_for(s->nV * GROUP, 256, 8), 256, smem, mv, gv, sv, dprops.p, transient, s->max_row_len, s->gen.p, s->acc.p);
-  } else {
-    constexpr int GROUP = 8;
-    size_t smem = (size_t)(256 / GROUP) * s->max_row_len * sizeof(double);
-    EFV_CUDA(cudaFuncSetAttribute(k_heat_rows<GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EFV_LAUNCH(k_heat_rows<GROUP>, grid_for(s->nV * GROUP, 256, 8), 256, smem, mv, gv, sv, dprops.p, transient, s->max_row_len, s->gen.p, s->acc.p);
+  if (!s->ev0) { EFV_CUDA(cudaEventCreate(&s->ev0)); EFV_CUDA(cudaEventCreate(&s->ev1)); }
+  EFV_CUDA(cudaEventRecord(s->ev0, stream()));
+  switch (m->uniform_code) {
+    case 0: launch_heat_rows<0>(s, s->props_dev.p, transient); break;
+    case 1: launch_heat_rows<1>(s, s->props_dev.p, transient); break;
+    case 2: launch_heat_rows<2>(s, s->props_dev.p, transient); break;
+    case 3: launch_heat_rows<3>(s, s->props_dev.p, transient); break;
+    default: launch_heat_rows<-1>(s, s->props_dev.p, transient); break;
   }
-  EFV_CUDA(cudaEventRecord(e1, stream()));
-  EFV_CUDA(cudaEventSynchronize(e1));
-  float ms = 0;
-  EFV_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-  s->t_assemble_ms = ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  s->dirichlet_mode = -1;
+  EFV_CUDA(cudaEventRecord(s->ev1, stream()));
+  s->assemble_timed = true;
+  s->dirichlet_mode = s->fuse_mode;
   s->physics = 0;
 }
 
@@ -324,6 +372,7 @@ __global__ void __launch_bounds__(256) k_apply_dirichlet(SysView s, const uint8_
 void apply_dirichlet(efv_system *s, int mode) {
   EFV_REQUIRE(mode == 0 || mode == 1, "bad Dirichlet mode");
   EFV_REQUIRE(s->vals.n, "assemble before applying Dirichlet conditions");
+  if (s->dirichlet_mode == mode) return;      // already applied inside the assembly kernel (efv_assemble_dirichlet_mode)
   EFV_REQUIRE(s->dirichlet_mode < 0, "Dirichlet conditions were already applied to these values; re-assemble first");
   if (!s->dir_flag.n) bc_clear(s);
   SysView sv = sys_view(s);

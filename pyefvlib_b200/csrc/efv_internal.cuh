@@ -24,6 +24,7 @@ struct ShapeGroup {
   DBuf<int32_t> ids;        // global element id of group member k (empty when the mesh is uniform: id = k)
   // SoA geometry (efv_geometry_build)
   DBuf<double> Jinv, S, vol;
+  DBuf<double> St;          // per face  J^-T s  (NF*d components): all the heat operator needs
 };
 
 struct Boundaries {
@@ -95,11 +96,15 @@ struct efv_system {
   efv::DBuf<double> dir_value;
   efv::DBuf<int32_t> dir_last;
   int dirichlet_mode = -1;
+  int fuse_mode = -1;                  // Dirichlet mode applied inside the next assembly kernel (-1: none)
   bool has_dirichlet = false;
   int physics = 0;
   // Krylov workspace
   efv::KrylovWork *kw = nullptr;
   double t_assemble_ms = 0, t_solve_ms = 0, t_spmv_ms = 0;
+  efv::DBuf<double> props_dev;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // assembly timing (read lazily: no host sync in the hot path)
+  bool assemble_timed = false;
 };
 
 namespace efv {

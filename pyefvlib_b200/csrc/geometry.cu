@@ -43,7 +43,7 @@ template <> struct SmallMat<3> {
 template <class Tab>
 __global__ void __launch_bounds__(128) k_geometry(MeshView m, const int32_t *__restrict__ ids, int64_t n,
                                                   double *__restrict__ Jinv, double *__restrict__ S,
-                                                  double *__restrict__ vol) {
+                                                  double *__restrict__ vol, double *__restrict__ St) {
   constexpr int M = Tab::M, D = Tab::DIM, NF = Tab::NF;
   int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (k >= n) return;
@@ -111,6 +111,14 @@ __global__ void __launch_bounds__(128) k_geometry(MeshView m, const int32_t *__r
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) S[(int64_t)(f * 3 + a) * n + k] = s[a];
+    // J^-T s : the heat flux coefficients are  k * D_f[j,:] . (J^-T s)   (InnerFace.py:25 + heat_transfer.py:47)
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < D; ++q) acc += R[q][a] * s[q];
+      St[(int64_t)(f * D + a) * n + k] = acc;
+    }
   }
 #pragma unroll
   for (int l = 0; l < M; ++l) {
@@ -153,9 +161,10 @@ void geometry_build(efv_mesh *m) {
     g.Jinv.alloc((size_t)nf * d * d * g.n);
     g.S.alloc((size_t)nf * 3 * g.n);
     g.vol.alloc((size_t)mm * g.n);
+    g.St.alloc((size_t)nf * d * g.n);
     const int32_t *ids = (m->uniform_code >= 0) ? nullptr : g.ids.p;
     unsigned grid = (unsigned)div_up(g.n, 128);
-    EFV_DISPATCH_SHAPE(code, EFV_LAUNCH(k_geometry<Tab>, grid, 128, 0, mv, ids, g.n, g.Jinv.p, g.S.p, g.vol.p));
+    EFV_DISPATCH_SHAPE(code, EFV_LAUNCH(k_geometry<Tab>, grid, 128, 0, mv, ids, g.n, g.Jinv.p, g.S.p, g.vol.p, g.St.p));
   }
   m->vertex_volume.alloc(m->nV);
   EFV_LAUNCH(k_vertex_volume, grid_for(m->nV, 256), 256, 0, mv, geom_of(m), m->vertex_volume.p);

@@ -32,7 +32,7 @@ static KrylovWork *work(efv_system *s) {
   if (!s->kw) {
     KrylovWork *w = new KrylovWork();
     w->n = s->rows;
-    w->grid = num_sms() * 4;
+    w->grid = num_sms() * 8;
     w->partial.alloc((size_t)4 * w->grid);
     w->sc.alloc(16);
     w->flags.alloc(4);
@@ -71,7 +71,10 @@ __device__ __forceinline__ double sum_partials(const double *__restrict__ part, 
 }
 
 // ---- SpMV: y = sigma * A x  (optionally y *= rowscale), partial[blockIdx] = sum_i w_i * y_i -------------------------
-template <int NDOF, int L>
+// A group of L lanes owns a row.  Each lane first issues U independent (value, column) loads -- U*L >= the usual row
+// length, so a whole row is in flight at once -- then the U gathers of x, then the FMAs; longer rows continue in a
+// plain loop.  Streaming data (values, columns) is read with evict-first hints so that x stays in L1/L2.
+template <int NDOF, int L, int U>
 __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__restrict__ gptr,
                                                  const int32_t *__restrict__ gcol, const double *__restrict__ vals,
                                                  const double *__restrict__ x, double *__restrict__ y, double sigma,
@@ -90,19 +93,31 @@ __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__re
     double acc[NDOF];
 #pragma unroll
     for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
-    for (int64_t t = r0 + gl; t < r1; t += L) {
-      const int64_t c = gcol[t];
-      if (NDOF == 1) {
-        acc[0] += vals[t] * x[c];
-      } else {
+    int64_t t = r0 + gl;
+    if (NDOF == 1) {
+      double vv[U];
+      int cc[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int64_t tk = t + (int64_t)k * L;
+        const bool ok = tk < r1;
+        cc[k] = ok ? __ldcs(gcol + tk) : -1;
+        vv[k] = ok ? __ldcs(vals + tk) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k) acc[0] += (cc[k] >= 0) ? vv[k] * __ldg(x + cc[k]) : 0.0;
+      for (t += (int64_t)U * L; t < r1; t += L) acc[0] += __ldcs(vals + t) * __ldg(x + __ldcs(gcol + t));
+    } else {
+      for (; t < r1; t += L) {
+        const int64_t c = __ldcs(gcol + t);
         double xv[NDOF];
 #pragma unroll
-        for (int j = 0; j < NDOF; ++j) xv[j] = x[c * NDOF + j];
+        for (int j = 0; j < NDOF; ++j) xv[j] = __ldg(x + c * NDOF + j);
         const double *blk = vals + t * (NDOF * NDOF);
 #pragma unroll
         for (int i = 0; i < NDOF; ++i)
 #pragma unroll
-          for (int j = 0; j < NDOF; ++j) acc[i] += blk[i * NDOF + j] * xv[j];
+          for (int j = 0; j < NDOF; ++j) acc[i] += __ldcs(blk + i * NDOF + j) * xv[j];
       }
     }
 #pragma unroll
@@ -128,7 +143,7 @@ static int pick_lanes(const efv_system *s) {
   if (env) { int l = atoi(env); if (l == 2 || l == 4 || l == 8 || l == 16 || l == 32) return l; }
   double avg = (double)s->nnzg / (double)(s->nV > 0 ? s->nV : 1);
   if (avg <= 6) return 2;
-  if (avg <= 20) return 4;
+  if (avg <= 16) return 4;
   if (avg <= 48) return 8;
   if (avg <= 96) return 16;
   return 32;
@@ -137,13 +152,17 @@ static int pick_lanes(const efv_system *s) {
 template <int NDOF>
 static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
                           const double *w, double *partial, const int *done) {
+#define EFV_SPMV_CASE(LL, UU)                                                                                          \
+  EFV_LAUNCH((k_spmv<NDOF, LL, UU>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, \
+             w, partial, done)
   switch (pick_lanes(s)) {
-    case 2: EFV_LAUNCH((k_spmv<NDOF, 2>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
-    case 4: EFV_LAUNCH((k_spmv<NDOF, 4>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
-    case 8: EFV_LAUNCH((k_spmv<NDOF, 8>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
-    case 16: EFV_LAUNCH((k_spmv<NDOF, 16>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
-    default: EFV_LAUNCH((k_spmv<NDOF, 32>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, w, partial, done); break;
+    case 2: EFV_SPMV_CASE(2, 4); break;
+    case 4: EFV_SPMV_CASE(4, 4); break;
+    case 8: EFV_SPMV_CASE(8, 4); break;
+    case 16: EFV_SPMV_CASE(16, 4); break;
+    default: EFV_SPMV_CASE(32, 4); break;
   }
+#undef EFV_SPMV_CASE
 }
 static void launch_spmv(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
                         const double *w, double *partial, const int *done) {
@@ -158,7 +177,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
 
 void spmv(efv_system *s, const double *x, double *y) {
   EFV_REQUIRE(s->vals.n, "no values assembled");
-  launch_spmv(s, num_sms() * 4, x, y, 1.0, nullptr, nullptr, nullptr, nullptr);
+  launch_spmv(s, num_sms() * 8, x, y, 1.0, nullptr, nullptr, nullptr, nullptr);
 }
 
 // ---- Jacobi -----------------------------------------------------------------------------------------------------------

@@ -25,10 +25,10 @@ struct MeshView {
   }
 };
 
-__host__ __device__ __forceinline__ int shape_m(int code) { return code == 0 ? 3 : (code == 3 ? 8 : 4); }
-__host__ __device__ __forceinline__ int shape_nf(int code) { return code == 0 ? 3 : (code == 1 ? 4 : (code == 2 ? 6 : 12)); }
-__host__ __device__ __forceinline__ int shape_dim(int code) { return code < 2 ? 2 : 3; }
-__host__ __device__ __forceinline__ int shape_nvf(int code) { return code < 2 ? 2 : 3; }
+__host__ __device__ constexpr __forceinline__ int shape_m(int code) { return code == 0 ? 3 : (code == 3 ? 8 : 4); }
+__host__ __device__ constexpr __forceinline__ int shape_nf(int code) { return code == 0 ? 3 : (code == 1 ? 4 : (code == 2 ? 6 : 12)); }
+__host__ __device__ constexpr __forceinline__ int shape_dim(int code) { return code < 2 ? 2 : 3; }
+__host__ __device__ constexpr __forceinline__ int shape_nvf(int code) { return code < 2 ? 2 : 3; }
 
 inline MeshView view_of(const efv_mesh *m) {
   MeshView v;
@@ -54,6 +54,7 @@ struct GeomView {
   const double *Jinv[kNumShapes];
   const double *S[kNumShapes];
   const double *vol[kNumShapes];
+  const double *St[kNumShapes];
   int64_t n[kNumShapes];
 };
 inline GeomView geom_of(const efv_mesh *m) {
@@ -62,6 +63,7 @@ inline GeomView geom_of(const efv_mesh *m) {
     g.Jinv[c] = m->groups[c].Jinv.p;
     g.S[c] = m->groups[c].S.p;
     g.vol[c] = m->groups[c].vol.p;
+    g.St[c] = m->groups[c].St.p;
     g.n[c] = m->groups[c].n;
   }
   return g;

@@ -43,6 +43,11 @@ class DeviceMesh:
             _lib.check(_lib.load().efv_geometry_build(self.handle))
             self._geometry = True
 
+    def release_geometry(self):
+        _lib.check(_lib.load().efv_geometry_release(self.handle))
+        self._geometry = False
+        self._vv = None
+
     def vertex_volume(self):
         if self._vv is None:
             self.build_geometry()
@@ -165,6 +170,10 @@ class DeviceSystem:
 
     def bc_neumann(self, boundary, dof, value, sign=1.0):
         _lib.check(_lib.load().efv_bc_neumann(self.handle, int(boundary), int(dof), float(value), float(sign)))
+
+    def assemble_dirichlet_mode(self, mode):
+        """Dirichlet treatment fused into the next assembly kernel (-1 = none)."""
+        _lib.check(_lib.load().efv_assemble_dirichlet_mode(self.handle, int(mode)))
 
     def apply_dirichlet(self, mode):
         _lib.check(_lib.load().efv_apply_dirichlet(self.handle, int(mode)))

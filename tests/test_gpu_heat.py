@@ -102,9 +102,12 @@ def test_steady_matrix_rhs_solution(tag):
     assert relres <= 1e-10
     T = s.download(D.VEC_X)
     assert util.rel_l2(T, z["heat_T"]) <= 1e-8, (iters, relres)
-    # the reference's own (row-replaced, non-symmetric) system solved by BiCGStab gives the same field
+    # the reference's own (row-replaced, non-symmetric) system solved by BiCGStab gives the same field;
+    # this time the Dirichlet rows are written by the assembly kernel itself (fused path)
+    s.assemble_dirichlet_mode(D.DIRICHLET_ROWS)
     s.heat_assemble(props_array(grid, case["props"]), 0.0, False)
-    s.apply_dirichlet(D.DIRICHLET_ROWS)
+    s.assemble_dirichlet_mode(-1)
+    assert util.row_rel_matrix_error(s.to_scipy(), Aref) <= 1e-12
     s.build_rhs(False)
     s.upload(D.VEC_X, np.zeros(s.rows))
     iters, relres = s.solve_bicgstab(1e-10, 5000)
@@ -165,8 +168,8 @@ def test_structured_against_oracle(n, kind, perturb):
     s.build_rhs(True)
     bref = O.heat_rhs(og, HEAT_PROPS, BC3D, transient=True, dt=dt, Told=Told)
     assert util.rel_max(s.download(D.VEC_B), bref) <= 1e-12
+    s.assemble_dirichlet_mode(D.DIRICHLET_SYMMETRIC)         # fused symmetric elimination
     s.heat_assemble(props_array(grid, HEAT_PROPS), dt, True)
-    s.apply_dirichlet(D.DIRICHLET_SYMMETRIC)
     s.build_rhs(True)
     s.upload(D.VEC_X, Told)
     iters, relres = (s.solve_bicgstab if (perturb and kind == "hex") else s.solve_pcg)(1e-10, 5000)
