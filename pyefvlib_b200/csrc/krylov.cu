@@ -155,12 +155,23 @@ static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, d
 #define EFV_SPMV_CASE(LL, UU)                                                                                          \
   EFV_LAUNCH((k_spmv<NDOF, LL, UU>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, \
              w, partial, done)
-  switch (pick_lanes(s)) {
-    case 2: EFV_SPMV_CASE(2, 4); break;
-    case 4: EFV_SPMV_CASE(4, 4); break;
-    case 8: EFV_SPMV_CASE(8, 4); break;
-    case 16: EFV_SPMV_CASE(16, 4); break;
-    default: EFV_SPMV_CASE(32, 4); break;
+  const char *envu = getenv("EFV_SPMV_UNROLL");
+  const int lanes = pick_lanes(s);
+  int unroll = envu ? atoi(envu) : 0;
+  if (!unroll) unroll = lanes <= 4 ? 8 : (lanes == 8 ? 4 : (lanes == 16 ? 2 : 1));
+  switch (lanes * 16 + unroll) {
+    case 2 * 16 + 8: EFV_SPMV_CASE(2, 8); break;
+    case 4 * 16 + 4: EFV_SPMV_CASE(4, 4); break;
+    case 4 * 16 + 8: EFV_SPMV_CASE(4, 8); break;
+    case 8 * 16 + 2: EFV_SPMV_CASE(8, 2); break;
+    case 8 * 16 + 4: EFV_SPMV_CASE(8, 4); break;
+    case 8 * 16 + 8: EFV_SPMV_CASE(8, 8); break;
+    case 16 * 16 + 1: EFV_SPMV_CASE(16, 1); break;
+    case 16 * 16 + 2: EFV_SPMV_CASE(16, 2); break;
+    case 16 * 16 + 4: EFV_SPMV_CASE(16, 4); break;
+    case 32 * 16 + 1: EFV_SPMV_CASE(32, 1); break;
+    case 32 * 16 + 2: EFV_SPMV_CASE(32, 2); break;
+    default: throw Error("unsupported EFV_SPMV_LANES / EFV_SPMV_UNROLL combination");
   }
 #undef EFV_SPMV_CASE
 }

@@ -1,0 +1,34 @@
+"""Sweep SpMV launch variants (lanes per row x unroll) on the C2 matrix; prints GB/s of algorithmic bytes."""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pyefvlib_b200 as P
+from pyefvlib_b200 import _lib
+from pyefvlib_b200.device import DeviceSystem, VEC_X, VEC_B, DIRICHLET_SYMMETRIC
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 216
+kind = sys.argv[2] if len(sys.argv) > 2 else "hex"
+L = _lib.load()
+grid = P.structured_grid(n, kind)
+s = DeviceSystem(grid, 1)
+s.heat_assemble(np.array([[1.0, 1.0, 1.0, 100.0]]), 1e-2, True)
+s.upload(VEC_X, np.random.default_rng(0).random(s.rows))
+stream = torch.cuda.ExternalStream(L.efv_get_stream())
+bytes_ = 12.0 * s.nnz + 24.0 * s.rows
+out = {}
+for lanes, unroll in [(8, 4), (8, 2), (8, 8), (4, 8), (4, 4), (16, 2), (16, 1), (16, 4), (32, 1), (32, 2)]:
+    os.environ["EFV_SPMV_LANES"] = str(lanes); os.environ["EFV_SPMV_UNROLL"] = str(unroll)
+    for _ in range(3):
+        s.spmv(VEC_X, VEC_B)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(20):
+        s.spmv(VEC_X, VEC_B)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    out[f"L{lanes}_U{unroll}"] = round(bytes_ / ms / 1e6, 1)
+    print(f"lanes={lanes:2d} unroll={unroll}  {ms:.4f} ms  {bytes_/ms/1e6:8.1f} GB/s", flush=True)
+print(json.dumps(out))
