@@ -233,7 +233,200 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
   s->physics = 0;
 }
 
-void elasticity_assemble(efv_system *, const double *, int) { throw Error("elasticity assembly: not implemented yet"); }
+// ---- linear elasticity ----------------------------------------------------------------------------------------------
+// Same row-centric scheme with an ndof x ndof block per graph entry.  For an inner face with area vector s and
+// column vertex c with global shape gradient g = G_f[:, c] = J^-1 D_f[c, :] the reference's
+//   M = At . Ce . Bv          (stress_equilibrium.py:50-67, :100;  Ce isotropic, :29-48)
+// is, in closed form,  M[i][j] = lambda s_i g_j + mu (s_j g_i + delta_ij s.g).  Row of the backward vertex gets +M,
+// row of the forward vertex -M (stress_equilibrium.py:105-117).  props per region: [0] lambda, [1] mu, [2] -rho*g.
+constexpr int kElRows = 16;          // rows (8-lane groups) per 128-thread block
+template <int UCODE, int NDOF>
+__global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g, SysView s, const double *__restrict__ props,
+                                                         int gravity, int max_row_len, int dir_mode,
+                                                         const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
+                                                         double *__restrict__ gen_out, double *__restrict__ elim_out) {
+  extern __shared__ double smem_dyn[];
+  __shared__ SmemTables T;
+  __shared__ double fbuf[kElRows][kAsmGroup][36];      // per pair: 3 faces x (J^-1 row-major 9 | s 3); 2-D uses 4 | 2 of each
+  __shared__ double aux[kElRows][kAsmGroup][3];        // lambda, mu, vol * (-rho g)
+  __shared__ unsigned long long posb[kElRows][kAsmGroup];
+  __shared__ int meta[kElRows][kAsmGroup];
+  load_tables(T);
+  constexpr int B = NDOF * NDOF;
+  const int grp = threadIdx.x / kAsmGroup, gl = threadIdx.x % kAsmGroup;
+  double *row = smem_dyn + (size_t)grp * max_row_len * B;
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) / kAsmGroup * kAsmGroup);
+  for (int64_t v0 = (int64_t)blockIdx.x * kElRows; v0 < m.nV; v0 += (int64_t)gridDim.x * kElRows) {
+    const int64_t v = v0 + grp;
+    if (v >= m.nV) continue;
+    const int64_t r0 = s.gptr[v];
+    const int len = (int)(s.gptr[v + 1] - r0);
+    for (int t = gl; t < len * B; t += kAsmGroup) row[t] = 0.0;
+    double grav = 0.0;
+    const int64_t p0 = m.inc_ptr[v], p1 = m.inc_ptr[v + 1];
+    for (int64_t pc = p0; pc < p1; pc += kAsmGroup) {
+      const int64_t p = pc + gl;
+      if (p < p1) {
+        const uint32_t pk = m.inc[p];
+        const int64_t e = pk >> 3;
+        const int l = pk & 7;
+        const int code = (UCODE >= 0) ? UCODE : m.code(e);
+        const int mm = shape_m(code), nvf = shape_nvf(code), d = shape_dim(code);
+        const int64_t gi = (UCODE >= 0) ? e : m.group_index(e);
+        const int64_t n = g.n[code];
+        const double *pr = props + 3 * m.region[e];
+        const double *Ji = g.Jinv[code], *Sv = g.S[code];
+        int mt = 1 | (code << 1);
+        for (int q = 0; q < nvf; ++q) {
+          const int enc = tab_vface(T, code, l, q);
+          const int f = enc >> 1;
+          mt |= f << (3 + 4 * q);
+          mt |= (enc & 1) << (15 + q);                 // 1: this vertex is the forward one -> sign -1
+          double *fb = &fbuf[grp][gl][q * 12];
+          for (int a = 0; a < d * d; ++a) fb[a] = Ji[(int64_t)(f * d * d + a) * n + gi];
+          for (int a = 0; a < d; ++a) fb[9 + a] = Sv[(int64_t)(f * 3 + a) * n + gi];
+        }
+        meta[grp][gl] = mt;
+        const uint8_t *sp = s.slotpos + ((UCODE >= 0) ? e * (int64_t)(mm * mm) : m.slot_begin(e)) + l * mm;
+        unsigned long long pb;
+        if (UCODE >= 0 && mm == 8) pb = *reinterpret_cast<const unsigned long long *>(sp);
+        else if (UCODE >= 0 && mm == 4) pb = *reinterpret_cast<const unsigned int *>(sp);
+        else {
+          pb = 0;
+          for (int j = 0; j < mm; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
+        }
+        posb[grp][gl] = pb;
+        aux[grp][gl][0] = pr[0];
+        aux[grp][gl][1] = pr[1];
+        aux[grp][gl][2] = g.vol[code][(int64_t)l * n + gi] * pr[2];
+      }
+      __syncwarp(gmask);
+      const int cnt = (int)((p1 - pc < kAsmGroup) ? (p1 - pc) : kAsmGroup);
+      for (int q = 0; q < cnt; ++q) {
+        const int mt = meta[grp][q];
+        const int code = (UCODE >= 0) ? UCODE : ((mt >> 1) & 3);
+        const int mm = shape_m(code), nvf = shape_nvf(code);
+        if (gl < mm) {
+          const double lam = aux[grp][q][0], mu = aux[grp][q][1];
+          double M[NDOF][NDOF];
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+            for (int j = 0; j < NDOF; ++j) M[i][j] = 0.0;
+          for (int k = 0; k < nvf; ++k) {
+            const int f = (mt >> (3 + 4 * k)) & 15;
+            const double sgn = ((mt >> (15 + k)) & 1) ? -1.0 : 1.0;
+            const double *fb = &fbuf[grp][q][k * 12];
+            double gv[NDOF], sv[NDOF], dl[NDOF];
+#pragma unroll
+            for (int a = 0; a < NDOF; ++a) { dl[a] = tab_ifD(T, code, f, gl, a); sv[a] = fb[9 + a]; }
+            double gs = 0.0;
+#pragma unroll
+            for (int i = 0; i < NDOF; ++i) {
+              double acc = 0.0;
+#pragma unroll
+              for (int a = 0; a < NDOF; ++a) acc += fb[i * NDOF + a] * dl[a];      // g_i = sum_a Jinv[i][a] D[c][a]
+              gv[i] = acc;
+              gs += acc * sv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+              for (int j = 0; j < NDOF; ++j)
+                M[i][j] += sgn * (lam * sv[i] * gv[j] + mu * (sv[j] * gv[i] + ((i == j) ? gs : 0.0)));
+          }
+          const int pos = (int)((posb[grp][q] >> (8 * gl)) & 0xff);
+          double *blk = row + pos * B;
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+            for (int j = 0; j < NDOF; ++j) blk[i * NDOF + j] += M[i][j];
+        }
+        if (gl == 0) grav += aux[grp][q][2];
+      }
+      __syncwarp(gmask);
+    }
+    if (gl == 0) {
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) gen_out[v * NDOF + i] = (gravity && i == 1) ? grav : 0.0;   // y component only (:81-90)
+    }
+    // epilogue: Dirichlet treatment + store (block layout [slot][i][j])
+    bool rowd[NDOF];
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) rowd[i] = (dir_mode >= 0) ? dflag[v * NDOF + i] : false;
+    double el[NDOF];
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) el[i] = 0.0;
+    for (int t = gl; t < len; t += kAsmGroup) {
+      const int64_t c = s.gcol[r0 + t];
+      double *blk = row + t * B;
+      double *out = s.vals + (r0 + t) * B;
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+        for (int j = 0; j < NDOF; ++j) {
+          double a = blk[i * NDOF + j];
+          if (rowd[i]) a = (c == v && i == j) ? 1.0 : 0.0;
+          else if (dir_mode == 1 && dflag[c * NDOF + j]) { el[i] -= a * dval[c * NDOF + j]; a = 0.0; }
+          out[i * NDOF + j] = a;
+        }
+    }
+    if (dir_mode == 1) {
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) {
+        double tot = el[i];
+#pragma unroll
+        for (int o = kAsmGroup / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(gmask, tot, o);
+        if (gl == 0) elim_out[v * NDOF + i] = rowd[i] ? 0.0 : tot;
+      }
+    }
+    __syncwarp(gmask);
+  }
+}
+
+template <int UCODE, int NDOF>
+static void launch_elasticity_rows(efv_system *s, const double *dprops, int gravity) {
+  efv_mesh *m = s->mesh;
+  size_t smem = (size_t)kElRows * s->max_row_len * NDOF * NDOF * sizeof(double);
+  EFV_CUDA(cudaFuncSetAttribute((k_elasticity_rows<UCODE, NDOF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EFV_LAUNCH((k_elasticity_rows<UCODE, NDOF>), grid_for(s->nV * kAsmGroup, 128, 12), 128, smem, view_of(m), geom_of(m),
+             sys_view(s), dprops, gravity, s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->elim.p);
+}
+
+void elasticity_assemble(efv_system *s, const double *props_host, int gravity) {
+  efv_mesh *m = s->mesh;
+  EFV_REQUIRE(s->ndof == m->dim, "elasticity needs ndof == dimension");
+  geometry_build(m);
+  if (!s->dir_flag.n) bc_clear(s);
+  std::vector<double> pr(3 * m->n_regions);
+  for (int r = 0; r < m->n_regions; ++r) {
+    const double *p = props_host + 4 * r;             // ShearModulus, PoissonsRatio, Density, Gravity
+    const double G = p[0], nu = p[1];
+    pr[3 * r + 0] = 2 * G * nu / (1 - 2 * nu);        // lameParameter (stress_equilibrium.py:33)
+    pr[3 * r + 1] = G;
+    pr[3 * r + 2] = -p[2] * p[3];                     // - density * gravity (stress_equilibrium.py:89)
+  }
+  if (s->props_dev.n < pr.size()) s->props_dev.alloc(pr.size());
+  s->props_dev.upload(pr.data(), pr.size());
+  if (!s->gen.n) s->gen.alloc(s->rows);
+  if (!s->ev0) { EFV_CUDA(cudaEventCreate(&s->ev0)); EFV_CUDA(cudaEventCreate(&s->ev1)); }
+  EFV_CUDA(cudaEventRecord(s->ev0, stream()));
+  const int uc = m->uniform_code;
+  if (m->dim == 2) {
+    if (uc == 0) launch_elasticity_rows<0, 2>(s, s->props_dev.p, gravity);
+    else if (uc == 1) launch_elasticity_rows<1, 2>(s, s->props_dev.p, gravity);
+    else launch_elasticity_rows<-1, 2>(s, s->props_dev.p, gravity);
+  } else {
+    if (uc == 2) launch_elasticity_rows<2, 3>(s, s->props_dev.p, gravity);
+    else if (uc == 3) launch_elasticity_rows<3, 3>(s, s->props_dev.p, gravity);
+    else launch_elasticity_rows<-1, 3>(s, s->props_dev.p, gravity);
+  }
+  EFV_CUDA(cudaEventRecord(s->ev1, stream()));
+  s->assemble_timed = true;
+  s->dirichlet_mode = s->fuse_mode;
+  s->physics = 1;
+}
+
 void biot_assemble(efv_system *, const double *, double, const double *) { throw Error("Biot assembly: not implemented yet"); }
 
 // ---- boundary conditions -----------------------------------------------------------------------------------------
