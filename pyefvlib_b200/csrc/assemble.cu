@@ -427,7 +427,295 @@ void elasticity_assemble(efv_system *s, const double *props_host, int gravity) {
   s->physics = 1;
 }
 
-void biot_assemble(efv_system *, const double *, double, const double *) { throw Error("Biot assembly: not implemented yet"); }
+// ---- Biot poroelasticity (fully coupled) ------------------------------------------------------------------------------
+// Unknowns per vertex: u_0..u_{d-1}, p (reference numbering [u_x | u_y | (u_z) | p], geomechanics.py:255-256).
+// Per inner face (area s, column vertex c, gradient g = G_f[:,c], shape value N = N_f[c]) the row of the backward vertex
+// receives +coef and the row of the forward vertex -coef with  (geomechanics.py:61-112)
+//   uu : lambda s_i g_j + mu (s_j g_i + delta_ij s.g)          (:89-100)
+//   up : -alpha s_i N                                          (:66-77)
+//   pp : -k*mu (s.g)                                           (:80-86; note k*mu, not k/mu)
+//   pu : alpha/dt N s_j                                        (:103-112)
+// plus S/dt vol_k on the pp diagonal (:62-63) and, on boundary vertices, alpha/dt N_outer s_outer_j in the p row of the
+// outer face's own vertex (:113-115).  The pre-Dirichlet p-row/u-column block is also kept (rhs_op) because the RHS of
+// a time step is that block applied to u_old (:185-196) plus S/dt vol p_old (:172-173).
+// props per region: [0] lambda [1] mu [2] alpha [3] k*mu [4] S/dt [5] alpha/dt [6] rho
+struct BndView {
+  const int32_t *vtx_to_bv;
+  const int64_t *bvo_ptr, *bvo, *outer_facet, *facet_element, *facet_ptr;
+  const int32_t *facet_local, *outer_local;
+  const double *facet_area;
+};
+__device__ __forceinline__ int tab_facetV(int code, int lf, int k) {
+  switch (code) {
+    case 0: return c_Triangle_facetV[lf][k];
+    case 1: return c_Quadrilateral_facetV[lf][k];
+    case 2: return c_Tetrahedron_facetV[lf][k];
+    default: return c_Hexahedron_facetV[lf][k];
+  }
+}
+__device__ __forceinline__ double tab_ofN(int code, int lf, int k, int j) {
+  switch (code) {
+    case 0: return c_Triangle_ofN[lf][k][j];
+    case 1: return c_Quadrilateral_ofN[lf][k][j];
+    case 2: return c_Tetrahedron_ofN[lf][k][j];
+    default: return c_Hexahedron_ofN[lf][k][j];
+  }
+}
+__device__ __forceinline__ double tab_ifN(int code, int f, int j) {
+  switch (code) {
+    case 0: return c_Triangle_ifN[f][j];
+    case 1: return c_Quadrilateral_ifN[f][j];
+    case 2: return c_Tetrahedron_ifN[f][j];
+    default: return c_Hexahedron_ifN[f][j];
+  }
+}
+
+constexpr int kBiotRows = 8;          // rows (8-lane groups) per 64-thread block
+template <int UCODE, int D>
+__global__ void __launch_bounds__(64) k_biot_rows(MeshView m, GeomView g, SysView s, BndView bd, const double *__restrict__ props,
+                                                  double gx, double gy, double gz, int max_row_len, int dir_mode,
+                                                  const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
+                                                  double *__restrict__ gen_out, double *__restrict__ acc_out,
+                                                  double *__restrict__ rhs_op, double *__restrict__ elim_out) {
+  constexpr int NDOF = D + 1, B = NDOF * NDOF;
+  extern __shared__ double smem_dyn[];
+  __shared__ SmemTables T;
+  __shared__ double fbuf[kBiotRows][kAsmGroup][36];
+  __shared__ double aux[kBiotRows][kAsmGroup][8];
+  __shared__ unsigned long long posb[kBiotRows][kAsmGroup];
+  __shared__ int meta[kBiotRows][kAsmGroup];
+  load_tables(T);
+  const double gvec[3] = {gx, gy, gz};
+  const int grp = threadIdx.x / kAsmGroup, gl = threadIdx.x % kAsmGroup;
+  double *row = smem_dyn + (size_t)grp * max_row_len * B;
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) / kAsmGroup * kAsmGroup);
+  for (int64_t v0 = (int64_t)blockIdx.x * kBiotRows; v0 < m.nV; v0 += (int64_t)gridDim.x * kBiotRows) {
+    const int64_t v = v0 + grp;
+    if (v >= m.nV) continue;
+    const int64_t r0 = s.gptr[v];
+    const int len = (int)(s.gptr[v + 1] - r0);
+    for (int t = gl; t < len * B; t += kAsmGroup) row[t] = 0.0;
+    double gen[NDOF], accv = 0.0;
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) gen[i] = 0.0;
+    const int64_t p0 = m.inc_ptr[v], p1 = m.inc_ptr[v + 1];
+    for (int64_t pc = p0; pc < p1; pc += kAsmGroup) {
+      const int64_t p = pc + gl;
+      if (p < p1) {
+        const uint32_t pk = m.inc[p];
+        const int64_t e = pk >> 3;
+        const int l = pk & 7;
+        const int code = (UCODE >= 0) ? UCODE : m.code(e);
+        const int mm = shape_m(code), nvf = shape_nvf(code);
+        const int64_t gi = (UCODE >= 0) ? e : m.group_index(e);
+        const int64_t n = g.n[code];
+        const double *pr = props + 7 * m.region[e];
+        const double *Ji = g.Jinv[code], *Sv = g.S[code];
+        int mt = 1 | (code << 1);
+        for (int q = 0; q < nvf; ++q) {
+          const int enc = tab_vface(T, code, l, q);
+          const int f = enc >> 1;
+          mt |= f << (3 + 4 * q);
+          mt |= (enc & 1) << (15 + q);
+          double *fb = &fbuf[grp][gl][q * 12];
+          for (int a = 0; a < D * D; ++a) fb[a] = Ji[(int64_t)(f * D * D + a) * n + gi];
+          for (int a = 0; a < D; ++a) fb[9 + a] = Sv[(int64_t)(f * 3 + a) * n + gi];
+        }
+        meta[grp][gl] = mt;
+        const uint8_t *sp = s.slotpos + ((UCODE >= 0) ? e * (int64_t)(mm * mm) : m.slot_begin(e)) + l * mm;
+        unsigned long long pb;
+        if (UCODE >= 0 && mm == 8) pb = *reinterpret_cast<const unsigned long long *>(sp);
+        else if (UCODE >= 0 && mm == 4) pb = *reinterpret_cast<const unsigned int *>(sp);
+        else {
+          pb = 0;
+          for (int j = 0; j < mm; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
+        }
+        posb[grp][gl] = pb;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) aux[grp][gl][k] = pr[k];
+        aux[grp][gl][7] = g.vol[code][(int64_t)l * n + gi];
+      }
+      __syncwarp(gmask);
+      const int cnt = (int)((p1 - pc < kAsmGroup) ? (p1 - pc) : kAsmGroup);
+      for (int q = 0; q < cnt; ++q) {
+        const int mt = meta[grp][q];
+        const int code = (UCODE >= 0) ? UCODE : ((mt >> 1) & 3);
+        const int mm = shape_m(code), nvf = shape_nvf(code);
+        const double lam = aux[grp][q][0], mu = aux[grp][q][1], alpha = aux[grp][q][2], kmu = aux[grp][q][3];
+        const double sdt = aux[grp][q][4], adt = aux[grp][q][5], rho = aux[grp][q][6], vol = aux[grp][q][7];
+        if (gl < mm) {
+          double M[NDOF][NDOF];
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+            for (int j = 0; j < NDOF; ++j) M[i][j] = 0.0;
+          for (int k = 0; k < nvf; ++k) {
+            const int f = (mt >> (3 + 4 * k)) & 15;
+            const double sgn = ((mt >> (15 + k)) & 1) ? -1.0 : 1.0;
+            const double *fb = &fbuf[grp][q][k * 12];
+            const double N = tab_ifN(code, f, gl);
+            double gv[D], sv[D], dl[D];
+#pragma unroll
+            for (int a = 0; a < D; ++a) { dl[a] = tab_ifD(T, code, f, gl, a); sv[a] = fb[9 + a]; }
+            double gs = 0.0;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+              double acc = 0.0;
+#pragma unroll
+              for (int a = 0; a < D; ++a) acc += fb[i * D + a] * dl[a];
+              gv[i] = acc;
+              gs += acc * sv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+#pragma unroll
+              for (int j = 0; j < D; ++j) M[i][j] += sgn * (lam * sv[i] * gv[j] + mu * (sv[j] * gv[i] + ((i == j) ? gs : 0.0)));
+              M[i][D] += sgn * (-alpha * sv[i] * N);
+              M[D][i] += sgn * (adt * N * sv[i]);
+            }
+            M[D][D] += sgn * (-kmu * gs);
+          }
+          const int pos = (int)((posb[grp][q] >> (8 * gl)) & 0xff);
+          double *blk = row + pos * B;
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+            for (int j = 0; j < NDOF; ++j) blk[i * NDOF + j] += M[i][j];
+        }
+        if (gl == 0) {
+          accv += vol * sdt;                                   // S/dt vol (geomechanics.py:62-63)
+#pragma unroll
+          for (int i = 0; i < D; ++i) gen[i] += vol * (-rho * gvec[i]);                 // (:166-169)
+          for (int k = 0; k < nvf; ++k) {                      // gravity flux (:176-183)
+            const double sgn = ((mt >> (15 + k)) & 1) ? -1.0 : 1.0;
+            const double *fb = &fbuf[grp][q][k * 12];
+            double sg = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) sg += fb[9 + a] * gvec[a];
+            gen[D] += sgn * (-kmu * rho * sg);
+          }
+        }
+      }
+      __syncwarp(gmask);
+    }
+    // outer faces of this vertex: alpha/dt N_outer[c] s_outer_j on (p row of v) x (u_j of every element vertex c)
+    const int bvi = bd.vtx_to_bv[v];
+    if (bvi >= 0) {
+      for (int64_t po = bd.bvo_ptr[bvi]; po < bd.bvo_ptr[bvi + 1]; ++po) {
+        const int64_t o = bd.bvo[po];
+        const int64_t f = bd.outer_facet[o];
+        const int64_t e = bd.facet_element[f];
+        const int lf = bd.facet_local[f], ol = bd.outer_local[o];
+        const int mf = (int)(bd.facet_ptr[f + 1] - bd.facet_ptr[f]);
+        const int code = (UCODE >= 0) ? UCODE : m.code(e);
+        const int mm = shape_m(code);
+        const int l = tab_facetV(code, lf, ol);
+        const double adt = props[7 * m.region[e] + 5];
+        if (gl < mm) {
+          const double N = tab_ofN(code, lf, ol, gl);
+          const int pos = s.slotpos[((UCODE >= 0) ? e * (int64_t)(mm * mm) : m.slot_begin(e)) + l * mm + gl];
+          double *blk = row + pos * B;
+#pragma unroll
+          for (int j = 0; j < D; ++j) blk[D * NDOF + j] += adt * N * (bd.facet_area[f * 3 + j] / mf);    // OuterFace.py:18-19
+        }
+        __syncwarp(gmask);
+      }
+    }
+    if (gl == 0) {
+      row[(s.diag_slot[v] - r0) * B + D * NDOF + D] += accv;
+      acc_out[v] = accv;
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) gen_out[v * NDOF + i] = gen[i];
+    }
+    __syncwarp(gmask);
+    bool rowd[NDOF];
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) rowd[i] = (dir_mode >= 0) ? dflag[v * NDOF + i] : false;
+    double el[NDOF];
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) el[i] = 0.0;
+    for (int t = gl; t < len; t += kAsmGroup) {
+      const int64_t c = s.gcol[r0 + t];
+      double *blk = row + t * B;
+      double *out = s.vals + (r0 + t) * B;
+#pragma unroll
+      for (int j = 0; j < D; ++j) rhs_op[(r0 + t) * D + j] = blk[D * NDOF + j];      // pre-Dirichlet p-row / u-col block
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+        for (int j = 0; j < NDOF; ++j) {
+          double a = blk[i * NDOF + j];
+          if (rowd[i]) a = (c == v && i == j) ? 1.0 : 0.0;                          // geomechanics.py:117-137
+          else if (dir_mode == 1 && dflag[c * NDOF + j]) { el[i] -= a * dval[c * NDOF + j]; a = 0.0; }
+          out[i * NDOF + j] = a;
+        }
+    }
+    if (dir_mode == 1) {
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) {
+        double tot = el[i];
+#pragma unroll
+        for (int o = kAsmGroup / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(gmask, tot, o);
+        if (gl == 0) elim_out[v * NDOF + i] = rowd[i] ? 0.0 : tot;
+      }
+    }
+    __syncwarp(gmask);
+  }
+}
+
+template <int UCODE, int D>
+static void launch_biot_rows(efv_system *s, const double *dprops, const double *gv) {
+  efv_mesh *m = s->mesh;
+  constexpr int NDOF = D + 1;
+  size_t smem = (size_t)kBiotRows * s->max_row_len * NDOF * NDOF * sizeof(double);
+  EFV_REQUIRE(smem <= 160 * 1024, "graph rows too long for the Biot assembly kernel");
+  const Boundaries &B = m->bnd;
+  EFV_REQUIRE(B.vtx_to_bv.n, "set the mesh boundaries before assembling the Biot system");
+  BndView bd{B.vtx_to_bv.p, B.bvo_ptr.p, B.bvo.p, B.outer_facet.p, B.facet_element.p, B.facet_ptr.p, B.facet_local.p, B.outer_local.p, B.facet_area.p};
+  EFV_CUDA(cudaFuncSetAttribute((k_biot_rows<UCODE, D>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EFV_LAUNCH((k_biot_rows<UCODE, D>), grid_for(s->nV * kAsmGroup, 64, 16), 64, smem, view_of(m), geom_of(m), sys_view(s), bd, dprops,
+             gv[0], gv[1], gv[2], s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->rhs_op.p, s->elim.p);
+}
+
+void biot_assemble(efv_system *s, const double *props_host, double dt, const double *gvec) {
+  efv_mesh *m = s->mesh;
+  EFV_REQUIRE(s->ndof == m->dim + 1, "Biot needs ndof == dimension + 1");
+  geometry_build(m);
+  if (!s->dir_flag.n) bc_clear(s);
+  std::vector<double> pr(7 * m->n_regions);
+  for (int r = 0; r < m->n_regions; ++r) {
+    const double *p = props_host + 9 * r;      // nu, G, cs, phi, k, cf, mu, rhos, rhof  (geomechanics.py:41-49)
+    const double nu = p[0], G = p[1], cs = p[2], phi = p[3], k = p[4], cf = p[5], mu = p[6], rhos = p[7], rhof = p[8];
+    const double lame = 2 * G * nu / (1 - 2 * nu);
+    const double rho = phi * rhof + (1 - phi) * rhos;
+    const double K = 2 * G * (1 + nu) / 3 * (1 - 2 * nu);     // precedence quirk of geomechanics.py:55, reproduced
+    const double cb = 1 / K;
+    const double alpha = 1 - cs / cb;
+    const double S = phi * cf + (alpha - phi) * cs;
+    pr[7 * r + 0] = lame; pr[7 * r + 1] = G; pr[7 * r + 2] = alpha; pr[7 * r + 3] = k * mu;
+    pr[7 * r + 4] = S * (1 / dt); pr[7 * r + 5] = alpha * (1 / dt); pr[7 * r + 6] = rho;
+  }
+  if (s->props_dev.n < pr.size()) s->props_dev.alloc(pr.size());
+  s->props_dev.upload(pr.data(), pr.size());
+  if (!s->gen.n) { s->gen.alloc(s->rows); s->acc.alloc(s->nV); s->rhs_op.alloc((size_t)s->nnzg * m->dim); }
+  double gv[3] = {gvec ? gvec[0] : 0.0, gvec ? gvec[1] : 0.0, gvec ? gvec[2] : 0.0};
+  if (!s->ev0) { EFV_CUDA(cudaEventCreate(&s->ev0)); EFV_CUDA(cudaEventCreate(&s->ev1)); }
+  EFV_CUDA(cudaEventRecord(s->ev0, stream()));
+  const int uc = m->uniform_code;
+  if (m->dim == 2) {
+    if (uc == 0) launch_biot_rows<0, 2>(s, s->props_dev.p, gv);
+    else if (uc == 1) launch_biot_rows<1, 2>(s, s->props_dev.p, gv);
+    else launch_biot_rows<-1, 2>(s, s->props_dev.p, gv);
+  } else {
+    if (uc == 2) launch_biot_rows<2, 3>(s, s->props_dev.p, gv);
+    else if (uc == 3) launch_biot_rows<3, 3>(s, s->props_dev.p, gv);
+    else launch_biot_rows<-1, 3>(s, s->props_dev.p, gv);
+  }
+  EFV_CUDA(cudaEventRecord(s->ev1, stream()));
+  s->assemble_timed = true;
+  s->dirichlet_mode = s->fuse_mode;
+  s->physics = 2;
+}
 
 // ---- boundary conditions -----------------------------------------------------------------------------------------
 // field-major DOF index (C-ABI) -> internal vertex-major index
@@ -612,10 +900,58 @@ void ensure_vectors(efv_system *s) {
   if (!s->xold.n) { s->xold.alloc(s->rows); s->xold.zero(); }
 }
 
+// Biot: u rows = body force + neumann; p row = gravity flux + S/dt vol p_old + (alpha/dt N s) . u_old + neumann
+// (geomechanics.py:166-221); Dirichlet rows <- g (:224-239).  One 8-lane group per vertex for the sparse product.
+template <int D>
+__global__ void __launch_bounds__(256) k_rhs_biot(SysView s, const double *__restrict__ gen, const double *__restrict__ acc,
+                                                  const double *__restrict__ rhs_op, const double *__restrict__ xold,
+                                                  const double *__restrict__ stat, const double *__restrict__ elim,
+                                                  const uint8_t *__restrict__ flag, const double *__restrict__ gval,
+                                                  int symmetric, double *__restrict__ b) {
+  constexpr int NDOF = D + 1, GROUP = 8;
+  const int gl = threadIdx.x % GROUP;
+  const int64_t rows_per_block = blockDim.x / GROUP;
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_block; base < s.nV; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t v = base + threadIdx.x / GROUP;
+    const bool valid = v < s.nV;
+    const int64_t r0 = valid ? s.gptr[v] : 0, r1 = valid ? s.gptr[v + 1] : 0;
+    double sum = 0.0;
+    for (int64_t t = r0 + gl; t < r1; t += GROUP) {
+      const int64_t c = s.gcol[t];
+#pragma unroll
+      for (int j = 0; j < D; ++j) sum += rhs_op[t * D + j] * xold[c * NDOF + j];
+    }
+    sum = group_sum<GROUP>(sum);
+    if (valid && gl == 0) {
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) {
+        const int64_t k = v * NDOF + i;
+        double r = gen[k] + stat[k];
+        if (i == D) r += acc[v] * xold[k] + sum;
+        if (symmetric) r += elim[k];
+        if (flag[k]) r = gval[k];
+        b[k] = r;
+      }
+    }
+  }
+}
+
 void build_rhs(efv_system *s, int transient) {
   ensure_vectors(s);
   if (!s->dir_flag.n) bc_clear(s);
   int sym = s->dirichlet_mode == 1;
+  if (s->physics == 2) {
+    EFV_REQUIRE(s->rhs_op.n, "efv_biot_assemble first");
+    SysView sv = sys_view(s);
+    int grid = grid_for(s->nV * 8, 256, 8);
+    if (s->mesh->dim == 2)
+      EFV_LAUNCH(k_rhs_biot<2>, grid, 256, 0, sv, s->gen.p, s->acc.p, s->rhs_op.p, s->xold.p, s->static_rhs.p, s->elim.p,
+                 s->dir_flag.p, s->dir_value.p, sym, s->b.p);
+    else
+      EFV_LAUNCH(k_rhs_biot<3>, grid, 256, 0, sv, s->gen.p, s->acc.p, s->rhs_op.p, s->xold.p, s->static_rhs.p, s->elim.p,
+                 s->dir_flag.p, s->dir_value.p, sym, s->b.p);
+    return;
+  }
   if (s->physics == 0) {
     EFV_REQUIRE(s->gen.n, "efv_heat_assemble first");
     EFV_LAUNCH(k_rhs_heat, grid_for(s->rows, 256), 256, 0, s->rows, s->gen.p, s->acc.p, s->xold.p, s->static_rhs.p,

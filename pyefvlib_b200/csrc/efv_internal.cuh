@@ -46,6 +46,7 @@ struct Boundaries {
   int64_t nbv = 0;
   DBuf<int32_t> bv;                        // nbv vertex ids (ascending)
   DBuf<int64_t> bvo_ptr, bvo;              // nbv+1, nOuter
+  DBuf<int32_t> vtx_to_bv;                 // nV: compact index of a boundary vertex, -1 otherwise
 };
 
 }  // namespace efv

@@ -219,9 +219,12 @@ __global__ void k_match_facets(MeshView m, int64_t nF, const int64_t *__restrict
 __global__ void k_flag_vertices(const int32_t *__restrict__ ov, int64_t n, int32_t *__restrict__ flags) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) flags[ov[i]] = 1;
 }
-__global__ void k_compact_vertices(int64_t nV, const int32_t *__restrict__ flags, const int64_t *__restrict__ cidx, int32_t *__restrict__ bv) {
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nV; v += (int64_t)gridDim.x * blockDim.x)
+__global__ void k_compact_vertices(int64_t nV, const int32_t *__restrict__ flags, const int64_t *__restrict__ cidx, int32_t *__restrict__ bv,
+                                   int32_t *__restrict__ vtx_to_bv) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nV; v += (int64_t)gridDim.x * blockDim.x) {
     if (flags[v]) bv[cidx[v]] = (int32_t)v;
+    vtx_to_bv[v] = flags[v] ? (int32_t)cidx[v] : -1;
+  }
 }
 __global__ void k_count_outer(const int32_t *__restrict__ ov, int64_t n, const int64_t *__restrict__ cidx, int32_t *__restrict__ cnt) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -282,7 +285,8 @@ void mesh_set_boundaries(efv_mesh *m, int nB, const int64_t *boundary_ptr, int64
   DBuf<int64_t> cidx(m->nV + 1);
   B.nbv = exclusive_scan_i32_to_i64(flags.p, cidx.p, m->nV);
   B.bv.alloc(B.nbv);
-  EFV_LAUNCH(k_compact_vertices, grid_for(m->nV, 256), 256, 0, m->nV, flags.p, cidx.p, B.bv.p);
+  B.vtx_to_bv.alloc(m->nV);
+  EFV_LAUNCH(k_compact_vertices, grid_for(m->nV, 256), 256, 0, m->nV, flags.p, cidx.p, B.bv.p, B.vtx_to_bv.p);
   DBuf<int32_t> cnt(B.nbv);
   cnt.zero();
   EFV_LAUNCH(k_count_outer, grid_for(B.nOuter, 256), 256, 0, B.outer_vertex.p, B.nOuter, cidx.p, cnt.p);
