@@ -125,6 +125,21 @@ int efv_apply_dirichlet(efv_system *s, int mode);
  * [ref: apps/geomechanics.py:166-239].  In symmetric mode the eliminated columns are folded in.            */
 int efv_build_rhs(efv_system *s, int transient);
 
+/* ---- multi-GPU: vertex-block partition with owned + ghost vertices (the reference has no
+ * distributed code).  One process per GPU.  The unique id is created on rank 0 and distributed by the host layer
+ * (torch.distributed); nccl_library_path names the NCCL shared object to dlopen (NULL: default search).  A partitioned
+ * system is created on the rank's LOCAL mesh whose vertices are numbered [owned | ghosts grouped by owner rank];
+ * efv_system_set_owned restricts assembly / SpMV / vector kernels to the owned rows, efv_system_set_halo registers, per
+ * neighbour rank, which owned vertices to send and which slice of the ghost block to receive.  PCG then exchanges the
+ * halo of the search direction before every SpMV and all-reduces its dot products.                                   */
+int efv_comm_unique_id(const char *nccl_library_path, char *out128);
+int efv_comm_init(const char *nccl_library_path, int rank, int nranks, const char *id128);
+int efv_comm_destroy(void);
+int efv_system_set_owned(efv_system *s, int64_t n_owned);
+int efv_system_set_halo(efv_system *s, int n_neighbours, const int *neighbour_ranks, const int64_t *send_ptr,
+                        const int32_t *send_idx, const int64_t *recv_ptr);
+int efv_halo_exchange(efv_system *s, int which);
+
 /* ---- Krylov solvers (north_star kernel 5) -----------------------------------------------------------------
  * replace the reference's sparse/dense inverse [ref: apps/heat_transfer.py:78-81,134-135;
  * apps/stress_equilibrium.py:170-173; apps/geomechanics.py:140,254].  Solve A x = B from initial guess X;

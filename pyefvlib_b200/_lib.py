@@ -61,6 +61,12 @@ PROTOTYPES = {
     "efv_assemble_dirichlet_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_apply_dirichlet": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_build_rhs": (C.c_int, [C.c_void_p, C.c_int]),
+    "efv_comm_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
+    "efv_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
+    "efv_comm_destroy": (C.c_int, []),
+    "efv_system_set_owned": (C.c_int, [C.c_void_p, C.c_int64]),
+    "efv_system_set_halo": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_i64p, c_i32p, c_i64p]),
+    "efv_halo_exchange": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_solve_pcg": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, c_intp, c_f64p]),
     "efv_solve_bicgstab": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_intp, c_f64p]),
     "efv_spmv": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

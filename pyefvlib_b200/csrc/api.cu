@@ -270,6 +270,45 @@ int efv_build_rhs(efv_system *s, int transient) {
   EFV_API_END
 }
 
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------
+int efv_comm_unique_id(const char *nccl_library_path, char *out128) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(out128, "null argument");
+  efv::comm_unique_id(nccl_library_path, out128);
+  EFV_API_END
+}
+int efv_comm_init(const char *nccl_library_path, int rank, int nranks, const char *id128) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(id128 && nranks >= 1 && rank >= 0 && rank < nranks, "bad communicator arguments");
+  efv::comm_init(nccl_library_path, rank, nranks, id128);
+  EFV_API_END
+}
+int efv_comm_destroy(void) {
+  EFV_API_BEGIN
+  efv::comm_destroy();
+  EFV_API_END
+}
+int efv_system_set_owned(efv_system *s, int64_t n_owned) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(n_owned >= 0 && n_owned <= s->nV, "owned count out of range");
+  s->n_owned = n_owned;
+  EFV_API_END
+}
+int efv_system_set_halo(efv_system *s, int n_neighbours, const int *neighbour_ranks, const int64_t *send_ptr,
+                        const int32_t *send_idx, const int64_t *recv_ptr) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && (n_neighbours == 0 || (neighbour_ranks && send_ptr && recv_ptr)), "null argument");
+  efv::halo_set(s, n_neighbours, neighbour_ranks, send_ptr, send_idx, recv_ptr);
+  EFV_API_END
+}
+int efv_halo_exchange(efv_system *s, int which) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::halo_exchange(s, pick_vec(s, which)->p);
+  EFV_API_END
+}
+
 // ---- solvers -------------------------------------------------------------------------------------------------------
 int efv_solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres) {
   EFV_API_BEGIN

@@ -22,7 +22,7 @@ struct SysView {
 };
 static SysView sys_view(efv_system *s) {
   SysView v;
-  v.ndof = s->ndof; v.nV = s->nV; v.nnzg = s->nnzg;
+  v.ndof = s->ndof; v.nV = s->n_owned; v.nnzg = s->nnzg;     // row kernels only visit owned rows
   v.gptr = s->gptr.p; v.gcol = s->gcol.p; v.slotpos = s->slotpos.p; v.diag_slot = s->diag_slot.p; v.vals = s->vals.p;
   return v;
 }
@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(256) k_heat_rows(MeshView m, GeomView g, SysVi
   const int grp = threadIdx.x / kAsmGroup, gl = threadIdx.x % kAsmGroup;
   double *row = smem_dyn + (size_t)grp * max_row_len;
   const unsigned gmask = 0xffu << ((threadIdx.x & 31) / kAsmGroup * kAsmGroup);
-  for (int64_t v0 = (int64_t)blockIdx.x * kAsmRows; v0 < m.nV; v0 += (int64_t)gridDim.x * kAsmRows) {
+  for (int64_t v0 = (int64_t)blockIdx.x * kAsmRows; v0 < s.nV; v0 += (int64_t)gridDim.x * kAsmRows) {
     const int64_t v = v0 + grp;
-    if (v >= m.nV) continue;               // whole groups drop out together; syncs below are group-scoped
+    if (v >= s.nV) continue;               // whole groups drop out together; syncs below are group-scoped
     const int64_t r0 = s.gptr[v];
     const int len = (int)(s.gptr[v + 1] - r0);
     for (int t = gl; t < len; t += kAsmGroup) row[t] = 0.0;
@@ -199,7 +199,7 @@ static void launch_heat_rows(efv_system *s, const double *dprops, int transient)
   SysView sv = sys_view(s);
   size_t smem = (size_t)kAsmRows * s->max_row_len * sizeof(double);
   EFV_CUDA(cudaFuncSetAttribute(k_heat_rows<UCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  EFV_LAUNCH(k_heat_rows<UCODE>, grid_for(s->nV * kAsmGroup, 256, 6), 256, smem, mv, gv, sv, dprops, transient,
+  EFV_LAUNCH(k_heat_rows<UCODE>, grid_for(s->n_owned * kAsmGroup, 256, 6), 256, smem, mv, gv, sv, dprops, transient,
              s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
 }
 
@@ -256,9 +256,9 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
   const int grp = threadIdx.x / kAsmGroup, gl = threadIdx.x % kAsmGroup;
   double *row = smem_dyn + (size_t)grp * max_row_len * B;
   const unsigned gmask = 0xffu << ((threadIdx.x & 31) / kAsmGroup * kAsmGroup);
-  for (int64_t v0 = (int64_t)blockIdx.x * kElRows; v0 < m.nV; v0 += (int64_t)gridDim.x * kElRows) {
+  for (int64_t v0 = (int64_t)blockIdx.x * kElRows; v0 < s.nV; v0 += (int64_t)gridDim.x * kElRows) {
     const int64_t v = v0 + grp;
-    if (v >= m.nV) continue;
+    if (v >= s.nV) continue;
     const int64_t r0 = s.gptr[v];
     const int len = (int)(s.gptr[v + 1] - r0);
     for (int t = gl; t < len * B; t += kAsmGroup) row[t] = 0.0;
@@ -389,7 +389,7 @@ static void launch_elasticity_rows(efv_system *s, const double *dprops, int grav
   efv_mesh *m = s->mesh;
   size_t smem = (size_t)kElRows * s->max_row_len * NDOF * NDOF * sizeof(double);
   EFV_CUDA(cudaFuncSetAttribute((k_elasticity_rows<UCODE, NDOF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  EFV_LAUNCH((k_elasticity_rows<UCODE, NDOF>), grid_for(s->nV * kAsmGroup, 128, 12), 128, smem, view_of(m), geom_of(m),
+  EFV_LAUNCH((k_elasticity_rows<UCODE, NDOF>), grid_for(s->n_owned * kAsmGroup, 128, 12), 128, smem, view_of(m), geom_of(m),
              sys_view(s), dprops, gravity, s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->elim.p);
 }
 
@@ -489,9 +489,9 @@ __global__ void __launch_bounds__(64) k_biot_rows(MeshView m, GeomView g, SysVie
   const int grp = threadIdx.x / kAsmGroup, gl = threadIdx.x % kAsmGroup;
   double *row = smem_dyn + (size_t)grp * max_row_len * B;
   const unsigned gmask = 0xffu << ((threadIdx.x & 31) / kAsmGroup * kAsmGroup);
-  for (int64_t v0 = (int64_t)blockIdx.x * kBiotRows; v0 < m.nV; v0 += (int64_t)gridDim.x * kBiotRows) {
+  for (int64_t v0 = (int64_t)blockIdx.x * kBiotRows; v0 < s.nV; v0 += (int64_t)gridDim.x * kBiotRows) {
     const int64_t v = v0 + grp;
-    if (v >= m.nV) continue;
+    if (v >= s.nV) continue;
     const int64_t r0 = s.gptr[v];
     const int len = (int)(s.gptr[v + 1] - r0);
     for (int t = gl; t < len * B; t += kAsmGroup) row[t] = 0.0;
@@ -673,7 +673,7 @@ static void launch_biot_rows(efv_system *s, const double *dprops, const double *
   EFV_REQUIRE(B.vtx_to_bv.n, "set the mesh boundaries before assembling the Biot system");
   BndView bd{B.vtx_to_bv.p, B.bvo_ptr.p, B.bvo.p, B.outer_facet.p, B.facet_element.p, B.facet_ptr.p, B.facet_local.p, B.outer_local.p, B.facet_area.p};
   EFV_CUDA(cudaFuncSetAttribute((k_biot_rows<UCODE, D>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  EFV_LAUNCH((k_biot_rows<UCODE, D>), grid_for(s->nV * kAsmGroup, 64, 16), 64, smem, view_of(m), geom_of(m), sys_view(s), bd, dprops,
+  EFV_LAUNCH((k_biot_rows<UCODE, D>), grid_for(s->n_owned * kAsmGroup, 64, 16), 64, smem, view_of(m), geom_of(m), sys_view(s), bd, dprops,
              gv[0], gv[1], gv[2], s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->rhs_op.p, s->elim.p);
 }
 
@@ -954,10 +954,10 @@ void build_rhs(efv_system *s, int transient) {
   }
   if (s->physics == 0) {
     EFV_REQUIRE(s->gen.n, "efv_heat_assemble first");
-    EFV_LAUNCH(k_rhs_heat, grid_for(s->rows, 256), 256, 0, s->rows, s->gen.p, s->acc.p, s->xold.p, s->static_rhs.p,
+    EFV_LAUNCH(k_rhs_heat, grid_for(s->n_owned, 256), 256, 0, s->n_owned, s->gen.p, s->acc.p, s->xold.p, s->static_rhs.p,
                s->elim.p, s->dir_flag.p, s->dir_value.p, transient, sym, s->b.p);
   } else {
-    EFV_LAUNCH(k_rhs_static, grid_for(s->rows, 256), 256, 0, s->rows, s->gen.n ? s->gen.p : nullptr, s->static_rhs.p,
+    EFV_LAUNCH(k_rhs_static, grid_for(s->n_owned * s->ndof, 256), 256, 0, s->n_owned * s->ndof, s->gen.n ? s->gen.p : nullptr, s->static_rhs.p,
                s->elim.p, s->dir_flag.p, s->dir_value.p, sym, s->b.p);
   }
 }

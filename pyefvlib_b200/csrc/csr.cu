@@ -109,6 +109,7 @@ void system_build_graph(efv_system *s) {
   efv_mesh *m = s->mesh;
   MeshView mv = view_of(m);
   s->nV = m->nV;
+  s->n_owned = m->nV;
   s->rows = m->nV * s->ndof;
   DBuf<int32_t> rowlen(m->nV);
   DBuf<int> err(2);

@@ -74,12 +74,23 @@ struct efv_mesh {
 
 namespace efv {
 struct KrylovWork;
+// owned/ghost exchange lists of a vertex-block partition
+struct Halo {
+  bool active = false;
+  std::vector<int> nbr;                 // neighbour ranks
+  std::vector<int64_t> send_ptr;        // per neighbour range into send_idx
+  std::vector<int64_t> recv_ptr;        // per neighbour range into the ghost block (ghosts are grouped by owner)
+  DBuf<int32_t> send_idx;               // local ids of owned vertices to send
+  DBuf<double> send_buf;
+};
 }
 
 struct efv_system {
   efv_mesh *mesh = nullptr;
   int ndof = 1;
   int64_t nV = 0, rows = 0, nnzg = 0, slot_size = 0;
+  int64_t n_owned = 0;                 // leading vertices owned by this rank (== nV on one GPU); the rest are ghosts
+  efv::Halo halo;
   int max_row_len = 0;
   efv::DBuf<int64_t> gptr;
   efv::DBuf<int32_t> gcol;
@@ -140,4 +151,15 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
 void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres);
 void spmv(efv_system *s, const double *x, double *y);
 double max_abs_diff(efv_system *s);
+// comm.cu
+void comm_unique_id(const char *nccl_path, char *out128);
+void comm_init(const char *nccl_path, int rank, int nranks, const char *id128);
+void comm_destroy();
+bool comm_active();
+int comm_rank();
+int comm_size();
+void comm_allreduce_sum(double *dev, int count);
+void comm_allreduce_max(double *dev, int count);
+void halo_set(efv_system *s, int n_nbr, const int *nbr, const int64_t *send_ptr, const int32_t *send_idx, const int64_t *recv_ptr);
+void halo_exchange(efv_system *s, double *vec);
 }  // namespace efv

@@ -34,10 +34,10 @@ static KrylovWork *work(efv_system *s) {
     w->n = s->rows;
     w->grid = num_sms() * 8;
     w->partial.alloc((size_t)4 * w->grid);
-    w->sc.alloc(16);
+    w->sc.alloc(64);
     w->flags.alloc(4);
     EFV_CUDA(cudaMallocHost(&w->h_flags, 4 * sizeof(int)));
-    EFV_CUDA(cudaMallocHost(&w->h_sc, 16 * sizeof(double)));
+    EFV_CUDA(cudaMallocHost(&w->h_sc, 64 * sizeof(double)));
     EFV_CUDA(cudaEventCreateWithFlags(&w->ev, cudaEventDisableTiming));
     EFV_CUDA(cudaEventCreate(&w->e0));
     EFV_CUDA(cudaEventCreate(&w->e1));
@@ -153,7 +153,7 @@ template <int NDOF>
 static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
                           const double *w, double *partial, const int *done) {
 #define EFV_SPMV_CASE(LL, UU)                                                                                          \
-  EFV_LAUNCH((k_spmv<NDOF, LL, UU>), grid, kBlock, 0, s->nV, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, \
+  EFV_LAUNCH((k_spmv<NDOF, LL, UU>), grid, kBlock, 0, s->n_owned, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, \
              w, partial, done)
   const char *envu = getenv("EFV_SPMV_UNROLL");
   const int lanes = pick_lanes(s);
@@ -189,6 +189,25 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
 void spmv(efv_system *s, const double *x, double *y) {
   EFV_REQUIRE(s->vals.n, "no values assembled");
   launch_spmv(s, num_sms() * 8, x, y, 1.0, nullptr, nullptr, nullptr, nullptr);
+}
+
+// multi-GPU: collapse `narr` partial arrays of length G into narr scalars (then all-reduced over the ranks); the
+// consumer kernels read them as "partial arrays of length 1"
+__global__ void k_reduce_partials(const double *__restrict__ partial, int G, int narr, double *__restrict__ out) {
+  __shared__ double red[32];
+  for (int a = 0; a < narr; ++a) {
+    double v = sum_partials(partial + (size_t)a * G, G, red);
+    if (threadIdx.x == 0) out[a] = v;
+  }
+}
+// returns the (pointer, length) pair the consumer kernels should use for `narr` consecutive partial arrays
+static const double *consolidate(KrylovWork *w, const double *partial, int narr, int slot, int *Gout) {
+  if (!comm_active()) { *Gout = w->grid; return partial; }
+  double *out = w->sc.p + 32 + 4 * slot;
+  EFV_LAUNCH(k_reduce_partials, 1, kBlock, 0, partial, w->grid, narr, out);
+  comm_allreduce_sum(out, narr);
+  *Gout = 1;
+  return out;
 }
 
 // ---- Jacobi -----------------------------------------------------------------------------------------------------------
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, con
                                                           const double *__restrict__ pAp_partial, int G,
                                                           const double *__restrict__ p, const double *__restrict__ Ap,
                                                           const double *__restrict__ dinv, double *__restrict__ x,
-                                                          double *__restrict__ r, double *__restrict__ partial,
+                                                          double *__restrict__ r, double *__restrict__ partial, int Gout,
                                                           const int *__restrict__ flags) {
   __shared__ double red[32];
   if (flags[0]) return;
@@ -255,7 +274,7 @@ __global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, con
     rr += ri * ri;
   }
   rz = block_sum(rz, red); if (threadIdx.x == 0) partial[blockIdx.x] = rz;
-  rr = block_sum(rr, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = rr;
+  rr = block_sum(rr, red); if (threadIdx.x == 0) partial[Gout + blockIdx.x] = rr;
 }
 // beta = rz_new / rz_old ; p = dinv r + beta p ; block 0 publishes the scalars and the convergence flag
 __global__ void __launch_bounds__(kBlock) k_pcg_update_p(int64_t n, int it, double *__restrict__ sc,
@@ -285,26 +304,33 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   EFV_REQUIRE(s->vals.n, "no values assembled");
   ensure_vectors(s);
   KrylovWork *w = work(s);
-  const int64_t n = s->rows;
-  if (!w->r.n) { w->r.alloc(n); w->p.alloc(n); w->Ap.alloc(n); w->dinv.alloc(n); }
+  const int64_t n = s->n_owned * s->ndof;          // owned entries; ghosts of x / p live behind them
+  if (!w->r.n) { w->r.alloc(s->rows); w->p.alloc(s->rows); w->Ap.alloc(s->rows); w->dinv.alloc(s->rows); }
   const double sigma = negate ? -1.0 : 1.0;
   const int G = w->grid;
+  double *P = w->partial.p;
+  int Gc = G;
   EFV_CUDA(cudaEventRecord(w->e0, stream()));
-  EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->nV, s->ndof, s->diag_slot.p, s->vals.p, sigma, w->dinv.p);
+  EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->n_owned, s->ndof, s->diag_slot.p, s->vals.p, sigma, w->dinv.p);
   EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
+  halo_exchange(s, s->x.p);
   launch_spmv(s, G, s->x.p, w->Ap.p, sigma, nullptr, nullptr, nullptr, nullptr);
-  EFV_LAUNCH(k_pcg_init, G, kBlock, 0, n, s->b.p, w->Ap.p, w->dinv.p, sigma, w->r.p, w->p.p, w->partial.p);
-  EFV_LAUNCH(k_pcg_init_scalars, 1, kBlock, 0, G, w->partial.p, w->sc.p, w->flags.p, rtol);
+  EFV_LAUNCH(k_pcg_init, G, kBlock, 0, n, s->b.p, w->Ap.p, w->dinv.p, sigma, w->r.p, w->p.p, P);
+  const double *c0 = consolidate(w, P, 3, 0, &Gc);
+  EFV_LAUNCH(k_pcg_init_scalars, 1, kBlock, 0, Gc, c0, w->sc.p, w->flags.p, rtol);
   const int check_every = 32;
   int it = 0;
   bool done = false;
   while (!done && it < maxit) {
     int batch_end = std::min(maxit, it + check_every);
     for (; it < batch_end; ++it) {
-      launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, w->partial.p + 3 * G, w->flags.p);
-      EFV_LAUNCH(k_pcg_update_xr, G, kBlock, 0, n, it, w->sc.p, w->partial.p + 3 * G, G, w->p.p, w->Ap.p, w->dinv.p, s->x.p,
-                 w->r.p, w->partial.p, w->flags.p);
-      EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, w->partial.p, G, w->r.p, w->dinv.p, w->p.p, w->flags.p);
+      halo_exchange(s, w->p.p);
+      launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, P + 3 * G, w->flags.p);
+      const double *c1 = consolidate(w, P + 3 * G, 1, 1, &Gc);
+      EFV_LAUNCH(k_pcg_update_xr, G, kBlock, 0, n, it, w->sc.p, c1, Gc, w->p.p, w->Ap.p, w->dinv.p, s->x.p, w->r.p, P, G,
+                 w->flags.p);
+      const double *c2 = consolidate(w, P, 2, 2, &Gc);
+      EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, c2, Gc, w->r.p, w->dinv.p, w->p.p, w->flags.p);
     }
     EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
     EFV_CUDA(cudaStreamSynchronize(stream()));
@@ -427,6 +453,7 @@ __global__ void k_bi_scalars(int it, int G, const double *__restrict__ partial, 
 
 void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres) {
   EFV_REQUIRE(s->vals.n, "no values assembled");
+  EFV_REQUIRE(!comm_active(), "BiCGStab is single-GPU in this version (the partitioned path implements PCG)");
   ensure_vectors(s);
   KrylovWork *w = work(s);
   const int64_t n = s->rows;
@@ -490,8 +517,9 @@ __global__ void k_max_final(int G, const double *__restrict__ partial, double *_
 double max_abs_diff(efv_system *s) {
   ensure_vectors(s);
   KrylovWork *w = work(s);
-  EFV_LAUNCH(k_max_abs_diff, w->grid, kBlock, 0, s->rows, s->x.p, s->xold.p, w->partial.p);
+  EFV_LAUNCH(k_max_abs_diff, w->grid, kBlock, 0, s->n_owned * s->ndof, s->x.p, s->xold.p, w->partial.p);
   EFV_LAUNCH(k_max_final, 1, kBlock, 0, w->grid, w->partial.p, w->sc.p + 15);
+  comm_allreduce_max(w->sc.p + 15, 1);
   double out = 0;
   EFV_CUDA(cudaMemcpyAsync(&out, w->sc.p + 15, sizeof(double), cudaMemcpyDeviceToHost, stream()));
   EFV_CUDA(cudaStreamSynchronize(stream()));

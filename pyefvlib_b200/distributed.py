@@ -1,0 +1,322 @@
+"""Multi-GPU: vertex-block domain decomposition.  The reference has no distributed code.
+
+One process per GPU (torch.distributed for the plumbing).  The global vertex range is cut into contiguous blocks;
+rank r owns the vertices (= matrix rows) of block r and assembles every element incident to one of them, so the
+layer of elements straddling an interface is assembled redundantly on both sides and assembly needs NO
+communication.  Local vertices are numbered [owned (global order) | ghosts (global order, hence grouped by owner)].
+The Krylov solver exchanges the halo of its search direction before every SpMV (NCCL send/recv inside the CUDA
+library, on its stream) and all-reduces its dot products.
+
+`partition_grid` cuts an arbitrary global Grid (host numpy; used by the tests and for unstructured meshes),
+`structured_part` builds the local slab of the synthetic benchmark meshes directly, without the global mesh.
+Both give the same LocalPart (tests/test_distributed_cpu.py).
+"""
+import os
+
+import numpy as np
+
+from . import grid as _grid
+
+
+def block_ranges(n_vertices, world, align=1):
+    """Contiguous vertex blocks, as even as possible, boundaries multiples of `align` (n^2 = one mesh plane for the
+    structured meshes)."""
+    units = n_vertices // align
+    assert units * align == n_vertices and units >= world
+    cuts = [(units * r) // world * align for r in range(world + 1)]
+    return np.array(cuts, dtype=np.int64)
+
+
+class LocalPart:
+    """What one rank holds: its local Grid, the owned/ghost split and the exchange lists."""
+
+    def __init__(self, rank, world, ranges, grid, n_owned, local_to_global, nbr, send_lists, recv_ptr, boundary_vertices):
+        self.rank, self.world, self.ranges = rank, world, ranges
+        self.grid, self.n_owned, self.local_to_global = grid, int(n_owned), local_to_global
+        self.nbr = list(nbr)                      # neighbour ranks, ascending
+        self.send_lists = send_lists              # per neighbour: local ids of owned vertices it needs (global order)
+        self.recv_ptr = np.asarray(recv_ptr, dtype=np.int64)   # per neighbour slice of the ghost block
+        self.boundary_vertices = boundary_vertices   # per boundary: local ids (owned and ghost) lying on it
+
+    @property
+    def n_ghost(self):
+        return self.grid.numberOfVertices - self.n_owned
+
+
+def _make_local_grid(dimension, coords, conn_local, region_names, region_of_elem, boundary_names, facets_local):
+    gd = _grid.GridData("partition")
+    gd.setDimension(dimension)
+    gd.setVertices(coords)
+    gd.setElementConnectivity(conn_local)
+    gd.setRegions(list(region_names), [np.nonzero(region_of_elem == h)[0] for h in range(len(region_names))])
+    sizes = [len(f) for f in facets_local]
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    if isinstance(conn_local, np.ndarray) and all(isinstance(f, np.ndarray) and f.ndim == 2 for f in facets_local) \
+            and len({f.shape[1] for f in facets_local if len(f)}) <= 1:
+        width = next((f.shape[1] for f in facets_local if len(f)), 2)
+        bconn = np.concatenate([f.reshape(-1, width) for f in facets_local]) if sum(sizes) else np.zeros((0, width), dtype=np.int32)
+        gd.setBoundaries(list(boundary_names), [np.arange(starts[h], starts[h + 1], dtype=np.int64) for h in range(len(sizes))],
+                         bconn.astype(np.int32))
+    else:
+        flat = [list(map(int, f)) for fl in facets_local for f in fl]
+        gd.setBoundaries(list(boundary_names), [list(range(starts[h], starts[h + 1])) for h in range(len(sizes))], flat)
+    gd.setShapes([[]] * 7)
+    return _grid.Grid(gd)
+
+
+def partition_grid(g, rank, world, ranges=None):
+    """Cut the global Grid `g` for `rank` (uniform element type per grid or mixed; host numpy)."""
+    nV = g.numberOfVertices
+    ranges = block_ranges(nV, world) if ranges is None else np.asarray(ranges, dtype=np.int64)
+    a, b = int(ranges[rank]), int(ranges[rank + 1])
+    ep, conn = g.elem_ptr, g.conn.astype(np.int64)
+    owner_of_vertex = np.searchsorted(ranges, np.arange(nV), side="right") - 1
+    elem_of_entry = np.repeat(np.arange(g.numberOfElements), np.diff(ep))
+    mine_entry = (conn >= a) & (conn < b)
+    elem_mask = np.zeros(g.numberOfElements, dtype=bool)
+    elem_mask[elem_of_entry[mine_entry]] = True
+    local_elems = np.nonzero(elem_mask)[0]
+    entry_mask = elem_mask[elem_of_entry]
+    used = np.unique(conn[entry_mask])
+    ghosts = used[(used < a) | (used >= b)]
+    n_owned = b - a
+    l2g = np.concatenate([np.arange(a, b, dtype=np.int64), ghosts])
+    g2l = np.full(nV, -1, dtype=np.int64)
+    g2l[l2g] = np.arange(len(l2g))
+    lens = np.diff(ep)[local_elems]
+    if len(np.unique(np.diff(ep))) == 1:
+        m = int(lens[0])
+        conn_local = g2l[conn.reshape(-1, m)[local_elems]].astype(np.int32)
+    else:
+        conn_local = [g2l[conn[ep[e]:ep[e + 1]]].tolist() for e in local_elems]
+    # boundary facets with at least one owned vertex (their owning element is then local); global order preserved
+    facets_local, bverts = [], []
+    for bd in g.boundaries:
+        fl = []
+        for k in range(bd.facet_begin, bd.facet_end):
+            fv = g.facet_conn[g.facet_ptr[k]:g.facet_ptr[k + 1]].astype(np.int64)
+            if ((fv >= a) & (fv < b)).any():
+                fl.append(g2l[fv])
+        widths = {len(f) for f in fl}
+        facets_local.append(np.array(fl, dtype=np.int32).reshape(len(fl), widths.pop()) if len(widths) == 1 else fl)
+        lv = g2l[bd.verticesIndexes]
+        bverts.append(lv[lv >= 0])
+    # neighbours and exchange lists (computed identically on both sides: sorted by global id)
+    ghost_owner = owner_of_vertex[ghosts]
+    nbr = sorted(set(ghost_owner.tolist()))
+    recv_ptr = np.concatenate([[0], np.cumsum([(ghost_owner == q).sum() for q in nbr])])
+    send_lists = []
+    vert_owner_entry = owner_of_vertex[conn]
+    for q in nbr:
+        # my owned vertices that appear in an element which also has a vertex owned by q
+        has_q = np.zeros(g.numberOfElements, dtype=bool)
+        has_q[elem_of_entry[vert_owner_entry == q]] = True
+        sel = has_q[elem_of_entry] & mine_entry
+        send_lists.append((np.unique(conn[sel]) - a).astype(np.int32))
+    grid = _make_local_grid(g.dimension, g.coords[l2g], conn_local, [r.name for r in g.regions], g.region_of_element[local_elems],
+                            [bd.name for bd in g.boundaries], facets_local)
+    return LocalPart(rank, world, ranges, grid, n_owned, l2g, nbr, send_lists, recv_ptr, bverts)
+
+
+def structured_part(n, kind, rank, world, perturb=0.0):
+    """Local slab of the n^3-vertex structured mesh for `rank`: planes are dealt out in contiguous blocks."""
+    n2 = n * n
+    ranges = block_ranges(n ** 3, world, align=n2)
+    k0, k1 = int(ranges[rank] // n2), int(ranges[rank + 1] // n2)           # owned planes [k0, k1)
+    lo, hi = max(k0 - 1, 0), min(k1 + 1, n)                                 # local planes [lo, hi)
+    arr = _grid.structured_arrays(n, kind, layer_lo=lo, layer_hi=min(hi - 1, n - 1))
+    n_owned = (k1 - k0) * n2
+    below = np.arange(lo * n2, k0 * n2, dtype=np.int64)
+    above = np.arange(k1 * n2, hi * n2, dtype=np.int64)
+    l2g = np.concatenate([np.arange(k0 * n2, k1 * n2, dtype=np.int64), below, above])
+
+    def to_local(gid):
+        gid = np.asarray(gid, dtype=np.int64)
+        out = gid - k0 * n2
+        out = np.where(gid < k0 * n2, n_owned + (gid - lo * n2), out)
+        out = np.where(gid >= k1 * n2, n_owned + len(below) + (gid - k1 * n2), out)
+        return out
+    conn_local = to_local(arr["conn"]).astype(np.int32)
+    facets_local = []
+    for name in _grid.BOUNDARY_NAMES_3D:
+        f = arr["facets"][name]
+        if len(f):
+            keep = ((f >= k0 * n2) & (f < k1 * n2)).any(axis=1)
+            f = f[keep]
+        facets_local.append(to_local(f).astype(np.int32).reshape(len(f), 4 if kind == "hex" else 3))
+    coords = _grid.structured_coords(n, l2g, perturb)
+    I, J, K = l2g % n, (l2g // n) % n, l2g // n2
+    on = {"West": I == 0, "East": I == n - 1, "South": J == 0, "North": J == n - 1, "Bottom": K == 0, "Top": K == n - 1}
+    bverts = [np.nonzero(on[name])[0].astype(np.int64) for name in _grid.BOUNDARY_NAMES_3D]
+    nbr, send_lists, recv = [], [], [0]
+    if len(below):
+        nbr.append(rank - 1); send_lists.append(np.arange(0, n2, dtype=np.int32)); recv.append(recv[-1] + len(below))
+    if len(above):
+        nbr.append(rank + 1); send_lists.append(np.arange(n_owned - n2, n_owned, dtype=np.int32)); recv.append(recv[-1] + len(above))
+    grid = _make_local_grid(3, coords, conn_local, ["Body"], np.zeros(len(conn_local), dtype=np.int32), _grid.BOUNDARY_NAMES_3D, facets_local)
+    return LocalPart(rank, world, ranges, grid, n_owned, l2g, nbr, send_lists, recv, bverts)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# device side
+# ---------------------------------------------------------------------------------------------------------------------
+def nccl_library_path():
+    """The NCCL shared object torch itself uses, so that the process holds one NCCL instance."""
+    try:
+        import torch
+        root = os.path.dirname(os.path.dirname(torch.__file__))
+        cand = os.path.join(root, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.isfile(cand):
+            return cand
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+_comm_ready = False
+
+
+def init_comm():
+    """Create the library's NCCL communicator; the unique id travels through torch.distributed."""
+    global _comm_ready
+    import ctypes as C
+    import torch.distributed as dist
+    from . import _lib
+    if _comm_ready:
+        return
+    L = _lib.load()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    path = nccl_library_path().encode()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(L.efv_comm_unique_id(path, buf))
+    box = [bytes(buf.raw)]
+    dist.broadcast_object_list(box, src=0)
+    _lib.check(L.efv_comm_init(path, rank, world, box[0]))
+    _comm_ready = True
+
+
+def make_system(part, ndof=1):
+    """DeviceSystem on the rank's local mesh, restricted to its owned rows, with the halo registered."""
+    import ctypes as C
+    from . import _lib
+    from .device import DeviceSystem
+    s = DeviceSystem(part.grid, ndof)
+    L = _lib.load()
+    _lib.check(L.efv_system_set_owned(s.handle, part.n_owned))
+    nb = np.asarray(part.nbr, dtype=np.int32)
+    sp = np.concatenate([[0], np.cumsum([len(x) for x in part.send_lists])]).astype(np.int64)
+    si = np.concatenate(part.send_lists).astype(np.int32) if part.send_lists else np.zeros(0, dtype=np.int32)
+    rp = np.asarray(part.recv_ptr, dtype=np.int64)
+    _lib.check(L.efv_system_set_halo(s.handle, len(nb), nb.ctypes.data_as(_lib.c_intp), sp.ctypes.data_as(_lib.c_i64p),
+                                     si.ctypes.data_as(_lib.c_i32p), rp.ctypes.data_as(_lib.c_i64p)))
+    return s
+
+
+def send_heat_bcs(system, part, bcs):
+    """Boundary conditions of the heat problem on a partition: Neumann through the local facets, Dirichlet on every
+    local vertex (owned or ghost) of the boundary, boundaries in grid order (heat_transfer.py:115-126)."""
+    system.bc_clear()
+    for b in part.grid.boundaries:
+        kind, val = bcs[b.name]
+        if kind == "neumann":
+            system.bc_neumann(b.handle, 0, val, 1.0)
+    for h, b in enumerate(part.grid.boundaries):
+        kind, val = bcs[b.name]
+        if kind == "dirichlet":
+            idx = part.boundary_vertices[h]
+            system.bc_dirichlet(idx, np.full(len(idx), val))
+
+
+def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
+    """N > 1 leg of bench.py: strong scaling of the C5/C2-style problem -- the SAME global mesh is cut into N slabs."""
+    import json
+    import time
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .device import DIRICHLET_SYMMETRIC, VEC_X, VEC_XOLD
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    L = _lib.load()
+    _lib.check(L.efv_set_device(local_rank))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    init_comm()
+    stream = torch.cuda.ExternalStream(L.efv_get_stream())
+    n = args.n
+    t0 = time.perf_counter()
+    part = structured_part(n, "hex", rank, world)
+    host_s = time.perf_counter() - t0
+    system = make_system(part, 1)
+    props = np.array([[PROPS["Body"]["Conductivity"], PROPS["Body"]["Density"], PROPS["Body"]["HeatCapacity"], PROPS["Body"]["HeatGeneration"]]])
+    system.upload(VEC_XOLD, np.zeros(system.rows))
+    system.upload(VEC_X, np.zeros(system.rows))
+
+    def step():
+        send_heat_bcs(system, part, BC3D)
+        system.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
+        system.heat_assemble(props, DT, True)
+        system.build_rhs(True)
+        it, rr = system.solve_pcg(RTOL, 20000)
+        system.advance()
+        return it, rr
+    warm = [step()[0] for _ in range(args.warmup)]
+    launches1 = L.efv_kernel_launch_count()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    iters, solve_ms, asm_ms = [], [], []
+    for _ in range(args.steps):
+        it, rr = step()
+        assert rr <= RTOL, f"PCG did not converge on rank {rank}: {rr}"
+        iters.append(it)
+        tm = system.timings(); solve_ms.append(tm["solve_ms"]); asm_ms.append(tm["assemble_ms"])
+    e1.record(stream)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    launches2 = L.efv_kernel_launch_count()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    nV = n ** 3
+    nnz_local = torch.tensor([float(system.nnz)], device="cuda", dtype=torch.float64)
+    ms_per_step = total_ms / args.steps
+    # e2e: mesh slab upload + setup + one step + field download, through the same Python API
+    del system
+    part.grid._device = None
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    sys2 = make_system(part, 1)
+    sys2.upload(VEC_XOLD, np.zeros(sys2.rows)); sys2.upload(VEC_X, np.zeros(sys2.rows))
+    send_heat_bcs(sys2, part, BC3D)
+    sys2.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
+    sys2.heat_assemble(props, DT, True)
+    sys2.build_rhs(True)
+    it0, rr0 = sys2.solve_pcg(RTOL, 20000)
+    T = sys2.download(VEC_X)[:part.n_owned]
+    _lib.check(L.efv_synchronize())
+    e2e_t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    g = part.grid
+    h2d = g.coords.nbytes + g.conn.nbytes + g.elem_ptr.nbytes + g.region_of_element.nbytes + g.facet_conn.nbytes + g.facet_ptr.nbytes + 2 * g.numberOfVertices * 8
+    hb = torch.tensor([float(h2d), float(part.n_owned * 8)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(hb)
+    if rank == 0:
+        line = {
+            "metric": "heat_transfer_3d_dof_per_s", "value": nV / (ms_per_step / 1e3), "unit": "DOF/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"3D transient heat conduction, structured hex mesh {n}^3 vertices cut into {world} vertex-block slabs, "
+                                   "dt=1e-2, 3-D BC set, PCG(Jacobi) rtol 1e-10, 1 time step per step",
+                       "vertices": nV, "pcg_iterations_per_step": iters, "warmup_iterations": warm,
+                       "assemble_ms_per_step": float(np.mean(asm_ms)), "solve_ms_per_step": float(np.mean(solve_ms)),
+                       "host_slab_generation_s": host_s, "halo": "NCCL send/recv of one n^2 plane per neighbour per SpMV",
+                       "l2_policy": "inputs larger than L2"},
+            "e2e": {"value": nV / float(e2e_t.item()), "unit": "DOF/s", "h2d_bytes_per_step": int(hb[0].item()),
+                    "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * float(e2e_t.item()),
+                    "what": "per-rank slab upload + setup + assembly + one time-step solve + owned field download"},
+            "gpu_launches": int(launches2 - launches1),
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    L.efv_comm_destroy()
+    dist.destroy_process_group()

@@ -310,37 +310,14 @@ _TET_SPLIT = [[(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], [(1, 0, 0), (1, 0, 1
 _HEX_CORNERS = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
 
 
-def structured_grid_data(n, kind="hex", perturb=0.0):
-    """Unit cube, n^3 vertices with id = i + n j + n^2 k (x fastest, like meshes/msh/3D/Hexas*.msh), hexahedra in
-    the bundled local order or the 6-tetrahedra-per-cube split of meshes/msh/3D/Tetras.msh, one region "Body",
-    boundaries West East South North Bottom Top.  `perturb` moves interior vertices by a smooth deterministic
-    perturb*h*sin(...) field to exercise non-affine hexahedra."""
-    ax = np.linspace(0.0, 1.0, n)
-    idx = np.arange(n ** 3, dtype=np.int64)
-    I, J, K = idx % n, (idx // n) % n, idx // (n * n)
-    coords = np.stack([ax[I], ax[J], ax[K]], axis=1)
-    if perturb:
-        h = 1.0 / (n - 1)
-        interior = ((I > 0) & (I < n - 1) & (J > 0) & (J < n - 1) & (K > 0) & (K < n - 1))[:, None]
-        x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
-        d = np.stack([np.sin(7 * x + 3 * y + 5 * z), np.sin(4 * x - 6 * y + 2 * z + 1.0), np.sin(5 * x + 2 * y - 7 * z + 2.0)], axis=1)
-        coords = coords + perturb * h * d * interior
+def _quad_faces(n, a, b):
+    """Boundary quads of the unit cube in the bundled orientation; a = slow, b = fast facet index (for the four
+    lateral faces a is the z layer)."""
     ne = n - 1
-    e = np.arange(ne ** 3, dtype=np.int64)
-    i, j, k = e % ne, (e // ne) % ne, e // (ne * ne)
-    vid = lambda a, b, c: a + n * b + n * n * c
-    corner = lambda bits: vid(i + bits[0], j + bits[1], k + bits[2])
-    if kind == "hex":
-        conn = np.stack([corner(b) for b in _HEX_CORNERS], axis=1).astype(np.int32)
-    elif kind == "tet":
-        conn = np.stack([np.stack([corner(b) for b in t], axis=1) for t in _TET_SPLIT], axis=1).reshape(-1, 4).astype(np.int32)
-    else:
-        raise Exception("kind must be 'hex' or 'tet'")
-    q = np.arange(ne * ne, dtype=np.int64)
-    a, b = q // ne, q % ne
+    vid = lambda i, j, k: i + n * j + n * n * k
     o = np.zeros_like(a)
     L = o + ne
-    quads = {
+    return {
         "West": [vid(o, b, a), vid(o, b, a + 1), vid(o, b + 1, a + 1), vid(o, b + 1, a)],
         "East": [vid(L, b, a), vid(L, b + 1, a), vid(L, b + 1, a + 1), vid(L, b, a + 1)],
         "South": [vid(b, o, a), vid(b + 1, o, a), vid(b + 1, o, a + 1), vid(b, o, a + 1)],
@@ -348,52 +325,98 @@ def structured_grid_data(n, kind="hex", perturb=0.0):
         "Bottom": [vid(b, a, o), vid(b, a + 1, o), vid(b + 1, a + 1, o), vid(b + 1, a, o)],
         "Top": [vid(b, a, L), vid(b + 1, a, L), vid(b + 1, a + 1, L), vid(b, a + 1, L)],
     }
-    names = list(quads.keys())
+
+
+BOUNDARY_NAMES_3D = ["West", "East", "South", "North", "Bottom", "Top"]
+_tet_diag_cache = {}
+
+
+def _tet_face_uses_first_diagonal():
+    """For each cube face: does the 6-tetrahedra split cut the boundary quad (v0 v1 v2 v3) along v0-v2?  The split is
+    the same in every cube, so a 2x2x2-vertex cube decides it."""
+    if not _tet_diag_cache:
+        n = 2
+        vid = lambda i, j, k: i + n * j + n * n * k
+        faces = set()
+        for t in _TET_SPLIT:
+            ids = [vid(*c) for c in t]
+            for tri in ((0, 2, 1), (0, 3, 2), (0, 1, 3), (1, 2, 3)):
+                faces.add(tuple(sorted(ids[k] for k in tri)))
+        z = np.zeros(1, dtype=np.int64)
+        for name, q in _quad_faces(2, z, z).items():
+            v = [int(x[0]) for x in q]
+            _tet_diag_cache[name] = tuple(sorted((v[0], v[1], v[2]))) in faces
+    return _tet_diag_cache
+
+
+def structured_arrays(n, kind="hex", layer_lo=0, layer_hi=None):
+    """Global-id connectivity of the cube layers [layer_lo, layer_hi) (a layer = all cubes with the same z index) and
+    the boundary facets attached to them: dict(conn, facets={name: array}).  Bottom / Top facets are included when
+    layer 0 / layer n-2 is."""
+    ne = n - 1
+    layer_hi = ne if layer_hi is None else layer_hi
+    vid = lambda i, j, k: i + n * j + n * n * k
+    e = np.arange(layer_lo * ne * ne, layer_hi * ne * ne, dtype=np.int64)
+    i, j, k = e % ne, (e // ne) % ne, e // (ne * ne)
+    corner = lambda bits: vid(i + bits[0], j + bits[1], k + bits[2])
     if kind == "hex":
-        bconn = np.concatenate([np.stack(quads[nm], axis=1) for nm in names]).astype(np.int32)
-        per = ne * ne
+        conn = np.stack([corner(b) for b in _HEX_CORNERS], axis=1)
+    elif kind == "tet":
+        conn = np.stack([np.stack([corner(b) for b in t], axis=1) for t in _TET_SPLIT], axis=1).reshape(-1, 4)
     else:
-        # the split uses the same diagonal on every cube face of one orientation: pick the diagonal that is an
-        # edge of the tetrahedra by testing it on cube 0
-        tetfaces = set()
-        for t in conn[:6].tolist():
-            for tri in ((t[0], t[2], t[1]), (t[0], t[3], t[2]), (t[0], t[1], t[3]), (t[1], t[2], t[3])):
-                tetfaces.add(tuple(sorted(tri)))
-        # faces of cube 0 at x=0,y=0,z=0 come from cube 0 itself; opposite faces use the same split by symmetry
-        # of the repeated pattern (verified against the oracle's exhaustive matching in tests)
-        parts = []
-        all_faces = None
-        for nm in names:
-            v = np.stack(quads[nm], axis=1)
-            parts.append(v)
-        # decide per boundary with the first quad of each boundary against the full face set of its cube
-        cubefaces = {}
-        def faces_of_cube(c):
-            if c not in cubefaces:
-                s = set()
-                for t in conn[6 * c:6 * c + 6].tolist():
-                    for tri in ((t[0], t[2], t[1]), (t[0], t[3], t[2]), (t[0], t[1], t[3]), (t[1], t[2], t[3])):
-                        s.add(tuple(sorted(tri)))
-                cubefaces[c] = s
-            return cubefaces[c]
-        cube_of_first = {"West": 0, "East": ne - 1, "South": 0, "North": ne * (ne - 1), "Bottom": 0, "Top": ne * ne * (ne - 1)}
-        tri_parts = []
-        for nm, v in zip(names, parts):
-            s = faces_of_cube(cube_of_first[nm])
-            v0 = v[0].tolist()
-            if tuple(sorted((v0[0], v0[1], v0[2]))) in s:
+        raise Exception("kind must be 'hex' or 'tet'")
+    facets = {}
+    ql = np.arange(layer_lo * ne, layer_hi * ne, dtype=np.int64)         # lateral faces: a = z layer
+    qf = np.arange(ne * ne, dtype=np.int64)                               # bottom / top: full face
+    lat = _quad_faces(n, ql // ne, ql % ne)
+    full = _quad_faces(n, qf // ne, qf % ne)
+    for name in BOUNDARY_NAMES_3D:
+        if name in ("Bottom", "Top"):
+            present = (layer_lo == 0) if name == "Bottom" else (layer_hi == ne)
+            v = np.stack(full[name], axis=1) if present else np.zeros((0, 4), dtype=np.int64)
+        else:
+            v = np.stack(lat[name], axis=1)
+        if kind == "tet":
+            if _tet_face_uses_first_diagonal()[name]:
                 t1, t2 = v[:, [0, 1, 2]], v[:, [0, 2, 3]]
             else:
                 t1, t2 = v[:, [0, 1, 3]], v[:, [1, 2, 3]]
-            tri_parts.append(np.stack([t1, t2], axis=1).reshape(-1, 3))
-        bconn = np.concatenate(tri_parts).astype(np.int32)
-        per = 2 * ne * ne
+            v = np.stack([t1, t2], axis=1).reshape(-1, 3)
+        facets[name] = v
+    return dict(conn=conn, facets=facets)
+
+
+def structured_coords(n, ids, perturb=0.0):
+    """Coordinates of the global vertex ids `ids` of the n^3 unit-cube lattice."""
+    ax = np.linspace(0.0, 1.0, n)
+    I, J, K = ids % n, (ids // n) % n, ids // (n * n)
+    coords = np.stack([ax[I], ax[J], ax[K]], axis=1)
+    if perturb:
+        h = 1.0 / (n - 1)
+        interior = ((I > 0) & (I < n - 1) & (J > 0) & (J < n - 1) & (K > 0) & (K < n - 1))[:, None]
+        x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
+        d = np.stack([np.sin(7 * x + 3 * y + 5 * z), np.sin(4 * x - 6 * y + 2 * z + 1.0), np.sin(5 * x + 2 * y - 7 * z + 2.0)], axis=1)
+        coords = coords + perturb * h * d * interior
+    return coords
+
+
+def structured_grid_data(n, kind="hex", perturb=0.0):
+    """Unit cube, n^3 vertices with id = i + n j + n^2 k (x fastest, like meshes/msh/3D/Hexas*.msh), hexahedra in
+    the bundled local order or the 6-tetrahedra-per-cube split of meshes/msh/3D/Tetras.msh, one region "Body",
+    boundaries West East South North Bottom Top.  `perturb` moves interior vertices by a smooth deterministic
+    perturb*h*sin(...) field to exercise non-affine hexahedra."""
+    arr = structured_arrays(n, kind)
+    coords = structured_coords(n, np.arange(n ** 3, dtype=np.int64), perturb)
+    conn = arr["conn"].astype(np.int32)
+    sizes = [len(arr["facets"][nm]) for nm in BOUNDARY_NAMES_3D]
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    bconn = np.concatenate([arr["facets"][nm] for nm in BOUNDARY_NAMES_3D]).astype(np.int32)
     gd = GridData(f"structured_{kind}_{n}")
     gd.setDimension(3)
     gd.setVertices(coords)
     gd.setElementConnectivity(conn)
     gd.setRegions(["Body"], [np.arange(len(conn), dtype=np.int64)])
-    gd.setBoundaries(names, [np.arange(h * per, (h + 1) * per, dtype=np.int64) for h in range(6)], bconn)
+    gd.setBoundaries(list(BOUNDARY_NAMES_3D), [np.arange(starts[h], starts[h + 1], dtype=np.int64) for h in range(6)], bconn)
     gd.setShapes([[]] * 7)
     return gd
 

@@ -1,0 +1,77 @@
+"""Worker of tests/test_gpu_distributed.py (launched with torch.distributed.run, one rank per GPU): partitioned heat
+solve, checked against the CPU oracle on the global mesh."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import pyefvlib_b200 as P  # noqa: E402
+from pyefvlib_b200 import _lib, distributed as efd  # noqa: E402
+from pyefvlib_b200.device import DIRICHLET_ROWS, DIRICHLET_SYMMETRIC, VEC_X, VEC_XOLD, VEC_B  # noqa: E402
+from oracle import efv_oracle as O  # noqa: E402
+from tests.cases import BC3D, HEAT_PROPS  # noqa: E402
+from tests import util  # noqa: E402
+
+
+def main():
+    kind = sys.argv[1] if len(sys.argv) > 1 else "hex"
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    _lib.check(_lib.load().efv_set_device(local_rank))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    efd.init_comm()
+    part = efd.structured_part(n, kind, rank, world, perturb=0.0)
+    s = efd.make_system(part, 1)
+    props = np.array([[1.0, 1.0, 1.0, 100.0]])
+    dt = 1e-2
+    nV = n ** 3
+    Told_global = 300.0 + 40.0 * np.sin(0.01 * np.arange(nV))
+    # oracle on the global mesh (every rank computes it; small)
+    og = O.OracleGrid(O.structured_grid_data(n, kind))
+    Aref = sp.csr_matrix(O.heat_matrix(og, HEAT_PROPS, BC3D, transient=True, dt=dt))
+    bref = O.heat_rhs(og, HEAT_PROPS, BC3D, transient=True, dt=dt, Told=Told_global)
+    xref = O.solve_direct(Aref, bref)
+    l2g = part.local_to_global
+    own = l2g[:part.n_owned]
+    # 1. owned rows of the reference-form matrix and RHS
+    efd.send_heat_bcs(s, part, BC3D)
+    s.assemble_dirichlet_mode(DIRICHLET_ROWS)
+    s.heat_assemble(props, dt, True)
+    s.upload(VEC_XOLD, Told_global[l2g])
+    s.build_rhs(True)
+    A = s.to_scipy()[:part.n_owned]
+    sub = Aref[own][:, l2g]
+    assert util.row_rel_matrix_error(A, sub) <= 1e-12, "owned rows differ from the global matrix"
+    assert util.rel_max(s.download(VEC_B)[:part.n_owned], bref[own]) <= 1e-12
+    # 2. distributed PCG on the symmetric form
+    s.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
+    s.heat_assemble(props, dt, True)
+    s.build_rhs(True)
+    s.upload(VEC_X, Told_global[l2g])
+    iters, relres = s.solve_pcg(1e-10, 5000)
+    assert relres <= 1e-10, (iters, relres)
+    x = s.download(VEC_X)[:part.n_owned]
+    err = np.array([np.sum((x - xref[own]) ** 2), np.sum(xref[own] ** 2)])
+    t = torch.tensor(err, device="cuda", dtype=torch.float64)
+    dist.all_reduce(t)
+    rel = float(torch.sqrt(t[0] / t[1]).item())
+    assert rel <= 1e-8, rel
+    # 3. max|x - xold| is a global reduction
+    d = s.max_abs_diff()
+    assert abs(d - np.abs(xref - Told_global).max()) <= 1e-6 * np.abs(xref - Told_global).max()
+    if rank == 0:
+        print(f"DIST_OK world={world} kind={kind} n={n} iters={iters} relres={relres:.2e} rel_l2={rel:.2e}")
+    dist.barrier()
+    _lib.load().efv_comm_destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
