@@ -190,7 +190,7 @@ def run_gpu(args):
     L = _lib.load()
     _lib.check(L.efv_set_device(local_rank))
     stream = torch.cuda.ExternalStream(L.efv_get_stream())
-    n = args.n
+    n = 368 if (args.workload == "c5" and args.n == 216) else args.n
     t_host = time.perf_counter()
     gd = P.structured_grid_data(n, "hex")
     keep = []
@@ -353,6 +353,8 @@ def main():
     ap.add_argument("--n", type=int, default=216, help="vertices per side of the structured mesh (216 = C2)")
     ap.add_argument("--cpu-n", type=int, default=30, help="vertices per side of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2: configs[1] (N>1: weak scaling, one C2 block per GPU); c5: configs[4] 368^3 strong scaling")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -118,13 +118,14 @@ def partition_grid(g, rank, world, ranges=None):
     return LocalPart(rank, world, ranges, grid, n_owned, l2g, nbr, send_lists, recv_ptr, bverts)
 
 
-def structured_part(n, kind, rank, world, perturb=0.0):
-    """Local slab of the n^3-vertex structured mesh for `rank`: planes are dealt out in contiguous blocks."""
+def structured_part(n, kind, rank, world, perturb=0.0, nz=None):
+    """Local slab of the n x n x nz (default n^3) structured mesh for `rank`: planes are dealt out in contiguous blocks."""
     n2 = n * n
-    ranges = block_ranges(n ** 3, world, align=n2)
+    nz = nz or n
+    ranges = block_ranges(n2 * nz, world, align=n2)
     k0, k1 = int(ranges[rank] // n2), int(ranges[rank + 1] // n2)           # owned planes [k0, k1)
-    lo, hi = max(k0 - 1, 0), min(k1 + 1, n)                                 # local planes [lo, hi)
-    arr = _grid.structured_arrays(n, kind, layer_lo=lo, layer_hi=min(hi - 1, n - 1))
+    lo, hi = max(k0 - 1, 0), min(k1 + 1, nz)                                # local planes [lo, hi)
+    arr = _grid.structured_arrays(n, kind, layer_lo=lo, layer_hi=min(hi - 1, nz - 1), nz=nz)
     n_owned = (k1 - k0) * n2
     below = np.arange(lo * n2, k0 * n2, dtype=np.int64)
     above = np.arange(k1 * n2, hi * n2, dtype=np.int64)
@@ -144,9 +145,9 @@ def structured_part(n, kind, rank, world, perturb=0.0):
             keep = ((f >= k0 * n2) & (f < k1 * n2)).any(axis=1)
             f = f[keep]
         facets_local.append(to_local(f).astype(np.int32).reshape(len(f), 4 if kind == "hex" else 3))
-    coords = _grid.structured_coords(n, l2g, perturb)
+    coords = _grid.structured_coords(n, l2g, perturb, nz)
     I, J, K = l2g % n, (l2g // n) % n, l2g // n2
-    on = {"West": I == 0, "East": I == n - 1, "South": J == 0, "North": J == n - 1, "Bottom": K == 0, "Top": K == n - 1}
+    on = {"West": I == 0, "East": I == n - 1, "South": J == 0, "North": J == n - 1, "Bottom": K == 0, "Top": K == nz - 1}
     bverts = [np.nonzero(on[name])[0].astype(np.int64) for name in _grid.BOUNDARY_NAMES_3D]
     nbr, send_lists, recv = [], [], [0]
     if len(below):
@@ -244,8 +245,16 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     init_comm()
     stream = torch.cuda.ExternalStream(L.efv_get_stream())
     n = args.n
+    # default: WEAK scaling of C2 -- every rank owns a 216 x 216 x 216 block of an elongated n x n x (n*world) box;
+    # --workload c5: STRONG scaling of the 368^3 cube (BASELINE.json configs[4])
+    strong = args.workload == "c5"
+    if strong:
+        n = 368 if args.n == 216 else args.n
+        nz = n
+    else:
+        nz = n * world
     t0 = time.perf_counter()
-    part = structured_part(n, "hex", rank, world)
+    part = structured_part(n, "hex", rank, world, nz=nz)
     host_s = time.perf_counter() - t0
     system = make_system(part, 1)
     props = np.array([[PROPS["Body"]["Conductivity"], PROPS["Body"]["Density"], PROPS["Body"]["HeatCapacity"], PROPS["Body"]["HeatGeneration"]]])
@@ -277,8 +286,7 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    nV = n ** 3
-    nnz_local = torch.tensor([float(system.nnz)], device="cuda", dtype=torch.float64)
+    nV = n * n * nz
     ms_per_step = total_ms / args.steps
     # e2e: mesh slab upload + setup + one step + field download, through the same Python API
     del system
@@ -303,10 +311,13 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     if rank == 0:
         line = {
             "metric": "heat_transfer_3d_dof_per_s", "value": nV / (ms_per_step / 1e3), "unit": "DOF/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"3D transient heat conduction, structured hex mesh {n}^3 vertices cut into {world} vertex-block slabs, "
-                                   "dt=1e-2, 3-D BC set, PCG(Jacobi) rtol 1e-10, 1 time step per step",
+            "config": {"workload": (f"C5 strong scaling: 3D transient heat conduction, structured hex mesh {n}^3 vertices cut into {world} "
+                                    "vertex-block slabs" if strong else
+                                    f"C2 weak scaling: each of the {world} ranks owns a {n}x{n}x{n}-vertex block of an {n}x{n}x{nz} hex box "
+                                    "(same spacing, same per-GPU work as the N=1 C2 run)") +
+                                   ", dt=1e-2, 3-D BC set, PCG(Jacobi) rtol 1e-10, 1 time step per step",
                        "vertices": nV, "pcg_iterations_per_step": iters, "warmup_iterations": warm,
                        "assemble_ms_per_step": float(np.mean(asm_ms)), "solve_ms_per_step": float(np.mean(solve_ms)),
                        "host_slab_generation_s": host_s, "halo": "NCCL send/recv of one n^2 plane per neighbour per SpMV",

@@ -310,20 +310,21 @@ _TET_SPLIT = [[(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)], [(1, 0, 0), (1, 0, 1
 _HEX_CORNERS = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
 
 
-def _quad_faces(n, a, b):
-    """Boundary quads of the unit cube in the bundled orientation; a = slow, b = fast facet index (for the four
-    lateral faces a is the z layer)."""
+def _quad_faces(n, a, b, nz=None):
+    """Boundary quads of the box in the bundled orientation; a = slow, b = fast facet index (for the four
+    lateral faces a is the z layer).  nz = number of vertex planes in z (default n: the unit cube)."""
     ne = n - 1
     vid = lambda i, j, k: i + n * j + n * n * k
     o = np.zeros_like(a)
     L = o + ne
+    Lz = o + ((nz or n) - 1)
     return {
         "West": [vid(o, b, a), vid(o, b, a + 1), vid(o, b + 1, a + 1), vid(o, b + 1, a)],
         "East": [vid(L, b, a), vid(L, b + 1, a), vid(L, b + 1, a + 1), vid(L, b, a + 1)],
         "South": [vid(b, o, a), vid(b + 1, o, a), vid(b + 1, o, a + 1), vid(b, o, a + 1)],
         "North": [vid(b, L, a), vid(b, L, a + 1), vid(b + 1, L, a + 1), vid(b + 1, L, a)],
         "Bottom": [vid(b, a, o), vid(b, a + 1, o), vid(b + 1, a + 1, o), vid(b + 1, a, o)],
-        "Top": [vid(b, a, L), vid(b + 1, a, L), vid(b + 1, a + 1, L), vid(b, a + 1, L)],
+        "Top": [vid(b, a, Lz), vid(b + 1, a, Lz), vid(b + 1, a + 1, Lz), vid(b, a + 1, Lz)],
     }
 
 
@@ -349,12 +350,13 @@ def _tet_face_uses_first_diagonal():
     return _tet_diag_cache
 
 
-def structured_arrays(n, kind="hex", layer_lo=0, layer_hi=None):
+def structured_arrays(n, kind="hex", layer_lo=0, layer_hi=None, nz=None):
     """Global-id connectivity of the cube layers [layer_lo, layer_hi) (a layer = all cubes with the same z index) and
     the boundary facets attached to them: dict(conn, facets={name: array}).  Bottom / Top facets are included when
-    layer 0 / layer n-2 is."""
+    layer 0 / the last layer is.  nz vertex planes in z (default n)."""
     ne = n - 1
-    layer_hi = ne if layer_hi is None else layer_hi
+    nez = (nz or n) - 1
+    layer_hi = nez if layer_hi is None else layer_hi
     vid = lambda i, j, k: i + n * j + n * n * k
     e = np.arange(layer_lo * ne * ne, layer_hi * ne * ne, dtype=np.int64)
     i, j, k = e % ne, (e // ne) % ne, e // (ne * ne)
@@ -368,11 +370,11 @@ def structured_arrays(n, kind="hex", layer_lo=0, layer_hi=None):
     facets = {}
     ql = np.arange(layer_lo * ne, layer_hi * ne, dtype=np.int64)         # lateral faces: a = z layer
     qf = np.arange(ne * ne, dtype=np.int64)                               # bottom / top: full face
-    lat = _quad_faces(n, ql // ne, ql % ne)
-    full = _quad_faces(n, qf // ne, qf % ne)
+    lat = _quad_faces(n, ql // ne, ql % ne, nz)
+    full = _quad_faces(n, qf // ne, qf % ne, nz)
     for name in BOUNDARY_NAMES_3D:
         if name in ("Bottom", "Top"):
-            present = (layer_lo == 0) if name == "Bottom" else (layer_hi == ne)
+            present = (layer_lo == 0) if name == "Bottom" else (layer_hi == nez)
             v = np.stack(full[name], axis=1) if present else np.zeros((0, 4), dtype=np.int64)
         else:
             v = np.stack(lat[name], axis=1)
@@ -386,27 +388,29 @@ def structured_arrays(n, kind="hex", layer_lo=0, layer_hi=None):
     return dict(conn=conn, facets=facets)
 
 
-def structured_coords(n, ids, perturb=0.0):
-    """Coordinates of the global vertex ids `ids` of the n^3 unit-cube lattice."""
+def structured_coords(n, ids, perturb=0.0, nz=None):
+    """Coordinates of the global vertex ids `ids` of the n x n x nz lattice with spacing 1/(n-1) (unit cube if nz = n)."""
     ax = np.linspace(0.0, 1.0, n)
     I, J, K = ids % n, (ids // n) % n, ids // (n * n)
-    coords = np.stack([ax[I], ax[J], ax[K]], axis=1)
+    nz = nz or n
+    az = ax if nz == n else np.arange(nz) * (1.0 / (n - 1))
+    coords = np.stack([ax[I], ax[J], az[K]], axis=1)
     if perturb:
         h = 1.0 / (n - 1)
-        interior = ((I > 0) & (I < n - 1) & (J > 0) & (J < n - 1) & (K > 0) & (K < n - 1))[:, None]
+        interior = ((I > 0) & (I < n - 1) & (J > 0) & (J < n - 1) & (K > 0) & (K < nz - 1))[:, None]
         x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
         d = np.stack([np.sin(7 * x + 3 * y + 5 * z), np.sin(4 * x - 6 * y + 2 * z + 1.0), np.sin(5 * x + 2 * y - 7 * z + 2.0)], axis=1)
         coords = coords + perturb * h * d * interior
     return coords
 
 
-def structured_grid_data(n, kind="hex", perturb=0.0):
-    """Unit cube, n^3 vertices with id = i + n j + n^2 k (x fastest, like meshes/msh/3D/Hexas*.msh), hexahedra in
+def structured_grid_data(n, kind="hex", perturb=0.0, nz=None):
+    """Unit cube (or, with nz, an n x n x nz box of the same spacing), n^3 vertices with id = i + n j + n^2 k (x fastest, like meshes/msh/3D/Hexas*.msh), hexahedra in
     the bundled local order or the 6-tetrahedra-per-cube split of meshes/msh/3D/Tetras.msh, one region "Body",
     boundaries West East South North Bottom Top.  `perturb` moves interior vertices by a smooth deterministic
     perturb*h*sin(...) field to exercise non-affine hexahedra."""
-    arr = structured_arrays(n, kind)
-    coords = structured_coords(n, np.arange(n ** 3, dtype=np.int64), perturb)
+    arr = structured_arrays(n, kind, nz=nz)
+    coords = structured_coords(n, np.arange(n * n * (nz or n), dtype=np.int64), perturb, nz)
     conn = arr["conn"].astype(np.int32)
     sizes = [len(arr["facets"][nm]) for nm in BOUNDARY_NAMES_3D]
     starts = np.concatenate([[0], np.cumsum(sizes)])
@@ -421,5 +425,5 @@ def structured_grid_data(n, kind="hex", perturb=0.0):
     return gd
 
 
-def structured_grid(n, kind="hex", perturb=0.0):
-    return Grid(structured_grid_data(n, kind, perturb))
+def structured_grid(n, kind="hex", perturb=0.0, nz=None):
+    return Grid(structured_grid_data(n, kind, perturb, nz))
