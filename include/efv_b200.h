@@ -79,6 +79,11 @@ int efv_boundary_export(const efv_mesh *m, int64_t *facet_element, int32_t *face
  * CSR sparsity = union of element cliques with sorted columns (north_star kernel 2), DOF-expanded field-major
  * exactly like LinearSystemCSR.initialize [ref: LinearSystem.py:114-128] with sorted stencils.              */
 efv_system *efv_system_create(efv_mesh *m, int ndof);
+/* a scalar system on a caller-supplied CSR pattern (no mesh): fill it with efv_system_set_values, put the RHS into
+ * EFV_VEC_B, solve.  Every row must contain its diagonal entry.  [ref: LinearSystem.py:113-183 used as in
+ * apps/csr/heat_transfer_csr.py:57-133]                                                                       */
+efv_system *efv_system_create_from_csr(int64_t n, const int64_t *indptr, const int32_t *indices);
+int efv_system_set_values(efv_system *s, const double *data);
 void efv_system_destroy(efv_system *s);
 int64_t efv_system_rows(const efv_system *s);
 int64_t efv_system_nnz(const efv_system *s);          /* DOF-expanded: ndof^2 * graph nnz */

@@ -11,3 +11,4 @@ from .shapes import SHAPES, TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON  # 
 from .problem import (ProblemData, NumericalSettings, PropertyData, BoundaryConditions, DirichletBoundaryCondition,  # noqa: F401
                       NeumannBoundaryCondition, Neumann, Dirichlet, Constant, Variable)
 from .solver import Solver, Saver, CsvSaver, NullSaver  # noqa: F401
+from .linear_system import LinearSystem, LinearSystemCSR  # noqa: F401

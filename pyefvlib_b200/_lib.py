@@ -40,6 +40,8 @@ PROTOTYPES = {
     "efv_vertex_volume_export": (C.c_int, [C.c_void_p, c_f64p]),
     "efv_boundary_export": (C.c_int, [C.c_void_p, c_i64p, c_i32p, c_f64p, c_i32p, c_f64p]),
     "efv_system_create": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "efv_system_create_from_csr": (C.c_void_p, [C.c_int64, c_i64p, c_i32p]),
+    "efv_system_set_values": (C.c_int, [C.c_void_p, c_f64p]),
     "efv_system_destroy": (None, [C.c_void_p]),
     "efv_system_rows": (C.c_int64, [C.c_void_p]),
     "efv_system_nnz": (C.c_int64, [C.c_void_p]),

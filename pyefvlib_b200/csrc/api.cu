@@ -149,6 +149,53 @@ efv_system *efv_system_create(efv_mesh *m, int ndof) {
     return s;
   EFV_API_END_PTR(s)
 }
+// a system on a caller-supplied CSR pattern (no mesh): the LinearSystemCSR seam (LinearSystem.py:113-183) for matrices
+// that were filled on the host
+__global__ void k_find_diag(int64_t n, const int64_t *__restrict__ ptr, const int32_t *__restrict__ col,
+                            int32_t *__restrict__ diag, int *__restrict__ err) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    int found = -1;
+    for (int64_t t = ptr[v]; t < ptr[v + 1]; ++t)
+      if (col[t] == v) found = (int)t;
+    if (found < 0) atomicExch(err, 1);
+    diag[v] = found < 0 ? 0 : found;
+  }
+}
+efv_system *efv_system_create_from_csr(int64_t n, const int64_t *indptr, const int32_t *indices) {
+  efv_system *s = nullptr;
+  try {
+    EFV_REQUIRE(n > 0 && indptr && indices, "bad CSR arguments");
+    EFV_REQUIRE(indptr[n] < (int64_t(1) << 31), "nnz exceeds int32 slot range");
+    for (int64_t k = 0; k < indptr[n]; ++k) EFV_REQUIRE(indices[k] >= 0 && indices[k] < n, "column index out of range");
+    s = new efv_system();
+    s->mesh = nullptr; s->ndof = 1; s->nV = s->n_owned = s->rows = n; s->nnzg = indptr[n];
+    s->gptr.upload(indptr, n + 1);
+    s->gcol.upload(indices, s->nnzg);
+    s->diag_slot.alloc(n);
+    efv::DBuf<int> err(1);
+    err.zero();
+    EFV_LAUNCH(k_find_diag, efv::grid_for(n, 256), 256, 0, n, s->gptr.p, s->gcol.p, s->diag_slot.p, err.p);
+    int herr = 0;
+    err.download(&herr, 1);
+    EFV_REQUIRE(herr == 0, "every row of the pattern must contain its diagonal entry");
+    s->vals.alloc(s->nnzg);
+    s->vals.zero();
+    efv::ensure_vectors(s);
+    efv::bc_clear(s);
+    s->physics = 1;      // generic: RHS = static part (+ eliminated columns), Dirichlet rows <- g
+    EFV_CUDA(cudaStreamSynchronize(efv::stream()));
+    return s;
+  EFV_API_END_PTR(s)
+}
+int efv_system_set_values(efv_system *s, const double *data) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && data, "null argument");
+  EFV_REQUIRE(s->ndof == 1, "efv_system_set_values expects a scalar (ndof = 1) system");
+  s->vals.upload(data, s->nnzg);
+  EFV_CUDA(cudaStreamSynchronize(efv::stream()));
+  s->dirichlet_mode = -1;
+  EFV_API_END
+}
 void efv_system_destroy(efv_system *s) {
   if (!s) return;
   efv::krylov_free(s);
@@ -178,6 +225,7 @@ int efv_system_export_graph(const efv_system *s, int64_t *gptr, int32_t *gcol) {
 int efv_system_export_slotmap(const efv_system *s, int64_t *slots) {
   EFV_API_BEGIN
   EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(s->mesh, "this system has no mesh (created from a CSR pattern)");
   efv::export_slotmap(s, slots);
   EFV_API_END
 }
@@ -213,6 +261,7 @@ int efv_vec_download(const efv_system *s, int which, double *host) {
 int efv_heat_assemble(efv_system *s, const double *props, double dt, int transient) {
   EFV_API_BEGIN
   EFV_REQUIRE(s && props, "null argument");
+  EFV_REQUIRE(s->mesh, "this system has no mesh (created from a CSR pattern)");
   EFV_REQUIRE(!transient || dt > 0, "transient assembly needs a positive time step");
   efv::heat_assemble(s, props, dt, transient);
   EFV_API_END
@@ -220,12 +269,14 @@ int efv_heat_assemble(efv_system *s, const double *props, double dt, int transie
 int efv_elasticity_assemble(efv_system *s, const double *props, int gravity) {
   EFV_API_BEGIN
   EFV_REQUIRE(s && props, "null argument");
+  EFV_REQUIRE(s->mesh, "this system has no mesh (created from a CSR pattern)");
   efv::elasticity_assemble(s, props, gravity);
   EFV_API_END
 }
 int efv_biot_assemble(efv_system *s, const double *props, double dt, const double *gvec) {
   EFV_API_BEGIN
   EFV_REQUIRE(s && props, "null argument");
+  EFV_REQUIRE(s->mesh, "this system has no mesh (created from a CSR pattern)");
   EFV_REQUIRE(dt > 0, "Biot assembly needs a positive time step");
   efv::biot_assemble(s, props, dt, gvec);
   EFV_API_END
@@ -247,6 +298,7 @@ int efv_bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, i
 int efv_bc_neumann(efv_system *s, int boundary, int dof, double value, double sign) {
   EFV_API_BEGIN
   EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(s->mesh, "this system has no mesh (created from a CSR pattern)");
   efv::bc_neumann(s, boundary, dof, value, sign);
   EFV_API_END
 }
