@@ -277,7 +277,7 @@ def run_gpu(args):
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_spmv<1,L> (CSR SpMV + fused p.Ap partial)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_spmv_sell<8> (SpMV on the solver's sliced-ELL copy of the CSR matrix + fused p.Ap partial)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": spmv_bytes, "launch_ms": spmv_ms,
                 "pcg_iteration_gbs": pcg_gbs, "pcg_iteration_frac": pcg_gbs / peak,

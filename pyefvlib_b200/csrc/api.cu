@@ -192,6 +192,7 @@ int efv_system_set_values(efv_system *s, const double *data) {
   EFV_REQUIRE(s && data, "null argument");
   EFV_REQUIRE(s->ndof == 1, "efv_system_set_values expects a scalar (ndof = 1) system");
   s->vals.upload(data, s->nnzg);
+  s->vals_version++;
   EFV_CUDA(cudaStreamSynchronize(efv::stream()));
   s->dirichlet_mode = -1;
   EFV_API_END

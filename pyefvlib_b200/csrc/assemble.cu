@@ -229,6 +229,7 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
   }
   EFV_CUDA(cudaEventRecord(s->ev1, stream()));
   s->assemble_timed = true;
+  s->vals_version++;
   s->dirichlet_mode = s->fuse_mode;
   s->physics = 0;
 }
@@ -423,6 +424,7 @@ void elasticity_assemble(efv_system *s, const double *props_host, int gravity) {
   }
   EFV_CUDA(cudaEventRecord(s->ev1, stream()));
   s->assemble_timed = true;
+  s->vals_version++;
   s->dirichlet_mode = s->fuse_mode;
   s->physics = 1;
 }
@@ -713,6 +715,7 @@ void biot_assemble(efv_system *s, const double *props_host, double dt, const dou
   }
   EFV_CUDA(cudaEventRecord(s->ev1, stream()));
   s->assemble_timed = true;
+  s->vals_version++;
   s->dirichlet_mode = s->fuse_mode;
   s->physics = 2;
 }
@@ -866,6 +869,7 @@ void apply_dirichlet(efv_system *s, int mode) {
     default: throw Error("unsupported ndof");
   }
   s->dirichlet_mode = mode;
+  s->vals_version++;
 }
 
 // ---- right-hand side -----------------------------------------------------------------------------------------------

@@ -108,6 +108,7 @@ struct efv_system {
   efv::DBuf<double> dir_value;
   efv::DBuf<int32_t> dir_last;
   int dirichlet_mode = -1;
+  uint64_t vals_version = 1;           // bumped whenever `vals` changes (the solver's SELL copy is rebuilt lazily)
   int fuse_mode = -1;                  // Dirichlet mode applied inside the next assembly kernel (-1: none)
   bool has_dirichlet = false;
   int physics = 0;

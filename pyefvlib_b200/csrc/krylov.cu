@@ -11,6 +11,7 @@
 #include "views.cuh"
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 namespace efv {
 
@@ -23,6 +24,13 @@ struct KrylovWork {
   DBuf<double> partial;     // 4 * grid
   DBuf<double> sc;          // device scalars
   DBuf<int> flags;          // [0] done, [1] iterations, [2] breakdown
+  // sliced-ELL copy of a scalar matrix for the solver (slices of 32 rows, column-major inside a slice)
+  DBuf<int64_t> sell_off;   // nslices+1, in units of 32-entry columns
+  DBuf<int32_t> sell_cols;
+  DBuf<double> sell_vals;
+  int64_t sell_slices = 0, sell_rows = 0;
+  uint64_t sell_version = 0;
+  bool sell_ok = false, sell_use = false;
   int *h_flags = nullptr;   // pinned
   double *h_sc = nullptr;   // pinned
   cudaEvent_t ev = nullptr, e0 = nullptr, e1 = nullptr;
@@ -138,6 +146,128 @@ __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__re
   }
 }
 
+// ---- sliced ELL (SELL-32) for the solver ---------------------------------------------------------------------------------
+// The CSR SpMV above is bound by L1 wavefronts (ncu: 86 % L1/TEX throughput, 16 of 32 B used per sector) because the
+// 27-entry row segments start at arbitrary 8-byte offsets.  For scalar systems the solver therefore keeps a copy of the
+// matrix in slices of 32 consecutive rows stored column-major: lane r of a warp owns row r of the slice, every load of
+// the warp is one aligned 256-byte (values) or 128-byte (columns) request, neighbouring rows gather neighbouring x, and
+// no shuffles or row pointers are needed.  CSR stays the canonical structure (export, parity, assembly); the copy is
+// rebuilt when the values change (one pass over the matrix, ~1 % of a solve).
+__global__ void k_sell_widths(int64_t nrows, const int64_t *__restrict__ gptr, int32_t *__restrict__ width) {
+  int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t nslices = (nrows + 31) >> 5;
+  for (; slice < nslices; slice += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    int64_t v = slice * 32 + lane;
+    int len = (v < nrows) ? (int)(gptr[v + 1] - gptr[v]) : 0;
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) width[slice] = len;
+  }
+}
+__global__ void k_sell_fill(int64_t nrows, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
+                            const double *__restrict__ vals, const int64_t *__restrict__ off, int32_t *__restrict__ scol,
+                            double *__restrict__ sval) {
+  int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t nslices = (nrows + 31) >> 5;
+  for (; slice < nslices; slice += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    int64_t v = slice * 32 + lane;
+    const bool valid = v < nrows;
+    const int64_t r0 = valid ? gptr[v] : 0;
+    const int len = valid ? (int)(gptr[v + 1] - r0) : 0;
+    const int width = (int)(off[slice + 1] - off[slice]);
+    const int64_t base = off[slice] * 32 + lane;
+    for (int k = 0; k < width; ++k) {
+      const bool in = k < len;
+      scol[base + (int64_t)k * 32] = in ? gcol[r0 + k] : (int32_t)(valid ? v : 0);   // padding: zero times a valid x entry
+      sval[base + (int64_t)k * 32] = in ? vals[r0 + k] : 0.0;
+    }
+  }
+}
+template <int U>
+__global__ void __launch_bounds__(kBlock) k_spmv_sell(int64_t nrows, const int64_t *__restrict__ off,
+                                                      const int32_t *__restrict__ scol, const double *__restrict__ sval,
+                                                      const double *__restrict__ x, double *__restrict__ y, double sigma,
+                                                      const double *__restrict__ rowscale, const double *__restrict__ w,
+                                                      double *__restrict__ partial, const int *__restrict__ done) {
+  __shared__ double red[32];
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0;
+  for (int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; slice < nslices; slice += warps) {
+    const int64_t o0 = off[slice];
+    const int width = (int)(off[slice + 1] - o0);
+    const int32_t *c = scol + o0 * 32 + lane;
+    const double *a = sval + o0 * 32 + lane;
+    double acc = 0.0;
+    // predicated batches of U columns: every batch issues all its (column, value) loads before the gathers
+    for (int k = 0; k < width; k += U) {
+      int cc[U];
+      double vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = k + u < width;
+        cc[u] = ok ? __ldcs(c + (int64_t)(k + u) * 32) : -1;
+        vv[u] = ok ? __ldcs(a + (int64_t)(k + u) * 32) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc += (cc[u] >= 0) ? vv[u] * __ldg(x + cc[u]) : 0.0;
+    }
+    const int64_t v = slice * 32 + lane;
+    if (v < nrows) {
+      double yi = sigma * acc;
+      if (rowscale) yi *= rowscale[v];
+      y[v] = yi;
+      if (w) dot += w[v] * yi;
+    }
+  }
+  if (partial) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+  }
+}
+
+// (re)build the SELL copy if the values changed; returns whether the SELL path should be used
+static bool sell_prepare(efv_system *s, KrylovWork *w) {
+  if (s->ndof != 1) return false;
+  const char *fmt = getenv("EFV_SPMV_FORMAT");
+  if (fmt && strcmp(fmt, "csr") == 0) { w->sell_use = false; return false; }
+  w->sell_use = true;
+  const int64_t nrows = s->n_owned;
+  if (w->sell_version == s->vals_version && w->sell_rows == nrows) return w->sell_ok;
+  w->sell_version = s->vals_version;
+  w->sell_rows = nrows;
+  const int64_t nslices = (nrows + 31) >> 5;
+  if (w->sell_slices != nslices) {
+    // structure pass (once per pattern): slice widths -> offsets
+    DBuf<int32_t> width(nslices);
+    EFV_LAUNCH(k_sell_widths, grid_for(nslices * 32, 256), 256, 0, nrows, s->gptr.p, width.p);
+    w->sell_off.alloc(nslices + 1);
+    const int64_t cols32 = exclusive_scan_i32_to_i64(width.p, w->sell_off.p, nslices);
+    w->sell_slices = nslices;
+    const double padded = 32.0 * (double)cols32;
+    int64_t nnz_owned = 0;
+    {
+      int64_t ends[2];
+      EFV_CUDA(cudaMemcpyAsync(&ends[0], s->gptr.p, sizeof(int64_t), cudaMemcpyDeviceToHost, stream()));
+      EFV_CUDA(cudaMemcpyAsync(&ends[1], s->gptr.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, stream()));
+      EFV_CUDA(cudaStreamSynchronize(stream()));
+      nnz_owned = ends[1] - ends[0];
+    }
+    const bool force = fmt && strcmp(fmt, "sell") == 0;
+    w->sell_ok = force || padded <= 1.2 * (double)nnz_owned;      // irregular rows: stay on CSR
+    if (!w->sell_ok) { w->sell_cols.release(); w->sell_vals.release(); return false; }
+    w->sell_cols.alloc((size_t)cols32 * 32);
+    w->sell_vals.alloc((size_t)cols32 * 32);
+  }
+  if (!w->sell_ok) return false;
+  EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->gptr.p, s->gcol.p, s->vals.p, w->sell_off.p,
+             w->sell_cols.p, w->sell_vals.p);
+  return true;
+}
+
 static int pick_lanes(const efv_system *s) {
   const char *env = getenv("EFV_SPMV_LANES");
   if (env) { int l = atoi(env); if (l == 2 || l == 4 || l == 8 || l == 16 || l == 32) return l; }
@@ -177,6 +307,23 @@ static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, d
 }
 static void launch_spmv(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
                         const double *w, double *partial, const int *done) {
+  KrylovWork *kw = s->kw;
+  if (kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned && s->ndof == 1) {
+    const char *eu = getenv("EFV_SELL_UNROLL");
+    const int U = eu ? atoi(eu) : 8;
+#define EFV_SELL_CASE(UU)                                                                                                  \
+  EFV_LAUNCH(k_spmv_sell<UU>, grid, kBlock, 0, s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, y, sigma, \
+             rowscale, w, partial, done)
+    switch (U) {
+      case 4: EFV_SELL_CASE(4); break;
+      case 7: EFV_SELL_CASE(7); break;
+      case 9: EFV_SELL_CASE(9); break;
+      case 14: EFV_SELL_CASE(14); break;
+      default: EFV_SELL_CASE(8); break;
+    }
+#undef EFV_SELL_CASE
+    return;
+  }
   switch (s->ndof) {
     case 1: launch_spmv_l<1>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
     case 2: launch_spmv_l<2>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
@@ -188,6 +335,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
 
 void spmv(efv_system *s, const double *x, double *y) {
   EFV_REQUIRE(s->vals.n, "no values assembled");
+  sell_prepare(s, work(s));
   launch_spmv(s, num_sms() * 8, x, y, 1.0, nullptr, nullptr, nullptr, nullptr);
 }
 
@@ -255,7 +403,7 @@ __global__ void k_pcg_init_scalars(int G, const double *__restrict__ partial, do
   }
 }
 // alpha = rz / p.Ap ; x += alpha p ; r -= alpha Ap ; partials [0] r.z(new) [1] r.r(new)
-__global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, const double *__restrict__ sc,
+__global__ void __launch_bounds__(kBlock, 6) k_pcg_update_xr(int64_t n, int it, const double *__restrict__ sc,
                                                           const double *__restrict__ pAp_partial, int G,
                                                           const double *__restrict__ p, const double *__restrict__ Ap,
                                                           const double *__restrict__ dinv, double *__restrict__ x,
@@ -277,7 +425,7 @@ __global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, con
   rr = block_sum(rr, red); if (threadIdx.x == 0) partial[Gout + blockIdx.x] = rr;
 }
 // beta = rz_new / rz_old ; p = dinv r + beta p ; block 0 publishes the scalars and the convergence flag
-__global__ void __launch_bounds__(kBlock) k_pcg_update_p(int64_t n, int it, double *__restrict__ sc,
+__global__ void __launch_bounds__(kBlock, 8) k_pcg_update_p(int64_t n, int it, double *__restrict__ sc,
                                                          const double *__restrict__ partial, int G,
                                                          const double *__restrict__ r, const double *__restrict__ dinv,
                                                          double *__restrict__ p, int *__restrict__ flags) {
@@ -311,6 +459,7 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   double *P = w->partial.p;
   int Gc = G;
   EFV_CUDA(cudaEventRecord(w->e0, stream()));
+  sell_prepare(s, w);
   EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->n_owned, s->ndof, s->diag_slot.p, s->vals.p, sigma, w->dinv.p);
   EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
   halo_exchange(s, s->x.p);
@@ -372,6 +521,7 @@ __global__ void k_bi_init_scalars(int G, const double *__restrict__ partial, dou
   double bb = sum_partials(partial + G, G, red);
   if (threadIdx.x == 0) {
     sc[0] = 1.0; sc[1] = 1.0; sc[2] = 1.0; sc[3] = bb; sc[4] = rr; sc[5] = rtol * rtol; sc[6] = rr;   // sc[6] = (rhat, r)
+    sc[8] = rr;                                                                                       // |rhat|^2
     flags[0] = (rr <= rtol * rtol * bb) ? 1 : 0;
     flags[1] = 0; flags[2] = 0; flags[3] = 0;
   }
@@ -379,8 +529,16 @@ __global__ void k_bi_init_scalars(int G, const double *__restrict__ partial, dou
 // beta = (rho_new/rho)(alpha/omega); p = r + beta (p - omega v)
 __global__ void __launch_bounds__(kBlock) k_bi_p(int64_t n, const double *__restrict__ sc, const double *__restrict__ r,
                                                  const double *__restrict__ v, double *__restrict__ p,
-                                                 const int *__restrict__ flags) {
+                                                 double *__restrict__ rhat, const int *__restrict__ flags) {
   if (flags[0]) return;
+  if (flags[2]) {     // restart after a breakdown ((rhat, r) or omega vanished): shadow residual <- r, p <- r
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const double ri = r[i];
+      rhat[i] = ri;
+      p[i] = ri;
+    }
+    return;
+  }
   double rho_new = sc[6], rho = sc[0], alpha = sc[1], omega = sc[2];
   double beta = (rho_new / rho) * (alpha / omega);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -398,6 +556,7 @@ __global__ void __launch_bounds__(kBlock) k_bi_s(int64_t n, double *__restrict__
     sv[i] = r[i] - alpha * v[i];
   if (blockIdx.x == 0 && threadIdx.x == 0) sc[7] = alpha;     // staged alpha (sc[1] still read by nobody in this kernel)
 }
+__global__ void k_bi_clear_restart(int *flags) { flags[2] = 0; }
 // t = A s done by spmv with partial (t,s); (t,t) needs its own pass fused here:
 __global__ void __launch_bounds__(kBlock) k_bi_tt(int64_t n, const double *__restrict__ t, double *__restrict__ partial,
                                                   const int *__restrict__ flags) {
@@ -447,7 +606,12 @@ __global__ void k_bi_scalars(int it, int G, const double *__restrict__ partial, 
     sc[4] = rr;
     flags[1] = it + 1;
     if (!(rr > sc[5] * sc[3])) flags[0] = 1;
-    else if (hr == 0.0 || sc[2] == 0.0) { flags[0] = 1; flags[2] = 1; }   // breakdown
+    else if (hr * hr <= 1e-28 * sc[8] * rr || sc[2] == 0.0 || !(fabs(sc[6]) < 1e300)) {
+      // breakdown: restart from the current residual (rhat <- r in the next k_bi_p)
+      sc[0] = 1.0; sc[1] = 1.0; sc[2] = 1.0; sc[6] = rr; sc[8] = rr;
+      flags[2] = 1;
+      flags[3] += 1;
+    }
   }
 }
 
@@ -462,6 +626,7 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
   const int G = w->grid;
   double *P = w->partial.p;
   EFV_CUDA(cudaEventRecord(w->e0, stream()));
+  sell_prepare(s, w);
   EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->nV, s->ndof, s->diag_slot.p, s->vals.p, 1.0, w->dinv.p);
   EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
   launch_spmv(s, G, s->x.p, w->Ap.p, 1.0, w->dinv.p, nullptr, nullptr, nullptr);
@@ -473,7 +638,8 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
   while (!done && it < maxit) {
     int batch_end = std::min(maxit, it + check_every);
     for (; it < batch_end; ++it) {
-      EFV_LAUNCH(k_bi_p, G, kBlock, 0, n, w->sc.p, w->r.p, w->v.p, w->p.p, w->flags.p);
+      EFV_LAUNCH(k_bi_p, G, kBlock, 0, n, w->sc.p, w->r.p, w->v.p, w->p.p, w->rhat.p, w->flags.p);
+      EFV_LAUNCH(k_bi_clear_restart, 1, 1, 0, w->flags.p);
       launch_spmv(s, G, w->p.p, w->v.p, 1.0, w->dinv.p, w->rhat.p, P + 2 * G, w->flags.p);          // v = D^-1 A p, (rhat,v)
       EFV_LAUNCH(k_bi_s, G, kBlock, 0, n, w->sc.p, P + 2 * G, G, w->r.p, w->v.p, w->sv.p, w->flags.p);
       launch_spmv(s, G, w->sv.p, w->t.p, 1.0, w->dinv.p, w->sv.p, P + 2 * G, w->flags.p);           // t = D^-1 A s, (t,s)

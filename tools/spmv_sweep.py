@@ -17,7 +17,27 @@ s.upload(VEC_X, np.random.default_rng(0).random(s.rows))
 stream = torch.cuda.ExternalStream(L.efv_get_stream())
 bytes_ = 12.0 * s.nnz + 24.0 * s.rows
 out = {}
-for lanes, unroll in [(8, 4), (8, 2), (8, 8), (4, 8), (4, 4), (16, 2), (16, 1), (16, 4), (32, 1), (32, 2)]:
+os.environ["EFV_SPMV_FORMAT"] = "sell"
+for U in (4, 7, 8, 9, 14):
+    os.environ["EFV_SELL_UNROLL"] = str(U)
+    for _ in range(3):
+        s.spmv(VEC_X, VEC_B)
+    torch.cuda.synchronize()
+    ysell = s.download(VEC_B)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(20):
+        s.spmv(VEC_X, VEC_B)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    out[f"SELL32_U{U}"] = round(bytes_ / ms / 1e6, 1)
+    print(f"SELL-32 unroll={U:2d}    {ms:.4f} ms  {bytes_/ms/1e6:8.1f} GB/s", flush=True)
+os.environ["EFV_SPMV_FORMAT"] = "csr"
+s.spmv(VEC_X, VEC_B)
+ycsr = s.download(VEC_B)
+print("max |y_sell - y_csr| / max|y| =", float(np.abs(ysell - ycsr).max() / np.abs(ycsr).max()))
+for lanes, unroll in [(8, 4), (4, 8), (16, 2)]:
     os.environ["EFV_SPMV_LANES"] = str(lanes); os.environ["EFV_SPMV_UNROLL"] = str(unroll)
     for _ in range(3):
         s.spmv(VEC_X, VEC_B)
