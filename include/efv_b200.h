@@ -47,6 +47,10 @@ int64_t efv_kernel_launch_count(void); /* kernels launched by this library since
  * region_of_elem[nE] in [0, n_regions).                                                                     */
 efv_mesh *efv_mesh_create(int dim, int64_t nV, const double *coords, int64_t nE, const int64_t *elem_ptr,
                           const int32_t *conn, const int32_t *region_of_elem, int n_regions);
+/* same for a mesh whose elements all have `vertices_per_element` vertices (conn is nE x m row-major): no pointer array.
+ * region_of_elem may be NULL when there is a single region.                                                        */
+efv_mesh *efv_mesh_create_uniform(int dim, int64_t nV, const double *coords, int64_t nE, int vertices_per_element,
+                                  const int32_t *conn, const int32_t *region_of_elem, int n_regions);
 /* boundary facets [ref: GridData.py:18-21; Grid.py:51-65; Boundary.py:27-75; Facet.py:22-36]:
  * facets of all boundaries concatenated in boundary order; boundary b owns facets
  * [boundary_ptr[b], boundary_ptr[b+1]); facet f has vertices facet_conn[facet_ptr[f] .. facet_ptr[f+1]).

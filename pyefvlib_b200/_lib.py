@@ -26,6 +26,7 @@ PROTOTYPES = {
     "efv_synchronize": (C.c_int, []),
     "efv_kernel_launch_count": (C.c_int64, []),
     "efv_mesh_create": (C.c_void_p, [C.c_int, C.c_int64, c_f64p, C.c_int64, c_i64p, c_i32p, c_i32p, C.c_int]),
+    "efv_mesh_create_uniform": (C.c_void_p, [C.c_int, C.c_int64, c_f64p, C.c_int64, C.c_int, c_i32p, c_i32p, C.c_int]),
     "efv_mesh_set_boundaries": (C.c_int, [C.c_void_p, C.c_int, c_i64p, C.c_int64, c_i64p, c_i32p]),
     "efv_mesh_destroy": (None, [C.c_void_p]),
     "efv_mesh_num_vertices": (C.c_int64, [C.c_void_p]),

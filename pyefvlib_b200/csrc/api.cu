@@ -53,25 +53,33 @@ int efv_synchronize(void) {
 int64_t efv_kernel_launch_count(void) { return efv::launch_count(); }
 
 // ---- mesh ----------------------------------------------------------------------------------------------------------
-efv_mesh *efv_mesh_create(int dim, int64_t nV, const double *coords, int64_t nE, const int64_t *elem_ptr,
-                          const int32_t *conn, const int32_t *region_of_elem, int n_regions) {
+static efv_mesh *mesh_create_impl(int dim, int64_t nV, const double *coords, int64_t nE, const int64_t *elem_ptr, int uniform_m,
+                                  const int32_t *conn, const int32_t *region_of_elem, int n_regions) {
   efv_mesh *m = nullptr;
   try {
     EFV_REQUIRE(dim == 2 || dim == 3, "dimension must be 2 or 3");
     EFV_REQUIRE(nV > 0 && nE > 0, "empty mesh");
     EFV_REQUIRE(nV < (int64_t(1) << 31), "vertex ids must fit int32");
-    EFV_REQUIRE(coords && elem_ptr && conn, "null mesh array");
+    EFV_REQUIRE(coords && conn && (elem_ptr || uniform_m > 0), "null mesh array");
     m = new efv_mesh();
     m->dim = dim; m->nV = nV; m->nE = nE; m->n_regions = n_regions > 0 ? n_regions : 1;
-    m->conn_size = elem_ptr[nE];
+    m->conn_size = elem_ptr ? elem_ptr[nE] : nE * (int64_t)uniform_m;
     m->coords.upload(coords, (size_t)nV * 3);
     m->conn.upload(conn, (size_t)m->conn_size);
-    if (region_of_elem) m->region.upload(region_of_elem, (size_t)nE);
+    if (region_of_elem && m->n_regions > 1) m->region.upload(region_of_elem, (size_t)nE);
     else { m->region.alloc(nE); m->region.zero(); }
-    std::vector<int64_t> ep(elem_ptr, elem_ptr + nE + 1);
-    efv::mesh_finalize(m, ep);
+    efv::mesh_finalize(m, elem_ptr, uniform_m);
     return m;
   EFV_API_END_PTR(m)
+}
+efv_mesh *efv_mesh_create(int dim, int64_t nV, const double *coords, int64_t nE, const int64_t *elem_ptr,
+                          const int32_t *conn, const int32_t *region_of_elem, int n_regions) {
+  if (!elem_ptr) { efv::set_last_error("null elem_ptr (use efv_mesh_create_uniform)"); return nullptr; }
+  return mesh_create_impl(dim, nV, coords, nE, elem_ptr, 0, conn, region_of_elem, n_regions);
+}
+efv_mesh *efv_mesh_create_uniform(int dim, int64_t nV, const double *coords, int64_t nE, int vertices_per_element,
+                                  const int32_t *conn, const int32_t *region_of_elem, int n_regions) {
+  return mesh_create_impl(dim, nV, coords, nE, nullptr, vertices_per_element, conn, region_of_elem, n_regions);
 }
 
 int efv_mesh_set_boundaries(efv_mesh *m, int n_boundaries, const int64_t *boundary_ptr, int64_t n_facets,

@@ -47,9 +47,11 @@ template <typename T> struct DBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) EFV_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    // stream-ordered allocation from the device pool (release threshold = infinity, see runtime.cu): re-creating a
+    // mesh / system of the same size re-uses the previous blocks instead of paying cudaMalloc for multi-GB buffers
+    if (count) EFV_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), stream()));
   }
-  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void release() { if (p) cudaFreeAsync(p, stream()); p = nullptr; n = 0; }
   void zero() { if (n) EFV_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), stream())); }
   void upload(const T *host, size_t count) {
     if (n < count) alloc(count);

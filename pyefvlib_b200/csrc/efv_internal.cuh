@@ -122,7 +122,7 @@ struct efv_system {
 
 namespace efv {
 // mesh.cu
-void mesh_finalize(efv_mesh *m, const std::vector<int64_t> &elem_ptr_host);
+void mesh_finalize(efv_mesh *m, const int64_t *elem_ptr_host, int uniform_m);
 void mesh_set_boundaries(efv_mesh *m, int nB, const int64_t *boundary_ptr, int64_t nF, const int64_t *facet_ptr,
                          const int32_t *facet_conn);
 // geometry.cu

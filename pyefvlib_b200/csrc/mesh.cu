@@ -36,24 +36,42 @@ __global__ void k_sort_incidence(int64_t nV, const int64_t *__restrict__ inc_ptr
   }
 }
 
-void mesh_finalize(efv_mesh *m, const std::vector<int64_t> &ep) {
+static int code_for(int mm, int dim) {
+  if (mm == 3 && dim == 2) return EFV_TRI;
+  if (mm == 4) return (dim == 2) ? EFV_QUAD : EFV_TET;
+  if (mm == 8 && dim == 3) return EFV_HEX;
+  throw Error("This element has not been registered in Grid yet");   // Element.py:27
+}
+
+// ep: host element pointer array (nE+1) or nullptr when every element has uniform_m vertices
+void mesh_finalize(efv_mesh *m, const int64_t *ep, int uniform_m) {
   // classify shapes on the host (nE integer ops), build groups
   const int64_t nE = m->nE;
   int64_t counts[kNumShapes] = {0, 0, 0, 0};
-  std::vector<uint8_t> shape(nE);
+  std::vector<uint8_t> shape;
   m->max_m = 0;
   m->n_inner_faces = 0;
-  for (int64_t e = 0; e < nE; ++e) {
-    int mm = (int)(ep[e + 1] - ep[e]);
-    int code;
-    if (mm == 3 && m->dim == 2) code = EFV_TRI;
-    else if (mm == 4) code = (m->dim == 2) ? EFV_QUAD : EFV_TET;
-    else if (mm == 8 && m->dim == 3) code = EFV_HEX;
-    else throw Error("This element has not been registered in Grid yet");   // Element.py:27
-    shape[e] = (uint8_t)code;
-    counts[code]++;
-    m->max_m = std::max(m->max_m, mm);
-    m->n_inner_faces += shape_nf(code);
+  if (ep && !uniform_m) {               // uniform stride written out explicitly? (the common case for big meshes)
+    const int64_t m0 = ep[1] - ep[0];
+    bool same = true;
+    for (int64_t e = 0; e < nE && same; ++e) same = (ep[e + 1] - ep[e]) == m0;
+    if (same) uniform_m = (int)m0;
+  }
+  if (uniform_m) {
+    const int code = code_for(uniform_m, m->dim);
+    counts[code] = nE;
+    m->max_m = uniform_m;
+    m->n_inner_faces = nE * shape_nf(code);
+  } else {
+    shape.resize(nE);
+    for (int64_t e = 0; e < nE; ++e) {
+      int mm = (int)(ep[e + 1] - ep[e]);
+      int code = code_for(mm, m->dim);
+      shape[e] = (uint8_t)code;
+      counts[code]++;
+      m->max_m = std::max(m->max_m, mm);
+      m->n_inner_faces += shape_nf(code);
+    }
   }
   EFV_REQUIRE(nE < (int64_t(1) << 29), "mesh too large for the packed incidence (2^29 elements)");
   int nonempty = 0, last = -1;
@@ -74,7 +92,7 @@ void mesh_finalize(efv_mesh *m, const std::vector<int64_t> &ep) {
     m->elem_shape.upload(shape.data(), nE);
     m->elem_gidx.upload(gidx.data(), nE);
     m->slot_ptr.upload(slot_ptr.data(), nE + 1);
-    m->elem_ptr.upload(ep.data(), nE + 1);
+    m->elem_ptr.upload(ep, nE + 1);
     for (int c = 0; c < kNumShapes; ++c)
       if (counts[c]) m->groups[c].ids.upload(ids[c].data(), ids[c].size());
     EFV_CUDA(cudaStreamSynchronize(stream()));

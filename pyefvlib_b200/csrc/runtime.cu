@@ -25,6 +25,10 @@ static void ensure_init() {
   EFV_CUDA(cudaGetDeviceProperties(&prop, g_device));
   g_num_sms = prop.multiProcessorCount;
   EFV_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  EFV_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
+  uint64_t keep = UINT64_MAX;
+  EFV_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 }
 
 void set_device(int device) {

@@ -18,11 +18,18 @@ class DeviceMesh:
         L = _lib.load()
         self.grid = grid
         self._coords, pc = _lib.f64(grid.coords)
-        self._ep, pe = _lib.i64(grid.elem_ptr)
         self._conn, pn = _lib.i32(grid.conn)
-        self._reg, pr = _lib.i32(grid.region_of_element)
-        self.handle = _lib.check_ptr(L.efv_mesh_create(grid.dimension, grid.numberOfVertices, pc, grid.numberOfElements,
-                                                       pe, pn, pr, max(1, len(grid.regions))))
+        nreg = max(1, len(grid.regions))
+        pr = None
+        if nreg > 1:
+            self._reg, pr = _lib.i32(grid.region_of_element)
+        if grid.uniform_m:
+            self.handle = _lib.check_ptr(L.efv_mesh_create_uniform(grid.dimension, grid.numberOfVertices, pc, grid.numberOfElements,
+                                                                   grid.uniform_m, pn, pr, nreg))
+        else:
+            self._ep, pe = _lib.i64(grid.elem_ptr)
+            self.handle = _lib.check_ptr(L.efv_mesh_create(grid.dimension, grid.numberOfVertices, pc, grid.numberOfElements,
+                                                           pe, pn, pr, nreg))
         _, pb = _lib.i64(grid.boundary_ptr)
         _, pf = _lib.i64(grid.facet_ptr)
         _, pfc = _lib.i32(grid.facet_conn)

@@ -233,23 +233,26 @@ class Grid:
         self.coords = np.ascontiguousarray(np.asarray(gridData.verticesCoordinates, dtype=np.float64).reshape(-1, 3))
         self.numberOfVertices = len(self.coords)
         ec = gridData.elementsConnectivities
+        self._elem_ptr = None
         if isinstance(ec, np.ndarray) and ec.ndim == 2:
             self.numberOfElements, m = ec.shape
-            self.elem_ptr = np.arange(self.numberOfElements + 1, dtype=np.int64) * m
+            self.uniform_m = int(m)                      # elem_ptr is implicit (built lazily if somebody asks)
             self.conn = np.ascontiguousarray(ec, dtype=np.int32).ravel()
+            _shapes.shape_code_for(self.uniform_m, self.dimension)                       # raises like Element.py:27
         else:
             self.numberOfElements = len(ec)
             lens = np.fromiter((len(c) for c in ec), dtype=np.int64, count=len(ec))
-            self.elem_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-            self.conn = np.fromiter((v for c in ec for v in c), dtype=np.int32, count=int(self.elem_ptr[-1]))
-        lens = np.diff(self.elem_ptr)
-        for m in np.unique(lens):
-            _shapes.shape_code_for(int(m), self.dimension)                               # raises like Element.py:27
+            self._elem_ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            self.conn = np.fromiter((v for c in ec for v in c), dtype=np.int32, count=int(self._elem_ptr[-1]))
+            for m in np.unique(lens):
+                _shapes.shape_code_for(int(m), self.dimension)
+            self.uniform_m = int(lens[0]) if len(np.unique(lens)) == 1 else 0
         self.region_of_element = np.zeros(self.numberOfElements, dtype=np.int32)
         self.regions = []
         for h, (idx, name) in enumerate(zip(gridData.regionsElementsIndexes, gridData.regionsNames)):
             idx = np.asarray(idx, dtype=np.int64)
-            self.region_of_element[idx] = h
+            if h > 0:
+                self.region_of_element[idx] = h
             self.regions.append(Region(self, idx, name, h))
         bcs = gridData.boundariesConnectivities
         if isinstance(bcs, np.ndarray) and bcs.ndim == 2:
@@ -274,6 +277,12 @@ class Grid:
         self.vertices = _Seq(self.numberOfVertices, lambda k: _VertexView(self, k))
         self.elements = _Seq(self.numberOfElements, lambda k: _ElementView(self, k))
         self._device = None
+
+    @property
+    def elem_ptr(self):
+        if self._elem_ptr is None:
+            self._elem_ptr = np.arange(self.numberOfElements + 1, dtype=np.int64) * self.uniform_m
+        return self._elem_ptr
 
     # -- element groups by shape (grid order inside each group) ---------------------------------------------
     def shape_groups(self):
