@@ -164,9 +164,10 @@ __global__ void k_sell_widths(int64_t nrows, const int64_t *__restrict__ gptr, i
     if (lane == 0) width[slice] = len;
   }
 }
-__global__ void k_sell_fill(int64_t nrows, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
+__global__ void k_sell_fill(int64_t nrows, int B, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
                             const double *__restrict__ vals, const int64_t *__restrict__ off, int32_t *__restrict__ scol,
                             double *__restrict__ sval) {
+  // block rows (vertices) of a slice are the lanes; values of entry k are stored as B consecutive 32-lane columns
   int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int64_t nslices = (nrows + 31) >> 5;
@@ -176,11 +177,11 @@ __global__ void k_sell_fill(int64_t nrows, const int64_t *__restrict__ gptr, con
     const int64_t r0 = valid ? gptr[v] : 0;
     const int len = valid ? (int)(gptr[v + 1] - r0) : 0;
     const int width = (int)(off[slice + 1] - off[slice]);
-    const int64_t base = off[slice] * 32 + lane;
+    const int64_t o0 = off[slice];
     for (int k = 0; k < width; ++k) {
       const bool in = k < len;
-      scol[base + (int64_t)k * 32] = in ? gcol[r0 + k] : (int32_t)(valid ? v : 0);   // padding: zero times a valid x entry
-      sval[base + (int64_t)k * 32] = in ? vals[r0 + k] : 0.0;
+      scol[(o0 + k) * 32 + lane] = in ? gcol[r0 + k] : (int32_t)(valid ? v : 0);   // padding: zero times a valid x entry
+      for (int q = 0; q < B; ++q) sval[((o0 + k) * B + q) * 32 + lane] = in ? vals[(r0 + k) * B + q] : 0.0;
     }
   }
 }
@@ -229,9 +230,68 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(int64_t nrows, const int64
   }
 }
 
+// block version: lane = block row (vertex), NDOF outputs per lane, one entry = one column index + NDOF*NDOF values
+template <int NDOF, int U>
+__global__ void __launch_bounds__(kBlock) k_spmv_sell_bsr(int64_t nrows, const int64_t *__restrict__ off,
+                                                          const int32_t *__restrict__ scol, const double *__restrict__ sval,
+                                                          const double *__restrict__ x, double *__restrict__ y, double sigma,
+                                                          const double *__restrict__ rowscale, const double *__restrict__ w,
+                                                          double *__restrict__ partial, const int *__restrict__ done) {
+  constexpr int B = NDOF * NDOF;
+  __shared__ double red[32];
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dot = 0.0;
+  for (int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; slice < nslices; slice += warps) {
+    const int64_t o0 = off[slice];
+    const int width = (int)(off[slice + 1] - o0);
+    double acc[NDOF];
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
+    for (int k = 0; k < width; k += U) {
+      int cc[U];
+      double vv[U][B];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool ok = k + u < width;
+        cc[u] = ok ? __ldcs(scol + (o0 + k + u) * 32 + lane) : -1;
+#pragma unroll
+        for (int q = 0; q < B; ++q) vv[u][q] = ok ? __ldcs(sval + ((o0 + k + u) * B + q) * 32 + lane) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (cc[u] >= 0) {
+          double xv[NDOF];
+#pragma unroll
+          for (int j = 0; j < NDOF; ++j) xv[j] = __ldg(x + (int64_t)cc[u] * NDOF + j);
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+            for (int j = 0; j < NDOF; ++j) acc[i] += vv[u][i * NDOF + j] * xv[j];
+        }
+      }
+    }
+    const int64_t v = slice * 32 + lane;
+    if (v < nrows) {
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) {
+        double yi = sigma * acc[i];
+        if (rowscale) yi *= rowscale[v * NDOF + i];
+        y[v * NDOF + i] = yi;
+        if (w) dot += w[v * NDOF + i] * yi;
+      }
+    }
+  }
+  if (partial) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+  }
+}
+
 // (re)build the SELL copy if the values changed; returns whether the SELL path should be used
 static bool sell_prepare(efv_system *s, KrylovWork *w) {
-  if (s->ndof != 1) return false;
   const char *fmt = getenv("EFV_SPMV_FORMAT");
   if (fmt && strcmp(fmt, "csr") == 0) { w->sell_use = false; return false; }
   w->sell_use = true;
@@ -260,10 +320,10 @@ static bool sell_prepare(efv_system *s, KrylovWork *w) {
     w->sell_ok = force || padded <= 1.2 * (double)nnz_owned;      // irregular rows: stay on CSR
     if (!w->sell_ok) { w->sell_cols.release(); w->sell_vals.release(); return false; }
     w->sell_cols.alloc((size_t)cols32 * 32);
-    w->sell_vals.alloc((size_t)cols32 * 32);
+    w->sell_vals.alloc((size_t)cols32 * 32 * s->ndof * s->ndof);
   }
   if (!w->sell_ok) return false;
-  EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->gptr.p, s->gcol.p, s->vals.p, w->sell_off.p,
+  EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->ndof * s->ndof, s->gptr.p, s->gcol.p, s->vals.p, w->sell_off.p,
              w->sell_cols.p, w->sell_vals.p);
   return true;
 }
@@ -308,20 +368,23 @@ static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, d
 static void launch_spmv(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
                         const double *w, double *partial, const int *done) {
   KrylovWork *kw = s->kw;
-  if (kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned && s->ndof == 1) {
-    const char *eu = getenv("EFV_SELL_UNROLL");
-    const int U = eu ? atoi(eu) : 8;
-#define EFV_SELL_CASE(UU)                                                                                                  \
-  EFV_LAUNCH(k_spmv_sell<UU>, grid, kBlock, 0, s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, y, sigma, \
-             rowscale, w, partial, done)
-    switch (U) {
-      case 4: EFV_SELL_CASE(4); break;
-      case 7: EFV_SELL_CASE(7); break;
-      case 9: EFV_SELL_CASE(9); break;
-      case 14: EFV_SELL_CASE(14); break;
-      default: EFV_SELL_CASE(8); break;
+  if (kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned) {
+#define EFV_SELL_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done
+    if (s->ndof == 1) {
+      const char *eu = getenv("EFV_SELL_UNROLL");
+      switch (eu ? atoi(eu) : 8) {
+        case 4: EFV_LAUNCH(k_spmv_sell<4>, grid, kBlock, 0, EFV_SELL_ARGS); break;
+        case 9: EFV_LAUNCH(k_spmv_sell<9>, grid, kBlock, 0, EFV_SELL_ARGS); break;
+        default: EFV_LAUNCH(k_spmv_sell<8>, grid, kBlock, 0, EFV_SELL_ARGS); break;
+      }
+    } else if (s->ndof == 2) {
+      EFV_LAUNCH((k_spmv_sell_bsr<2, 4>), grid, kBlock, 0, EFV_SELL_ARGS);
+    } else if (s->ndof == 3) {
+      EFV_LAUNCH((k_spmv_sell_bsr<3, 2>), grid, kBlock, 0, EFV_SELL_ARGS);
+    } else {
+      EFV_LAUNCH((k_spmv_sell_bsr<4, 2>), grid, kBlock, 0, EFV_SELL_ARGS);
     }
-#undef EFV_SELL_CASE
+#undef EFV_SELL_ARGS
     return;
   }
   switch (s->ndof) {
