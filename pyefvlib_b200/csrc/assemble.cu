@@ -8,6 +8,8 @@
 // the byte slot map.  Every CSR entry is therefore summed by exactly one lane group in a fixed order: no float
 // atomics, bit-reproducible, values written with coalesced stores.  (apps/heat_transfer.py:41-68)
 #include "views.cuh"
+#include <cstdlib>
+#include <cstring>
 
 namespace efv {
 
@@ -103,8 +105,8 @@ __global__ void __launch_bounds__(256) k_heat_rows(MeshView m, GeomView g, SysVi
       const int64_t p = pc + gl;
       if (p < p1) {
         const uint32_t pk = m.inc[p];
-        const int64_t e = pk >> 3;
-        const int l = pk & 7;
+        const int64_t e = inc_elem(pk);
+        const int l = inc_local(pk);
         const int code = (UCODE >= 0) ? UCODE : m.code(e);
         const int mm = shape_m(code), nvf = shape_nvf(code), d = shape_dim(code);
         const int64_t gi = (UCODE >= 0) ? e : m.group_index(e);
@@ -191,6 +193,138 @@ __global__ void __launch_bounds__(256) k_heat_rows(MeshView m, GeomView g, SysVi
   }
 }
 
+// ---- two-phase assembly for uniform meshes (EFV_ASSEMBLY=two_phase; measured slower than the fused row kernel) ---------------------------------------------------------
+// Phase A `k_heat_local`: one thread per element of an element batch, fully unrolled: the 12 (hex) face vectors J^-T s
+// are streamed from the SoA, the table entries are constant-bank operands, the M x M local matrix lives in registers
+// and is written component-major (coalesced) into a scratch array  Ke[(i*M+j)][e].
+// Phase B `k_local_to_csr`: deterministic segmented reduction through the slot map.  An 8-lane group owns a CSR row; for
+// a chunk of up to 8 (element, local vertex) pairs of the row every lane first issues ALL its loads (pair ids, its own
+// entry Ke[l][j] of each pair, the slot byte), then adds them to the shared-memory row in (l, element) order and writes
+// the row with coalesced stores (plus the lumped vectors and the Dirichlet epilogue).  No float atomics anywhere.
+template <class Tab>
+__global__ void __launch_bounds__(128) k_heat_local(int64_t n, const int32_t *__restrict__ region, const double *__restrict__ props,
+                                                    const double *__restrict__ St, double *__restrict__ Ke) {
+  constexpr int M = Tab::M, D = Tab::DIM, NF = Tab::NF;
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const double cond = props[3 * region[e]];
+  double K[M][M];
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) K[i][j] = 0.0;
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    double t[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) t[a] = cond * St[(int64_t)(f * D + a) * n + e];
+    constexpr int dummy = 0; (void)dummy;
+    const int b = Tab::nbr(f, 0), fw = Tab::nbr(f, 1);
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      double w = 0.0;
+#pragma unroll
+      for (int a = 0; a < D; ++a) w += Tab::ifD(f, j, a) * t[a];       // k * G^T s  (heat_transfer.py:47)
+      K[b][j] -= w;                                                    // heat_transfer.py:52-54
+      K[fw][j] += w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i)
+#pragma unroll
+    for (int j = 0; j < M; ++j) Ke[(int64_t)(i * M + j) * n + e] = K[i][j];
+}
+
+template <class Tab>
+__global__ void __launch_bounds__(256) k_local_to_csr(MeshView m, SysView s, int64_t n, const double *__restrict__ Ke,
+                                                      const double *__restrict__ vol, const double *__restrict__ props,
+                                                      int transient, int max_row_len, int dir_mode,
+                                                      const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
+                                                      double *__restrict__ gen_out, double *__restrict__ acc_out,
+                                                      double *__restrict__ elim_out) {
+  constexpr int M = Tab::M, GROUP = 8, ROWS = 256 / GROUP;
+  extern __shared__ double smem_dyn[];
+  const int grp = threadIdx.x / GROUP, gl = threadIdx.x % GROUP;
+  double *row = smem_dyn + (size_t)grp * max_row_len;
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) / GROUP * GROUP);
+  const int jl = gl < M ? gl : 0;
+  for (int64_t v0 = (int64_t)blockIdx.x * ROWS; v0 < s.nV; v0 += (int64_t)gridDim.x * ROWS) {
+    const int64_t v = v0 + grp;
+    if (v >= s.nV) continue;
+    const int64_t r0 = s.gptr[v];
+    const int len = (int)(s.gptr[v + 1] - r0);
+    for (int t = gl; t < len; t += GROUP) row[t] = 0.0;
+    __syncwarp(gmask);
+    double gen = 0.0, accv = 0.0;
+    const int64_t p0 = m.inc_ptr[v], p1 = m.inc_ptr[v + 1];
+    for (int64_t pc = p0; pc < p1; pc += GROUP) {
+      uint32_t pk[GROUP];
+      double val[GROUP], vq[GROUP];
+      int pos[GROUP], reg[GROUP];
+#pragma unroll
+      for (int q = 0; q < GROUP; ++q) pk[q] = (pc + q < p1) ? m.inc[pc + q] : 0xffffffffu;
+#pragma unroll
+      for (int q = 0; q < GROUP; ++q) {
+        const bool ok = pk[q] != 0xffffffffu;
+        const int64_t e = ok ? inc_elem(pk[q]) : 0;
+        const int l = ok ? inc_local(pk[q]) : 0;
+        val[q] = ok ? __ldcs(Ke + (int64_t)(l * M + jl) * n + e) : 0.0;
+        pos[q] = ok ? (int)s.slotpos[e * (int64_t)(M * M) + l * M + jl] : 0;
+        vq[q] = (ok && gl == 0) ? vol[(int64_t)l * n + e] : 0.0;
+        reg[q] = (ok && gl == 0) ? m.region[e] : 0;
+      }
+#pragma unroll
+      for (int q = 0; q < GROUP; ++q) {
+        if (pk[q] != 0xffffffffu) {
+          if (gl < M) row[pos[q]] += val[q];
+          if (gl == 0) { gen += vq[q] * props[3 * reg[q] + 2]; accv += vq[q] * props[3 * reg[q] + 1]; }
+        }
+        __syncwarp(gmask);
+      }
+    }
+    if (gl == 0) {
+      if (transient) row[s.diag_slot[v] - r0] += accv;       // heat_transfer.py:62-67
+      gen_out[v] = gen;
+      acc_out[v] = accv;
+    }
+    __syncwarp(gmask);
+    if (dir_mode < 0) {
+      for (int t = gl; t < len; t += GROUP) s.vals[r0 + t] = row[t];
+    } else {
+      const bool rowd = dflag[v];
+      double el = 0.0;
+      for (int t = gl; t < len; t += GROUP) {
+        const int c = s.gcol[r0 + t];
+        double a = row[t];
+        if (rowd) a = (c == v) ? 1.0 : 0.0;                    // heat_transfer.py:70-76
+        else if (dir_mode == 1 && dflag[c]) { el -= a * dval[c]; a = 0.0; }
+        s.vals[r0 + t] = a;
+      }
+      if (dir_mode == 1) {
+#pragma unroll
+        for (int o = GROUP / 2; o > 0; o >>= 1) el += __shfl_xor_sync(gmask, el, o);
+        if (gl == 0) elim_out[v] = rowd ? 0.0 : el;
+      }
+    }
+    __syncwarp(gmask);
+  }
+}
+
+template <class Tab>
+static void launch_heat_two_phase(efv_system *s, const double *dprops, int transient) {
+  efv_mesh *m = s->mesh;
+  constexpr int M = Tab::M;
+  const int64_t n = m->nE;
+  if (s->scratch.n < (size_t)n * M * M) s->scratch.alloc((size_t)n * M * M);
+  GeomView g = geom_of(m);
+  EFV_LAUNCH(k_heat_local<Tab>, (unsigned)div_up(n, 128), 128, 0, n, m->region.p, dprops, g.St[Tab::CODE], s->scratch.p);
+  size_t smem = (size_t)(256 / 8) * s->max_row_len * sizeof(double);
+  EFV_CUDA(cudaFuncSetAttribute(k_local_to_csr<Tab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EFV_LAUNCH(k_local_to_csr<Tab>, grid_for(s->n_owned * 8, 256, 8), 256, smem, view_of(m), sys_view(s), n, s->scratch.p,
+             g.vol[Tab::CODE], dprops, transient, s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p,
+             s->elim.p);
+}
+
 template <int UCODE>
 static void launch_heat_rows(efv_system *s, const double *dprops, int transient) {
   efv_mesh *m = s->mesh;
@@ -220,12 +354,26 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
   if (!s->gen.n) { s->gen.alloc(s->nV); s->acc.alloc(s->nV); }
   if (!s->ev0) { EFV_CUDA(cudaEventCreate(&s->ev0)); EFV_CUDA(cudaEventCreate(&s->ev1)); }
   EFV_CUDA(cudaEventRecord(s->ev0, stream()));
-  switch (m->uniform_code) {
-    case 0: launch_heat_rows<0>(s, s->props_dev.p, transient); break;
-    case 1: launch_heat_rows<1>(s, s->props_dev.p, transient); break;
-    case 2: launch_heat_rows<2>(s, s->props_dev.p, transient); break;
-    case 3: launch_heat_rows<3>(s, s->props_dev.p, transient); break;
-    default: launch_heat_rows<-1>(s, s->props_dev.p, transient); break;
+  // default: the fused row kernel (k_heat_rows).  EFV_ASSEMBLY=two_phase selects the element-batch kernel + segmented
+  // reduction (k_heat_local + k_local_to_csr) on uniform meshes: same values to the last bit, 10.9 ms vs 8.1 ms at C2
+  // (profiles/r01_assembly_variants.json) because the reduction phase is latency-bound.
+  const char *mode = getenv("EFV_ASSEMBLY");
+  const bool two_phase = mode && strcmp(mode, "two_phase") == 0 && m->uniform_code >= 0;
+  if (two_phase) {
+    switch (m->uniform_code) {
+      case 0: launch_heat_two_phase<TriangleTab>(s, s->props_dev.p, transient); break;
+      case 1: launch_heat_two_phase<QuadrilateralTab>(s, s->props_dev.p, transient); break;
+      case 2: launch_heat_two_phase<TetrahedronTab>(s, s->props_dev.p, transient); break;
+      default: launch_heat_two_phase<HexahedronTab>(s, s->props_dev.p, transient); break;
+    }
+  } else {
+    switch (m->uniform_code) {
+      case 0: launch_heat_rows<0>(s, s->props_dev.p, transient); break;
+      case 1: launch_heat_rows<1>(s, s->props_dev.p, transient); break;
+      case 2: launch_heat_rows<2>(s, s->props_dev.p, transient); break;
+      case 3: launch_heat_rows<3>(s, s->props_dev.p, transient); break;
+      default: launch_heat_rows<-1>(s, s->props_dev.p, transient); break;
+    }
   }
   EFV_CUDA(cudaEventRecord(s->ev1, stream()));
   s->assemble_timed = true;
@@ -269,8 +417,8 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
       const int64_t p = pc + gl;
       if (p < p1) {
         const uint32_t pk = m.inc[p];
-        const int64_t e = pk >> 3;
-        const int l = pk & 7;
+        const int64_t e = inc_elem(pk);
+        const int l = inc_local(pk);
         const int code = (UCODE >= 0) ? UCODE : m.code(e);
         const int mm = shape_m(code), nvf = shape_nvf(code), d = shape_dim(code);
         const int64_t gi = (UCODE >= 0) ? e : m.group_index(e);
@@ -505,8 +653,8 @@ __global__ void __launch_bounds__(64) k_biot_rows(MeshView m, GeomView g, SysVie
       const int64_t p = pc + gl;
       if (p < p1) {
         const uint32_t pk = m.inc[p];
-        const int64_t e = pk >> 3;
-        const int l = pk & 7;
+        const int64_t e = inc_elem(pk);
+        const int l = inc_local(pk);
         const int code = (UCODE >= 0) ? UCODE : m.code(e);
         const int mm = shape_m(code), nvf = shape_nvf(code);
         const int64_t gi = (UCODE >= 0) ? e : m.group_index(e);

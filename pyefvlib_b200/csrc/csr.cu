@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_graph_rows(MeshView m, int32
     int n = 0;
     int64_t p0 = m.inc_ptr[v], p1 = m.inc_ptr[v + 1];
     for (int64_t p = p0; p < p1; ++p) {
-      int64_t e = m.inc[p] >> 3;
+      int64_t e = inc_elem(m.inc[p]);
       int mm = shape_m(m.code(e));
       int64_t b = m.begin(e);
       if (n + mm > kMaxCand) { if (lane == 0) atomicExch(error_flag, 1); break; }

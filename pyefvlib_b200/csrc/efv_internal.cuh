@@ -116,6 +116,7 @@ struct efv_system {
   efv::KrylovWork *kw = nullptr;
   double t_assemble_ms = 0, t_solve_ms = 0, t_spmv_ms = 0;
   efv::DBuf<double> props_dev;
+  efv::DBuf<double> scratch;            // local element matrices of the two-phase assembly, component-major
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // assembly timing (read lazily: no host sync in the hot path)
   bool assemble_timed = false;
 };

@@ -142,8 +142,8 @@ __global__ void k_vertex_volume(MeshView m, GeomView g, double *__restrict__ vv)
     double acc = 0.0;
     for (int64_t p = m.inc_ptr[v]; p < m.inc_ptr[v + 1]; ++p) {
       uint32_t pk = m.inc[p];
-      int64_t e = pk >> 3;
-      int l = pk & 7;
+      int64_t e = inc_elem(pk);
+      int l = inc_local(pk);
       int code = m.code(e);
       acc += g.vol[code][(int64_t)l * g.n[code] + m.group_index(e)];
     }

@@ -18,12 +18,12 @@ __global__ void k_fill_incidence(MeshView m, int32_t *__restrict__ cursor, uint3
     for (int l = 0; l < mm; ++l) {
       int v = m.conn[b + l];
       int pos = atomicAdd(&cursor[v], 1);
-      inc[m.inc_ptr[v] + pos] = ((uint32_t)e << 3) | (uint32_t)l;
+      inc[m.inc_ptr[v] + pos] = inc_pack(e, l);
     }
   }
 }
 
-// deterministic order: ascending (element, local) inside every vertex list
+// deterministic order: ascending (local vertex, element) inside every vertex list
 __global__ void k_sort_incidence(int64_t nV, const int64_t *__restrict__ inc_ptr, uint32_t *__restrict__ inc) {
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nV; v += (int64_t)gridDim.x * blockDim.x) {
     int64_t a = inc_ptr[v], b = inc_ptr[v + 1];
@@ -73,7 +73,7 @@ void mesh_finalize(efv_mesh *m, const int64_t *ep, int uniform_m) {
       m->n_inner_faces += shape_nf(code);
     }
   }
-  EFV_REQUIRE(nE < (int64_t(1) << 29), "mesh too large for the packed incidence (2^29 elements)");
+  EFV_REQUIRE(nE < (int64_t(1) << kIncShift), "mesh too large for the packed incidence (2^29 elements)");
   int nonempty = 0, last = -1;
   for (int c = 0; c < kNumShapes; ++c)
     if (counts[c]) { nonempty++; last = c; }
@@ -152,19 +152,24 @@ __global__ void k_match_facets(MeshView m, int64_t nF, const int64_t *__restrict
     // owner search through the incidence list of the first facet vertex (ascending element id)
     int64_t owner = -1;
     int loc[4] = {0, 0, 0, 0};
-    for (int64_t p = m.inc_ptr[fv[0]]; p < m.inc_ptr[fv[0] + 1] && owner < 0; ++p) {
-      int64_t e = m.inc[p] >> 3;
+    for (int64_t p = m.inc_ptr[fv[0]]; p < m.inc_ptr[fv[0] + 1]; ++p) {
+      int64_t e = inc_elem(m.inc[p]);
+      if (owner >= 0 && e > owner) continue;          // keep the FIRST element in grid order (Boundary.py:37-41)
       int64_t b = m.begin(e);
       int mm = shape_m(m.code(e));
+      int cand[4] = {0, 0, 0, 0};
       bool all = true;
       for (int k = 0; k < mf && all; ++k) {
         int where = -1;
         for (int j = 0; j < mm; ++j)
           if (m.conn[b + j] == fv[k]) where = j;
-        loc[k] = where;
+        cand[k] = where;
         all &= (where >= 0);
       }
-      if (all) owner = e;
+      if (all) {
+        owner = e;
+        for (int k = 0; k < 4; ++k) loc[k] = cand[k];
+      }
     }
     if (owner < 0) { atomicExch(error_flag, 1); continue; }
     int code = m.code(owner);

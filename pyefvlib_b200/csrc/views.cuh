@@ -25,6 +25,13 @@ struct MeshView {
   }
 };
 
+// packed incidence entry: local vertex in the top 3 bits, element id below => a vertex list sorted ascending is ordered by
+// (local vertex, element): the deterministic reduction order of the row kernels (independent of the partition)
+constexpr int kIncShift = 29;
+__host__ __device__ __forceinline__ uint32_t inc_pack(int64_t e, int l) { return ((uint32_t)l << kIncShift) | (uint32_t)e; }
+__host__ __device__ __forceinline__ int64_t inc_elem(uint32_t pk) { return (int64_t)(pk & ((1u << kIncShift) - 1u)); }
+__host__ __device__ __forceinline__ int inc_local(uint32_t pk) { return (int)(pk >> kIncShift); }
+
 __host__ __device__ constexpr __forceinline__ int shape_m(int code) { return code == 0 ? 3 : (code == 3 ? 8 : 4); }
 __host__ __device__ constexpr __forceinline__ int shape_nf(int code) { return code == 0 ? 3 : (code == 1 ? 4 : (code == 2 ? 6 : 12)); }
 __host__ __device__ constexpr __forceinline__ int shape_dim(int code) { return code < 2 ? 2 : 3; }

@@ -259,6 +259,7 @@ def generate_cuda_tables():
             f"  __device__ static __forceinline__ int facetV(int f, int k) {{ return c_{n}_facetV[f][k]; }}",
             f"  __device__ static __forceinline__ double ofN(int f, int k, int j) {{ return c_{n}_ofN[f][k][j]; }}",
             f"  __device__ static __forceinline__ int vface(int l, int k) {{ return c_{n}_vface[l][k]; }}",
+            f"  __host__ __device__ static constexpr int vface_c(int l, int k) {{ constexpr int T[{m}][{nvf}] = {_c_array(vf, fi).replace(chr(10), '')}; return T[l][k]; }}",
             "};",
             "",
         ]

@@ -1,0 +1,31 @@
+"""Time the heat assembly variants (EFV_ASSEMBLY = two_phase | rows | generic) on the C2 mesh and check they agree."""
+import os, sys, json
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pyefvlib_b200 as P
+from pyefvlib_b200.device import DeviceSystem, DIRICHLET_SYMMETRIC
+import bench
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 216
+kind = sys.argv[2] if len(sys.argv) > 2 else "hex"
+grid = P.structured_grid(n, kind)
+s = DeviceSystem(grid, 1)
+props = np.array([[1.0, 1.0, 1.0, 100.0]])
+bench.send_bcs(s, grid)
+s.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
+ref = None
+out = {}
+for mode in ("rows", "two_phase"):   # "rows" = anything but two_phase = the default fused row kernel
+    os.environ["EFV_ASSEMBLY"] = mode
+    ts = []
+    for _ in range(4):
+        s.heat_assemble(props, 1e-2, True)
+        ts.append(s.timings()["assemble_ms"])
+    vals = s.values()
+    if ref is None:
+        ref = vals
+    err = float(np.abs(vals - ref).max() / np.abs(ref).max())
+    out[mode] = dict(ms=min(ts[1:]), max_rel_diff_vs_default=err)
+    print(mode, ts, err, flush=True)
+nE = grid.numberOfElements
+print(json.dumps(dict(n=n, kind=kind, elements=nE, **{k: v for k, v in out.items()})))
