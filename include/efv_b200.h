@@ -134,6 +134,17 @@ int efv_apply_dirichlet(efv_system *s, int mode);
  * [ref: apps/geomechanics.py:166-239].  In symmetric mode the eliminated columns are folded in.            */
 int efv_build_rhs(efv_system *s, int transient);
 
+/* ---- fixed-stress split [ref: apps/fixed_stress.py:39-329] ------------------------------------------------------------
+ * Three systems on one mesh: `biot` (d+1 DOF, efv_biot_assemble with Dirichlet mode -1: the unmodified coupled operator;
+ * X = current iterate (u_k, p_k), XOLD = previous time step), `mass` (1 DOF: efv_heat_assemble with Conductivity = k*mu,
+ * Density*HeatCapacity = S + cb*alpha^2, transient dt [ref: :64-77]) and `geo` (d DOF: efv_elasticity_assemble [ref: :80-92]).
+ *   efv_fs_mass_rhs : mass.B = S/dt vol p_prev + cb alpha^2/dt vol p_k + A_pu (u_prev - u_k) + Neumann; Dirichlet <- g [ref: :119-199]
+ *   efv_fs_geo_rhs  : geo.B  = - A_up p_next (= mass.X) + Neumann; Dirichlet <- g                                    [ref: :201-275]
+ *   efv_fs_update   : difference = max(|p_next - p_k|, |u_next - u_k|); (u_k, p_k) <- (geo.X, mass.X)                [ref: :298-303] */
+int efv_fs_mass_rhs(efv_system *biot, efv_system *mass);
+int efv_fs_geo_rhs(efv_system *biot, efv_system *mass, efv_system *geo);
+int efv_fs_update(efv_system *biot, efv_system *mass, efv_system *geo, double *difference);
+
 /* ---- multi-GPU: vertex-block partition with owned + ghost vertices (the reference has no
  * distributed code).  One process per GPU.  The unique id is created on rank 0 and distributed by the host layer
  * (torch.distributed); nccl_library_path names the NCCL shared object to dlopen (NULL: default search).  A partitioned

@@ -653,6 +653,103 @@ def biot_system(grid, props, bcs, dt, u_old, p_old, g_vec=None):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# fixed-stress split  (apps/fixed_stress.py:39-329)
+# ---------------------------------------------------------------------------------------------------------
+def fixed_stress_operators(grid, props, bcs, dt):
+    """Mass (p) and geo (u) matrices of fixed_stress.py:39-117 plus the coupling blocks its right-hand sides apply
+    (:163-184 mass, :239-248 geo).  All of them are blocks of the coupled Biot operator (same element terms), except the
+    extra  cb alpha^2 / dt  vol  on the mass diagonal (:68)."""
+    d, nV = grid.dimension, grid.numberOfVertices
+    names = (["u_x", "u_y", "u_z"][:d]) + ["p"]
+    free = {v: {b.name: ("neumann", 0.0) for b in grid.boundaries} for v in names}
+    A, _ = biot_system(grid, props, free, dt, np.zeros(d * nV), np.zeros(nV))        # no Dirichlet rows: raw operator
+    A = sp.csr_matrix(A)
+    P0 = d * nV
+    Auu, Aup, Apu, App = A[:P0, :P0], A[:P0, P0:], A[P0:, :P0], A[P0:, P0:]
+    par_r = _region_param(grid, props, lambda p: biot_params(p, d))
+    accS, accC = np.zeros(nV), np.zeros(nV)
+    for g in grid.groups:
+        reg = grid.region_of_element[g.ids]
+        S = np.array([par_r[r]["S"] for r in reg])
+        # cb = 1/K with the precedence quirk of K (fixed_stress.py:60-61)
+        K = np.array([2 * props[grid.gridData.regionsNames[r]]["G"] * (1 + props[grid.gridData.regionsNames[r]]["nu"]) / 3 *
+                      (1 - 2 * props[grid.gridData.regionsNames[r]]["nu"]) for r in reg])
+        alpha = np.array([par_r[r]["alpha"] for r in reg])
+        np.add.at(accS, g.conn.ravel(), (g.vol * (S / dt)[:, None]).ravel())
+        np.add.at(accC, g.conn.ravel(), (g.vol * ((1 / K) * (1 / dt) * alpha ** 2)[:, None]).ravel())
+    mass = sp.lil_matrix(App + sp.diags(accC))
+    geo = sp.lil_matrix(Auu)
+    dir_p = np.zeros(nV, dtype=bool)
+    dir_u = np.zeros(P0, dtype=bool)
+    for bd in grid.boundaries:
+        if bcs["p"][bd.name][0] == "dirichlet":
+            dir_p[bd.vertices] = True
+        for i, var in enumerate(names[:d]):
+            if bcs[var][bd.name][0] == "dirichlet":
+                dir_u[bd.vertices + i * nV] = True
+    mass = sp.csr_matrix(mass)
+    geo = sp.csr_matrix(geo)
+    keep_p = sp.diags((~dir_p).astype(float))
+    keep_u = sp.diags((~dir_u).astype(float))
+    mass = keep_p @ mass + sp.diags(dir_p.astype(float))                               # fixed_stress.py:109-112
+    geo = keep_u @ geo + sp.diags(dir_u.astype(float))                                 # fixed_stress.py:94-107
+    return dict(mass=sp.csr_matrix(mass), geo=sp.csr_matrix(geo), Aup=Aup, Apu=Apu, accS=accS, accC=accC)
+
+
+def fixed_stress_mass_rhs(grid, ops, bcs, p_prev, u_prev, p_k, u_k):
+    """fixed_stress.py:119-199 (gravity vector is zero in the reference)."""
+    b = ops["accS"] * p_prev + ops["accC"] * p_k + ops["Apu"] @ (u_prev - u_k)
+    for bd in grid.boundaries:
+        kind, val = bcs["p"][bd.name]
+        if kind == "neumann":
+            np.add.at(b, bd.outer_vertex, float(val) * np.linalg.norm(bd.outer_area, axis=1))
+    for bd in grid.boundaries:
+        kind, val = bcs["p"][bd.name]
+        if kind == "dirichlet":
+            b[bd.vertices] = float(val)
+    return b
+
+
+def fixed_stress_geo_rhs(grid, ops, bcs, p_next):
+    """fixed_stress.py:201-275."""
+    d, nV = grid.dimension, grid.numberOfVertices
+    b = -(ops["Aup"] @ p_next)
+    names = ["u_x", "u_y", "u_z"][:d]
+    for i, var in enumerate(names):
+        for bd in grid.boundaries:
+            kind, val = bcs[var][bd.name]
+            if kind == "neumann":
+                np.add.at(b, bd.outer_vertex + i * nV, float(val) * np.linalg.norm(bd.outer_area, axis=1))
+    for i, var in enumerate(names):
+        for bd in grid.boundaries:
+            kind, val = bcs[var][bd.name]
+            if kind == "dirichlet":
+                b[bd.vertices + i * nV] = float(val)
+    return b
+
+
+def fixed_stress_run(grid, props, bcs, dt, steps, tolerance):
+    """Time loop of fixed_stress.py:284-329 with direct solves; returns per time step (u, p, inner iterations)."""
+    d, nV = grid.dimension, grid.numberOfVertices
+    ops = fixed_stress_operators(grid, props, bcs, dt)
+    lu_m, lu_g = spla.splu(sp.csc_matrix(ops["mass"])), spla.splu(sp.csc_matrix(ops["geo"]))
+    p_prev, u_prev = np.zeros(nV), np.zeros(d * nV)
+    out = []
+    for _ in range(steps):
+        p_k, u_k = p_prev.copy(), u_prev.copy()
+        difference, it = 2 * tolerance, 0
+        while difference >= tolerance or it <= 1:
+            p_n = lu_m.solve(fixed_stress_mass_rhs(grid, ops, bcs, p_prev, u_prev, p_k, u_k))
+            u_n = lu_g.solve(fixed_stress_geo_rhs(grid, ops, bcs, p_n))
+            difference = max(np.abs(p_n - p_k).max(), np.abs(u_n - u_k).max())
+            p_k, u_k = p_n, u_n
+            it += 1
+        p_prev, u_prev = p_k.copy(), u_k.copy()
+        out.append((u_k.copy(), p_k.copy(), it))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
 # solves  (heat_transfer.py:78-81,134-135 ; stress_equilibrium.py:170-173 ; geomechanics.py:140,254)
 # ---------------------------------------------------------------------------------------------------------
 def solve_direct(A, b):

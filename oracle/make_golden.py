@@ -287,6 +287,59 @@ def biot_case(mesh, props, bcs, tag, dt=20.0, steps=2):
     print(f"biot_{tag}: n={len(b)} A {merr:.1e} b {berr:.1e} u {uerr:.1e} p {perr:.1e} ({time.time()-t0:.1f}s)")
 
 
+def fixed_stress_case(mesh, props, bcs, tag, dt=20.0, steps=2, tolerance=1e-4):
+    t0 = time.time()
+    path = R.mesh_path(mesh)
+    gd = P.MSHReader(path).getData()
+    d = gd.dimension
+    variables = ["u_x", "u_y", "u_z"][:d] + ["p"]
+    pd = P.ProblemData(meshFilePath=path, outputFilePath="tmp/efv_golden",
+                       numericalSettings=P.NumericalSettings(timeStep=dt, finalTime=dt * steps - 1e-9, tolerance=tolerance, maxNumberOfIterations=10 ** 9),
+                       propertyData=P.PropertyData(props),
+                       boundaryConditions=P.BoundaryConditions(bc_dict(bcs, gd.boundariesNames, variables)))
+    fs = ns["fixed_stress"]
+    saved = []
+
+    class Rec:
+        def __init__(self, *a, **k):
+            pass
+
+        def save(self, name, values, t):
+            saved.append((name, np.array(values), t))
+
+        def finalize(self, *a, **k):
+            pass
+
+    class Nop(Rec):
+        def save(self, *a, **k):
+            pass
+    old = (P.CsvSaver, P.MeshioSaver)
+    P.CsvSaver, P.MeshioSaver = Rec, Nop
+    import io, contextlib
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            fs.geomechanics(pd)
+    finally:
+        P.CsvSaver, P.MeshioSaver = old
+    inner = [int(line.split()[0]) for line in buf.getvalue().strip().splitlines()]
+    nV = pd.grid.numberOfVertices
+    times = sorted(set(t for _, _, t in saved))
+    U, Pf = [], []
+    for t in times:
+        comp = {n: v for n, v, tt in saved if tt == t}
+        U.append(np.concatenate([comp[v] for v in variables[:d]])); Pf.append(comp["p"])
+    out = griddata_arrays(pd.grid.gridData)
+    out.update(u=np.array(U), p=np.array(Pf), inner_iterations=np.array(inner), dt=np.float64(dt), tolerance=np.float64(tolerance))
+    og = O.OracleGrid(O.read_msh(path))
+    res = O.fixed_stress_run(og, props, bcs, dt, len(times), tolerance)
+    uerr = max(rel(r[0], U[k]) for k, r in enumerate(res)); perr = max(rel(r[1], Pf[k]) for k, r in enumerate(res))
+    assert [r[2] for r in res] == inner, ([r[2] for r in res], inner)
+    assert uerr < 1e-7 and perr < 1e-7, (uerr, perr)
+    np.savez_compressed(os.path.join(GOLDEN, f"fixed_stress_{tag}.npz"), **out)
+    print(f"fixed_stress_{tag}: steps={len(times)} inner={inner} u {uerr:.1e} p {perr:.1e} ({time.time()-t0:.1f}s)")
+
+
 from tests.cases import HEAT_CASES, STRESS_CASES, BIOT_CASES  # noqa: E402
 
 
@@ -298,6 +351,9 @@ def main():
         stress_case(c["mesh"], c["props"], c["bcs"], tag, gravity=c["gravity"])
     for tag, c in BIOT_CASES.items():
         biot_case(c["mesh"], c["props"], c["bcs"], tag, dt=c["dt"], steps=c["steps"])
+    for tag in ("Square", "Hexas3x3x3"):
+        c = BIOT_CASES[tag]
+        fixed_stress_case(c["mesh"], c["props"], c["bcs"], tag, dt=c["dt"], steps=2)
 
 
 if __name__ == "__main__":

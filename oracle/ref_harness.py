@@ -44,6 +44,7 @@ def load():
     import heat_transfer  # noqa
     import stress_equilibrium  # noqa
     import geomechanics  # noqa
+    import fixed_stress  # noqa
 
     class _Sparse:
         linalg = scipy.sparse.linalg
@@ -56,7 +57,7 @@ def load():
 
     heat_transfer.sparse = stress_equilibrium.sparse = _Sparse
     _loaded.update(PyEFVLib=PyEFVLib, heat_transfer=heat_transfer,
-                   stress_equilibrium=stress_equilibrium, geomechanics=geomechanics)
+                   stress_equilibrium=stress_equilibrium, geomechanics=geomechanics, fixed_stress=fixed_stress)
     return _loaded
 
 

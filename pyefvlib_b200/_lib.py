@@ -64,6 +64,9 @@ PROTOTYPES = {
     "efv_assemble_dirichlet_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_apply_dirichlet": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_build_rhs": (C.c_int, [C.c_void_p, C.c_int]),
+    "efv_fs_mass_rhs": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "efv_fs_geo_rhs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "efv_fs_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f64p]),
     "efv_comm_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "efv_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "efv_comm_destroy": (C.c_int, []),

@@ -331,6 +331,24 @@ int efv_build_rhs(efv_system *s, int transient) {
   EFV_API_END
 }
 
+// ---- fixed-stress split ------------------------------------------------------------------------------------------
+int efv_fs_mass_rhs(efv_system *biot, efv_system *mass) {
+  EFV_API_BEGIN
+  efv::fs_mass_rhs(biot, mass);
+  EFV_API_END
+}
+int efv_fs_geo_rhs(efv_system *biot, efv_system *mass, efv_system *geo) {
+  EFV_API_BEGIN
+  efv::fs_geo_rhs(biot, mass, geo);
+  EFV_API_END
+}
+int efv_fs_update(efv_system *biot, efv_system *mass, efv_system *geo, double *difference) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(difference, "null argument");
+  *difference = efv::fs_update(biot, mass, geo);
+  EFV_API_END
+}
+
 // ---- multi-GPU ---------------------------------------------------------------------------------------------------
 int efv_comm_unique_id(const char *nccl_library_path, char *out128) {
   EFV_API_BEGIN

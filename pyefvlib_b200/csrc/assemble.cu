@@ -1114,6 +1114,145 @@ void build_rhs(efv_system *s, int transient) {
   }
 }
 
+// ---- fixed-stress split: right-hand sides from the blocks of the coupled operator (apps/fixed_stress.py:119-275) ----
+// `biot` holds the UNMODIFIED coupled operator (assembled with Dirichlet mode -1), the current iterate (u_k, p_k) in X and
+// the previous time step in XOLD; `mass` (1 DOF) and `geo` (d DOF) are the two systems actually solved.
+//   mass RHS = S/dt vol p_prev + cb alpha^2/dt vol p_k + A_pu (u_prev - u_k) + Neumann(p);   Dirichlet rows <- g   (:142-199)
+//   geo  RHS = - A_up p_next + Neumann(u);                                                   Dirichlet rows <- g   (:225-275)
+template <int D>
+__global__ void __launch_bounds__(256) k_fs_mass_rhs(SysView sb, const double *__restrict__ xk, const double *__restrict__ xprev,
+                                                     const double *__restrict__ accS, const double *__restrict__ accM,
+                                                     const double *__restrict__ stat, const double *__restrict__ elim,
+                                                     const uint8_t *__restrict__ flag, const double *__restrict__ gval,
+                                                     int symmetric, double *__restrict__ b) {
+  constexpr int NDOF = D + 1, B = NDOF * NDOF, GROUP = 8;
+  const int gl = threadIdx.x % GROUP;
+  const int64_t rows_per_block = blockDim.x / GROUP;
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_block; base < sb.nV; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t v = base + threadIdx.x / GROUP;
+    const bool valid = v < sb.nV;
+    const int64_t r0 = valid ? sb.gptr[v] : 0, r1 = valid ? sb.gptr[v + 1] : 0;
+    double sum = 0.0;
+    for (int64_t t = r0 + gl; t < r1; t += GROUP) {
+      const int64_t c = sb.gcol[t];
+#pragma unroll
+      for (int j = 0; j < D; ++j) sum += sb.vals[t * B + D * NDOF + j] * (xprev[c * NDOF + j] - xk[c * NDOF + j]);
+    }
+    sum = group_sum<GROUP>(sum);
+    if (valid && gl == 0) {
+      double r = accS[v] * xprev[v * NDOF + D] + (accM[v] - accS[v]) * xk[v * NDOF + D] + sum + stat[v];
+      if (symmetric) r += elim[v];
+      if (flag[v]) r = gval[v];
+      b[v] = r;
+    }
+  }
+}
+template <int D>
+__global__ void __launch_bounds__(256) k_fs_geo_rhs(SysView sb, const double *__restrict__ pnext, const double *__restrict__ stat,
+                                                    const double *__restrict__ elim, const uint8_t *__restrict__ flag,
+                                                    const double *__restrict__ gval, int symmetric, double *__restrict__ b) {
+  constexpr int NDOF = D + 1, B = NDOF * NDOF, GROUP = 8;
+  const int gl = threadIdx.x % GROUP;
+  const int64_t rows_per_block = blockDim.x / GROUP;
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_block; base < sb.nV; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t v = base + threadIdx.x / GROUP;
+    const bool valid = v < sb.nV;
+    const int64_t r0 = valid ? sb.gptr[v] : 0, r1 = valid ? sb.gptr[v + 1] : 0;
+    double sum[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) sum[i] = 0.0;
+    for (int64_t t = r0 + gl; t < r1; t += GROUP) {
+      const double pc = pnext[sb.gcol[t]];
+#pragma unroll
+      for (int i = 0; i < D; ++i) sum[i] += sb.vals[t * B + i * NDOF + D] * pc;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) sum[i] = group_sum<GROUP>(sum[i]);
+    if (valid && gl == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const int64_t k = v * D + i;
+        double r = -sum[i] + stat[k];
+        if (symmetric) r += elim[k];
+        if (flag[k]) r = gval[k];
+        b[k] = r;
+      }
+    }
+  }
+}
+// difference = max(|p_next - p_k|, |u_next - u_k|) (fixed_stress.py:300), then (u_k, p_k) <- (u_next, p_next)
+template <int D>
+__global__ void __launch_bounds__(256) k_fs_update(int64_t nV, const double *__restrict__ unext, const double *__restrict__ pnext,
+                                                   double *__restrict__ xk, double *__restrict__ partial) {
+  constexpr int NDOF = D + 1;
+  __shared__ double red[32];
+  double mx = 0.0;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nV; v += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double un = unext[v * D + i];
+      mx = fmax(mx, fabs(un - xk[v * NDOF + i]));
+      xk[v * NDOF + i] = un;
+    }
+    const double pn = pnext[v];
+    mx = fmax(mx, fabs(pn - xk[v * NDOF + D]));
+    xk[v * NDOF + D] = pn;
+  }
+  mx = block_max(mx, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = mx;
+}
+__global__ void k_fs_max_final(int G, const double *__restrict__ partial, double *__restrict__ out) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < G; i += blockDim.x) m = fmax(m, partial[i]);
+  m = block_max(m, red);
+  if (threadIdx.x == 0) *out = m;
+}
+
+static void fs_check(efv_system *biot, efv_system *mass, efv_system *geo) {
+  EFV_REQUIRE(biot && biot->mesh && biot->physics == 2 && biot->dirichlet_mode < 0,
+              "fixed-stress: the coupled system must be assembled by efv_biot_assemble with Dirichlet mode -1");
+  const int d = biot->mesh->dim;
+  if (mass) EFV_REQUIRE(mass->mesh == biot->mesh && mass->ndof == 1 && mass->acc.n, "fixed-stress: mass system must be a 1-DOF heat-type system on the same mesh");
+  if (geo) EFV_REQUIRE(geo->mesh == biot->mesh && geo->ndof == d, "fixed-stress: geo system must be a d-DOF elasticity system on the same mesh");
+}
+void fs_mass_rhs(efv_system *biot, efv_system *mass) {
+  fs_check(biot, mass, nullptr);
+  ensure_vectors(biot); ensure_vectors(mass);
+  SysView sb = sys_view(biot);
+  int grid = grid_for(biot->n_owned * 8, 256, 8);
+  int sym = mass->dirichlet_mode == 1;
+  if (biot->mesh->dim == 2)
+    EFV_LAUNCH(k_fs_mass_rhs<2>, grid, 256, 0, sb, biot->x.p, biot->xold.p, biot->acc.p, mass->acc.p, mass->static_rhs.p, mass->elim.p,
+               mass->dir_flag.p, mass->dir_value.p, sym, mass->b.p);
+  else
+    EFV_LAUNCH(k_fs_mass_rhs<3>, grid, 256, 0, sb, biot->x.p, biot->xold.p, biot->acc.p, mass->acc.p, mass->static_rhs.p, mass->elim.p,
+               mass->dir_flag.p, mass->dir_value.p, sym, mass->b.p);
+}
+void fs_geo_rhs(efv_system *biot, efv_system *mass, efv_system *geo) {
+  fs_check(biot, mass, geo);
+  ensure_vectors(geo);
+  SysView sb = sys_view(biot);
+  int grid = grid_for(biot->n_owned * 8, 256, 8);
+  int sym = geo->dirichlet_mode == 1;
+  if (biot->mesh->dim == 2)
+    EFV_LAUNCH(k_fs_geo_rhs<2>, grid, 256, 0, sb, mass->x.p, geo->static_rhs.p, geo->elim.p, geo->dir_flag.p, geo->dir_value.p, sym, geo->b.p);
+  else
+    EFV_LAUNCH(k_fs_geo_rhs<3>, grid, 256, 0, sb, mass->x.p, geo->static_rhs.p, geo->elim.p, geo->dir_flag.p, geo->dir_value.p, sym, geo->b.p);
+}
+double fs_update(efv_system *biot, efv_system *mass, efv_system *geo) {
+  fs_check(biot, mass, geo);
+  const int G = num_sms() * 4;
+  DBuf<double> partial(G + 1);
+  if (biot->mesh->dim == 2) EFV_LAUNCH(k_fs_update<2>, G, 256, 0, biot->n_owned, geo->x.p, mass->x.p, biot->x.p, partial.p);
+  else EFV_LAUNCH(k_fs_update<3>, G, 256, 0, biot->n_owned, geo->x.p, mass->x.p, biot->x.p, partial.p);
+  EFV_LAUNCH(k_fs_max_final, 1, 256, 0, G, partial.p, partial.p + G);
+  double out = 0.0;
+  EFV_CUDA(cudaMemcpyAsync(&out, partial.p + G, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+  return out;
+}
+
 // ---- exports / vector transfer --------------------------------------------------------------------------------------
 __global__ void k_export_values(int64_t nV, int ndof, int64_t nnzg, const int64_t *__restrict__ gptr,
                                 const double *__restrict__ vals, double *__restrict__ out) {

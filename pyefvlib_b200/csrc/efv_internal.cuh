@@ -145,6 +145,9 @@ void ensure_vectors(efv_system *s);
 void export_csr(const efv_system *s, int64_t *indptr, int32_t *indices);
 void export_slotmap(const efv_system *s, int64_t *slots);
 void export_values(const efv_system *s, double *data);
+void fs_mass_rhs(efv_system *biot, efv_system *mass);
+void fs_geo_rhs(efv_system *biot, efv_system *mass, efv_system *geo);
+double fs_update(efv_system *biot, efv_system *mass, efv_system *geo);
 void vec_upload(efv_system *s, DBuf<double> &dst, const double *host);
 void vec_download(const efv_system *s, const DBuf<double> &src, double *host);
 // krylov.cu

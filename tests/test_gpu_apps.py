@@ -128,3 +128,25 @@ def test_linear_system_csr_gpu_backend():
     import scipy.sparse.linalg as spla
     ref = spla.spsolve(sp.csc_matrix(ls.matrix), ls.rhs)
     assert relres <= 1e-12 and util.rel_l2(x, ref) <= 1e-9
+
+
+@pytest.mark.parametrize("tag", ["Square", "Hexas3x3x3"])
+def test_fixed_stress_app(tag):
+    """apps/fixed_stress.py: same inner fixed-point iteration counts and the same fields as the reference."""
+    from pyefvlib_b200.apps.fixed_stress import fixedStress
+    z = util.load("fixed_stress_" + tag)
+    c = BIOT_CASES[tag]
+    grid = util.product_grid(z)
+    d, nV = grid.dimension, grid.numberOfVertices
+    names = [b.name for b in grid.boundaries]
+    variables = ["u_x", "u_y", "u_z"][:d] + ["p"]
+    steps = len(z["p"])
+    pd = P.ProblemData(grid, P.PropertyData(c["props"]), P.BoundaryConditions(bc_dict(c["bcs"], names, variables)),
+                       P.NumericalSettings(timeStep=float(z["dt"]), finalTime=float(z["dt"]) * steps - 1e-9,
+                                           tolerance=float(z["tolerance"]), maxNumberOfIterations=10 ** 9))
+    out = fixedStress(pd, verbosity=False)
+    assert out["inner_iterations"] == z["inner_iterations"].tolist()
+    for k in range(steps):
+        assert util.rel_l2(out["saver"].fields["p"][k], z["p"][k]) <= 1e-7
+        u = np.concatenate([out["saver"].fields[v][k] for v in variables[:d]])
+        assert util.rel_l2(u, z["u"][k]) <= 1e-7
