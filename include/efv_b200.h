@@ -121,7 +121,10 @@ int efv_biot_assemble(efv_system *s, const double *props, double dt, const doubl
 int efv_bc_clear(efv_system *s);
 int efv_bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int64_t n);
 /* Neumann: static_rhs[dof(outer vertex)] += sign * value * |outer face area| over the outer faces of
- * `boundary`  [ref: apps/heat_transfer.py:115-120 (sign +1); apps/stress_equilibrium.py:131-141 (sign -1)] */
+ * `boundary`  [ref: apps/heat_transfer.py:115-120 (sign +1); apps/stress_equilibrium.py:131-141 (sign -1)].
+ * Calls are ORDER-SENSITIVE like the reference's loops: a Neumann call made after a Dirichlet call that prescribed the same
+ * DOF adds its flux to the prescribed value (the elasticity app visits boundary by boundary, stress_equilibrium.py:119-163);
+ * a later Dirichlet call overwrites it.                                                                              */
 int efv_bc_neumann(efv_system *s, int boundary, int dof, double value, double sign);
 /* how the next assembly call treats the recorded Dirichlet set: -1 leave the interior operator (apply later with
  * efv_apply_dirichlet), EFV_DIRICHLET_ROWS or EFV_DIRICHLET_SYMMETRIC applied inside the assembly kernel.          */
@@ -155,6 +158,14 @@ int efv_fs_update(efv_system *biot, efv_system *mass, efv_system *geo, double *d
 int efv_comm_unique_id(const char *nccl_library_path, char *out128);
 int efv_comm_init(const char *nccl_library_path, int rank, int nranks, const char *id128);
 int efv_comm_destroy(void);
+/* peer-memory collectives over NVLink (CUDA IPC): every rank exports a 64-byte handle of its scalar region, the host
+ * layer all-gathers them (rank order) and hands the table back; the Krylov all-reduces then run as one kernel that stores
+ * into every peer and sums in rank order.  Same for the halo: export the system's staging buffer, import the neighbours'
+ * handles with the ghost offset / flag slot this rank owns inside each of them.  Without these calls NCCL is used.   */
+int efv_comm_peer_export(char *out64);
+int efv_comm_peer_import(const char *handles);
+int efv_halo_stage_export(efv_system *s, char *out64);
+int efv_halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_offsets, const int *remote_slots);
 int efv_system_set_owned(efv_system *s, int64_t n_owned);
 int efv_system_set_halo(efv_system *s, int n_neighbours, const int *neighbour_ranks, const int64_t *send_ptr,
                         const int32_t *send_idx, const int64_t *recv_ptr);

@@ -70,6 +70,10 @@ PROTOTYPES = {
     "efv_comm_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "efv_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_char_p]),
     "efv_comm_destroy": (C.c_int, []),
+    "efv_comm_peer_export": (C.c_int, [C.c_char_p]),
+    "efv_comm_peer_import": (C.c_int, [C.c_char_p]),
+    "efv_halo_stage_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "efv_halo_stage_import": (C.c_int, [C.c_void_p, C.c_char_p, c_i64p, c_intp]),
     "efv_system_set_owned": (C.c_int, [C.c_void_p, C.c_int64]),
     "efv_system_set_halo": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_i64p, c_i32p, c_i64p]),
     "efv_halo_exchange": (C.c_int, [C.c_void_p, C.c_int]),

@@ -367,6 +367,30 @@ int efv_comm_destroy(void) {
   efv::comm_destroy();
   EFV_API_END
 }
+int efv_comm_peer_export(char *out64) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(out64, "null argument");
+  efv::comm_peer_export(out64);
+  EFV_API_END
+}
+int efv_comm_peer_import(const char *handles) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(handles, "null argument");
+  efv::comm_peer_import(handles);
+  EFV_API_END
+}
+int efv_halo_stage_export(efv_system *s, char *out64) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && out64, "null argument");
+  efv::halo_stage_export(s, out64);
+  EFV_API_END
+}
+int efv_halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_offsets, const int *remote_slots) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && handles && remote_offsets && remote_slots, "null argument");
+  efv::halo_stage_import(s, handles, remote_offsets, remote_slots);
+  EFV_API_END
+}
 int efv_system_set_owned(efv_system *s, int64_t n_owned) {
   EFV_API_BEGIN
   EFV_REQUIRE(s, "null system");

@@ -928,7 +928,8 @@ void bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int6
 // reference's facet order (heat_transfer.py:115-120) -> deterministic
 __global__ void k_neumann(int64_t nbv, const int32_t *__restrict__ bv, const int64_t *__restrict__ bvo_ptr,
                           const int64_t *__restrict__ bvo, const double *__restrict__ norm, int64_t o0, int64_t o1,
-                          int ndof, int dof, double coef, double *__restrict__ rhs) {
+                          int ndof, int dof, double coef, double *__restrict__ rhs, const uint8_t *__restrict__ dflag,
+                          double *__restrict__ dvalue) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nbv; k += (int64_t)gridDim.x * blockDim.x) {
     double acc = 0.0;
     bool any = false;
@@ -936,7 +937,14 @@ __global__ void k_neumann(int64_t nbv, const int32_t *__restrict__ bv, const int
       int64_t o = bvo[p];
       if (o >= o0 && o < o1) { acc += coef * norm[o]; any = true; }
     }
-    if (any) rhs[(int64_t)bv[k] * ndof + dof] += acc;
+    if (any) {
+      const int64_t idx = (int64_t)bv[k] * ndof + dof;
+      rhs[idx] += acc;
+      // the reference applies boundary conditions in visiting order: a Neumann boundary visited AFTER a Dirichlet one
+      // that shares the vertex adds its flux on top of the prescribed value (stress_equilibrium.py:119-163 loops
+      // boundary by boundary); a later Dirichlet visit overwrites it again (k_dir_set)
+      if (dflag[idx]) dvalue[idx] += acc;
+    }
   }
 }
 
@@ -948,7 +956,8 @@ void bc_neumann(efv_system *s, int boundary, int dof, double value, double sign)
   if (!s->dir_flag.n) bc_clear(s);
   if (value == 0.0 || B.nbv == 0) return;
   EFV_LAUNCH(k_neumann, grid_for(B.nbv, 128), 128, 0, B.nbv, B.bv.p, B.bvo_ptr.p, B.bvo.p, B.outer_area_norm.p,
-             B.outer_ptr_host[boundary], B.outer_ptr_host[boundary + 1], s->ndof, dof, sign * value, s->static_rhs.p);
+             B.outer_ptr_host[boundary], B.outer_ptr_host[boundary + 1], s->ndof, dof, sign * value, s->static_rhs.p, s->dir_flag.p,
+             s->dir_value.p);
 }
 
 // Dirichlet on the matrix: GROUP lanes per row-vertex.

@@ -82,12 +82,133 @@ bool comm_active() { return g_comm != nullptr && g_nranks > 1; }
 int comm_rank() { return g_rank; }
 int comm_size() { return g_nranks; }
 
+// ---- peer-memory collectives (NVLink / NVSwitch loads and stores, no NCCL on the critical path) ---------------------------
+// Every rank owns a small cudaMalloc'ed region that all other ranks map through CUDA IPC:
+//   double slot[2][kMaxRanks][4]   all-reduce operands, double-buffered by the parity of the sequence number
+//   uint32 flag[2][kMaxRanks]      flag[parity][r] = sequence number once rank r's operands have landed
+//   int    error                   set when a spin wait times out
+// k_allreduce_peer folds the per-block partials of a Krylov kernel (fixed order), stores the result into EVERY rank's
+// slot[parity][me], publishes the flag with a system-scope fence, waits for all ranks' flags and sums the slots in rank
+// order -- so every rank obtains bit-identical scalars.  One launch replaces "consolidation kernel + ncclAllReduce".
+// Double buffering is safe: a rank cannot finish all-reduce k+1 before every peer has entered it, i.e. finished reading k.
+constexpr int kMaxRanks = 16;
+constexpr size_t kSlotBytes = 2 * kMaxRanks * 4 * sizeof(double);
+constexpr size_t kFlagBytes = 2 * kMaxRanks * sizeof(uint32_t);
+constexpr size_t kPeerBytes = kSlotBytes + kFlagBytes + 64;
+constexpr long long kSpinLimit = 1LL << 24;     // ~ seconds; a rank that never arrives turns into an error, not a hang
+
+struct PeerPtrs { char *p[kMaxRanks]; };
+struct PeerRegion {
+  bool active = false;
+  char *local = nullptr;
+  PeerPtrs all;
+  uint32_t seq = 0;
+};
+static PeerRegion g_peer;
+
+__device__ __forceinline__ double *peer_slot(char *base, int parity, int r) {
+  return reinterpret_cast<double *>(base) + ((size_t)parity * kMaxRanks + r) * 4;
+}
+__device__ __forceinline__ volatile uint32_t *peer_flag(char *base, int parity, int r) {
+  return reinterpret_cast<volatile uint32_t *>(base + kSlotBytes) + (size_t)parity * kMaxRanks + r;
+}
+__device__ __forceinline__ int *peer_error(char *base) { return reinterpret_cast<int *>(base + kSlotBytes + kFlagBytes); }
+
+// op: 0 sum, 1 max.  narr <= 4 arrays of G partials each.
+__global__ void k_allreduce_peer(const double *__restrict__ partial, int G, int narr, double *__restrict__ out, PeerPtrs peers,
+                                 int me, int nranks, uint32_t seq, int op) {
+  __shared__ double red[32];
+  __shared__ double mine[4];
+  for (int a = 0; a < narr; ++a) {
+    double v = 0.0;
+    if (op == 0) {
+      for (int i = threadIdx.x; i < G; i += blockDim.x) v += partial[(size_t)a * G + i];
+      v = block_sum(v, red);
+    } else {
+      for (int i = threadIdx.x; i < G; i += blockDim.x) v = fmax(v, partial[(size_t)a * G + i]);
+      v = block_max(v, red);
+    }
+    if (threadIdx.x == 0) mine[a] = v;
+    __syncthreads();
+  }
+  const int parity = seq & 1;
+  if (threadIdx.x < nranks) {
+    char *dst = peers.p[threadIdx.x];
+    double *slot = peer_slot(dst, parity, me);
+    for (int a = 0; a < narr; ++a) slot[a] = mine[a];
+    __threadfence_system();
+    *peer_flag(dst, parity, me) = seq;
+  }
+  char *self = peers.p[me];
+  if (threadIdx.x < nranks) {
+    volatile uint32_t *f = peer_flag(self, parity, threadIdx.x);
+    long long spins = 0;
+    while ((int32_t)(*f - seq) < 0) {
+      if (++spins > kSpinLimit) { atomicExch(peer_error(self), 1); break; }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  if (threadIdx.x < narr) {
+    double acc = 0.0;
+    for (int r = 0; r < nranks; ++r) {
+      const double v = *reinterpret_cast<volatile double *>(peer_slot(self, parity, r) + threadIdx.x);
+      acc = (op == 0) ? acc + v : fmax(acc, v);
+    }
+    out[threadIdx.x] = acc;
+  }
+}
+
+void comm_peer_export(char *out64) {
+  EFV_REQUIRE(comm_active(), "initialise the communicator first");
+  EFV_REQUIRE(g_nranks <= kMaxRanks, "peer collectives support at most 16 ranks");
+  if (!g_peer.local) {
+    EFV_CUDA(cudaMalloc((void **)&g_peer.local, kPeerBytes));
+    EFV_CUDA(cudaMemset(g_peer.local, 0, kPeerBytes));
+  }
+  cudaIpcMemHandle_t h;
+  EFV_CUDA(cudaIpcGetMemHandle(&h, g_peer.local));
+  static_assert(sizeof(h) == 64, "IPC handle size");
+  memcpy(out64, &h, 64);
+}
+void comm_peer_import(const char *handles) {
+  EFV_REQUIRE(g_peer.local, "export the peer region first");
+  for (int r = 0; r < g_nranks; ++r) {
+    if (r == g_rank) { g_peer.all.p[r] = g_peer.local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * (size_t)r, 64);
+    void *ptr = nullptr;
+    EFV_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    g_peer.all.p[r] = (char *)ptr;
+  }
+  g_peer.active = true;
+  g_peer.seq = 0;
+}
+bool comm_peer_active() { return g_peer.active && comm_active(); }
+
+// all-reduce `narr` arrays of G per-block partials into out[0..narr) (device), on every rank
+void comm_allreduce_partials(const double *partial, int G, int narr, double *out, int op) {
+  EFV_REQUIRE(comm_peer_active(), "peer collectives are not initialised");
+  EFV_REQUIRE(narr >= 1 && narr <= 4, "at most 4 scalars per all-reduce");
+  g_peer.seq++;
+  EFV_LAUNCH(k_allreduce_peer, 1, 256, 0, partial, G, narr, out, g_peer.all, g_rank, g_nranks, g_peer.seq, op);
+}
+int comm_peer_error() {
+  if (!g_peer.local) return 0;
+  int e = 0;
+  EFV_CUDA(cudaMemcpyAsync(&e, g_peer.local + kSlotBytes + kFlagBytes, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+  return e;
+}
+
 void comm_allreduce_sum(double *dev, int count) {
   if (!comm_active()) return;
+  if (comm_peer_active() && count <= 4) { comm_allreduce_partials(dev, 1, count, dev, 0); return; }
   EFV_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclSum, g_comm, stream()));
 }
 void comm_allreduce_max(double *dev, int count) {
   if (!comm_active()) return;
+  if (comm_peer_active() && count <= 4) { comm_allreduce_partials(dev, 1, count, dev, 1); return; }
   EFV_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclMax, g_comm, stream()));
 }
 
@@ -117,12 +238,99 @@ void halo_set(efv_system *s, int n_nbr, const int *nbr, const int64_t *send_ptr,
   h.active = true;
 }
 
+// peer-memory halo: every rank owns a staging buffer [64-byte flag block | ghost values]; neighbours store their
+// boundary values straight into it over NVLink and then raise the flag of their slot; the owner waits for the flags and
+// copies the values behind its owned entries.  The all-reduces of the Krylov iteration order successive exchanges, so
+// one staging buffer per system suffices.
+constexpr size_t kHaloFlagBytes = 256;
+struct HaloPush { double *dst[8]; int64_t begin[9]; uint32_t *flag[8]; int n; };
+
+__global__ void k_halo_push(HaloPush hp, const int32_t *__restrict__ idx, int ndof, const double *__restrict__ vec) {
+  const int64_t total = hp.begin[hp.n] * ndof;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = i / ndof;
+    const int f = (int)(i % ndof);
+    int nb = 0;
+    while (k >= hp.begin[nb + 1]) ++nb;
+    hp.dst[nb][(k - hp.begin[nb]) * ndof + f] = vec[(int64_t)idx[k] * ndof + f];
+  }
+  __threadfence_system();
+}
+__global__ void k_halo_flag(HaloPush hp, uint32_t seq) {
+  __threadfence_system();
+  if (threadIdx.x < hp.n) *reinterpret_cast<volatile uint32_t *>(hp.flag[threadIdx.x]) = seq;
+}
+__global__ void k_halo_wait_copy(const char *__restrict__ stage, int n_nbr, uint32_t seq, int64_t count, double *__restrict__ dst,
+                                 int *__restrict__ err) {
+  if (threadIdx.x < n_nbr) {
+    volatile const uint32_t *f = reinterpret_cast<volatile const uint32_t *>(stage) + threadIdx.x;
+    long long spins = 0;
+    while ((int32_t)(*f - seq) < 0) {
+      if (++spins > kSpinLimit) { atomicExch(err, 2); break; }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  const volatile double *src = reinterpret_cast<const volatile double *>(stage + kHaloFlagBytes);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+void halo_stage_export(efv_system *s, char *out64) {
+  Halo &h = s->halo;
+  EFV_REQUIRE(h.active, "register the halo first");
+  const size_t bytes = kHaloFlagBytes + (size_t)(s->nV - s->n_owned) * s->ndof * sizeof(double) + 64;
+  if (!h.stage) {
+    EFV_CUDA(cudaMalloc((void **)&h.stage, bytes));
+    EFV_CUDA(cudaMemset(h.stage, 0, bytes));
+  }
+  cudaIpcMemHandle_t hd;
+  EFV_CUDA(cudaIpcGetMemHandle(&hd, h.stage));
+  memcpy(out64, &hd, 64);
+}
+// handles: one per neighbour (same order as the neighbour list); remote_off[i]: first ghost slot (in vertices) of
+// neighbour i's staging area that belongs to this rank; remote_slot[i]: which flag of neighbour i this rank raises
+void halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_off, const int *remote_slot) {
+  Halo &h = s->halo;
+  EFV_REQUIRE(h.stage, "export the staging buffer first");
+  const int n = (int)h.nbr.size();
+  EFV_REQUIRE(n <= 8, "peer halo supports at most 8 neighbours per rank");
+  h.remote.assign(n, nullptr);
+  h.remote_off.assign(remote_off, remote_off + n);
+  h.remote_slot.assign(remote_slot, remote_slot + n);
+  for (int i = 0; i < n; ++i) {
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handles + 64 * (size_t)i, 64);
+    void *ptr = nullptr;
+    EFV_CUDA(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    h.remote[i] = (char *)ptr;
+  }
+  h.peer = true;
+  h.seq = 0;
+}
+
 // ghost entries of `vec` <- owner ranks' values
 void halo_exchange(efv_system *s, double *vec) {
   Halo &h = s->halo;
   if (!h.active || !comm_active()) return;
   const int n_nbr = (int)h.nbr.size();
   const int64_t n_send = h.send_ptr[n_nbr];
+  if (h.peer && comm_peer_active()) {
+    h.seq++;
+    HaloPush hp;
+    hp.n = n_nbr;
+    for (int i = 0; i < n_nbr; ++i) {
+      hp.dst[i] = reinterpret_cast<double *>(h.remote[i] + kHaloFlagBytes) + h.remote_off[i] * s->ndof;
+      hp.flag[i] = reinterpret_cast<uint32_t *>(h.remote[i]) + h.remote_slot[i];
+      hp.begin[i] = h.send_ptr[i];
+    }
+    hp.begin[n_nbr] = n_send;
+    if (n_send) EFV_LAUNCH(k_halo_push, grid_for(n_send * s->ndof, 256, 2), 256, 0, hp, h.send_idx.p, s->ndof, vec);
+    EFV_LAUNCH(k_halo_flag, 1, 32, 0, hp, h.seq);
+    const int64_t count = (s->nV - s->n_owned) * s->ndof;
+    EFV_LAUNCH(k_halo_wait_copy, grid_for(count, 256, 1), 256, 0, h.stage, n_nbr, h.seq, count, vec + s->n_owned * s->ndof,
+               reinterpret_cast<int *>(g_peer.local + kSlotBytes + kFlagBytes));
+    return;
+  }
   if (n_send) EFV_LAUNCH(k_pack, grid_for(n_send * s->ndof, 256), 256, 0, h.send_idx.p, n_send, s->ndof, vec, h.send_buf.p);
   EFV_NCCL(g_nccl.GroupStart());
   for (int i = 0; i < n_nbr; ++i) {

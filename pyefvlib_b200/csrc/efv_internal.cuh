@@ -82,6 +82,13 @@ struct Halo {
   std::vector<int64_t> recv_ptr;        // per neighbour range into the ghost block (ghosts are grouped by owner)
   DBuf<int32_t> send_idx;               // local ids of owned vertices to send
   DBuf<double> send_buf;
+  // peer-memory path (CUDA IPC): own staging buffer [flags | ghost values] and the neighbours' mapped buffers
+  bool peer = false;
+  char *stage = nullptr;
+  std::vector<char *> remote;
+  std::vector<int64_t> remote_off;
+  std::vector<int> remote_slot;
+  uint32_t seq = 0;
 };
 }
 
@@ -165,6 +172,13 @@ int comm_rank();
 int comm_size();
 void comm_allreduce_sum(double *dev, int count);
 void comm_allreduce_max(double *dev, int count);
+void comm_peer_export(char *out64);
+void comm_peer_import(const char *handles);
+bool comm_peer_active();
+void comm_allreduce_partials(const double *partial, int G, int narr, double *out, int op);
+int comm_peer_error();
+void halo_stage_export(efv_system *s, char *out64);
+void halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_off, const int *remote_slot);
 void halo_set(efv_system *s, int n_nbr, const int *nbr, const int64_t *send_ptr, const int32_t *send_idx, const int64_t *recv_ptr);
 void halo_exchange(efv_system *s, double *vec);
 }  // namespace efv

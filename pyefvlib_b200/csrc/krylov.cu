@@ -415,8 +415,12 @@ __global__ void k_reduce_partials(const double *__restrict__ partial, int G, int
 static const double *consolidate(KrylovWork *w, const double *partial, int narr, int slot, int *Gout) {
   if (!comm_active()) { *Gout = w->grid; return partial; }
   double *out = w->sc.p + 32 + 4 * slot;
-  EFV_LAUNCH(k_reduce_partials, 1, kBlock, 0, partial, w->grid, narr, out);
-  comm_allreduce_sum(out, narr);
+  if (comm_peer_active()) {
+    comm_allreduce_partials(partial, w->grid, narr, out, 0);     // one launch: fold partials + all-reduce over peer memory
+  } else {
+    EFV_LAUNCH(k_reduce_partials, 1, kBlock, 0, partial, w->grid, narr, out);
+    comm_allreduce_sum(out, narr);
+  }
   *Gout = 1;
   return out;
 }
@@ -555,6 +559,7 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   float ms = 0;
   EFV_CUDA(cudaEventElapsedTime(&ms, w->e0, w->e1));
   s->t_solve_ms = ms;
+  if (comm_peer_active()) EFV_REQUIRE(comm_peer_error() == 0, "peer-memory collective timed out (a rank did not arrive)");
   if (iters) *iters = w->h_flags[1];
   if (relres) *relres = (w->h_sc[2] > 0) ? std::sqrt(w->h_sc[3] / w->h_sc[2]) : 0.0;
 }

@@ -5,6 +5,21 @@
 
 namespace efv {
 
+// ---- input validation: vertex ids must lie in [0, nV) (fail loudly instead of faulting later) --------------------------
+__global__ void k_check_range(const int32_t *__restrict__ a, int64_t n, int64_t nV, int *__restrict__ bad) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (a[i] < 0 || a[i] >= nV) atomicExch(bad, 1);
+}
+static void check_vertex_ids(const int32_t *dev, int64_t n, int64_t nV, const char *what) {
+  if (!n) return;
+  DBuf<int> bad(1);
+  bad.zero();
+  EFV_LAUNCH(k_check_range, grid_for(n, 256), 256, 0, dev, n, nV, bad.p);
+  int h = 0;
+  bad.download(&h, 1);
+  EFV_REQUIRE(h == 0, std::string(what) + " refers to a vertex id outside [0, numberOfVertices)");
+}
+
 // ---- incidence ------------------------------------------------------------------------------------------------
 __global__ void k_count_incidence(const int32_t *__restrict__ conn, int64_t n, int32_t *__restrict__ cnt) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -97,6 +112,7 @@ void mesh_finalize(efv_mesh *m, const int64_t *ep, int uniform_m) {
       if (counts[c]) m->groups[c].ids.upload(ids[c].data(), ids[c].size());
     EFV_CUDA(cudaStreamSynchronize(stream()));
   }
+  check_vertex_ids(m->conn.p, m->conn_size, m->nV, "element connectivity");
   // incidence
   MeshView mv = view_of(m);
   DBuf<int32_t> cnt(m->nV);
@@ -284,6 +300,11 @@ void mesh_set_boundaries(efv_mesh *m, int nB, const int64_t *boundary_ptr, int64
   for (int b = 0; b <= nB; ++b) B.outer_ptr_host[b] = facet_ptr[boundary_ptr[b]];
   B.facet_ptr.upload(facet_ptr, nF + 1);
   B.facet_conn.upload(facet_conn, B.nOuter);
+  check_vertex_ids(B.facet_conn.p, B.nOuter, m->nV, "boundary connectivity");
+  for (int64_t f = 0; f < nF; ++f) {
+    const int64_t mf = facet_ptr[f + 1] - facet_ptr[f];
+    EFV_REQUIRE(mf >= 2 && mf <= 4 && mf == (m->dim == 2 ? 2 : mf) && (m->dim == 3 ? mf >= 3 : true), "boundary facet with an unsupported vertex count");
+  }
   B.facet_element.alloc(nF);
   B.facet_local.alloc(nF);
   B.facet_area.alloc(nF * 3);

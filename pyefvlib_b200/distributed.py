@@ -194,6 +194,13 @@ def init_comm():
     box = [bytes(buf.raw)]
     dist.broadcast_object_list(box, src=0)
     _lib.check(L.efv_comm_init(path, rank, world, box[0]))
+    if os.environ.get("EFV_COMM", "peer") == "peer" and world <= 16:
+        # scalar all-reduce region of every rank, mapped everywhere through CUDA IPC
+        mine = C.create_string_buffer(64)
+        _lib.check(L.efv_comm_peer_export(mine))
+        table = [None] * world
+        dist.all_gather_object(table, bytes(mine.raw))
+        _lib.check(L.efv_comm_peer_import(b"".join(table)))
     _comm_ready = True
 
 
@@ -211,6 +218,18 @@ def make_system(part, ndof=1):
     rp = np.asarray(part.recv_ptr, dtype=np.int64)
     _lib.check(L.efv_system_set_halo(s.handle, len(nb), nb.ctypes.data_as(_lib.c_intp), sp.ctypes.data_as(_lib.c_i64p),
                                      si.ctypes.data_as(_lib.c_i32p), rp.ctypes.data_as(_lib.c_i64p)))
+    if os.environ.get("EFV_COMM", "peer") == "peer" and part.world <= 16 and len(nb) <= 8:
+        import torch.distributed as dist
+        # staging buffers: everybody publishes (handle, {neighbour: (ghost offset, flag slot) it reserves for that neighbour})
+        mine = C.create_string_buffer(64)
+        _lib.check(L.efv_halo_stage_export(s.handle, mine))
+        info = {int(q): (int(part.recv_ptr[i]), i) for i, q in enumerate(part.nbr)}
+        table = [None] * part.world
+        dist.all_gather_object(table, (bytes(mine.raw), info))
+        handles = b"".join(table[int(q)][0] for q in part.nbr)
+        offs = np.array([table[int(q)][1][part.rank][0] for q in part.nbr], dtype=np.int64)
+        slots = np.array([table[int(q)][1][part.rank][1] for q in part.nbr], dtype=np.int32)
+        _lib.check(L.efv_halo_stage_import(s.handle, handles, offs.ctypes.data_as(_lib.c_i64p), slots.ctypes.data_as(_lib.c_intp)))
     return s
 
 

@@ -99,3 +99,59 @@ def test_structured_against_oracle(n, kind):
     iters, relres = s.solve_pcg(1e-10, 20000, negate=True)
     assert relres <= 1e-10
     assert util.rel_l2(s.download(D.VEC_X), O.solve_equilibrated(Aref, bref)) <= 1e-8
+
+
+def test_mixed_mesh_elasticity_and_biot_against_oracle():
+    """Mixed triangle + quadrilateral mesh with two regions (meshes/msh/2D/test.msh, taken from the heat fixture):
+    the generic (non-uniform) kernels for elasticity and Biot against the oracle."""
+    import pyefvlib_b200.device as D
+    from oracle import efv_oracle as O
+    z = util.load("heat_test_mixed")
+    grid = util.product_grid(z)
+    og = util.oracle_grid(z)
+    nV = grid.numberOfVertices
+    N0 = ("neumann", 0.0)
+    names = [b.name for b in grid.boundaries]
+    eb = {"u": {n: N0 for n in names}, "v": {n: N0 for n in names}}
+    eb["u"]["W"] = ("dirichlet", 0.0); eb["v"]["W"] = ("dirichlet", 0.0); eb["u"]["E"] = ("dirichlet", 1e-3); eb["v"]["NE"] = ("neumann", -5e3)
+    sp_props = {"WEST": {"Density": 1800.0, "PoissonsRatio": 0.4, "ShearModulus": 6.0e6, "Gravity": 10.0},
+                "EAST": {"Density": 2500.0, "PoissonsRatio": 0.25, "ShearModulus": 2.0e7, "Gravity": 10.0}}
+    s = D.DeviceSystem(grid, 2)
+    send_bcs(s, grid, eb)
+    s.assemble_dirichlet_mode(D.DIRICHLET_ROWS)
+    s.elasticity_assemble(props_array(grid, sp_props), True)
+    s.build_rhs(False)
+    Aref, bref = O.elasticity_system(og, sp_props, eb, gravity=True)
+    assert util.row_rel_matrix_error(s.to_scipy(), Aref) <= 1e-12
+    assert util.rel_max(s.download(D.VEC_B), bref) <= 1e-12
+    s.upload(D.VEC_X, np.zeros(s.rows))
+    iters, relres = s.solve_bicgstab(1e-12, 20000)          # general quadrilaterals: non-symmetric operator
+    assert relres <= 1e-12
+    assert util.rel_l2(s.download(D.VEC_X), O.solve_equilibrated(Aref, bref)) <= 1e-8
+    # Biot on the same mesh
+    from tests.test_gpu_biot import props_array as bprops, send_bcs as bsend
+    bp = {"WEST": dict(nu=0.2, G=6.0e9, cs=0.0, phi=0.19, k=1.9e-15, cf=3.0303e-10, mu=1000.0, rhos=2700.0, rhof=1000.0),
+          "EAST": dict(nu=0.3, G=2.0e9, cs=1e-11, phi=0.3, k=5e-15, cf=4.0e-10, mu=1000.0, rhos=2500.0, rhof=1000.0)}
+    bb = {v: {n: N0 for n in names} for v in ("u_x", "u_y", "p")}
+    bb["u_x"]["W"] = ("dirichlet", 0.0); bb["u_y"]["W"] = ("dirichlet", 0.0); bb["u_y"]["NE"] = ("neumann", 1e5); bb["p"]["E"] = ("dirichlet", 0.0)
+    sb = D.DeviceSystem(grid, 3)
+    bsend(sb, grid, bb)
+    sb.assemble_dirichlet_mode(D.DIRICHLET_ROWS)
+    sb.biot_assemble(bprops(grid, bp), 20.0)
+    u_old = 1e-6 * np.sin(np.arange(2 * nV)); p_old = 1e3 * np.cos(np.arange(nV))
+    sb.upload(D.VEC_XOLD, np.concatenate([u_old, p_old]))
+    sb.build_rhs(True)
+    Ab, bbv = O.biot_system(og, bp, bb, 20.0, u_old, p_old)
+    assert util.row_rel_matrix_error(sb.to_scipy(), Ab) <= 1e-12
+    scale = np.maximum(np.abs(bbv), abs(Ab) @ np.abs(np.concatenate([u_old, p_old])))
+    assert (np.abs(sb.download(D.VEC_B) - bbv) / np.maximum(scale, 1e-300)).max() <= 1e-11
+
+
+def test_bad_connectivity_is_rejected():
+    import pyefvlib_b200 as P
+    from pyefvlib_b200 import _lib
+    gd = P.structured_grid_data(3, "hex")
+    gd.elementsConnectivities = gd.elementsConnectivities.copy()
+    gd.elementsConnectivities[0, 0] = 10 ** 6
+    with pytest.raises(_lib.EfvError, match="outside"):
+        P.Grid(gd).device
