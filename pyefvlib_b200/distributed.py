@@ -344,7 +344,7 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
                                     ", STEADY, 3-D BC set, PCG(Jacobi) rtol 1e-10 from x0 = 0, one full assemble + solve per step"),
                        "vertices": nV, "pcg_iterations_per_step": iters, "warmup_iterations": warm,
                        "assemble_ms_per_step": float(np.mean(asm_ms)), "solve_ms_per_step": float(np.mean(solve_ms)),
-                       "host_slab_generation_s": host_s, "halo": "NCCL send/recv of one n^2 plane per neighbour per SpMV",
+                       "host_slab_generation_s": host_s, "halo": ("peer-memory stores over NVLink (CUDA IPC) + peer-memory all-reduce" if os.environ.get("EFV_COMM", "peer") == "peer" else "NCCL send/recv + ncclAllReduce") + ", one n^2 plane per neighbour per SpMV",
                        "l2_policy": "inputs larger than L2"},
             "e2e": {"value": nV / float(e2e_t.item()), "unit": "DOF/s", "h2d_bytes_per_step": int(hb[0].item()),
                     "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * float(e2e_t.item()),
