@@ -470,7 +470,7 @@ __global__ void k_pcg_init_scalars(int G, const double *__restrict__ partial, do
   }
 }
 // alpha = rz / p.Ap ; x += alpha p ; r -= alpha Ap ; partials [0] r.z(new) [1] r.r(new)
-__global__ void __launch_bounds__(kBlock, 6) k_pcg_update_xr(int64_t n, int it, const double *__restrict__ sc,
+__global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, const double *__restrict__ sc,
                                                           const double *__restrict__ pAp_partial, int G,
                                                           const double *__restrict__ p, const double *__restrict__ Ap,
                                                           const double *__restrict__ dinv, double *__restrict__ x,
@@ -481,9 +481,24 @@ __global__ void __launch_bounds__(kBlock, 6) k_pcg_update_xr(int64_t n, int it, 
   double pAp = sum_partials(pAp_partial, G, red);
   double alpha = sc[it & 1] / pAp;
   double rz = 0, rr = 0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  // 16-byte accesses (buffers come from the pool: 256-byte aligned); the odd tail entry is done by one thread
+  const int64_t n2 = n >> 1;
+  const double2 *p2 = reinterpret_cast<const double2 *>(p), *Ap2 = reinterpret_cast<const double2 *>(Ap);
+  const double2 *d2 = reinterpret_cast<const double2 *>(dinv);
+  double2 *x2 = reinterpret_cast<double2 *>(x), *r2 = reinterpret_cast<double2 *>(r);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 pv = p2[i], av = Ap2[i], dv = d2[i];
+    double2 xv = x2[i], rv = r2[i];
+    xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+    rv.x -= alpha * av.x; rv.y -= alpha * av.y;
+    x2[i] = xv; r2[i] = rv;
+    rz += rv.x * rv.x * dv.x + rv.y * rv.y * dv.y;
+    rr += rv.x * rv.x + rv.y * rv.y;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t i = n - 1;
     x[i] += alpha * p[i];
-    double ri = r[i] - alpha * Ap[i];
+    const double ri = r[i] - alpha * Ap[i];
     r[i] = ri;
     rz += ri * ri * dinv[i];
     rr += ri * ri;
@@ -492,7 +507,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_pcg_update_xr(int64_t n, int it, 
   rr = block_sum(rr, red); if (threadIdx.x == 0) partial[Gout + blockIdx.x] = rr;
 }
 // beta = rz_new / rz_old ; p = dinv r + beta p ; block 0 publishes the scalars and the convergence flag
-__global__ void __launch_bounds__(kBlock, 8) k_pcg_update_p(int64_t n, int it, double *__restrict__ sc,
+__global__ void __launch_bounds__(kBlock) k_pcg_update_p(int64_t n, int it, double *__restrict__ sc,
                                                          const double *__restrict__ partial, int G,
                                                          const double *__restrict__ r, const double *__restrict__ dinv,
                                                          double *__restrict__ p, int *__restrict__ flags) {
@@ -501,8 +516,17 @@ __global__ void __launch_bounds__(kBlock, 8) k_pcg_update_p(int64_t n, int it, d
   double rz_new = sum_partials(partial, G, red);
   double rr = sum_partials(partial + G, G, red);
   double beta = rz_new / sc[it & 1];
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    p[i] = dinv[i] * r[i] + beta * p[i];
+  const int64_t n2 = n >> 1;
+  const double2 *r2 = reinterpret_cast<const double2 *>(r), *d2 = reinterpret_cast<const double2 *>(dinv);
+  double2 *p2 = reinterpret_cast<double2 *>(p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+    const double2 rv = r2[i], dv = d2[i];
+    double2 pv = p2[i];
+    pv.x = dv.x * rv.x + beta * pv.x;
+    pv.y = dv.y * rv.y + beta * pv.y;
+    p2[i] = pv;
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) p[n - 1] = dinv[n - 1] * r[n - 1] + beta * p[n - 1];
   // every block must have read flags[0]/sc before block 0 overwrites them: the values written here are only
   // consumed by the NEXT kernel (sc[(it+1)&1] is the slot nobody reads in this one)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
