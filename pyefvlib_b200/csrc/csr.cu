@@ -41,6 +41,52 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_graph_rows(MeshView m, int32
       n = 1;
     }
     __syncwarp();
+    if (n <= 64) {
+      // fast path (hexahedra: 64 candidates, tetrahedra on structured meshes: <= 96 -> slow path): bitonic sort of
+      // 64 keys held two per lane (key i lives in lane i & 31, slot i >> 5), then neighbour comparison for uniqueness
+      int k0 = (lane < n) ? cand[lane] : 0x7fffffff;
+      int k1 = (lane + 32 < n) ? cand[lane + 32] : 0x7fffffff;
+#pragma unroll
+      for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+          if (j == 32) {                                  // partner = other slot of the same lane (only when size == 64)
+            const int lo = min(k0, k1), hi = max(k0, k1);
+            k0 = lo; k1 = hi;
+          } else {
+            const int o0 = __shfl_xor_sync(0xffffffffu, k0, j), o1 = __shfl_xor_sync(0xffffffffu, k1, j);
+            const bool lower = (lane & j) == 0;           // this lane holds the lower index of the pair
+            const bool asc0 = (size == 64) ? true : ((lane & size) == 0);
+            const bool asc1 = (size == 64) ? true : (((lane + 32) & size) == 0);
+            k0 = (lower == asc0) ? min(k0, o0) : max(k0, o0);
+            k1 = (lower == asc1) ? min(k1, o1) : max(k1, o1);
+          }
+        }
+      }
+      int q0 = __shfl_up_sync(0xffffffffu, k0, 1), q1 = __shfl_up_sync(0xffffffffu, k1, 1);
+      const int last0 = __shfl_sync(0xffffffffu, k0, 31);
+      if (lane == 0) { q0 = -1; q1 = last0; }
+      const bool u0 = (k0 != 0x7fffffff) && (k0 != q0), u1 = (k1 != 0x7fffffff) && (k1 != q1);
+      const unsigned b0 = __ballot_sync(0xffffffffu, u0), b1 = __ballot_sync(0xffffffffu, u1);
+      if (!FILL) {
+        if (lane == 0) rowlen[v] = __popc(b0) + __popc(b1);
+      } else {
+        const int64_t base = gptr[v];
+        const unsigned lt = (1u << lane) - 1u;
+        if (u0) {
+          const int r = __popc(b0 & lt);
+          gcol[base + r] = k0;
+          if (k0 == (int32_t)v) diag_slot[v] = (int32_t)(base + r);
+        }
+        if (u1) {
+          const int r = __popc(b0) + __popc(b1 & lt);
+          gcol[base + r] = k1;
+          if (k1 == (int32_t)v) diag_slot[v] = (int32_t)(base + r);
+        }
+      }
+      __syncwarp();
+      continue;
+    }
     int count = 0;
     for (int i = lane; i < n; i += 32) {
       int32_t c = cand[i];
