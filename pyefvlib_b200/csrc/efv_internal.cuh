@@ -57,6 +57,7 @@ struct efv_mesh {
   int n_regions = 0;
   int uniform_code = -1;     // shape code when every element has the same shape, else -1
   int max_m = 0;
+  int max_incidence = 0;     // largest number of elements around a vertex
   efv::DBuf<double> coords;
   efv::DBuf<int64_t> elem_ptr;
   efv::DBuf<int32_t> conn;
@@ -124,6 +125,8 @@ struct efv_system {
   double t_assemble_ms = 0, t_solve_ms = 0, t_spmv_ms = 0;
   efv::DBuf<double> props_dev;
   efv::DBuf<double> scratch;            // local element matrices of the two-phase assembly, component-major
+  efv::DBuf<uint8_t> tmap_off;          // transposed slot map: per CSR entry the offset of its contribution list in the row block
+  efv::DBuf<uint32_t> tmap_idx;         // contributions: element | (l*M + j) << 26
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // assembly timing (read lazily: no host sync in the hot path)
   bool assemble_timed = false;
 };

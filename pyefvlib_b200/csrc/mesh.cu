@@ -20,6 +20,13 @@ static void check_vertex_ids(const int32_t *dev, int64_t n, int64_t nV, const ch
   EFV_REQUIRE(h == 0, std::string(what) + " refers to a vertex id outside [0, numberOfVertices)");
 }
 
+__global__ void k_max_count(const int32_t *__restrict__ a, int64_t n, int *__restrict__ out) {
+  int mx = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mx = max(mx, a[i]);
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
 // ---- incidence ------------------------------------------------------------------------------------------------
 __global__ void k_count_incidence(const int32_t *__restrict__ conn, int64_t n, int32_t *__restrict__ cnt) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -121,6 +128,12 @@ void mesh_finalize(efv_mesh *m, const int64_t *ep, int uniform_m) {
   m->inc_ptr.alloc(m->nV + 1);
   int64_t total = exclusive_scan_i32_to_i64(cnt.p, m->inc_ptr.p, m->nV);
   EFV_REQUIRE(total == m->conn_size, "incidence scan mismatch");
+  {
+    DBuf<int> mx(1);
+    mx.zero();
+    EFV_LAUNCH(k_max_count, grid_for(m->nV, 256), 256, 0, cnt.p, m->nV, mx.p);
+    mx.download(&m->max_incidence, 1);
+  }
   m->inc.alloc(total);
   cnt.zero();
   mv = view_of(m);
