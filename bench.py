@@ -331,7 +331,8 @@ def run_gpu(args):
                                "PCG(Jacobi) rtol 1e-10, 1 time step per step (assembly + BCs + RHS + solve)",
                    "vertices": nV, "elements": nE, "nnz": nnz, "pcg_iterations_per_step": timed_iters,
                    "warmup_iterations": iters_log, "assemble_ms_per_step": float(np.mean(asm_ms)),
-                   "solve_ms_per_step": float(np.mean(solve_ms)), "setup_ms": setup_ms, "mesh_upload_ms": upload_ms,
+                   "solve_ms_per_step": float(np.mean(solve_ms)), "solve_dof_per_s": nV / (float(np.mean(solve_ms)) * 1e-3),
+                   "time_to_solution_s_per_step": ms_per_step * 1e-3, "setup_ms": setup_ms, "mesh_upload_ms": upload_ms,
                    "host_mesh_generation_s": host_mesh_s, "l2_policy": "inputs (matrix of 12 B/nnz) larger than the 126 MB L2",
                    "assembled_elements_per_s": nE / (float(np.mean(asm_ms)) * 1e-3)},
         "roofline": roofline,

@@ -248,6 +248,15 @@ def send_heat_bcs(system, part, bcs):
             system.bc_dirichlet(idx, np.full(len(idx), val))
 
 
+def _peak_gbs():
+    import json
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
 def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     """N > 1 leg of bench.py: strong scaling of the C5/C2-style problem -- the SAME global mesh is cut into N slabs."""
     import json
@@ -311,6 +320,13 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     total_ms = float(t.item())
     nV = n * n * nz
     ms_per_step = total_ms / args.steps
+    # aggregate algorithmic bytes of the PCG iterations (12 nnz + 112 rows per iteration, owned rows only) over the ranks
+    nnz_owned = float(system.nnz)                  # local graph incl. ghost rows (values exist only for owned rows)
+    gb = torch.tensor([(12.0 * 27.0 * part.n_owned + 112.0 * part.n_owned) * float(np.sum(iters)), float(np.sum(solve_ms))],
+                      device="cuda", dtype=torch.float64)
+    gb_sum = gb.clone(); dist.all_reduce(gb_sum)
+    gb_max = gb.clone(); dist.all_reduce(gb_max, op=dist.ReduceOp.MAX)
+    pcg_gbs_total = float(gb_sum[0].item()) / (float(gb_max[1].item()) * 1e-3) / 1e9
     # e2e: mesh slab upload + setup + one step + field download, through the same Python API
     del system
     part.grid._device = None
@@ -344,8 +360,13 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
                                     ", STEADY, 3-D BC set, PCG(Jacobi) rtol 1e-10 from x0 = 0, one full assemble + solve per step"),
                        "vertices": nV, "pcg_iterations_per_step": iters, "warmup_iterations": warm,
                        "assemble_ms_per_step": float(np.mean(asm_ms)), "solve_ms_per_step": float(np.mean(solve_ms)),
+                       "solve_dof_per_s": nV / (float(np.mean(solve_ms)) * 1e-3), "time_to_solution_s_per_step": ms_per_step * 1e-3,
                        "host_slab_generation_s": host_s, "halo": ("peer-memory stores over NVLink (CUDA IPC) + peer-memory all-reduce" if os.environ.get("EFV_COMM", "peer") == "peer" else "NCCL send/recv + ncclAllReduce") + ", one n^2 plane per neighbour per SpMV",
                        "l2_policy": "inputs larger than L2"},
+            "roofline": {"bound": "hbm", "kernel": "PCG iteration (k_spmv_sell + k_pcg_update_xr + k_pcg_update_p), all ranks",
+                         "achieved": pcg_gbs_total, "peak": _peak_gbs() * world, "unit": "GB/s", "frac": pcg_gbs_total / (_peak_gbs() * world),
+                         "traffic": None, "note": "algorithmic bytes 12*27*rows + 112*rows per iteration per rank (interior 27-point rows), "
+                                                  "summed over ranks / slowest rank's solve time; peak = N x measured single-GPU copy bandwidth"},
             "e2e": {"value": nV / float(e2e_t.item()), "unit": "DOF/s", "h2d_bytes_per_step": int(hb[0].item()),
                     "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * float(e2e_t.item()),
                     "what": "per-rank slab upload + setup + assembly + one time-step solve + owned field download"},

@@ -66,8 +66,42 @@ def main():
     # 3. max|x - xold| is a global reduction
     d = s.max_abs_diff()
     assert abs(d - np.abs(xref - Told_global).max()) <= 1e-6 * np.abs(xref - Told_global).max()
+    # 4. partitioned linear elasticity (3 DOF per vertex: block halo, block SELL SpMV, negated PCG)
+    N0 = ("neumann", 0.0)
+    ebc = {"u": {"West": ("dirichlet", 0.0), "East": ("dirichlet", 0.0), "South": N0, "North": N0, "Bottom": N0, "Top": N0},
+           "v": {"West": N0, "East": N0, "South": ("dirichlet", 0.0), "North": ("neumann", -1e4), "Bottom": N0, "Top": N0},
+           "w": {"West": N0, "East": N0, "South": N0, "North": N0, "Bottom": ("dirichlet", 0.0), "Top": N0}}
+    eprops = {"Body": {"Density": 1800.0, "PoissonsRatio": 0.4, "ShearModulus": 6.0e6, "Gravity": 10.0}}
+    Ae, be = O.elasticity_system(og, eprops, ebc, gravity=True)
+    xe = O.solve_equilibrated(Ae, be)
+    se = efd.make_system(part, 3)
+    nl = part.grid.numberOfVertices
+    se.bc_clear()
+    for h, b in enumerate(part.grid.boundaries):
+        for i, var in enumerate("uvw"):
+            kind, val = ebc[var][b.name]
+            if kind == "neumann":
+                se.bc_neumann(b.handle, i, val, -1.0)
+        for i, var in enumerate("uvw"):
+            kind, val = ebc[var][b.name]
+            if kind == "dirichlet":
+                idx = part.boundary_vertices[h]
+                se.bc_dirichlet(idx + i * nl, np.full(len(idx), val))
+    se.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
+    se.elasticity_assemble(np.array([[6.0e6, 0.4, 1800.0, 10.0]]), True)
+    se.build_rhs(False)
+    se.upload(VEC_X, np.zeros(se.rows))
+    it_e, rr_e = se.solve_pcg(1e-10, 50000, negate=True)
+    assert rr_e <= 1e-10, (it_e, rr_e)
+    xl = se.download(VEC_X).reshape(3, nl)[:, :part.n_owned]
+    xg = xe.reshape(3, nV)[:, own]
+    t = torch.tensor([np.sum((xl - xg) ** 2), np.sum(xg ** 2)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t)
+    rel_e = float(torch.sqrt(t[0] / t[1]).item())
+    assert rel_e <= 1e-8, rel_e
     if rank == 0:
-        print(f"DIST_OK world={world} kind={kind} n={n} iters={iters} relres={relres:.2e} rel_l2={rel:.2e}")
+        print(f"DIST_OK world={world} kind={kind} n={n} iters={iters} relres={relres:.2e} rel_l2={rel:.2e} "
+              f"elasticity iters={it_e} rel_l2={rel_e:.2e}")
     dist.barrier()
     _lib.load().efv_comm_destroy()
     dist.destroy_process_group()
