@@ -29,9 +29,7 @@ enum { EFV_TRIANGLE = 0, EFV_QUADRILATERAL = 1, EFV_TETRAHEDRON = 2, EFV_HEXAHED
 enum { EFV_DIRICHLET_ROWS = 0,       /* reference form: row <- e_i^T, b_i = g  [ref: apps/heat_transfer.py:70-76,122-126] */
        EFV_DIRICHLET_SYMMETRIC = 1   /* + column elimination into the RHS (same solution, CG-ready)  */ };
 /* vectors owned by a system (efv_vec_upload / efv_vec_download); all have rows = ndof * nV entries, field-major */
-enum { EFV_VEC_X = 0, EFV_VEC_B = 1, EFV_VEC_XOLD = 2, EFV_VEC_DIAG = 3 };
-/* physics selector of efv_system_create (decides which lumped per-vertex vectors exist) */
-enum { EFV_PHYS_HEAT = 0, EFV_PHYS_ELASTICITY = 1, EFV_PHYS_BIOT = 2 };
+enum { EFV_VEC_X = 0, EFV_VEC_B = 1, EFV_VEC_XOLD = 2 };
 
 /* ---- process-level -------------------------------------------------------------------------------------- */
 const char *efv_last_error(void);
