@@ -9,6 +9,7 @@
 // These solvers replace the reference's explicit inverses (apps/heat_transfer.py:78-81,134-135,
 // apps/stress_equilibrium.py:170-173, apps/geomechanics.py:140,254).
 #include "views.cuh"
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,7 @@ struct KrylovWork {
   // sliced-ELL copy of a scalar matrix for the solver (slices of 32 rows, column-major inside a slice)
   DBuf<int64_t> sell_off;   // nslices+1, in units of 32-entry columns
   DBuf<int32_t> sell_cols;
+  DBuf<int32_t> sell_delta; // one per 32-entry column: common (column - row) offset, or kNoDelta
   DBuf<double> sell_vals;
   int64_t sell_slices = 0, sell_rows = 0;
   uint64_t sell_version = 0;
@@ -164,10 +166,18 @@ __global__ void k_sell_widths(int64_t nrows, const int64_t *__restrict__ gptr, i
     if (lane == 0) width[slice] = len;
   }
 }
-__global__ void k_sell_fill(int64_t nrows, int B, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
-                            const double *__restrict__ vals, const int64_t *__restrict__ off, int32_t *__restrict__ scol,
+constexpr int32_t kNoDelta = INT32_MIN;
+// Offsets of slice s start at a 16-byte aligned position of the offset array so that the TMA kernel can bulk-copy
+// them: q(s) = floor4(off[s] + 3 s) leaves room for width(s) entries before q(s+1).  Array length: off[n] + 3 n + 4.
+__device__ __host__ __forceinline__ int64_t sell_delta_pos(int64_t o0, int64_t slice) { return (o0 + 3 * slice) & ~(int64_t)3; }
+__global__ void k_sell_fill(int64_t nrows, int64_t ncols, int B, int compress, const int64_t *__restrict__ gptr,
+                            const int32_t *__restrict__ gcol, const double *__restrict__ vals,
+                            const int64_t *__restrict__ off, int32_t *__restrict__ scol, int32_t *__restrict__ sdelta,
                             double *__restrict__ sval) {
-  // block rows (vertices) of a slice are the lanes; values of entry k are stored as B consecutive 32-lane columns
+  // block rows (vertices) of a slice are the lanes; values of entry k are stored as B consecutive 32-lane columns.
+  // Index compression: when every lane of a 32-entry column has the same (column - row) offset -- the rule on meshes
+  // numbered like a structured grid -- the column is described by that one offset (sdelta) and the kernel never
+  // reads its 32 indices; otherwise sdelta = kNoDelta and the indices are read.  Lossless either way.
   int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   int64_t nslices = (nrows + 31) >> 5;
@@ -180,17 +190,28 @@ __global__ void k_sell_fill(int64_t nrows, int B, const int64_t *__restrict__ gp
     const int64_t o0 = off[slice];
     for (int k = 0; k < width; ++k) {
       const bool in = k < len;
-      scol[(o0 + k) * 32 + lane] = in ? gcol[r0 + k] : (int32_t)(valid ? v : 0);   // padding: zero times a valid x entry
+      int32_t col = in ? gcol[r0 + k] : 0;
+      const unsigned real = __ballot_sync(0xffffffffu, in);        // non-empty: width = longest row of the slice
+      const int64_t d = (int64_t)col - v;
+      const int64_t dref = __shfl_sync(0xffffffffu, d, __ffs(real) - 1);
+      // padded lanes multiply a zero by some valid x entry; they can join the common offset if it stays in range
+      const bool fits = in ? (d == dref) : (v + dref >= 0 && v + dref < ncols);
+      const bool uniform = compress && __all_sync(0xffffffffu, fits);
+      if (!in) col = uniform ? (int32_t)(v + dref) : (int32_t)(valid ? v : 0);
+      scol[(o0 + k) * 32 + lane] = col;
+      if (lane == 0) sdelta[sell_delta_pos(o0, slice) + k] = uniform ? (int32_t)dref : kNoDelta;
       for (int q = 0; q < B; ++q) sval[((o0 + k) * B + q) * 32 + lane] = in ? vals[(r0 + k) * B + q] : 0.0;
     }
   }
 }
-template <int U>
-__global__ void __launch_bounds__(kBlock) k_spmv_sell(int64_t nrows, const int64_t *__restrict__ off,
-                                                      const int32_t *__restrict__ scol, const double *__restrict__ sval,
+template <int U, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_spmv_sell(int64_t nrows, const int64_t *__restrict__ off,
+                                                      const int32_t *__restrict__ scol, const int32_t *__restrict__ sdelta,
+                                                      const double *__restrict__ sval,
                                                       const double *__restrict__ x, double *__restrict__ y, double sigma,
                                                       const double *__restrict__ rowscale, const double *__restrict__ w,
                                                       double *__restrict__ partial, const int *__restrict__ done) {
+  static_assert(32 % U == 0, "a batch must not straddle the 32 offsets a warp holds");
   __shared__ double red[32];
   if (done && *done) return;
   const int lane = threadIdx.x & 31;
@@ -202,19 +223,26 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(int64_t nrows, const int64
     const int width = (int)(off[slice + 1] - o0);
     const int32_t *c = scol + o0 * 32 + lane;
     const double *a = sval + o0 * 32 + lane;
+    const int vi = (int)(slice * 32 + lane);
     double acc = 0.0;
-    // predicated batches of U columns: every batch issues all its (column, value) loads before the gathers
-    for (int k = 0; k < width; k += U) {
-      int cc[U];
-      double vv[U];
+    for (int k0 = 0; k0 < width; k0 += 32) {
+      // one coalesced load brings the offsets of the next 32 columns; lane j keeps column k0+j's
+      const int myd = (k0 + lane < width) ? __ldg(sdelta + sell_delta_pos(o0, slice) + k0 + lane) : 0;
+      const int kend = min(width, k0 + 32);
+      // predicated batches of U columns: every batch issues all its (column, value) loads before the gathers
+      for (int k = k0; k < kend; k += U) {
+        int cc[U];
+        double vv[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool ok = k + u < width;
-        cc[u] = ok ? __ldcs(c + (int64_t)(k + u) * 32) : -1;
-        vv[u] = ok ? __ldcs(a + (int64_t)(k + u) * 32) : 0.0;
+        for (int u = 0; u < U; ++u) {
+          const bool ok = k + u < width;
+          const int d = __shfl_sync(0xffffffffu, myd, (k + u - k0) & 31);     // warp-uniform
+          cc[u] = !ok ? -1 : (d != kNoDelta ? vi + d : __ldcs(c + (int64_t)(k + u) * 32));
+          vv[u] = ok ? __ldcs(a + (int64_t)(k + u) * 32) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += (cc[u] >= 0) ? vv[u] * __ldg(x + cc[u]) : 0.0;
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) acc += (cc[u] >= 0) ? vv[u] * __ldg(x + cc[u]) : 0.0;
     }
     const int64_t v = slice * 32 + lane;
     if (v < nrows) {
@@ -227,6 +255,161 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell(int64_t nrows, const int64
   if (partial) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+  }
+}
+
+// ---- TMA-staged SELL SpMV (scalar matrices) ----------------------------------------------------------------------------
+// The register-staged kernel above keeps at most (resident warps x U) 256-byte loads in flight, which is what bounds it
+// once the index stream is compressed away.  Here the value stream does not pass through registers at all: every warp
+// owns a ring of kSellStages shared-memory buffers and one lane issues 1-D bulk copies (cp.async.bulk, the TMA engine)
+// of the next chunks -- a chunk is kSellChunk consecutive 32-entry columns of a slice, contiguous in the SELL layout --
+// completing on an mbarrier.  Registers only hold the x gathers.  One persistent block per SM.
+template <int CH, int ST, int W> struct SellTma {
+  static constexpr int kChunk = CH, kStages = ST, kWarps = W;      // columns per chunk, ring depth, warps per block
+  static constexpr size_t kStageBytes = (size_t)CH * 32 * sizeof(double) + CH * sizeof(int32_t);
+  static constexpr size_t kSmem = (size_t)W * ST * kStageBytes + (size_t)W * ST * 8 + 32 * 8;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+template <class C>
+__global__ void __launch_bounds__(C::kWarps * 32, 1)
+k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *__restrict__ scol,
+                const int32_t *__restrict__ sdelta_al, const double *__restrict__ sval, const double *__restrict__ x,
+                double *__restrict__ y, double sigma, const double *__restrict__ rowscale, const double *__restrict__ w,
+                double *__restrict__ partial, int npartial, const int *__restrict__ done) {
+  constexpr int kSellChunk = C::kChunk, kSellStages = C::kStages, kSellWarps = C::kWarps;
+  constexpr size_t kSellStageBytes = C::kStageBytes;
+  extern __shared__ __align__(128) unsigned char smem[];
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double *vbuf = reinterpret_cast<double *>(smem) + (size_t)wid * kSellStages * kSellChunk * 32;
+  int32_t *dbuf = reinterpret_cast<int32_t *>(smem + (size_t)kSellWarps * kSellStages * kSellChunk * 32 * sizeof(double)) +
+                  (size_t)wid * kSellStages * kSellChunk;
+  unsigned char *tail = smem + kSellWarps * kSellStages * kSellStageBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail) + wid * kSellStages;
+  double *red = reinterpret_cast<double *>(tail + kSellWarps * kSellStages * 8);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kSellStages; ++i) mbar_init(smem_u32(bars + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+  const int64_t nslices = (nrows + 31) >> 5;
+  // every warp owns a contiguous range of slices; the slice offsets are fetched 32 at a time (lane j holds slice
+  // base+j's) so that neither cursor waits on a global load per slice
+  const int64_t per = (nslices + (int64_t)gridDim.x * kSellWarps - 1) / ((int64_t)gridDim.x * kSellWarps);
+  const int64_t s_begin = min(nslices, ((int64_t)blockIdx.x * kSellWarps + wid) * per);
+  const int64_t s_end = min(nslices, s_begin + per);
+  struct Cursor { int64_t s, base, h0, h1, o0; int k, width; };
+  auto fetch = [&](Cursor &c) {            // (o0, width) of slice c.s
+    if (c.s >= s_end) return;
+    if (c.s >= c.base + 32) {
+      c.base = c.s;
+      c.h0 = off[min(c.s + lane, nslices)];
+      c.h1 = off[min(c.s + lane + 1, nslices)];
+    }
+    const int j = (int)(c.s - c.base);
+    c.o0 = __shfl_sync(0xffffffffu, c.h0, j);
+    c.width = (int)(__shfl_sync(0xffffffffu, c.h1, j) - c.o0);
+  };
+  Cursor pc{s_begin, s_begin - 32, 0, 0, 0, 0, 0}, cc = pc;
+  fetch(pc);
+  fetch(cc);
+  unsigned issued = 0, consumed = 0;
+  auto issue = [&]() {
+    const int n = min(kSellChunk, pc.width - pc.k);
+    const unsigned st = issued % kSellStages;
+    if (lane == 0) {
+      const uint32_t bar = smem_u32(bars + st);
+      const uint32_t vbytes = (uint32_t)n * 256u, dbytes = (uint32_t)((n + 3) & ~3) * 4u;
+      mbar_expect_tx(bar, vbytes + dbytes);
+      if (n > 0) {
+        bulk_g2s(smem_u32(vbuf + (size_t)st * kSellChunk * 32), sval + (pc.o0 + pc.k) * 32, vbytes, bar, policy);
+        bulk_g2s(smem_u32(dbuf + (size_t)st * kSellChunk), sdelta_al + sell_delta_pos(pc.o0, pc.s) + pc.k, dbytes, bar,
+                 policy);
+      }
+    }
+    ++issued;
+    pc.k += kSellChunk;
+    if (pc.k >= pc.width) { ++pc.s; pc.k = 0; fetch(pc); }
+  };
+#pragma unroll 1
+  for (int i = 0; i < kSellStages - 1 && pc.s < s_end; ++i) issue();
+  double dot = 0.0, acc = 0.0;
+#pragma unroll 1
+  while (cc.s < s_end) {
+    if (pc.s < s_end) issue();
+    const unsigned st = consumed % kSellStages;
+    mbar_wait(smem_u32(bars + st), (consumed / kSellStages) & 1u);
+    const int n = min(kSellChunk, cc.width - cc.k);
+    const double *sv = vbuf + (size_t)st * kSellChunk * 32 + lane;
+    const int myd = dbuf[(size_t)st * kSellChunk + (lane & (kSellChunk - 1))];
+    static_assert(kSellChunk <= 32 && (kSellChunk & (kSellChunk - 1)) == 0, "chunk offsets live in one warp");
+    const int vi = (int)(cc.s * 32 + lane);
+    // indices first, gathers second: a column load between two gathers would make every gather wait for the
+    // previous one on the shared scoreboard
+    int idx[kSellChunk];
+    if (__ballot_sync(0xffffffffu, lane < n && myd == kNoDelta) == 0u) {
+#pragma unroll
+      for (int u = 0; u < kSellChunk; ++u) idx[u] = vi + __shfl_sync(0xffffffffu, myd, u);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kSellChunk; ++u) {
+        const int d = __shfl_sync(0xffffffffu, myd, u);                       // warp-uniform
+        idx[u] = (u < n && d == kNoDelta) ? __ldcs(scol + (cc.o0 + cc.k + u) * 32 + lane) : vi + d;
+      }
+    }
+    double xv[kSellChunk];
+#pragma unroll
+    for (int u = 0; u < kSellChunk; ++u) xv[u] = (u < n) ? __ldg(x + idx[u]) : 0.0;
+#pragma unroll
+    for (int u = 0; u < kSellChunk; ++u) acc += (u < n) ? sv[u * 32] * xv[u] : 0.0;
+    __syncwarp();                                                            // buffer free for the copy issued next turn
+    ++consumed;
+    cc.k += kSellChunk;
+    if (cc.k >= cc.width) {
+      const int64_t v = cc.s * 32 + lane;
+      if (v < nrows) {
+        double yi = sigma * acc;
+        if (rowscale) yi *= rowscale[v];
+        y[v] = yi;
+        if (w) dot += w[v] * yi;
+      }
+      acc = 0.0;
+      ++cc.s;
+      cc.k = 0;
+      fetch(cc);
+    }
+  }
+  if (partial) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+    for (int i = blockIdx.x + (int)gridDim.x * (1 + (int)threadIdx.x); i < npartial; i += gridDim.x * blockDim.x)
+      partial[i] = 0.0;                                                      // the consumers sum npartial entries
   }
 }
 
@@ -318,13 +501,16 @@ static bool sell_prepare(efv_system *s, KrylovWork *w) {
     }
     const bool force = fmt && strcmp(fmt, "sell") == 0;
     w->sell_ok = force || padded <= 1.2 * (double)nnz_owned;      // irregular rows: stay on CSR
-    if (!w->sell_ok) { w->sell_cols.release(); w->sell_vals.release(); return false; }
+    if (!w->sell_ok) { w->sell_cols.release(); w->sell_delta.release(); w->sell_vals.release(); return false; }
     w->sell_cols.alloc((size_t)cols32 * 32);
+    w->sell_delta.alloc((size_t)cols32 + 3 * (size_t)nslices + 4);
     w->sell_vals.alloc((size_t)cols32 * 32 * s->ndof * s->ndof);
   }
   if (!w->sell_ok) return false;
-  EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->ndof * s->ndof, s->gptr.p, s->gcol.p, s->vals.p, w->sell_off.p,
-             w->sell_cols.p, w->sell_vals.p);
+  const char *cmp = getenv("EFV_SELL_DELTA");
+  const int compress = (s->ndof == 1 && !(cmp && atoi(cmp) == 0)) ? 1 : 0;      // block kernels read the indices
+  EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->nV, s->ndof * s->ndof, compress, s->gptr.p,
+             s->gcol.p, s->vals.p, w->sell_off.p, w->sell_cols.p, w->sell_delta.p, w->sell_vals.p);
   return true;
 }
 
@@ -370,12 +556,42 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
   KrylovWork *kw = s->kw;
   if (kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned) {
 #define EFV_SELL_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done
-    if (s->ndof == 1) {
+#define EFV_SELL1_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done
+    const char *ek = getenv("EFV_SELL_KERNEL");
+    if (s->ndof == 1 && !(ek && strcmp(ek, "reg") == 0)) {
+#define EFV_SELL_TMA(CH, ST, W)                                                                                       \
+  do {                                                                                                                 \
+    using C = SellTma<CH, ST, W>;                                                                                      \
+    static bool configured = false;                                                                                    \
+    if (!configured) {                                                                                                 \
+      EFV_CUDA(cudaFuncSetAttribute(k_spmv_sell_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));  \
+      configured = true;                                                                                               \
+    }                                                                                                                  \
+    EFV_LAUNCH(k_spmv_sell_tma<C>, num_sms(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,            \
+               kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, grid, done);                      \
+  } while (0)
+      const char *ec = getenv("EFV_SELL_TMA");
+      switch (ec ? atoi(ec) : 0) {
+        case 1: EFV_SELL_TMA(32, 2, 12); break;
+        case 2: EFV_SELL_TMA(32, 3, 8); break;
+        case 3: EFV_SELL_TMA(16, 2, 24); break;
+        case 4: EFV_SELL_TMA(8, 4, 24); break;
+        case 5: EFV_SELL_TMA(8, 3, 32); break;
+        case 6: EFV_SELL_TMA(16, 3, 16); break;
+        default: EFV_SELL_TMA(16, 2, 24); break;
+      }
+#undef EFV_SELL_TMA
+    } else if (s->ndof == 1) {
       const char *eu = getenv("EFV_SELL_UNROLL");
-      switch (eu ? atoi(eu) : 8) {
-        case 4: EFV_LAUNCH(k_spmv_sell<4>, grid, kBlock, 0, EFV_SELL_ARGS); break;
-        case 9: EFV_LAUNCH(k_spmv_sell<9>, grid, kBlock, 0, EFV_SELL_ARGS); break;
-        default: EFV_LAUNCH(k_spmv_sell<8>, grid, kBlock, 0, EFV_SELL_ARGS); break;
+      const char *eb = getenv("EFV_SELL_MINB");
+      switch ((eu ? atoi(eu) : 8) * 16 + (eb ? atoi(eb) : 4)) {
+        case 4 * 16 + 4: EFV_LAUNCH((k_spmv_sell<4, 4>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
+        case 4 * 16 + 6: EFV_LAUNCH((k_spmv_sell<4, 6>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
+        case 4 * 16 + 8: EFV_LAUNCH((k_spmv_sell<4, 8>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
+        case 16 * 16 + 4: EFV_LAUNCH((k_spmv_sell<16, 3>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
+        case 8 * 16 + 5: EFV_LAUNCH((k_spmv_sell<8, 5>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
+        case 8 * 16 + 6: EFV_LAUNCH((k_spmv_sell<8, 6>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
+        default: EFV_LAUNCH((k_spmv_sell<8, 4>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
       }
     } else if (s->ndof == 2) {
       EFV_LAUNCH((k_spmv_sell_bsr<2, 4>), grid, kBlock, 0, EFV_SELL_ARGS);
@@ -385,6 +601,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
       EFV_LAUNCH((k_spmv_sell_bsr<4, 2>), grid, kBlock, 0, EFV_SELL_ARGS);
     }
 #undef EFV_SELL_ARGS
+#undef EFV_SELL1_ARGS
     return;
   }
   switch (s->ndof) {

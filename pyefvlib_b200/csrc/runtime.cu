@@ -52,8 +52,6 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __global__ void scan_tile_sums(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ tile_sums) {
-  __shared__ double red[32];
-  (void)red;
   int64_t base = (int64_t)blockIdx.x * kScanTile;
   int64_t local = 0;
   for (int k = 0; k < kScanItems; ++k) {

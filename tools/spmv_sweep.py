@@ -18,21 +18,28 @@ stream = torch.cuda.ExternalStream(L.efv_get_stream())
 bytes_ = 12.0 * s.nnz + 24.0 * s.rows
 out = {}
 os.environ["EFV_SPMV_FORMAT"] = "sell"
-for U in (4, 7, 8, 9, 14):
-    os.environ["EFV_SELL_UNROLL"] = str(U)
-    for _ in range(3):
-        s.spmv(VEC_X, VEC_B)
-    torch.cuda.synchronize()
-    ysell = s.download(VEC_B)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(20):
-        s.spmv(VEC_X, VEC_B)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    out[f"SELL32_U{U}"] = round(bytes_ / ms / 1e6, 1)
-    print(f"SELL-32 unroll={U:2d}    {ms:.4f} ms  {bytes_/ms/1e6:8.1f} GB/s", flush=True)
+for delta in (1, 0):
+    os.environ["EFV_SELL_DELTA"] = str(delta)
+    s.heat_assemble(np.array([[1.0, 1.0, 1.0, 100.0]]), 1e-2, True)      # new values version -> SELL copy rebuilt
+    for U in ("tma", 4, 8, 16):
+        os.environ["EFV_SELL_KERNEL"] = "tma" if U == "tma" else "reg"
+        os.environ["EFV_SELL_UNROLL"] = str(U)
+        for _ in range(3):
+            s.spmv(VEC_X, VEC_B)
+        torch.cuda.synchronize()
+        ysell = s.download(VEC_B)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(20):
+            s.spmv(VEC_X, VEC_B)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        out[f"SELL32_delta{delta}_U{U}"] = round(bytes_ / ms / 1e6, 1)
+        print(f"SELL-32 delta={delta} unroll={U!s:>3}    {ms:.4f} ms  {bytes_/ms/1e6:8.1f} GB/s (algorithmic bytes)", flush=True)
+os.environ["EFV_SELL_DELTA"] = "1"
+os.environ.pop("EFV_SELL_UNROLL")
+os.environ.pop("EFV_SELL_KERNEL")
 os.environ["EFV_SPMV_FORMAT"] = "csr"
 s.spmv(VEC_X, VEC_B)
 ycsr = s.download(VEC_B)
