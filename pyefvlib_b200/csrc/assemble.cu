@@ -401,6 +401,267 @@ static void launch_heat_rows(efv_system *s, const double *dprops, int transient)
              s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
 }
 
+// ---- tile kernel (default heat assembly) ---------------------------------------------------------------------------------
+// k_heat_rows spends its time in the load/store unit: every lane of a row group re-reads the 9 staged face components
+// and 9 table entries from shared memory for every (row, element) pair.  k_heat_tiles keeps the row ownership (one
+// 8-lane group sums a row in ascending (local vertex, element) order: no float atomics, bit-reproducible)
+// but computes the pair contributions PAIR-centric: a block owns a tile of R consecutive rows, buckets the tile's
+// (element, local vertex) pairs by (shape, local vertex) so that every warp works on one local vertex l, and a thread
+// computes the whole local-matrix row l of its pair in registers with the table entries as constant-bank operands
+// (statically unrolled for that l).  The m coefficients go to a shared-memory slab indexed by the pair's position in
+// the row-major incidence order, from which the row groups then accumulate them through the byte slot map.
+constexpr int kTileThreads = 256;
+// byte offsets of the tile kernel's shared-memory arrays (32-bit shared addressing instead of seven generic pointers)
+struct TileSmem {
+  int rowacc, slab, posb, pks, order, krank, pkey, total;
+  __host__ __device__ TileSmem(int R, int max_row_len, int cap, int mmax) {
+    rowacc = 0;
+    slab = rowacc + R * max_row_len * 8;
+    posb = slab + (mmax + 2) * cap * 8;
+    pks = posb + cap * 8;
+    order = pks + cap * 4;                  // cap + 1024 work-list slots
+    krank = order + (cap + 1024) * 2;
+    pkey = krank + cap * 2;
+    total = (pkey + cap + 15) & ~15;
+  }
+};
+extern __shared__ __align__(16) unsigned char tile_smem[];
+template <class Tab, int L>
+__device__ __forceinline__ void heat_pair_row(const MeshView &m, const GeomView &g, const SysView &s, const double *__restrict__ props,
+                                              int64_t e, bool uniform, int idx, int cap, int slab_off, int posb_off, int mmax) {
+  // idx = compact position of the pair inside its (shape, local vertex) bucket: consecutive over the lanes of a warp
+  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE;
+  const int64_t gi = uniform ? e : m.group_index(e);
+  int64_t n = g.n[CODE];
+  // keep the SoA strides out of loop-invariant hoisting: 36 precomputed 64-bit plane offsets would not fit in registers
+  asm volatile("" : "+l"(n));
+  const double *pr = props + 3 * m.region[e];
+  const double cond = pr[0];
+  const double *St = g.St[CODE] + gi;
+  double t[NVF][D];
+#pragma unroll
+  for (int k = 0; k < NVF; ++k) {
+    const int f = Tab::vface_c(L, k) >> 1;
+#pragma unroll
+    for (int a = 0; a < D; ++a) t[k][a] = St[(int64_t)(f * D + a) * n];
+  }
+  const uint8_t *sp = s.slotpos + (uniform ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
+  unsigned long long pb;
+  if (uniform && M == 8) pb = *reinterpret_cast<const unsigned long long *>(sp);
+  else if (uniform && M == 4) pb = *reinterpret_cast<const unsigned int *>(sp);
+  else {
+    pb = 0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
+  }
+  const double vol = g.vol[CODE][(int64_t)L * n + gi];
+  *reinterpret_cast<unsigned long long *>(tile_smem + posb_off + idx * 8) = pb;
+  double *out = reinterpret_cast<double *>(tile_smem + slab_off) + idx;
+  out[mmax * cap] = vol * pr[2];
+  out[(mmax + 1) * cap] = vol * pr[1];
+#pragma unroll
+  for (int k = 0; k < NVF; ++k) {
+    const double sg = (Tab::vface_c(L, k) & 1) ? cond : -cond;    // forward vertex +flux, backward -flux (heat_transfer.py:52-54)
+#pragma unroll
+    for (int a = 0; a < D; ++a) t[k][a] *= sg;
+  }
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    double w = 0.0;
+#pragma unroll
+    for (int k = 0; k < NVF; ++k) {
+      const int f = Tab::vface_c(L, k) >> 1;
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+        if (Tab::ifD_c(f, j, a) != 0.0) w += Tab::ifD_c(f, j, a) * t[k][a];       // k * G^T s (heat_transfer.py:47)
+    }
+    out[j * cap] = w;
+  }
+}
+template <class Tab, int UCODE>
+__device__ __forceinline__ void heat_pair_shape(int l, const MeshView &m, const GeomView &g, const SysView &s,
+                                                const double *__restrict__ props, int64_t e, int idx, int cap, int slab_off,
+                                                int posb_off, int mmax) {
+  if constexpr (UCODE < 0 || UCODE == Tab::CODE) {
+    constexpr bool U = UCODE >= 0;
+    switch (l) {
+      case 0: heat_pair_row<Tab, 0>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      case 1: heat_pair_row<Tab, 1>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      case 2: heat_pair_row<Tab, 2>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      case 3: if constexpr (Tab::M > 3) heat_pair_row<Tab, 3>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      case 4: if constexpr (Tab::M > 4) heat_pair_row<Tab, 4>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      case 5: if constexpr (Tab::M > 4) heat_pair_row<Tab, 5>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      case 6: if constexpr (Tab::M > 4) heat_pair_row<Tab, 6>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      case 7: if constexpr (Tab::M > 4) heat_pair_row<Tab, 7>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      default: break;
+    }
+  }
+}
+
+template <int UCODE>
+__global__ void __launch_bounds__(kTileThreads, 4) k_heat_tiles(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
+                                                                const __grid_constant__ SysView s, const double *__restrict__ props,
+                                                                int transient, int max_row_len, int R, int cap, int mmax, int dir_mode,
+                                                                const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
+                                                                double *__restrict__ gen_out, double *__restrict__ acc_out,
+                                                                double *__restrict__ elim_out) {
+  const TileSmem off(R, max_row_len, cap, mmax);
+#define T_ROWACC reinterpret_cast<double *>(tile_smem + off.rowacc)
+#define T_SLAB reinterpret_cast<double *>(tile_smem + off.slab)
+#define T_POSB reinterpret_cast<unsigned long long *>(tile_smem + off.posb)
+#define T_PKS reinterpret_cast<uint32_t *>(tile_smem + off.pks)
+#define T_ORDER reinterpret_cast<uint16_t *>(tile_smem + off.order)
+#define T_KRANK reinterpret_cast<uint16_t *>(tile_smem + off.krank)
+#define T_PKEY (tile_smem + off.pkey)
+  __shared__ int cnt[32], base[33], cbase[32], rp[33];
+  __shared__ uint8_t okey[(2048 + 1024) / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid / kAsmGroup, gl = tid % kAsmGroup;
+  const unsigned gmask = 0xffu << ((tid & 31) / kAsmGroup * kAsmGroup);
+  const int64_t ntiles = (s.nV + R - 1) / R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t v0 = tile * R;
+    const int rows = (int)min((int64_t)R, s.nV - v0);
+    const int64_t P0 = m.inc_ptr[v0];
+    if (tid <= rows) rp[tid] = (int)(m.inc_ptr[v0 + tid] - P0);
+    if (tid < 32) cnt[tid] = 0;
+    for (int i = tid; i < rows * max_row_len; i += kTileThreads) T_ROWACC[i] = 0.0;
+    __syncthreads();
+    const int np = rp[rows];
+    // ---- bucket the tile's pairs by (shape, local vertex) ------------------------------------------------------------
+    for (int i = tid; i < np; i += kTileThreads) {
+      const uint32_t pk = m.inc[P0 + i];
+      const int code = (UCODE >= 0) ? UCODE : m.code(inc_elem(pk));
+      const int key = code * 8 + inc_local(pk);
+      const int rank = atomicAdd(&cnt[key], 1);          // the rank only decides which thread computes the pair and where
+                                                         // in the slab its coefficients wait; the sums do not depend on it
+      T_PKS[i] = pk;
+      T_PKEY[i] = (uint8_t)key;
+      T_KRANK[i] = (uint16_t)rank;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int padded = (cnt[tid] + 31) & ~31;
+      int incl = padded, cincl = cnt[tid];               // padded prefix: work-list slots; unpadded: compact slab positions
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o), cup = __shfl_up_sync(0xffffffffu, cincl, o);
+        if (lane >= o) { incl += up; cincl += cup; }
+      }
+      const int b0 = incl - padded;
+      base[tid] = b0;
+      cbase[tid] = cincl - cnt[tid];
+      if (tid == 31) base[32] = incl;
+      for (int q = b0 + cnt[tid]; q < b0 + padded; ++q) T_ORDER[q] = 0xffffu;
+      for (int q = b0; q < b0 + padded; q += 32) okey[q >> 5] = (uint8_t)tid;
+    }
+    __syncthreads();
+    for (int i = tid; i < np; i += kTileThreads) {
+      const int key = T_PKEY[i], rank = T_KRANK[i];
+      T_ORDER[base[key] + rank] = (uint16_t)i;
+      T_KRANK[i] = (uint16_t)(cbase[key] + rank);         // from here on: pair -> compact slab position
+    }
+    __syncthreads();
+    // ---- pair phase: one thread = one (element, local vertex) pair, a warp = one (shape, local vertex) ---------------
+    const int nslots = base[32];
+    for (int slot = tid; slot < nslots; slot += kTileThreads) {
+      const int pair = T_ORDER[slot];
+      if (pair == 0xffff) continue;
+      const int key = okey[slot >> 5];
+      const int64_t e = inc_elem(T_PKS[pair]);
+      const int l = key & 7;
+      const int idx = cbase[key] + (slot - base[key]);
+      switch (key >> 3) {
+        case 0: heat_pair_shape<TriangleTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 1: heat_pair_shape<QuadrilateralTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 2: heat_pair_shape<TetrahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        default: heat_pair_shape<HexahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+      }
+    }
+    __syncthreads();
+    // ---- row phase: 8-lane group per row, pairs in ascending (local vertex, element) order ----------------------------
+    if (grp < rows) {
+      const int64_t v = v0 + grp;
+      double *row = T_ROWACC + grp * max_row_len;
+      double gen = 0.0, accv = 0.0;
+      for (int q = rp[grp]; q < rp[grp + 1]; ++q) {
+        const int mm = (UCODE >= 0) ? shape_m(UCODE) : shape_m(T_PKEY[q] >> 3);
+        const int c = T_KRANK[q];
+        if (gl < mm) {
+          const int pos = (int)((T_POSB[c] >> (8 * gl)) & 0xff);
+          row[pos] += T_SLAB[gl * cap + c];
+        }
+        if (gl == 0) { gen += T_SLAB[mmax * cap + c]; accv += T_SLAB[(mmax + 1) * cap + c]; }
+      }
+      const int64_t r0 = s.gptr[v];
+      const int len = (int)(s.gptr[v + 1] - r0);
+      if (gl == 0) {
+        if (transient) row[s.diag_slot[v] - r0] += accv;       // heat_transfer.py:62-67
+        gen_out[v] = gen;
+        acc_out[v] = accv;
+      }
+      __syncwarp(gmask);
+      if (dir_mode < 0) {
+        for (int t = gl; t < len; t += kAsmGroup) s.vals[r0 + t] = row[t];
+      } else {
+        const bool rowd = dflag[v];
+        double el = 0.0;
+        for (int t = gl; t < len; t += kAsmGroup) {
+          const int c = s.gcol[r0 + t];
+          double a = row[t];
+          if (rowd) a = (c == v) ? 1.0 : 0.0;                    // heat_transfer.py:70-76
+          else if (dir_mode == 1 && dflag[c]) { el -= a * dval[c]; a = 0.0; }
+          s.vals[r0 + t] = a;
+        }
+        if (dir_mode == 1) {
+#pragma unroll
+          for (int o = kAsmGroup / 2; o > 0; o >>= 1) el += __shfl_xor_sync(gmask, el, o);
+          if (gl == 0) elim_out[v] = rowd ? 0.0 : el;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#undef T_ROWACC
+#undef T_SLAB
+#undef T_POSB
+#undef T_PKS
+#undef T_ORDER
+#undef T_KRANK
+#undef T_PKEY
+}
+// rows per tile and pair capacity for a mesh; false when even 8-row tiles do not fit
+static bool heat_tile_shape(const efv_system *s, int *R, int *cap, int *mmax, size_t *smem) {
+  const efv_mesh *m = s->mesh;
+  *mmax = m->uniform_code >= 0 ? shape_m(m->uniform_code) : (m->dim == 3 ? 8 : 4);
+  for (int r = 32; r >= 8; r >>= 1) {
+    const int64_t pairs = (int64_t)r * m->max_incidence;
+    if (pairs > 2047) continue;                                   // 11-bit ranks, 16-bit work-list entries
+    const int c = (int)((pairs + 15) & ~(int64_t)15) + 1;          // = 1 (mod 16): the slab planes start in different banks
+    const size_t bytes = (size_t)TileSmem(r, s->max_row_len, c, *mmax).total;
+    if (bytes > 64 * 1024 && r > 8) continue;                      // keep several blocks per SM
+    if (bytes > 200 * 1024) return false;
+    *R = r; *cap = c; *smem = bytes;
+    return true;
+  }
+  return false;
+}
+template <int UCODE>
+static bool launch_heat_tiles(efv_system *s, const double *dprops, int transient) {
+  int R, cap, mmax;
+  size_t smem;
+  if (!heat_tile_shape(s, &R, &cap, &mmax, &smem)) return false;
+  efv_mesh *m = s->mesh;
+  MeshView mv = view_of(m);
+  GeomView gv = geom_of(m);
+  SysView sv = sys_view(s);
+  EFV_CUDA(cudaFuncSetAttribute(k_heat_tiles<UCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t ntiles = div_up(s->n_owned, R);
+  EFV_LAUNCH(k_heat_tiles<UCODE>, grid_for(ntiles * kTileThreads, kTileThreads, 8), kTileThreads, smem, mv, gv, sv, dprops,
+             transient, s->max_row_len, R, cap, mmax, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
+  return true;
+}
+
 void heat_assemble(efv_system *s, const double *props_host, double dt, int transient) {
   efv_mesh *m = s->mesh;
   EFV_REQUIRE(s->ndof == 1, "heat needs a 1-DOF system");
@@ -431,6 +692,13 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
       case 2: launch_heat_two_phase<TetrahedronTab>(s, s->props_dev.p, transient); break;
       default: launch_heat_two_phase<HexahedronTab>(s, s->props_dev.p, transient); break;
     }
+  } else if (!(mode && strcmp(mode, "rows") == 0) &&
+             (m->uniform_code == 0   ? launch_heat_tiles<0>(s, s->props_dev.p, transient)
+              : m->uniform_code == 1 ? launch_heat_tiles<1>(s, s->props_dev.p, transient)
+              : m->uniform_code == 2 ? launch_heat_tiles<2>(s, s->props_dev.p, transient)
+              : m->uniform_code == 3 ? launch_heat_tiles<3>(s, s->props_dev.p, transient)
+                                     : launch_heat_tiles<-1>(s, s->props_dev.p, transient))) {
+    // default: pair-centric tile kernel
   } else {
     switch (m->uniform_code) {
       case 0: launch_heat_rows<0>(s, s->props_dev.p, transient); break;

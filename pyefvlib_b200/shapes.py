@@ -260,6 +260,8 @@ def generate_cuda_tables():
             f"  __device__ static __forceinline__ double ofN(int f, int k, int j) {{ return c_{n}_ofN[f][k][j]; }}",
             f"  __device__ static __forceinline__ int vface(int l, int k) {{ return c_{n}_vface[l][k]; }}",
             f"  __host__ __device__ static constexpr int vface_c(int l, int k) {{ constexpr int T[{m}][{nvf}] = {_c_array(vf, fi).replace(chr(10), '')}; return T[l][k]; }}",
+            f"  // literal copy of ifD: with static indices the entries become immediates of the DFMAs",
+            f"  __host__ __device__ static constexpr double ifD_c(int f, int j, int a) {{ constexpr double T[{nf}][{m}][{d}] = {_c_array(t.innerFaceShapeFunctionDerivatives, fd).replace(chr(10), '')}; return T[f][j][a]; }}",
             "};",
             "",
         ]
