@@ -401,6 +401,32 @@ static void launch_heat_rows(efv_system *s, const double *dprops, int transient)
              s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
 }
 
+// rows whose columns contain a Dirichlet DOF: the fused assembly epilogue only inspects the columns of those
+// (the mesh graph is structurally symmetric, so the neighbours of row d are the columns of row d)
+__global__ void k_mark_scatter(const int64_t *__restrict__ rows, int64_t n, const int64_t *__restrict__ gptr,
+                               const int32_t *__restrict__ gcol, uint8_t *__restrict__ mark) {
+  const int lane = threadIdx.x & 7;
+  for (int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; k < n; k += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const int64_t v = rows[k];
+    for (int64_t t = gptr[v] + lane; t < gptr[v + 1]; t += 8) mark[gcol[t]] = 1;
+  }
+}
+__global__ void k_mark_rows(int64_t nrows, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
+                            const uint8_t *__restrict__ flag, uint8_t *__restrict__ mark) {
+  const int lane = threadIdx.x & 7;
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+  const int64_t groups = ((int64_t)gridDim.x * blockDim.x) >> 3;
+  const int64_t rounds = (nrows + groups - 1) / groups;
+  for (int64_t it = 0; it < rounds; ++it) {
+    const int64_t v = it * groups + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3);
+    int any = 0;
+    if (v < nrows)
+      for (int64_t t = gptr[v] + lane; t < gptr[v + 1]; t += 8) any |= flag[gcol[t]];
+    any = __any_sync(gmask, any);
+    if (v < nrows && lane == 0) mark[v] = (uint8_t)(any != 0);
+  }
+}
+
 // ---- tile kernel (default heat assembly) ---------------------------------------------------------------------------------
 // k_heat_rows spends its time in the load/store unit: every lane of a row group re-reads the 9 staged face components
 // and 9 table entries from shared memory for every (row, element) pair.  k_heat_tiles keeps the row ownership (one
@@ -499,10 +525,11 @@ __device__ __forceinline__ void heat_pair_shape(int l, const MeshView &m, const 
 }
 
 template <int UCODE>
-__global__ void __launch_bounds__(kTileThreads, 4) k_heat_tiles(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
+__global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
                                                                 const __grid_constant__ SysView s, const double *__restrict__ props,
                                                                 int transient, int max_row_len, int R, int cap, int mmax, int dir_mode,
-                                                                const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
+                                                                const uint8_t *__restrict__ dflag, const uint8_t *__restrict__ rmark,
+                                                                const double *__restrict__ dval,
                                                                 double *__restrict__ gen_out, double *__restrict__ acc_out,
                                                                 double *__restrict__ elim_out) {
   const TileSmem off(R, max_row_len, cap, mmax);
@@ -601,8 +628,9 @@ __global__ void __launch_bounds__(kTileThreads, 4) k_heat_tiles(const __grid_con
         acc_out[v] = accv;
       }
       __syncwarp(gmask);
-      if (dir_mode < 0) {
+      if (dir_mode < 0 || !rmark[v]) {                           // no Dirichlet DOF among the columns: plain copy
         for (int t = gl; t < len; t += kAsmGroup) s.vals[r0 + t] = row[t];
+        if (dir_mode == 1 && gl == 0) elim_out[v] = 0.0;
       } else {
         const bool rowd = dflag[v];
         double el = 0.0;
@@ -658,7 +686,8 @@ static bool launch_heat_tiles(efv_system *s, const double *dprops, int transient
   EFV_CUDA(cudaFuncSetAttribute(k_heat_tiles<UCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = div_up(s->n_owned, R);
   EFV_LAUNCH(k_heat_tiles<UCODE>, grid_for(ntiles * kTileThreads, kTileThreads, 8), kTileThreads, smem, mv, gv, sv, dprops,
-             transient, s->max_row_len, R, cap, mmax, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
+             transient, s->max_row_len, R, cap, mmax, s->fuse_mode, s->dir_flag.p, s->row_mark.p, s->dir_value.p, s->gen.p, s->acc.p,
+             s->elim.p);
   return true;
 }
 
@@ -678,6 +707,10 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
   s->props_dev.upload(pr.data(), pr.size());
   if (!s->gen.n) { s->gen.alloc(s->nV); s->acc.alloc(s->nV); }
   if (!s->ev0) { EFV_CUDA(cudaEventCreate(&s->ev0)); EFV_CUDA(cudaEventCreate(&s->ev1)); }
+  if (s->fuse_mode >= 0 && !s->marks_valid) {
+    EFV_LAUNCH(k_mark_rows, grid_for(s->n_owned * 8, 256), 256, 0, s->n_owned, s->gptr.p, s->gcol.p, s->dir_flag.p, s->row_mark.p);
+    s->marks_valid = true;
+  }
   EFV_CUDA(cudaEventRecord(s->ev0, stream()));
   // default: the fused row kernel (k_heat_rows).  EFV_ASSEMBLY=two_phase selects the element-batch kernel + segmented
   // reduction (k_heat_local + k_local_to_csr) on uniform meshes: same values to the last bit, 10.9 ms vs 8.1 ms at C2
@@ -1234,6 +1267,11 @@ void bc_clear(efv_system *s) {
   }
   s->dir_flag.zero();
   s->dir_value.zero();
+  if (s->ndof == 1) {
+    if (!s->row_mark.n) s->row_mark.alloc(s->rows);
+    s->row_mark.zero();
+    s->marks_valid = true;
+  }
   EFV_CUDA(cudaMemsetAsync(s->dir_last.p, 0xff, s->dir_last.bytes(), stream()));   // -1
   s->static_rhs.zero();
   s->elim.zero();
@@ -1252,6 +1290,12 @@ void bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int6
   EFV_LAUNCH(k_dir_last, grid_for(n, 256), 256, 0, dr.p, n, g_dir_counter, s->nV, s->ndof, s->dir_last.p);
   EFV_LAUNCH(k_dir_set, grid_for(n, 256), 256, 0, dr.p, dv.p, n, g_dir_counter, s->nV, s->ndof, s->dir_last.p,
              s->dir_flag.p, s->dir_value.p);
+  if (s->ndof == 1 && s->marks_valid) {
+    if (s->n_owned == s->nV && s->gptr.n)
+      EFV_LAUNCH(k_mark_scatter, grid_for(n * 8, 256), 256, 0, dr.p, n, s->gptr.p, s->gcol.p, s->row_mark.p);
+    else
+      s->marks_valid = false;            // ghost Dirichlet rows have no graph row here: recomputed before the assembly
+  }
   EFV_CUDA(cudaStreamSynchronize(stream()));
   g_dir_counter += (int)n;
   s->has_dirichlet = true;

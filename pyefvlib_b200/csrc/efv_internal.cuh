@@ -113,6 +113,8 @@ struct efv_system {
   efv::DBuf<double> rhs_op;
   // Dirichlet set
   efv::DBuf<uint8_t> dir_flag;
+  efv::DBuf<uint8_t> row_mark;         // ndof == 1: row has a Dirichlet DOF among its columns (itself included)
+  bool marks_valid = false;
   efv::DBuf<double> dir_value;
   efv::DBuf<int32_t> dir_last;
   int dirichlet_mode = -1;
