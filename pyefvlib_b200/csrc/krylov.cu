@@ -33,6 +33,8 @@ struct KrylovWork {
   int64_t sell_slices = 0, sell_rows = 0;
   uint64_t sell_version = 0;
   bool sell_ok = false, sell_use = false;
+  bool sell_indexed = false;  // columns / offsets of the current pattern are in place (values-only refills)
+  int sell_compress = -1;
   int *h_flags = nullptr;   // pinned
   double *h_sc = nullptr;   // pinned
   cudaEvent_t ev = nullptr, e0 = nullptr, e1 = nullptr;
@@ -170,7 +172,7 @@ constexpr int32_t kNoDelta = INT32_MIN;
 // Offsets of slice s start at a 16-byte aligned position of the offset array so that the TMA kernel can bulk-copy
 // them: q(s) = floor4(off[s] + 3 s) leaves room for width(s) entries before q(s+1).  Array length: off[n] + 3 n + 4.
 __device__ __host__ __forceinline__ int64_t sell_delta_pos(int64_t o0, int64_t slice) { return (o0 + 3 * slice) & ~(int64_t)3; }
-__global__ void k_sell_fill(int64_t nrows, int64_t ncols, int B, int compress, const int64_t *__restrict__ gptr,
+__global__ void k_sell_fill(int64_t nrows, int64_t ncols, int B, int compress, int values_only, const int64_t *__restrict__ gptr,
                             const int32_t *__restrict__ gcol, const double *__restrict__ vals,
                             const int64_t *__restrict__ off, int32_t *__restrict__ scol, int32_t *__restrict__ sdelta,
                             double *__restrict__ sval) {
@@ -188,6 +190,13 @@ __global__ void k_sell_fill(int64_t nrows, int64_t ncols, int B, int compress, c
     const int len = valid ? (int)(gptr[v + 1] - r0) : 0;
     const int width = (int)(off[slice + 1] - off[slice]);
     const int64_t o0 = off[slice];
+    if (values_only) {                                             // the index part only depends on the pattern
+      for (int k = 0; k < width; ++k) {
+        const bool in = k < len;
+        for (int q = 0; q < B; ++q) sval[((o0 + k) * B + q) * 32 + lane] = in ? vals[(r0 + k) * B + q] : 0.0;
+      }
+      continue;
+    }
     for (int k = 0; k < width; ++k) {
       const bool in = k < len;
       int32_t col = in ? gcol[r0 + k] : 0;
@@ -481,6 +490,7 @@ static bool sell_prepare(efv_system *s, KrylovWork *w) {
   const int64_t nrows = s->n_owned;
   if (w->sell_version == s->vals_version && w->sell_rows == nrows) return w->sell_ok;
   w->sell_version = s->vals_version;
+  if (w->sell_rows != nrows) w->sell_slices = 0;          // different row range: rebuild the structure
   w->sell_rows = nrows;
   const int64_t nslices = (nrows + 31) >> 5;
   if (w->sell_slices != nslices) {
@@ -502,6 +512,7 @@ static bool sell_prepare(efv_system *s, KrylovWork *w) {
     const bool force = fmt && strcmp(fmt, "sell") == 0;
     w->sell_ok = force || padded <= 1.2 * (double)nnz_owned;      // irregular rows: stay on CSR
     if (!w->sell_ok) { w->sell_cols.release(); w->sell_delta.release(); w->sell_vals.release(); return false; }
+    w->sell_indexed = false;
     w->sell_cols.alloc((size_t)cols32 * 32);
     w->sell_delta.alloc((size_t)cols32 + 3 * (size_t)nslices + 4);
     w->sell_vals.alloc((size_t)cols32 * 32 * s->ndof * s->ndof);
@@ -509,8 +520,11 @@ static bool sell_prepare(efv_system *s, KrylovWork *w) {
   if (!w->sell_ok) return false;
   const char *cmp = getenv("EFV_SELL_DELTA");
   const int compress = (s->ndof == 1 && !(cmp && atoi(cmp) == 0)) ? 1 : 0;      // block kernels read the indices
-  EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->nV, s->ndof * s->ndof, compress, s->gptr.p,
-             s->gcol.p, s->vals.p, w->sell_off.p, w->sell_cols.p, w->sell_delta.p, w->sell_vals.p);
+  const int values_only = (w->sell_indexed && w->sell_compress == compress) ? 1 : 0;
+  EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->nV, s->ndof * s->ndof, compress, values_only,
+             s->gptr.p, s->gcol.p, s->vals.p, w->sell_off.p, w->sell_cols.p, w->sell_delta.p, w->sell_vals.p);
+  w->sell_indexed = true;
+  w->sell_compress = compress;
   return true;
 }
 
