@@ -11,4 +11,5 @@ from .shapes import SHAPES, TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON  # 
 from .problem import (ProblemData, NumericalSettings, PropertyData, BoundaryConditions, DirichletBoundaryCondition,  # noqa: F401
                       NeumannBoundaryCondition, Neumann, Dirichlet, Constant, Variable)
 from .solver import Solver, Saver, CsvSaver, NullSaver  # noqa: F401
+from .savers import VtuSaver, VtuSeriesSaver  # noqa: F401
 from .linear_system import LinearSystem, LinearSystemCSR  # noqa: F401

@@ -79,6 +79,12 @@ class Solver:
         self.outputPath = self.problemData.outputFilePath
         if self.saverType == "none":
             self.saver = NullSaver(self.grid, self.outputPath, self.problemData.libraryPath)
+        elif self.saverType in ("stream", "series"):
+            from .savers import VtuSeriesSaver
+            self.saver = VtuSeriesSaver(self.grid, self.outputPath, self.problemData.libraryPath)
+        elif self.extension == "vtu":
+            from .savers import VtuSaver
+            self.saver = VtuSaver(self.grid, self.outputPath, self.problemData.libraryPath)
         else:
             self.saver = Saver(self.grid, self.outputPath, self.problemData.libraryPath, extension=self.extension)
         self.numberOfVertices = self.grid.numberOfVertices
