@@ -24,7 +24,7 @@ typedef struct efv_mesh efv_mesh;       /* device mesh: vertices, elements, boun
 typedef struct efv_system efv_system;   /* linear system on a mesh: CSR graph, slot map, values, vectors, Krylov */
 
 /* shape codes [ref: PyEFVLib/Shape.py:7,35,63,98 ; Grid.py:41] */
-enum { EFV_TRIANGLE = 0, EFV_QUADRILATERAL = 1, EFV_TETRAHEDRON = 2, EFV_HEXAHEDRON = 3 };
+enum { EFV_TRIANGLE = 0, EFV_QUADRILATERAL = 1, EFV_TETRAHEDRON = 2, EFV_HEXAHEDRON = 3, EFV_PRISM = 4, EFV_PYRAMID = 5 };
 /* Dirichlet application modes */
 enum { EFV_DIRICHLET_ROWS = 0,       /* reference form: row <- e_i^T, b_i = g  [ref: apps/heat_transfer.py:70-76,122-126] */
        EFV_DIRICHLET_SYMMETRIC = 1   /* + column elimination into the RHS (same solution, CG-ready)  */ };

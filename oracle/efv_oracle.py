@@ -21,7 +21,8 @@ import scipy.sparse.linalg as spla
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _TABLES = os.path.join(_HERE, os.pardir, "tests", "golden", "shape_tables.npz")
 
-SHAPE_OF = {(3, 2): "Triangle", (4, 2): "Quadrilateral", (4, 3): "Tetrahedron", (8, 3): "Hexahedron"}
+SHAPE_OF = {(3, 2): "Triangle", (4, 2): "Quadrilateral", (4, 3): "Tetrahedron", (8, 3): "Hexahedron",
+            (6, 3): "Prism", (5, 3): "Pyramid"}
 
 
 class _Tab:
@@ -32,11 +33,12 @@ _tables = {}
 
 
 def tables():
-    """Reference-element constants exactly as the reference holds them (dumped from PyEFVLib/Shape.py:7-139
-    by oracle/make_golden.py into tests/golden/shape_tables.npz)."""
+    """Reference-element constants exactly as the reference holds them (dumped from PyEFVLib/Shape.py:7-199
+    by oracle/make_golden.py into tests/golden/shape_tables.npz; the ragged prism / pyramid tables are padded:
+    facet vertices with -1, neighbour vertices and outer-face values with 0)."""
     if not _tables:
         z = np.load(_TABLES)
-        for name in ("Triangle", "Quadrilateral", "Tetrahedron", "Hexahedron"):
+        for name in ("Triangle", "Quadrilateral", "Tetrahedron", "Hexahedron", "Prism", "Pyramid"):
             t = _Tab()
             t.name = name
             for key in ("ifD", "ifN", "ifNbr", "subD", "subN", "subT", "facetV", "ofN"):
@@ -44,6 +46,7 @@ def tables():
             t.m = t.ifD.shape[1]
             t.nf = t.ifD.shape[0]
             t.dim = t.ifD.shape[2]
+            t.facetN = (t.facetV >= 0).sum(axis=1)
             _tables[name] = t
     return _tables
 
@@ -235,10 +238,22 @@ class OracleGrid:
                 if t.name == "Tetrahedron":                    # Shape.py:84-96
                     p1 = (vb + vf + X3[:, t.ifNbr[:, 2], :]) / 3.0
                     p3 = (vb + vf + X3[:, t.ifNbr[:, 3], :]) / 3.0
-                else:                                          # Shape.py:119-139
+                elif t.name == "Hexahedron":                   # Shape.py:119-139
                     p1 = (vb + vf + X3[:, t.ifNbr[:, 2], :] + X3[:, t.ifNbr[:, 3], :]) / 4.0
                     p3 = (vb + vf + X3[:, t.ifNbr[:, 4], :] + X3[:, t.ifNbr[:, 5], :]) / 4.0
-                g.S[sl] = 0.5 * (np.cross(p1 - p0, p3 - p0) + np.cross(p3 - p2, p1 - p2))
+                elif t.name == "Prism":                        # Shape.py:162-185: quad facet, then triangle (faces 0-5) or quad
+                    p1 = (vb + vf + X3[:, t.ifNbr[:, 2], :] + X3[:, t.ifNbr[:, 3], :]) / 4.0
+                    p3 = (vb + vf + X3[:, t.ifNbr[:, 4], :]) / 3.0
+                    p3[:, 6:] = (vb[:, 6:] + vf[:, 6:] + X3[:, t.ifNbr[6:, 4], :] + X3[:, t.ifNbr[6:, 5], :]) / 4.0
+                else:                                          # Pyramid, Shape.py:208-247: p0 is the centre of the BASE
+                    p0 = (X3[:, :4, :].sum(axis=1) / 4.0)[:, None, :]
+                    p1 = (vb + vf + X3[:, t.ifNbr[:, 2], :]) / 3.0
+                    p1[:, :4] = (vb[:, :4] + vf[:, :4] + X3[:, 4:5, :]) / 3.0
+                    p3 = (vb + vf + X3[:, t.ifNbr[:, 3], :]) / 3.0
+                S = 0.5 * (np.cross(p1 - p0, p3 - p0) + np.cross(p3 - p2, p1 - p2))
+                if t.name == "Pyramid":                        # base edges: the triangle p0-p1-p2 only (Shape.py:222-231)
+                    S[:, :4] = 0.5 * np.cross(p1[:, :4] - p0, p2[:, :4] - p0)
+                g.S[sl] = S
 
     # -- boundaries -----------------------------------------------------------------------------------------
     def _boundaries(self):
@@ -261,13 +276,13 @@ class OracleGrid:
         # facet vertex set -> (first element in grid order containing it, local facet)  (Boundary.py:37-47)
         owner = {}
         for g in self.groups:
-            fverts = g.conn[:, g.tab.facetV]                    # [e, nfacets, mf]
-            ei, lf = np.nonzero(is_bv[fverts].all(axis=2))
-            for a, l in zip(ei.tolist(), lf.tolist()):
-                key = tuple(sorted(fverts[a, l].tolist()))
-                e = int(g.ids[a])
-                if key not in owner or e < owner[key][0]:
-                    owner[key] = (e, l)
+            for l in range(len(g.tab.facetV)):
+                fverts = g.conn[:, g.tab.facetV[l, :g.tab.facetN[l]]]      # [e, mf] (facets of a prism / pyramid differ in size)
+                for a in np.nonzero(is_bv[fverts].all(axis=1))[0].tolist():
+                    key = tuple(sorted(fverts[a].tolist()))
+                    e = int(g.ids[a])
+                    if key not in owner or e < owner[key][0]:
+                        owner[key] = (e, l)
         for b in self.boundaries:
             nF = len(b.facets)
             b.facet_element = np.zeros(nF, dtype=np.int64)

@@ -25,18 +25,27 @@ ns = R.load()
 P = ns["PyEFVLib"]
 
 
+def _padded(rows, fill, dtype):
+    rows = [list(r) for r in rows]
+    w = max(len(r) for r in rows)
+    return np.array([r + [fill] * (w - len(r)) for r in rows], dtype=dtype)
+
+
 def dump_shape_tables():
     out = {}
-    for name in ("Triangle", "Quadrilateral", "Tetrahedron", "Hexahedron"):
+    for name in ("Triangle", "Quadrilateral", "Tetrahedron", "Hexahedron", "Prism", "Pyramid"):
         c = getattr(P, name)
+        m = len(c.subelementTransformedVolumes)
         out[f"{name}_ifD"] = np.asarray(c.innerFaceShapeFunctionDerivatives, dtype=np.float64)
         out[f"{name}_ifN"] = np.asarray(c.innerFaceShapeFunctionValues, dtype=np.float64)
-        out[f"{name}_ifNbr"] = np.asarray(c.innerFaceNeighborVertices, dtype=np.int64)
+        out[f"{name}_ifNbr"] = _padded(c.innerFaceNeighborVertices, 0, np.int64)           # pyramid rows are ragged
         out[f"{name}_subD"] = np.asarray(c.subelementShapeFunctionDerivatives, dtype=np.float64)
         out[f"{name}_subN"] = np.asarray(c.subelementShapeFunctionValues, dtype=np.float64)
         out[f"{name}_subT"] = np.asarray(c.subelementTransformedVolumes, dtype=np.float64)
-        out[f"{name}_facetV"] = np.asarray(c.facetVerticesIndexes, dtype=np.int64)
-        out[f"{name}_ofN"] = np.asarray(c.outerFaceShapeFunctionValues, dtype=np.float64)
+        out[f"{name}_facetV"] = _padded(c.facetVerticesIndexes, -1, np.int64)              # prism / pyramid: 3- and 4-vertex facets
+        of = [[list(r) for r in f] for f in c.outerFaceShapeFunctionValues]
+        w = max(len(f) for f in of)
+        out[f"{name}_ofN"] = np.array([f + [[0.0] * m] * (w - len(f)) for f in of], dtype=np.float64)
     np.savez_compressed(os.path.join(GOLDEN, "shape_tables.npz"), **out)
 
 
@@ -344,16 +353,23 @@ from tests.cases import HEAT_CASES, STRESS_CASES, BIOT_CASES  # noqa: E402
 
 
 def main():
+    """No arguments: every fixture.  With arguments: only the named ones (e.g. `heat_Prisms_3d stress_Square`)."""
     os.makedirs(GOLDEN, exist_ok=True)
+    only = set(sys.argv[1:])
+    want = lambda name: not only or name in only
     for tag, c in HEAT_CASES.items():
-        heat_case(c["mesh"], c["props"], c["bcs"], tag, transient_steps=c["transient_steps"])
+        if want(f"heat_{tag}"):
+            heat_case(c["mesh"], c["props"], c["bcs"], tag, transient_steps=c["transient_steps"])
     for tag, c in STRESS_CASES.items():
-        stress_case(c["mesh"], c["props"], c["bcs"], tag, gravity=c["gravity"])
+        if want(f"stress_{tag}"):
+            stress_case(c["mesh"], c["props"], c["bcs"], tag, gravity=c["gravity"])
     for tag, c in BIOT_CASES.items():
-        biot_case(c["mesh"], c["props"], c["bcs"], tag, dt=c["dt"], steps=c["steps"])
+        if want(f"biot_{tag}"):
+            biot_case(c["mesh"], c["props"], c["bcs"], tag, dt=c["dt"], steps=c["steps"])
     for tag in ("Square", "Hexas3x3x3"):
-        c = BIOT_CASES[tag]
-        fixed_stress_case(c["mesh"], c["props"], c["bcs"], tag, dt=c["dt"], steps=2)
+        if want(f"fixed_stress_{tag}"):
+            c = BIOT_CASES[tag]
+            fixed_stress_case(c["mesh"], c["props"], c["bcs"], tag, dt=c["dt"], steps=2)
 
 
 if __name__ == "__main__":

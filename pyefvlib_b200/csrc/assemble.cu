@@ -401,6 +401,13 @@ static void launch_heat_rows(efv_system *s, const double *dprops, int transient)
              s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
 }
 
+// prisms and pyramids (Shape.py:141-247) are assembled by the tile kernel of the heat path; the row-group kernels
+// (k_heat_rows, elasticity, Biot) keep 3 faces per local vertex in their staging buffers
+static void require_classic_shapes(const efv_mesh *m, const char *what) {
+  EFV_REQUIRE(m->groups[EFV_PRISM].n == 0 && m->groups[EFV_PYRAMID].n == 0,
+              std::string("prism / pyramid elements are not supported by ") + what);
+}
+
 // rows whose columns contain a Dirichlet DOF: the fused assembly epilogue only inspects the columns of those
 // (the mesh graph is structurally symmetric, so the neighbours of row d are the columns of row d)
 __global__ void k_mark_scatter(const int64_t *__restrict__ rows, int64_t n, const int64_t *__restrict__ gptr,
@@ -445,8 +452,8 @@ struct TileSmem {
     slab = rowacc + R * max_row_len * 8;
     posb = slab + (mmax + 2) * cap * 8;
     pks = posb + cap * 8;
-    order = pks + cap * 4;                  // cap + 1024 work-list slots
-    krank = order + (cap + 1024) * 2;
+    order = pks + cap * 4;                  // cap + 2048 work-list slots (64 buckets padded to warp multiples)
+    krank = order + (cap + 2048) * 2;
     pkey = krank + cap * 2;
     total = (pkey + cap + 15) & ~15;
   }
@@ -469,7 +476,7 @@ __device__ __forceinline__ void heat_pair_row(const MeshView &m, const GeomView 
   for (int k = 0; k < NVF; ++k) {
     const int f = Tab::vface_c(L, k) >> 1;
 #pragma unroll
-    for (int a = 0; a < D; ++a) t[k][a] = St[(int64_t)(f * D + a) * n];
+    for (int a = 0; a < D; ++a) t[k][a] = (Tab::vface_c(L, k) >= 0) ? St[(int64_t)(f * D + a) * n] : 0.0;   // -1: no such face
   }
   const uint8_t *sp = s.slotpos + (uniform ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
   unsigned long long pb;
@@ -499,7 +506,8 @@ __device__ __forceinline__ void heat_pair_row(const MeshView &m, const GeomView 
       const int f = Tab::vface_c(L, k) >> 1;
 #pragma unroll
       for (int a = 0; a < D; ++a)
-        if (Tab::ifD_c(f, j, a) != 0.0) w += Tab::ifD_c(f, j, a) * t[k][a];       // k * G^T s (heat_transfer.py:47)
+        if (Tab::vface_c(L, k) >= 0 && Tab::ifD_c(f < 0 ? 0 : f, j, a) != 0.0)
+          w += Tab::ifD_c(f < 0 ? 0 : f, j, a) * t[k][a];                         // k * G^T s (heat_transfer.py:47)
     }
     out[j * cap] = w;
   }
@@ -511,14 +519,11 @@ __device__ __forceinline__ void heat_pair_shape(int l, const MeshView &m, const 
   if constexpr (UCODE < 0 || UCODE == Tab::CODE) {
     constexpr bool U = UCODE >= 0;
     switch (l) {
-      case 0: heat_pair_row<Tab, 0>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
-      case 1: heat_pair_row<Tab, 1>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
-      case 2: heat_pair_row<Tab, 2>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
-      case 3: if constexpr (Tab::M > 3) heat_pair_row<Tab, 3>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
-      case 4: if constexpr (Tab::M > 4) heat_pair_row<Tab, 4>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
-      case 5: if constexpr (Tab::M > 4) heat_pair_row<Tab, 5>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
-      case 6: if constexpr (Tab::M > 4) heat_pair_row<Tab, 6>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
-      case 7: if constexpr (Tab::M > 4) heat_pair_row<Tab, 7>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+#define EFV_PAIR_CASE(LL) \
+  case LL: if constexpr (Tab::M > LL) heat_pair_row<Tab, LL>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      EFV_PAIR_CASE(0) EFV_PAIR_CASE(1) EFV_PAIR_CASE(2) EFV_PAIR_CASE(3)
+      EFV_PAIR_CASE(4) EFV_PAIR_CASE(5) EFV_PAIR_CASE(6) EFV_PAIR_CASE(7)
+#undef EFV_PAIR_CASE
       default: break;
     }
   }
@@ -540,8 +545,8 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
 #define T_ORDER reinterpret_cast<uint16_t *>(tile_smem + off.order)
 #define T_KRANK reinterpret_cast<uint16_t *>(tile_smem + off.krank)
 #define T_PKEY (tile_smem + off.pkey)
-  __shared__ int cnt[32], base[33], cbase[32], rp[33];
-  __shared__ uint8_t okey[(2048 + 1024) / 32];
+  __shared__ int cnt[64], base[65], cbase[64], rp[33];           // buckets: shape code * 8 + local vertex
+  __shared__ uint8_t okey[(2048 + 2048) / 32];
   const int tid = threadIdx.x, lane = tid & 31;
   const int grp = tid / kAsmGroup, gl = tid % kAsmGroup;
   const unsigned gmask = 0xffu << ((tid & 31) / kAsmGroup * kAsmGroup);
@@ -551,7 +556,7 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
     const int rows = (int)min((int64_t)R, s.nV - v0);
     const int64_t P0 = m.inc_ptr[v0];
     if (tid <= rows) rp[tid] = (int)(m.inc_ptr[v0 + tid] - P0);
-    if (tid < 32) cnt[tid] = 0;
+    if (tid < 64) cnt[tid] = 0;
     for (int i = tid; i < rows * max_row_len; i += kTileThreads) T_ROWACC[i] = 0.0;
     __syncthreads();
     const int np = rp[rows];
@@ -567,20 +572,25 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
       T_KRANK[i] = (uint16_t)rank;
     }
     __syncthreads();
-    if (tid < 32) {
-      const int padded = (cnt[tid] + 31) & ~31;
-      int incl = padded, cincl = cnt[tid];               // padded prefix: work-list slots; unpadded: compact slab positions
+    if (tid < 32) {                                      // lane t scans buckets 2t and 2t+1
+      const int c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
+      const int p0 = (c0 + 31) & ~31, p1 = (c1 + 31) & ~31;
+      int incl = p0 + p1, cincl = c0 + c1;               // padded prefix: work-list slots; unpadded: compact slab positions
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int up = __shfl_up_sync(0xffffffffu, incl, o), cup = __shfl_up_sync(0xffffffffu, cincl, o);
         if (lane >= o) { incl += up; cincl += cup; }
       }
-      const int b0 = incl - padded;
-      base[tid] = b0;
-      cbase[tid] = cincl - cnt[tid];
-      if (tid == 31) base[32] = incl;
-      for (int q = b0 + cnt[tid]; q < b0 + padded; ++q) T_ORDER[q] = 0xffffu;
-      for (int q = b0; q < b0 + padded; q += 32) okey[q >> 5] = (uint8_t)tid;
+      const int b0 = incl - p0 - p1, cb0 = cincl - c0 - c1;
+      base[2 * tid] = b0;
+      base[2 * tid + 1] = b0 + p0;
+      cbase[2 * tid] = cb0;
+      cbase[2 * tid + 1] = cb0 + c0;
+      if (tid == 31) base[64] = incl;
+      for (int q = b0 + c0; q < b0 + p0; ++q) T_ORDER[q] = 0xffffu;
+      for (int q = b0 + p0 + c1; q < b0 + p0 + p1; ++q) T_ORDER[q] = 0xffffu;
+      for (int q = b0; q < b0 + p0; q += 32) okey[q >> 5] = (uint8_t)(2 * tid);
+      for (int q = b0 + p0; q < b0 + p0 + p1; q += 32) okey[q >> 5] = (uint8_t)(2 * tid + 1);
     }
     __syncthreads();
     for (int i = tid; i < np; i += kTileThreads) {
@@ -590,7 +600,7 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
     }
     __syncthreads();
     // ---- pair phase: one thread = one (element, local vertex) pair, a warp = one (shape, local vertex) ---------------
-    const int nslots = base[32];
+    const int nslots = base[64];
     for (int slot = tid; slot < nslots; slot += kTileThreads) {
       const int pair = T_ORDER[slot];
       if (pair == 0xffff) continue;
@@ -602,7 +612,9 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
         case 0: heat_pair_shape<TriangleTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
         case 1: heat_pair_shape<QuadrilateralTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
         case 2: heat_pair_shape<TetrahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        default: heat_pair_shape<HexahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 3: heat_pair_shape<HexahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 4: heat_pair_shape<PrismTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        default: heat_pair_shape<PyramidTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
       }
     }
     __syncthreads();
@@ -716,7 +728,7 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
   // reduction (k_heat_local + k_local_to_csr) on uniform meshes: same values to the last bit, 10.9 ms vs 8.1 ms at C2
   // (profiles/r01_assembly_variants.json) because the reduction phase is latency-bound.
   const char *mode = getenv("EFV_ASSEMBLY");
-  const bool fits = m->uniform_code >= 0 && (int64_t)m->max_incidence * shape_m(m->uniform_code) <= 255 && m->nE < (int64_t(1) << 26);
+  const bool fits = m->uniform_code >= 0 && m->uniform_code <= 3 && (int64_t)m->max_incidence * shape_m(m->uniform_code) <= 255 && m->nE < (int64_t(1) << 26);
   const bool two_phase = mode && strcmp(mode, "two_phase") == 0 && fits;
   if (two_phase) {
     switch (m->uniform_code) {
@@ -730,9 +742,12 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
               : m->uniform_code == 1 ? launch_heat_tiles<1>(s, s->props_dev.p, transient)
               : m->uniform_code == 2 ? launch_heat_tiles<2>(s, s->props_dev.p, transient)
               : m->uniform_code == 3 ? launch_heat_tiles<3>(s, s->props_dev.p, transient)
+              : m->uniform_code == 4 ? launch_heat_tiles<4>(s, s->props_dev.p, transient)
+              : m->uniform_code == 5 ? launch_heat_tiles<5>(s, s->props_dev.p, transient)
                                      : launch_heat_tiles<-1>(s, s->props_dev.p, transient))) {
     // default: pair-centric tile kernel
   } else {
+    require_classic_shapes(m, "the row-group heat kernel");
     switch (m->uniform_code) {
       case 0: launch_heat_rows<0>(s, s->props_dev.p, transient); break;
       case 1: launch_heat_rows<1>(s, s->props_dev.p, transient); break;
@@ -911,6 +926,7 @@ static void launch_elasticity_rows(efv_system *s, const double *dprops, int grav
 void elasticity_assemble(efv_system *s, const double *props_host, int gravity) {
   efv_mesh *m = s->mesh;
   EFV_REQUIRE(s->ndof == m->dim, "elasticity needs ndof == dimension");
+  require_classic_shapes(m, "the elasticity assembly");
   geometry_build(m);
   if (!s->dir_flag.n) bc_clear(s);
   std::vector<double> pr(3 * m->n_regions);
@@ -1196,6 +1212,7 @@ static void launch_biot_rows(efv_system *s, const double *dprops, const double *
 void biot_assemble(efv_system *s, const double *props_host, double dt, const double *gvec) {
   efv_mesh *m = s->mesh;
   EFV_REQUIRE(s->ndof == m->dim + 1, "Biot needs ndof == dimension + 1");
+  require_classic_shapes(m, "the Biot assembly");
   geometry_build(m);
   if (!s->dir_flag.n) bc_clear(s);
   std::vector<double> pr(7 * m->n_regions);

@@ -14,9 +14,9 @@
 
 namespace efv {
 
-constexpr int kNumShapes = 4;
+constexpr int kNumShapes = 6;
 constexpr int kMaxM = 8;
-enum { EFV_TRI = 0, EFV_QUAD = 1, EFV_TET = 2, EFV_HEX = 3 };
+enum { EFV_TRI = 0, EFV_QUAD = 1, EFV_TET = 2, EFV_HEX = 3, EFV_PRISM = 4, EFV_PYRAMID = 5 };
 
 struct ShapeGroup {
   int code = -1;

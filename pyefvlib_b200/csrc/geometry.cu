@@ -56,14 +56,16 @@ __global__ void __launch_bounds__(128) k_geometry(MeshView m, const int32_t *__r
 #pragma unroll
     for (int a = 0; a < 3; ++a) X[j][a] = m.coords[v * 3 + a];
   }
-  // element centroid: sum(vertices) / m  (Element.py:59)
+  // element centroid: sum(vertices) / m  (Element.py:59); the pyramid's area vectors use the centre of its base
+  // instead (Shape.py:213-216)
+  constexpr int MC = (Tab::CODE == 5) ? 4 : M;
   double c[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     double sum = X[0][a];
 #pragma unroll
-    for (int j = 1; j < M; ++j) sum += X[j][a];
-    c[a] = sum / M;
+    for (int j = 1; j < MC; ++j) sum += X[j][a];
+    c[a] = sum / MC;
   }
 #pragma unroll
   for (int f = 0; f < NF; ++f) {
@@ -90,24 +92,39 @@ __global__ void __launch_bounds__(128) k_geometry(MeshView m, const int32_t *__r
       double ay = c[1] - (X[vb][1] + X[vf][1]) / 2.0;
       s[0] = ay; s[1] = -ax; s[2] = 0.0;
     } else {
+      // p1 / p3: centroids of the two element facets that share the edge (triangles or quadrilaterals: Shape.py:84-96
+      // tet, :119-139 hex, :162-185 prism, :208-247 pyramid); the neighbour table lists their remaining vertices
+      const int NA = Tab::adjn(f, 0), NB = Tab::adjn(f, 1);        // compile-time after unrolling
       double p1[3], p2[3], p3[3];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         p2[a] = (X[vb][a] + X[vf][a]) / 2.0;
-        if constexpr (Tab::NNBR == 4) {
-          p1[a] = (X[vb][a] + X[vf][a] + X[Tab::nbr(f, 2)][a]) / 3.0;
-          p3[a] = (X[vb][a] + X[vf][a] + X[Tab::nbr(f, 3)][a]) / 3.0;
-        } else {
-          p1[a] = (X[vb][a] + X[vf][a] + X[Tab::nbr(f, 2)][a] + X[Tab::nbr(f, 3)][a]) / 4.0;
-          p3[a] = (X[vb][a] + X[vf][a] + X[Tab::nbr(f, 4)][a] + X[Tab::nbr(f, 5)][a]) / 4.0;
-        }
-      }
-      double u[3], w[3], y[3], z[3];
+        double sa = X[vb][a] + X[vf][a], sb = sa;
 #pragma unroll
-      for (int a = 0; a < 3; ++a) { u[a] = p1[a] - c[a]; w[a] = p3[a] - c[a]; y[a] = p3[a] - p2[a]; z[a] = p1[a] - p2[a]; }
-      s[0] = 0.5 * (u[1] * w[2] - w[1] * u[2] + y[1] * z[2] - z[1] * y[2]);
-      s[1] = 0.5 * (w[0] * u[2] - u[0] * w[2] + z[0] * y[2] - y[0] * z[2]);
-      s[2] = 0.5 * (u[0] * w[1] - w[0] * u[1] + y[0] * z[1] - z[0] * y[1]);
+        for (int q = 0; q < 2; ++q)
+          if (q < NA) sa += X[Tab::nbr(f, 2 + q)][a];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+          if (q < NB) sb += X[Tab::nbr(f, (2 + NA + q) < Tab::NNBR ? (2 + NA + q) : 0)][a];
+        p1[a] = sa / (2.0 + NA);
+        p3[a] = sb / (2.0 + NB);
+      }
+      if (NB == 0) {
+        // triangular face  centroid -> facet centroid -> edge midpoint  (pyramid base edges, Shape.py:222-231)
+        double u[3], w[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { u[a] = p1[a] - c[a]; w[a] = p2[a] - c[a]; }
+        s[0] = 0.5 * (u[1] * w[2] - w[1] * u[2]);
+        s[1] = 0.5 * (w[0] * u[2] - u[0] * w[2]);
+        s[2] = 0.5 * (u[0] * w[1] - w[0] * u[1]);
+      } else {
+        double u[3], w[3], y[3], z[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { u[a] = p1[a] - c[a]; w[a] = p3[a] - c[a]; y[a] = p3[a] - p2[a]; z[a] = p1[a] - p2[a]; }
+        s[0] = 0.5 * (u[1] * w[2] - w[1] * u[2] + y[1] * z[2] - z[1] * y[2]);
+        s[1] = 0.5 * (w[0] * u[2] - u[0] * w[2] + z[0] * y[2] - y[0] * z[2]);
+        s[2] = 0.5 * (u[0] * w[1] - w[0] * u[1] + y[0] * z[1] - z[0] * y[1]);
+      }
     }
 #pragma unroll
     for (int a = 0; a < 3; ++a) S[(int64_t)(f * 3 + a) * n + k] = s[a];
@@ -132,7 +149,7 @@ __global__ void __launch_bounds__(128) k_geometry(MeshView m, const int32_t *__r
         for (int j = 0; j < M; ++j) acc += Tab::subD(l, j, a) * X[j][q];
         Js[a][q] = acc;
       }
-    vol[(int64_t)l * n + k] = Tab::SUBVOL * SmallMat<D>::det(Js);
+    vol[(int64_t)l * n + k] = Tab::subvol(l) * SmallMat<D>::det(Js);
   }
 }
 

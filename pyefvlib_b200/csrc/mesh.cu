@@ -62,6 +62,8 @@ static int code_for(int mm, int dim) {
   if (mm == 3 && dim == 2) return EFV_TRI;
   if (mm == 4) return (dim == 2) ? EFV_QUAD : EFV_TET;
   if (mm == 8 && dim == 3) return EFV_HEX;
+  if (mm == 6 && dim == 3) return EFV_PRISM;
+  if (mm == 5 && dim == 3) return EFV_PYRAMID;
   throw Error("This element has not been registered in Grid yet");   // Element.py:27
 }
 
@@ -69,7 +71,7 @@ static int code_for(int mm, int dim) {
 void mesh_finalize(efv_mesh *m, const int64_t *ep, int uniform_m) {
   // classify shapes on the host (nE integer ops), build groups
   const int64_t nE = m->nE;
-  int64_t counts[kNumShapes] = {0, 0, 0, 0};
+  int64_t counts[kNumShapes] = {0, 0, 0, 0, 0, 0};
   std::vector<uint8_t> shape;
   m->max_m = 0;
   m->n_inner_faces = 0;
@@ -148,12 +150,12 @@ void mesh_finalize(efv_mesh *m, const int64_t *ep, int uniform_m) {
 // outward correction (Boundary.py:56-60), outer faces (Facet.py:41-45, Boundary.py:62-70, OuterFace.py:18-19)
 template <class Tab>
 __device__ bool match_local_facet(const int *loc, int mf, int &lf_out) {
-  if (mf != Tab::MF) return false;
   for (int lf = 0; lf < Tab::NFACETS; ++lf) {
+    if (Tab::facetN(lf) != mf) continue;            // prisms and pyramids have 3- and 4-vertex facets
     bool all = true;
     for (int k = 0; k < mf && all; ++k) {
       bool found = false;
-      for (int q = 0; q < Tab::MF; ++q) found |= (Tab::facetV(lf, q) == loc[k]);
+      for (int q = 0; q < mf; ++q) found |= (Tab::facetV(lf, q) == loc[k]);
       all &= found;
     }
     if (all) { lf_out = lf; return true; }
@@ -208,7 +210,9 @@ __global__ void k_match_facets(MeshView m, int64_t nF, const int64_t *__restrict
       case 0: ok = match_local_facet<TriangleTab>(loc, mf, lf); break;
       case 1: ok = match_local_facet<QuadrilateralTab>(loc, mf, lf); break;
       case 2: ok = match_local_facet<TetrahedronTab>(loc, mf, lf); break;
-      default: ok = match_local_facet<HexahedronTab>(loc, mf, lf); break;
+      case 3: ok = match_local_facet<HexahedronTab>(loc, mf, lf); break;
+      case 4: ok = match_local_facet<PrismTab>(loc, mf, lf); break;
+      default: ok = match_local_facet<PyramidTab>(loc, mf, lf); break;
     }
     if (!ok) { atomicExch(error_flag, 2); continue; }
     facet_element[f] = owner;
@@ -261,7 +265,9 @@ __global__ void k_match_facets(MeshView m, int64_t nF, const int64_t *__restrict
         case 0: pos = local_pos_in_facet<TriangleTab>(lf, loc[k]); break;
         case 1: pos = local_pos_in_facet<QuadrilateralTab>(lf, loc[k]); break;
         case 2: pos = local_pos_in_facet<TetrahedronTab>(lf, loc[k]); break;
-        default: pos = local_pos_in_facet<HexahedronTab>(lf, loc[k]); break;
+        case 3: pos = local_pos_in_facet<HexahedronTab>(lf, loc[k]); break;
+        case 4: pos = local_pos_in_facet<PrismTab>(lf, loc[k]); break;
+        default: pos = local_pos_in_facet<PyramidTab>(lf, loc[k]); break;
       }
       outer_local[o] = pos;
     }

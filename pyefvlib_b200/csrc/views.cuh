@@ -32,10 +32,16 @@ __host__ __device__ __forceinline__ uint32_t inc_pack(int64_t e, int l) { return
 __host__ __device__ __forceinline__ int64_t inc_elem(uint32_t pk) { return (int64_t)(pk & ((1u << kIncShift) - 1u)); }
 __host__ __device__ __forceinline__ int inc_local(uint32_t pk) { return (int)(pk >> kIncShift); }
 
-__host__ __device__ constexpr __forceinline__ int shape_m(int code) { return code == 0 ? 3 : (code == 3 ? 8 : 4); }
-__host__ __device__ constexpr __forceinline__ int shape_nf(int code) { return code == 0 ? 3 : (code == 1 ? 4 : (code == 2 ? 6 : 12)); }
+// shape codes: 0 triangle, 1 quadrilateral, 2 tetrahedron, 3 hexahedron, 4 prism, 5 pyramid
+__host__ __device__ constexpr __forceinline__ int shape_m(int code) {
+  return code == 0 ? 3 : (code == 3 ? 8 : (code == 4 ? 6 : (code == 5 ? 5 : 4)));
+}
+__host__ __device__ constexpr __forceinline__ int shape_nf(int code) {
+  return code == 0 ? 3 : (code == 1 ? 4 : (code == 2 ? 6 : (code == 3 ? 12 : (code == 4 ? 9 : 8))));
+}
 __host__ __device__ constexpr __forceinline__ int shape_dim(int code) { return code < 2 ? 2 : 3; }
-__host__ __device__ constexpr __forceinline__ int shape_nvf(int code) { return code < 2 ? 2 : 3; }
+// inner faces touching a local vertex (the apex of a pyramid has 4, its base vertices 3: padded with -1 in the tables)
+__host__ __device__ constexpr __forceinline__ int shape_nvf(int code) { return code < 2 ? 2 : (code == 5 ? 4 : 3); }
 
 inline MeshView view_of(const efv_mesh *m) {
   MeshView v;
@@ -84,6 +90,8 @@ inline GeomView geom_of(const efv_mesh *m) {
       case 1: { using Tab = QuadrilateralTab; __VA_ARGS__; } break;           \
       case 2: { using Tab = TetrahedronTab; __VA_ARGS__; } break;             \
       case 3: { using Tab = HexahedronTab; __VA_ARGS__; } break;              \
+      case 4: { using Tab = PrismTab; __VA_ARGS__; } break;                   \
+      case 5: { using Tab = PyramidTab; __VA_ARGS__; } break;                 \
       default: throw efv::Error("unknown shape code");                        \
     }                                                                         \
   } while (0)

@@ -24,9 +24,9 @@ from itertools import combinations
 import numpy as np
 
 # shape codes shared with the C-ABI (include/efv_b200.h: EFV_SHAPE_*)
-TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON = 0, 1, 2, 3
+TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON, PRISM, PYRAMID = 0, 1, 2, 3, 4, 5
 SHAPE_NAMES = {TRIANGLE: "Triangle", QUADRILATERAL: "Quadrilateral", TETRAHEDRON: "Tetrahedron",
-               HEXAHEDRON: "Hexahedron"}
+               HEXAHEDRON: "Hexahedron", PRISM: "Prism", PYRAMID: "Pyramid"}
 
 
 def _N_simplex(xi):
@@ -66,6 +66,42 @@ def _dN_tensor(verts):
     return dN
 
 
+def _N_prism(xi):
+    """Triangle (xi, eta) x line (zeta): vertices 0-2 at zeta = 0, 3-5 at zeta = 1 (Shape.py:141-153)."""
+    x, y, z = xi
+    tri = [1 - x - y, x, y]
+    return [t * (1 - z) for t in tri] + [t * z for t in tri]
+
+
+def _dN_prism(xi):
+    x, y, z = xi
+    tri, dtri = [1 - x - y, x, y], [(Fr(-1), Fr(-1)), (Fr(1), Fr(0)), (Fr(0), Fr(1))]
+    return [[d[0] * (1 - z), d[1] * (1 - z), -t] for t, d in zip(tri, dtri)] + \
+           [[d[0] * z, d[1] * z, t] for t, d in zip(tri, dtri)]
+
+
+_PYR_SIGNS = [(-1, -1), (1, -1), (1, 1), (-1, 1)]
+
+
+def _N_pyramid(xi):
+    """Rational pyramid functions on the base [0,1]^2 with the apex above its centre: with X = 2 xi - 1, Y = 2 eta - 1,
+    N_i = 1/4 [(1 + a X)(1 + b Y) - zeta + a b X Y zeta / (1 - zeta)], N_4 = zeta.  Reproduces Shape.py:187-199."""
+    x, y, z = xi
+    X, Y = 2 * x - 1, 2 * y - 1
+    return [Fr(1, 4) * ((1 + a * X) * (1 + b * Y) - z + a * b * X * Y * z / (1 - z)) for a, b in _PYR_SIGNS] + [z]
+
+
+def _dN_pyramid(xi):
+    x, y, z = xi
+    X, Y = 2 * x - 1, 2 * y - 1
+    rows = []
+    for a, b in _PYR_SIGNS:
+        rows.append([Fr(1, 2) * (a * (1 + b * Y) + a * b * Y * z / (1 - z)),
+                     Fr(1, 2) * (b * (1 + a * X) + a * b * X * z / (1 - z)),
+                     Fr(1, 4) * (-1 + a * b * X * Y / ((1 - z) * (1 - z)))])
+    return rows + [[Fr(0), Fr(0), Fr(1)]]
+
+
 def _mean(points):
     n = len(points)
     return [sum(p[k] for p in points) / n for k in range(len(points[0]))]
@@ -74,7 +110,14 @@ def _mean(points):
 class ShapeTable:
     """Exact reference-element data of one shape.  Arrays mirror the reference attribute names."""
 
-    def __init__(self, code, dim, verts, edges, facets, N, dN, sub_volume):
+    def __init__(self, code, dim, verts, edges, facets, N, dN, sub_volume, centroid=None, facet_a_first=None,
+                 triangular_faces=(), sub_point_override=None):
+        """centroid: parametric point used as "element centroid" (default: vertex mean; the reference's pyramid uses
+        the centre of its base, Shape.py:213-216).  facet_a_first(b, f, facets): which of the two facets adjacent to
+        edge (b, f) the reference lists first (default: the one that makes the area vector point from b to f).
+        triangular_faces: edges whose inner face is the triangle centroid - facet centroid - edge midpoint
+        (pyramid base edges, Shape.py:222-231).  Ragged tables are padded: facet vertices with -1, neighbour
+        vertices and outer-face values with 0."""
         self.code = code
         self.name = SHAPE_NAMES[code]
         self.dimension = dim
@@ -82,21 +125,31 @@ class ShapeTable:
         self.numberOfInnerFaces = len(edges)
         self.numberOfFacets = len(facets)
         self.vertices = [[Fr(c) for c in v] for v in verts]
-        self.facetVerticesIndexes = np.array(facets, dtype=np.int32)
-        centroid = _mean(self.vertices)
+        mf_max = max(len(fc) for fc in facets)
+        self.facetSizes = np.array([len(fc) for fc in facets], dtype=np.int32)
+        self.facetVerticesIndexes = np.array([list(fc) + [-1] * (mf_max - len(fc)) for fc in facets], dtype=np.int32)
+        centroid = [Fr(c) for c in centroid] if centroid is not None else _mean(self.vertices)
 
         def midpoint(ids):
             return _mean([self.vertices[i] for i in ids])
 
         # ---- inner faces -----------------------------------------------------------------------
-        nbr, ipoints = [], []
+        nbr, ipoints, adjn = [], [], []
         for b, f in edges:
             if dim == 2:
                 nbr.append([b, f])
+                adjn.append([0, 0])
                 ipoints.append(_mean([midpoint([b, f]), centroid]))
                 continue
             adj = [list(fc) for fc in facets if b in fc and f in fc]
             assert len(adj) == 2
+            if (b, f) in triangular_faces:
+                # triangle  centroid -> centroid of the facet that is not the base -> edge midpoint
+                fa = [fc for fc in adj if len(fc) == 3][0]
+                nbr.append([b, f] + [v for v in fa if v not in (b, f)])
+                adjn.append([1, 0])
+                ipoints.append(_mean([midpoint([b, f]), midpoint(fa), centroid]))
+                continue
             # order the two adjacent facets so that the area vector
             #   s = 1/2 [(p1-p0)x(p3-p0) + (p3-p2)x(p1-p2)]   (Shape.py:84-96, :119-139)
             # points from b to f on the reference element
@@ -115,9 +168,18 @@ class ShapeTable:
             s = area(adj[0], adj[1])
             if sum(s[k] * e[k] for k in range(3)) < 0:
                 adj = [adj[1], adj[0]]
+            self_oriented = True
+            if facet_a_first is not None and list(facet_a_first(b, f, adj)) != adj[0]:
+                adj = [adj[1], adj[0]]
+                self_oriented = False
             others = [[v for v in fc if v not in (b, f)] for fc in adj]
             nbr.append([b, f] + others[0] + others[1])
+            adjn.append([len(others[0]), len(others[1])])
             ipoints.append(_mean([midpoint([b, f]), midpoint(adj[0]), midpoint(adj[1]), centroid]))
+            del self_oriented
+        width = max(len(r) for r in nbr)
+        nbr = [r + [0] * (width - len(r)) for r in nbr]
+        self.innerFaceAdjacentCounts = np.array(adjn, dtype=np.int32)
         self.innerFaceNeighborVertices = np.array(nbr, dtype=np.int32)
         self.innerFacePoints = ipoints
         self.innerFaceShapeFunctionValues = np.array([[float(x) for x in N(p)] for p in ipoints])
@@ -132,6 +194,9 @@ class ShapeTable:
         # ---- sub-elements ----------------------------------------------------------------------
         spoints = []
         for k in range(m):
+            if sub_point_override and k in sub_point_override:
+                spoints.append([Fr(c) for c in sub_point_override[k]])
+                continue
             corners = [self.vertices[k], centroid]
             corners += [midpoint(e) for e in edges if k in e]
             if dim == 3:
@@ -140,7 +205,8 @@ class ShapeTable:
         self.subelementPoints = spoints
         self.subelementShapeFunctionValues = np.array([[float(x) for x in N(p)] for p in spoints])
         self.subelementShapeFunctionDerivatives = np.array([[[float(x) for x in r] for r in dN(p)] for p in spoints])
-        self.subelementTransformedVolumes = np.array([float(sub_volume)] * m)
+        sub_volume = list(sub_volume) if isinstance(sub_volume, (list, tuple)) else [sub_volume] * m
+        self.subelementTransformedVolumes = np.array([float(v) for v in sub_volume])
 
         # ---- outer faces (per facet, per facet vertex) -----------------------------------------
         ofv = []
@@ -156,6 +222,7 @@ class ShapeTable:
                     ring = [midpoint([fc[i], fc[(i + 1) % n]]), midpoint([fc[i], fc[(i - 1) % n]])]
                     pt = _mean([self.vertices[k], midpoint(fc)] + ring)
                 rows.append([float(x) for x in N(pt)])
+            rows += [[0.0] * m] * (mf_max - len(fc))
             ofv.append(rows)
         self.outerFaceShapeFunctionValues = np.array(ofv)
 
@@ -165,6 +232,8 @@ def _build():
     quad_v = [(0, 0), (1, 0), (1, 1), (0, 1)]
     tet_v = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1)]
     hex_v = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    prism_v = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (0, 1, 1)]
+    pyr_v = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (Fr(1, 2), Fr(1, 2), 1)]
     return {
         # edge (b, f) lists and facet vertex lists are topology; they follow Shape.py:13,17 / :41,45 /
         # :69,73 / :104,108 so that per-face arrays line up with the reference's face numbering
@@ -179,6 +248,16 @@ def _build():
                                 (4, 0), (5, 1), (6, 2), (7, 3)],
                                [(0, 3, 2, 1), (0, 4, 7, 3), (0, 1, 5, 4), (4, 5, 6, 7), (1, 2, 6, 5), (2, 3, 7, 6)],
                                _N_tensor(hex_v), _dN_tensor(hex_v), Fr(1, 8)),
+        # Shape.py:141-153: the quadrilateral facet of an in-triangle edge is listed before the triangle
+        PRISM: ShapeTable(PRISM, 3, prism_v, [(0, 1), (1, 2), (2, 0), (4, 3), (5, 4), (3, 5), (3, 0), (4, 1), (5, 2)],
+                          [(0, 2, 1), (3, 4, 5), (0, 3, 5, 2), (0, 1, 4, 3), (1, 2, 5, 4)], _N_prism, _dN_prism, Fr(1, 12)),
+        # Shape.py:187-199: "centroid" = centre of the base; base edges carry triangular faces; the tabulated apex
+        # sub-element point is (1/2, 1/2, 13/24)
+        PYRAMID: ShapeTable(PYRAMID, 3, pyr_v, [(0, 1), (1, 2), (2, 3), (3, 0), (0, 4), (1, 4), (2, 4), (3, 4)],
+                            [(0, 4, 3), (0, 1, 4), (1, 2, 4), (2, 3, 4), (0, 3, 2, 1)], _N_pyramid, _dN_pyramid,
+                            [Fr(1, 18)] * 4 + [Fr(1, 9)], centroid=(Fr(1, 2), Fr(1, 2), 0),
+                            triangular_faces=((0, 1), (1, 2), (2, 3), (3, 0)),
+                            sub_point_override={4: (Fr(1, 2), Fr(1, 2), Fr(13, 24))}),
     }
 
 
@@ -196,6 +275,10 @@ def shape_code_for(n_vertices, dimension):
         return QUADRILATERAL if dimension == 2 else TETRAHEDRON
     if n_vertices == 8:
         return HEXAHEDRON
+    if n_vertices == 6:
+        return PRISM
+    if n_vertices == 5:
+        return PYRAMID
     raise Exception("This element has not been registered in Grid yet")   # Element.py:27
 
 
@@ -210,7 +293,8 @@ def _c_array(a, fmt):
 
 
 def vertex_faces(t):
-    """Per local vertex the inner faces that touch it, encoded 2*face + (1 if the vertex is the forward one).
+    """Per local vertex the inner faces that touch it, encoded 2*face + (1 if the vertex is the forward one), padded with
+    -1 (the apex of a pyramid touches 4 faces, its base vertices 3).
     The heat flux of face f enters row b with sign -1 and row f with sign +1 (heat_transfer.py:52-54)."""
     rows = []
     for l in range(t.numberOfVertices):
@@ -221,8 +305,8 @@ def vertex_faces(t):
             elif nb[1] == l:
                 enc.append(2 * f + 1)
         rows.append(enc)
-    assert len(set(len(r) for r in rows)) == 1
-    return np.array(rows, dtype=np.int32)
+    width = max(len(r) for r in rows)
+    return np.array([r + [-1] * (width - len(r)) for r in rows], dtype=np.int32)
 
 
 def generate_cuda_tables():
@@ -231,7 +315,7 @@ def generate_cuda_tables():
     fi = lambda x: str(int(x))
     out = ["// GENERATED by `python -m pyefvlib_b200.shapes` -- do not edit.",
            "// Reference-element tables (see pyefvlib_b200/shapes.py for the derivation).", "#pragma once", ""]
-    for code in (TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON):
+    for code in (TRIANGLE, QUADRILATERAL, TETRAHEDRON, HEXAHEDRON, PRISM, PYRAMID):
         t = SHAPES[code]
         n = t.name
         m, nf, d = t.numberOfVertices, t.numberOfInnerFaces, t.dimension
@@ -247,9 +331,14 @@ def generate_cuda_tables():
             f"static __constant__ int c_{n}_facetV[{nfc}][{mf}] =\n {_c_array(t.facetVerticesIndexes, fi)};",
             f"static __constant__ double c_{n}_ofN[{nfc}][{mf}][{m}] =\n {_c_array(t.outerFaceShapeFunctionValues, fd)};",
             f"static __constant__ int c_{n}_vface[{m}][{nvf}] =\n {_c_array(vf, fi)};",
+            f"static __constant__ int c_{n}_facetN[{nfc}] = {_c_array(t.facetSizes, fi)};",
             f"struct {n}Tab {{",
             f"  static constexpr int CODE = {code}, DIM = {d}, M = {m}, NF = {nf}, NFACETS = {nfc}, MF = {mf}, NNBR = {nn}, NVF = {nvf};",
             f"  static constexpr double SUBVOL = {fd(t.subelementTransformedVolumes[0])};",
+            f"  __host__ __device__ static constexpr double subvol(int l) {{ constexpr double T[{m}] = {_c_array(t.subelementTransformedVolumes, fd)}; return T[l]; }}",
+            f"  // extra vertices (beyond b, f) of the two facets adjacent to the edge of inner face f; (1, 0) = triangular face",
+            f"  __host__ __device__ static constexpr int adjn(int f, int k) {{ constexpr int T[{nf}][2] = {_c_array(t.innerFaceAdjacentCounts, fi).replace(chr(10), '')}; return T[f][k]; }}",
+            f"  __device__ static __forceinline__ int facetN(int f) {{ return c_{n}_facetN[f]; }}",
             f"  __device__ static __forceinline__ double ifD(int f, int j, int a) {{ return c_{n}_ifD[f][j][a]; }}",
             f"  __device__ static __forceinline__ double ifN(int f, int j) {{ return c_{n}_ifN[f][j]; }}",
             f"  // compile-time copy for statically unrolled code (keeps vertex arrays in registers)",

@@ -24,6 +24,8 @@ HEAT_CASES = {
                          bcs={"Outer": ("dirichlet", 300.0), "InnerZ": ("neumann", 10.0), "InnerY": ("dirichlet", 350.0),
                               "InnerX": N0}, transient_steps=2),
     "Tetras_we": dict(mesh="3D/Tetras.msh", props=HEAT_PROPS, bcs=_we3, transient_steps=0),
+    "Prisms_3d": dict(mesh="3D/Prisms.msh", props=HEAT_PROPS, bcs=BC3D, transient_steps=2),
+    "Pyrams_3d": dict(mesh="3D/Pyrams.msh", props=HEAT_PROPS, bcs=BC3D, transient_steps=2),
 }
 
 STRESS_PROPS = {"Body": {"Density": 1800.0, "PoissonsRatio": 0.4, "ShearModulus": 6.0e6, "Gravity": 10.0}}

@@ -102,7 +102,7 @@ def test_grid_views_and_errors():
     with pytest.raises(Exception, match="Grid argument must be of class GridData"):
         P.Grid("nope")
     gd = P.GridData("bad")
-    gd.setDimension(3); gd.setVertices(np.zeros((5, 3))); gd.setElementConnectivity([[0, 1, 2, 3, 4]])
+    gd.setDimension(3); gd.setVertices(np.zeros((7, 3))); gd.setElementConnectivity([[0, 1, 2, 3, 4, 5, 6]])
     gd.setRegions(["Body"], [[0]]); gd.setBoundaries([], [], [])
     with pytest.raises(Exception, match="not been registered"):
         P.Grid(gd)                                                                       # Element.py:27

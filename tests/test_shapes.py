@@ -28,9 +28,15 @@ def test_neighbour_table(code):
     t = S.SHAPES[code]
     ref, mine = Z[f"{t.name}_ifNbr"], t.innerFaceNeighborVertices
     assert np.array_equal(ref[:, :2], mine[:, :2])
-    if t.dimension == 3 and t.name == "Hexahedron":
-        for r, m in zip(ref, mine):
-            assert set(r[2:4]) == set(m[2:4]) and set(r[4:6]) == set(m[4:6])
+    if t.name == "Pyramid":
+        # Shape.py:192 lists only (b, f) for the base edges (their triangular face uses the apex implicitly,
+        # Shape.py:222-225); the apex edges list the third vertex of each adjacent triangle
+        assert np.array_equal(ref[4:], mine[4:]) and (mine[:4, 2] == 4).all()
+        assert t.innerFaceAdjacentCounts.tolist() == [[1, 0]] * 4 + [[1, 1]] * 4
+    elif t.dimension == 3 and t.name in ("Hexahedron", "Prism"):
+        for r, m, (na, nb) in zip(ref, mine, t.innerFaceAdjacentCounts):
+            assert set(r[2:2 + na]) == set(m[2:2 + na]) and set(r[2 + na:2 + na + nb]) == set(m[2 + na:2 + na + nb])
+            assert (m[2 + na + nb:] == 0).all() and (r[2 + na + nb:] == 0).all()
     elif t.dimension == 3:
         assert np.array_equal(ref, mine)
 
@@ -44,4 +50,6 @@ def test_partition_of_unity_and_volume():
     for t in S.SHAPES.values():
         assert np.allclose(t.innerFaceShapeFunctionValues.sum(axis=1), 1.0, atol=1e-15)
         assert np.allclose(t.innerFaceShapeFunctionDerivatives.sum(axis=1), 0.0, atol=1e-15)
-        assert np.allclose(t.outerFaceShapeFunctionValues.sum(axis=2), 1.0, atol=1e-15)
+        for lf, n in enumerate(t.facetSizes):         # rows beyond the facet's vertex count are padding
+            assert np.allclose(t.outerFaceShapeFunctionValues[lf, :n].sum(axis=1), 1.0, atol=1e-15)
+            assert (t.outerFaceShapeFunctionValues[lf, n:] == 0).all()
