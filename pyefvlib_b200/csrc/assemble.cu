@@ -31,8 +31,8 @@ static SysView sys_view(efv_system *s) {
 
 // shared-memory copy of the inner-face derivative tables of all shapes (dynamic face index per lane)
 struct SmemTables {
-  double ifD_tri[3][3][2], ifD_quad[4][4][2], ifD_tet[6][4][3], ifD_hex[12][8][3];
-  int vface_tri[3][2], vface_quad[4][2], vface_tet[4][3], vface_hex[8][3];
+  double ifD_tri[3][3][2], ifD_quad[4][4][2], ifD_tet[6][4][3], ifD_hex[12][8][3], ifD_prism[9][6][3], ifD_pyr[8][5][3];
+  int vface_tri[3][2], vface_quad[4][2], vface_tet[4][3], vface_hex[8][3], vface_prism[6][3], vface_pyr[5][4];
 };
 __device__ __forceinline__ void load_tables(SmemTables &T) {
   for (int i = threadIdx.x; i < 3 * 3 * 2; i += blockDim.x) (&T.ifD_tri[0][0][0])[i] = (&c_Triangle_ifD[0][0][0])[i];
@@ -43,6 +43,10 @@ __device__ __forceinline__ void load_tables(SmemTables &T) {
   for (int i = threadIdx.x; i < 4 * 2; i += blockDim.x) (&T.vface_quad[0][0])[i] = (&c_Quadrilateral_vface[0][0])[i];
   for (int i = threadIdx.x; i < 4 * 3; i += blockDim.x) (&T.vface_tet[0][0])[i] = (&c_Tetrahedron_vface[0][0])[i];
   for (int i = threadIdx.x; i < 8 * 3; i += blockDim.x) (&T.vface_hex[0][0])[i] = (&c_Hexahedron_vface[0][0])[i];
+  for (int i = threadIdx.x; i < 9 * 6 * 3; i += blockDim.x) (&T.ifD_prism[0][0][0])[i] = (&c_Prism_ifD[0][0][0])[i];
+  for (int i = threadIdx.x; i < 8 * 5 * 3; i += blockDim.x) (&T.ifD_pyr[0][0][0])[i] = (&c_Pyramid_ifD[0][0][0])[i];
+  for (int i = threadIdx.x; i < 6 * 3; i += blockDim.x) (&T.vface_prism[0][0])[i] = (&c_Prism_vface[0][0])[i];
+  for (int i = threadIdx.x; i < 5 * 4; i += blockDim.x) (&T.vface_pyr[0][0])[i] = (&c_Pyramid_vface[0][0])[i];
   __syncthreads();
 }
 __device__ __forceinline__ int tab_vface(const SmemTables &T, int code, int l, int q) {
@@ -50,7 +54,9 @@ __device__ __forceinline__ int tab_vface(const SmemTables &T, int code, int l, i
     case 0: return T.vface_tri[l][q];
     case 1: return T.vface_quad[l][q];
     case 2: return T.vface_tet[l][q];
-    default: return T.vface_hex[l][q];
+    case 3: return T.vface_hex[l][q];
+    case 4: return T.vface_prism[l][q];
+    default: return T.vface_pyr[l][q];           // -1: a base vertex of a pyramid touches only 3 faces
   }
 }
 __device__ __forceinline__ double tab_ifD(const SmemTables &T, int code, int f, int j, int a) {
@@ -58,9 +64,19 @@ __device__ __forceinline__ double tab_ifD(const SmemTables &T, int code, int f, 
     case 0: return T.ifD_tri[f][j][a];
     case 1: return T.ifD_quad[f][j][a];
     case 2: return T.ifD_tet[f][j][a];
-    default: return T.ifD_hex[f][j][a];
+    case 3: return T.ifD_hex[f][j][a];
+    case 4: return T.ifD_prism[f][j][a];
+    default: return T.ifD_pyr[f][j][a];
   }
 }
+
+// per-pair descriptor of the row-group kernels: bit 0 valid | shape code (3 bits) | up to 4 faces (4 bits each) |
+// their "this vertex is the forward one" bits.  A missing 4th face (pyramid base vertices) is staged as zeros.
+constexpr int kMaxVF = 4;
+__device__ __forceinline__ int mt_code(int mt) { return (mt >> 1) & 7; }
+__device__ __forceinline__ int mt_face(int mt, int k) { return (mt >> (4 + 4 * k)) & 15; }
+__device__ __forceinline__ int mt_fwd(int mt, int k) { return (mt >> (20 + k)) & 1; }
+__device__ __forceinline__ int mt_pack_face(int enc, int k) { return enc < 0 ? 0 : (((enc >> 1) << (4 + 4 * k)) | ((enc & 1) << (20 + k))); }
 
 // ---- heat ---------------------------------------------------------------------------------------------------------
 // One group of 8 lanes per graph row.  The incidence list of the row is processed in chunks of 8 (element,
@@ -84,7 +100,7 @@ __global__ void __launch_bounds__(256) k_heat_rows(MeshView m, GeomView g, SysVi
                                                    double *__restrict__ elim_out) {
   extern __shared__ double smem_dyn[];
   __shared__ SmemTables T;
-  __shared__ double tbuf[kAsmRows][kAsmGroup][9];
+  __shared__ double tbuf[kAsmRows][kAsmGroup][3 * kMaxVF];
   __shared__ double volq[kAsmRows][kAsmGroup][2];
   __shared__ unsigned long long posb[kAsmRows][kAsmGroup];
   __shared__ int meta[kAsmRows][kAsmGroup];
@@ -116,12 +132,12 @@ __global__ void __launch_bounds__(256) k_heat_rows(MeshView m, GeomView g, SysVi
         const double *St = g.St[code];
         int mt = 1 | (code << 1);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+        for (int q = 0; q < kMaxVF; ++q) {
           if (q < nvf) {
             const int enc = tab_vface(T, code, l, q);
-            const int f = enc >> 1;
-            const double sg = (enc & 1) ? cond : -cond;     // forward vertex +flux, backward -flux (heat_transfer.py:52-54)
-            mt |= f << (3 + 4 * q);
+            const int f = enc < 0 ? 0 : enc >> 1;
+            const double sg = enc < 0 ? 0.0 : ((enc & 1) ? cond : -cond);     // forward vertex +flux, backward -flux (heat_transfer.py:52-54)
+            mt |= mt_pack_face(enc, q);
 #pragma unroll
             for (int a = 0; a < 3; ++a) tbuf[grp][gl][q * 3 + a] = (a < d) ? sg * St[(int64_t)(f * d + a) * n + gi] : 0.0;
           }
@@ -145,14 +161,14 @@ __global__ void __launch_bounds__(256) k_heat_rows(MeshView m, GeomView g, SysVi
       const int cnt = (int)((p1 - pc < kAsmGroup) ? (p1 - pc) : kAsmGroup);
       for (int q = 0; q < cnt; ++q) {
         const int mt = meta[grp][q];
-        const int code = (UCODE >= 0) ? UCODE : ((mt >> 1) & 3);
+        const int code = (UCODE >= 0) ? UCODE : mt_code(mt);
         const int mm = shape_m(code), nvf = shape_nvf(code);
         if (gl < mm) {
           double w = 0.0;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
+          for (int k = 0; k < kMaxVF; ++k) {
             if (k < nvf) {
-              const int f = (mt >> (3 + 4 * k)) & 15;
+              const int f = mt_face(mt, k);
               w += tab_ifD(T, code, f, gl, 0) * tbuf[grp][q][k * 3] + tab_ifD(T, code, f, gl, 1) * tbuf[grp][q][k * 3 + 1];
               if (code >= 2) w += tab_ifD(T, code, f, gl, 2) * tbuf[grp][q][k * 3 + 2];
             }
@@ -399,13 +415,6 @@ static void launch_heat_rows(efv_system *s, const double *dprops, int transient)
   EFV_CUDA(cudaFuncSetAttribute(k_heat_rows<UCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   EFV_LAUNCH(k_heat_rows<UCODE>, grid_for(s->n_owned * kAsmGroup, 256, 6), 256, smem, mv, gv, sv, dprops, transient,
              s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
-}
-
-// prisms and pyramids (Shape.py:141-247) are assembled by the tile kernel of the heat path; the row-group kernels
-// (k_heat_rows, elasticity, Biot) keep 3 faces per local vertex in their staging buffers
-static void require_classic_shapes(const efv_mesh *m, const char *what) {
-  EFV_REQUIRE(m->groups[EFV_PRISM].n == 0 && m->groups[EFV_PYRAMID].n == 0,
-              std::string("prism / pyramid elements are not supported by ") + what);
 }
 
 // rows whose columns contain a Dirichlet DOF: the fused assembly epilogue only inspects the columns of those
@@ -747,7 +756,6 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
                                      : launch_heat_tiles<-1>(s, s->props_dev.p, transient))) {
     // default: pair-centric tile kernel
   } else {
-    require_classic_shapes(m, "the row-group heat kernel");
     switch (m->uniform_code) {
       case 0: launch_heat_rows<0>(s, s->props_dev.p, transient); break;
       case 1: launch_heat_rows<1>(s, s->props_dev.p, transient); break;
@@ -777,7 +785,9 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
                                                          double *__restrict__ gen_out, double *__restrict__ elim_out) {
   extern __shared__ double smem_dyn[];
   __shared__ SmemTables T;
-  __shared__ double fbuf[kElRows][kAsmGroup][36];      // per pair: 3 faces x (J^-1 row-major 9 | s 3); 2-D uses 4 | 2 of each
+  // per pair: up to 4 faces x (J^-1 row-major 9 | s 3); 2-D uses 4 | 2 of each.  Lives behind the row accumulators in
+  // dynamic shared memory (16 rows x 8 pairs x 48 doubles exceed the static limit)
+  double(*fbuf)[kAsmGroup][12 * kMaxVF] = reinterpret_cast<double(*)[kAsmGroup][12 * kMaxVF]>(smem_dyn + (size_t)kElRows * max_row_len * NDOF * NDOF);
   __shared__ double aux[kElRows][kAsmGroup][3];        // lambda, mu, vol * (-rho g)
   __shared__ unsigned long long posb[kElRows][kAsmGroup];
   __shared__ int meta[kElRows][kAsmGroup];
@@ -809,12 +819,11 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
         int mt = 1 | (code << 1);
         for (int q = 0; q < nvf; ++q) {
           const int enc = tab_vface(T, code, l, q);
-          const int f = enc >> 1;
-          mt |= f << (3 + 4 * q);
-          mt |= (enc & 1) << (15 + q);                 // 1: this vertex is the forward one -> sign -1
+          const int f = enc < 0 ? 0 : enc >> 1;
+          mt |= mt_pack_face(enc, q);                  // forward bit: this vertex is the forward one -> sign -1
           double *fb = &fbuf[grp][gl][q * 12];
-          for (int a = 0; a < d * d; ++a) fb[a] = Ji[(int64_t)(f * d * d + a) * n + gi];
-          for (int a = 0; a < d; ++a) fb[9 + a] = Sv[(int64_t)(f * 3 + a) * n + gi];
+          for (int a = 0; a < d * d; ++a) fb[a] = enc < 0 ? 0.0 : Ji[(int64_t)(f * d * d + a) * n + gi];
+          for (int a = 0; a < d; ++a) fb[9 + a] = enc < 0 ? 0.0 : Sv[(int64_t)(f * 3 + a) * n + gi];
         }
         meta[grp][gl] = mt;
         const uint8_t *sp = s.slotpos + ((UCODE >= 0) ? e * (int64_t)(mm * mm) : m.slot_begin(e)) + l * mm;
@@ -834,7 +843,7 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
       const int cnt = (int)((p1 - pc < kAsmGroup) ? (p1 - pc) : kAsmGroup);
       for (int q = 0; q < cnt; ++q) {
         const int mt = meta[grp][q];
-        const int code = (UCODE >= 0) ? UCODE : ((mt >> 1) & 3);
+        const int code = (UCODE >= 0) ? UCODE : mt_code(mt);
         const int mm = shape_m(code), nvf = shape_nvf(code);
         if (gl < mm) {
           const double lam = aux[grp][q][0], mu = aux[grp][q][1];
@@ -844,8 +853,8 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) M[i][j] = 0.0;
           for (int k = 0; k < nvf; ++k) {
-            const int f = (mt >> (3 + 4 * k)) & 15;
-            const double sgn = ((mt >> (15 + k)) & 1) ? -1.0 : 1.0;
+            const int f = mt_face(mt, k);
+            const double sgn = mt_fwd(mt, k) ? -1.0 : 1.0;
             const double *fb = &fbuf[grp][q][k * 12];
             double gv[NDOF], sv[NDOF], dl[NDOF];
 #pragma unroll
@@ -917,7 +926,7 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
 template <int UCODE, int NDOF>
 static void launch_elasticity_rows(efv_system *s, const double *dprops, int gravity) {
   efv_mesh *m = s->mesh;
-  size_t smem = (size_t)kElRows * s->max_row_len * NDOF * NDOF * sizeof(double);
+  size_t smem = ((size_t)kElRows * s->max_row_len * NDOF * NDOF + (size_t)kElRows * kAsmGroup * 12 * kMaxVF) * sizeof(double);
   EFV_CUDA(cudaFuncSetAttribute((k_elasticity_rows<UCODE, NDOF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   EFV_LAUNCH((k_elasticity_rows<UCODE, NDOF>), grid_for(s->n_owned * kAsmGroup, 128, 12), 128, smem, view_of(m), geom_of(m),
              sys_view(s), dprops, gravity, s->max_row_len, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->elim.p);
@@ -926,7 +935,6 @@ static void launch_elasticity_rows(efv_system *s, const double *dprops, int grav
 void elasticity_assemble(efv_system *s, const double *props_host, int gravity) {
   efv_mesh *m = s->mesh;
   EFV_REQUIRE(s->ndof == m->dim, "elasticity needs ndof == dimension");
-  require_classic_shapes(m, "the elasticity assembly");
   geometry_build(m);
   if (!s->dir_flag.n) bc_clear(s);
   std::vector<double> pr(3 * m->n_regions);
@@ -982,7 +990,9 @@ __device__ __forceinline__ int tab_facetV(int code, int lf, int k) {
     case 0: return c_Triangle_facetV[lf][k];
     case 1: return c_Quadrilateral_facetV[lf][k];
     case 2: return c_Tetrahedron_facetV[lf][k];
-    default: return c_Hexahedron_facetV[lf][k];
+    case 3: return c_Hexahedron_facetV[lf][k];
+    case 4: return c_Prism_facetV[lf][k];
+    default: return c_Pyramid_facetV[lf][k];
   }
 }
 __device__ __forceinline__ double tab_ofN(int code, int lf, int k, int j) {
@@ -990,7 +1000,9 @@ __device__ __forceinline__ double tab_ofN(int code, int lf, int k, int j) {
     case 0: return c_Triangle_ofN[lf][k][j];
     case 1: return c_Quadrilateral_ofN[lf][k][j];
     case 2: return c_Tetrahedron_ofN[lf][k][j];
-    default: return c_Hexahedron_ofN[lf][k][j];
+    case 3: return c_Hexahedron_ofN[lf][k][j];
+    case 4: return c_Prism_ofN[lf][k][j];
+    default: return c_Pyramid_ofN[lf][k][j];
   }
 }
 __device__ __forceinline__ double tab_ifN(int code, int f, int j) {
@@ -998,7 +1010,9 @@ __device__ __forceinline__ double tab_ifN(int code, int f, int j) {
     case 0: return c_Triangle_ifN[f][j];
     case 1: return c_Quadrilateral_ifN[f][j];
     case 2: return c_Tetrahedron_ifN[f][j];
-    default: return c_Hexahedron_ifN[f][j];
+    case 3: return c_Hexahedron_ifN[f][j];
+    case 4: return c_Prism_ifN[f][j];
+    default: return c_Pyramid_ifN[f][j];
   }
 }
 
@@ -1012,7 +1026,7 @@ __global__ void __launch_bounds__(64) k_biot_rows(MeshView m, GeomView g, SysVie
   constexpr int NDOF = D + 1, B = NDOF * NDOF;
   extern __shared__ double smem_dyn[];
   __shared__ SmemTables T;
-  __shared__ double fbuf[kBiotRows][kAsmGroup][36];
+  __shared__ double fbuf[kBiotRows][kAsmGroup][12 * kMaxVF];
   __shared__ double aux[kBiotRows][kAsmGroup][8];
   __shared__ unsigned long long posb[kBiotRows][kAsmGroup];
   __shared__ int meta[kBiotRows][kAsmGroup];
@@ -1046,12 +1060,11 @@ __global__ void __launch_bounds__(64) k_biot_rows(MeshView m, GeomView g, SysVie
         int mt = 1 | (code << 1);
         for (int q = 0; q < nvf; ++q) {
           const int enc = tab_vface(T, code, l, q);
-          const int f = enc >> 1;
-          mt |= f << (3 + 4 * q);
-          mt |= (enc & 1) << (15 + q);
+          const int f = enc < 0 ? 0 : enc >> 1;
+          mt |= mt_pack_face(enc, q);
           double *fb = &fbuf[grp][gl][q * 12];
-          for (int a = 0; a < D * D; ++a) fb[a] = Ji[(int64_t)(f * D * D + a) * n + gi];
-          for (int a = 0; a < D; ++a) fb[9 + a] = Sv[(int64_t)(f * 3 + a) * n + gi];
+          for (int a = 0; a < D * D; ++a) fb[a] = enc < 0 ? 0.0 : Ji[(int64_t)(f * D * D + a) * n + gi];
+          for (int a = 0; a < D; ++a) fb[9 + a] = enc < 0 ? 0.0 : Sv[(int64_t)(f * 3 + a) * n + gi];
         }
         meta[grp][gl] = mt;
         const uint8_t *sp = s.slotpos + ((UCODE >= 0) ? e * (int64_t)(mm * mm) : m.slot_begin(e)) + l * mm;
@@ -1071,7 +1084,7 @@ __global__ void __launch_bounds__(64) k_biot_rows(MeshView m, GeomView g, SysVie
       const int cnt = (int)((p1 - pc < kAsmGroup) ? (p1 - pc) : kAsmGroup);
       for (int q = 0; q < cnt; ++q) {
         const int mt = meta[grp][q];
-        const int code = (UCODE >= 0) ? UCODE : ((mt >> 1) & 3);
+        const int code = (UCODE >= 0) ? UCODE : mt_code(mt);
         const int mm = shape_m(code), nvf = shape_nvf(code);
         const double lam = aux[grp][q][0], mu = aux[grp][q][1], alpha = aux[grp][q][2], kmu = aux[grp][q][3];
         const double sdt = aux[grp][q][4], adt = aux[grp][q][5], rho = aux[grp][q][6], vol = aux[grp][q][7];
@@ -1082,8 +1095,8 @@ __global__ void __launch_bounds__(64) k_biot_rows(MeshView m, GeomView g, SysVie
 #pragma unroll
             for (int j = 0; j < NDOF; ++j) M[i][j] = 0.0;
           for (int k = 0; k < nvf; ++k) {
-            const int f = (mt >> (3 + 4 * k)) & 15;
-            const double sgn = ((mt >> (15 + k)) & 1) ? -1.0 : 1.0;
+            const int f = mt_face(mt, k);
+            const double sgn = mt_fwd(mt, k) ? -1.0 : 1.0;
             const double *fb = &fbuf[grp][q][k * 12];
             const double N = tab_ifN(code, f, gl);
             double gv[D], sv[D], dl[D];
@@ -1119,7 +1132,7 @@ __global__ void __launch_bounds__(64) k_biot_rows(MeshView m, GeomView g, SysVie
 #pragma unroll
           for (int i = 0; i < D; ++i) gen[i] += vol * (-rho * gvec[i]);                 // (:166-169)
           for (int k = 0; k < nvf; ++k) {                      // gravity flux (:176-183)
-            const double sgn = ((mt >> (15 + k)) & 1) ? -1.0 : 1.0;
+            const double sgn = mt_fwd(mt, k) ? -1.0 : 1.0;
             const double *fb = &fbuf[grp][q][k * 12];
             double sg = 0.0;
 #pragma unroll
@@ -1212,7 +1225,6 @@ static void launch_biot_rows(efv_system *s, const double *dprops, const double *
 void biot_assemble(efv_system *s, const double *props_host, double dt, const double *gvec) {
   efv_mesh *m = s->mesh;
   EFV_REQUIRE(s->ndof == m->dim + 1, "Biot needs ndof == dimension + 1");
-  require_classic_shapes(m, "the Biot assembly");
   geometry_build(m);
   if (!s->dir_flag.n) bc_clear(s);
   std::vector<double> pr(7 * m->n_regions);

@@ -37,6 +37,8 @@ STRESS_CASES = {
     "Square": dict(mesh="2D/Square.msh", props=STRESS_PROPS, bcs=_s2, gravity=False),
     "10x10_gravity": dict(mesh="2D/10x10.msh", props=STRESS_PROPS, bcs=_s2, gravity=True),
     "Hexas4x4x4": dict(mesh="3D/Hexas4x4x4.msh", props=STRESS_PROPS, bcs=_s3, gravity=False),
+    "Prisms": dict(mesh="3D/Prisms.msh", props=STRESS_PROPS, bcs=_s3, gravity=True),
+    "Pyrams": dict(mesh="3D/Pyrams.msh", props=STRESS_PROPS, bcs=_s3, gravity=False),
     "eight_sphere": dict(mesh="3D/eight_sphere.msh", props=STRESS_PROPS, gravity=False,
                          bcs={"u": {"Outer": N0, "InnerZ": N0, "InnerY": N0, "InnerX": ("dirichlet", 0.0)},
                               "v": {"Outer": N0, "InnerZ": N0, "InnerY": ("dirichlet", 0.0), "InnerX": N0},
@@ -54,6 +56,8 @@ _b3 = {"u_x": dict(_b2["u_x"], Bottom=N0, Top=N0), "u_y": dict(_b2["u_y"], Botto
 BIOT_CASES = {
     "Square": dict(mesh="2D/Square.msh", props=BIOT_PROPS, bcs=_b2, dt=20.0, steps=2),
     "Hexas3x3x3": dict(mesh="3D/Hexas3x3x3.msh", props=BIOT_PROPS, bcs=_b3, dt=20.0, steps=2),
+    "Prisms": dict(mesh="3D/Prisms.msh", props=BIOT_PROPS, bcs=_b3, dt=20.0, steps=1),
+    "Pyrams": dict(mesh="3D/Pyrams.msh", props=BIOT_PROPS, bcs=_b3, dt=20.0, steps=1),
     "eight_sphere": dict(mesh="3D/eight_sphere.msh", props=BIOT_PROPS, dt=20.0, steps=1,
                          bcs={"u_x": {"Outer": N0, "InnerZ": N0, "InnerY": N0, "InnerX": ("dirichlet", 0.0)},
                               "u_y": {"Outer": N0, "InnerZ": N0, "InnerY": ("dirichlet", 0.0), "InnerX": N0},

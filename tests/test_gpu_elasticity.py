@@ -32,6 +32,9 @@ def send_bcs(system, grid, bcs):
                 system.bc_dirichlet(b.verticesIndexes + i * nV, np.full(len(b.verticesIndexes), val))
 
 
+NONSYMMETRIC = ("Prisms", "Pyrams")
+
+
 @pytest.mark.parametrize("tag", list(STRESS_CASES))
 def test_matrix_rhs_solution(tag):
     import pyefvlib_b200.device as D
@@ -58,9 +61,15 @@ def test_matrix_rhs_solution(tag):
     s.elasticity_assemble(props_array(grid, c["props"]), c["gravity"])
     s.build_rhs(False)
     As = s.to_scipy()
-    assert abs(As - As.T).max() <= 1e-10 * abs(As).max()
     s.upload(D.VEC_X, np.zeros(n))
-    iters, relres = s.solve_pcg(1e-10, 20000, negate=True)
+    if tag in NONSYMMETRIC:
+        # the EbFVM elasticity operator of prisms / pyramids is not symmetric (nor is the reference's): BiCGStab, which is
+        # also what the app falls over to (pyefvlib_b200/apps/stress_equilibrium.py:68-70)
+        assert abs(As - As.T).max() > 1e-6 * abs(As).max()
+        iters, relres = s.solve_bicgstab(1e-10, 20000)
+    else:
+        assert abs(As - As.T).max() <= 1e-10 * abs(As).max()
+        iters, relres = s.solve_pcg(1e-10, 20000, negate=True)
     assert relres <= 1e-10, (iters, relres)
     x = s.download(D.VEC_X)
     assert util.rel_l2(x, z["x_equilibrated"]) <= 1e-8, (iters, relres)
