@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 from oracle import ref_harness  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
-MESHES = ["2D/Square.msh", "2D/10x10.msh", "3D/Hexas3x3x3.msh", "3D/Tetras.msh"]
+MESHES = ["2D/Square.msh", "2D/10x10.msh", "3D/Hexas3x3x3.msh", "3D/Tetras.msh", "3D/Prisms.msh", "3D/Pyrams.msh"]
 
 
 def field(coords, step):

@@ -12,9 +12,9 @@ import numpy as np
 
 from .solver import Saver
 
-# VTK cell types (`VtuSaver.py:11`): triangle 5, quadrilateral 9, tetrahedron 10, hexahedron 12
+# VTK cell types (`VtuSaver.py:11`): triangle 5, quadrilateral 9, tetrahedron 10, hexahedron 12, prism 13, pyramid 14
 _VTK_2D = {3: 5, 4: 9}
-_VTK_3D = {4: 10, 8: 12}
+_VTK_3D = {4: 10, 8: 12, 6: 13, 5: 14}
 
 
 def _cell_arrays(grid):

@@ -8,7 +8,8 @@ import pytest
 
 from tests import util
 
-CASES = [("heat_Square", "Square"), ("heat_10x10", "10x10"), ("heat_Hexas3x3x3_we", "Hexas3x3x3"), ("heat_Tetras_we", "Tetras")]
+CASES = [("heat_Square", "Square"), ("heat_10x10", "10x10"), ("heat_Hexas3x3x3_we", "Hexas3x3x3"), ("heat_Tetras_we", "Tetras"),
+         ("heat_Prisms_3d", "Prisms"), ("heat_Pyrams_3d", "Pyrams")]
 
 
 def field(coords, step):          # same closed form as oracle/make_golden_savers.py
