@@ -1284,7 +1284,7 @@ __global__ void k_dir_set(const int64_t *__restrict__ rows, const double *__rest
   }
 }
 
-static int g_dir_counter = 0;
+
 
 void bc_clear(efv_system *s) {
   if (!s->dir_flag.n) {
@@ -1305,19 +1305,19 @@ void bc_clear(efv_system *s) {
   s->static_rhs.zero();
   s->elim.zero();
   s->has_dirichlet = false;
-  g_dir_counter = 0;
+  s->dir_counter = 0;
 }
 
 void bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int64_t n) {
   if (!s->dir_flag.n) bc_clear(s);
   if (n == 0) return;
-  EFV_REQUIRE(g_dir_counter + n < (int64_t(1) << 31), "too many Dirichlet entries");
+  EFV_REQUIRE(s->dir_counter + n < (int64_t(1) << 31), "too many Dirichlet entries");
   DBuf<int64_t> dr;
   DBuf<double> dv;
   dr.upload(rows, n);
   dv.upload(values, n);
-  EFV_LAUNCH(k_dir_last, grid_for(n, 256), 256, 0, dr.p, n, g_dir_counter, s->nV, s->ndof, s->dir_last.p);
-  EFV_LAUNCH(k_dir_set, grid_for(n, 256), 256, 0, dr.p, dv.p, n, g_dir_counter, s->nV, s->ndof, s->dir_last.p,
+  EFV_LAUNCH(k_dir_last, grid_for(n, 256), 256, 0, dr.p, n, s->dir_counter, s->nV, s->ndof, s->dir_last.p);
+  EFV_LAUNCH(k_dir_set, grid_for(n, 256), 256, 0, dr.p, dv.p, n, s->dir_counter, s->nV, s->ndof, s->dir_last.p,
              s->dir_flag.p, s->dir_value.p);
   if (s->ndof == 1 && s->marks_valid) {
     if (s->n_owned == s->nV && s->gptr.n)
@@ -1326,7 +1326,7 @@ void bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int6
       s->marks_valid = false;            // ghost Dirichlet rows have no graph row here: recomputed before the assembly
   }
   EFV_CUDA(cudaStreamSynchronize(stream()));
-  g_dir_counter += (int)n;
+  s->dir_counter += (int)n;
   s->has_dirichlet = true;
 }
 

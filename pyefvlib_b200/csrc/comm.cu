@@ -3,6 +3,7 @@
 // NCCL is dlopen'ed (the path of the copy already loaded by torch is handed in) so that the process holds a single
 // NCCL instance.  Everything runs on the library stream.
 #include "views.cuh"
+#include "peer.cuh"
 #include <dlfcn.h>
 #include <cstring>
 
@@ -83,21 +84,8 @@ int comm_rank() { return g_rank; }
 int comm_size() { return g_nranks; }
 
 // ---- peer-memory collectives (NVLink / NVSwitch loads and stores, no NCCL on the critical path) ---------------------------
-// Every rank owns a small cudaMalloc'ed region that all other ranks map through CUDA IPC:
-//   double slot[2][kMaxRanks][4]   all-reduce operands, double-buffered by the parity of the sequence number
-//   uint32 flag[2][kMaxRanks]      flag[parity][r] = sequence number once rank r's operands have landed
-//   int    error                   set when a spin wait times out
-// k_allreduce_peer folds the per-block partials of a Krylov kernel (fixed order), stores the result into EVERY rank's
-// slot[parity][me], publishes the flag with a system-scope fence, waits for all ranks' flags and sums the slots in rank
-// order -- so every rank obtains bit-identical scalars.  One launch replaces "consolidation kernel + ncclAllReduce".
-// Double buffering is safe: a rank cannot finish all-reduce k+1 before every peer has entered it, i.e. finished reading k.
-constexpr int kMaxRanks = 16;
-constexpr size_t kSlotBytes = 2 * kMaxRanks * 4 * sizeof(double);
-constexpr size_t kFlagBytes = 2 * kMaxRanks * sizeof(uint32_t);
-constexpr size_t kPeerBytes = kSlotBytes + kFlagBytes + 64;
-constexpr long long kSpinLimit = 1LL << 24;     // ~ seconds; a rank that never arrives turns into an error, not a hang
-
-struct PeerPtrs { char *p[kMaxRanks]; };
+// Layout of the per-rank region and the device pieces fused into the Krylov kernels: peer.cuh.  k_allreduce_peer is
+// the stand-alone form (one launch = fold partials + exchange) used outside the PCG iteration.
 struct PeerRegion {
   bool active = false;
   char *local = nullptr;
@@ -106,13 +94,17 @@ struct PeerRegion {
 };
 static PeerRegion g_peer;
 
-__device__ __forceinline__ double *peer_slot(char *base, int parity, int r) {
-  return reinterpret_cast<double *>(base) + ((size_t)parity * kMaxRanks + r) * 4;
+PeerAR comm_peer_ar(unsigned *counter) {
+  EFV_REQUIRE(g_peer.active, "peer collectives are not initialised");
+  PeerAR ar;
+  ar.peers = g_peer.all;
+  ar.me = g_rank;
+  ar.nranks = g_nranks;
+  ar.counter = counter;
+  ar.seq = ++g_peer.seq;
+  ar.enabled = 1;
+  return ar;
 }
-__device__ __forceinline__ volatile uint32_t *peer_flag(char *base, int parity, int r) {
-  return reinterpret_cast<volatile uint32_t *>(base + kSlotBytes) + (size_t)parity * kMaxRanks + r;
-}
-__device__ __forceinline__ int *peer_error(char *base) { return reinterpret_cast<int *>(base + kSlotBytes + kFlagBytes); }
 
 // op: 0 sum, 1 max.  narr <= 4 arrays of G partials each.
 __global__ void k_allreduce_peer(const double *__restrict__ partial, int G, int narr, double *__restrict__ out, PeerPtrs peers,

@@ -121,6 +121,7 @@ struct efv_system {
   uint64_t vals_version = 1;           // bumped whenever `vals` changes (the solver's SELL copy is rebuilt lazily)
   int fuse_mode = -1;                  // Dirichlet mode applied inside the next assembly kernel (-1: none)
   bool has_dirichlet = false;
+  int dir_counter = 0;                 // running index of the Dirichlet visits since the last bc_clear (last visit wins)
   int physics = 0;
   // Krylov workspace
   efv::KrylovWork *kw = nullptr;

@@ -9,6 +9,7 @@
 // These solvers replace the reference's explicit inverses (apps/heat_transfer.py:78-81,134-135,
 // apps/stress_equilibrium.py:170-173, apps/geomechanics.py:140,254).
 #include "views.cuh"
+#include "peer.cuh"
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__re
                                                  const int32_t *__restrict__ gcol, const double *__restrict__ vals,
                                                  const double *__restrict__ x, double *__restrict__ y, double sigma,
                                                  const double *__restrict__ rowscale, const double *__restrict__ w,
-                                                 double *__restrict__ partial, const int *__restrict__ done) {
+                                                 double *__restrict__ partial, const int *__restrict__ done, PeerAR ar) {
   __shared__ double red[32];
   if (done && *done) return;
   const int gl = threadIdx.x % L;
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__re
   if (partial) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+    if (ar.enabled) ar_publish(ar, partial, (int)gridDim.x, 1, red);          // fused all-reduce: producer side
   }
 }
 
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_spmv_sell(int64_t nrows, const
                                                       const double *__restrict__ sval,
                                                       const double *__restrict__ x, double *__restrict__ y, double sigma,
                                                       const double *__restrict__ rowscale, const double *__restrict__ w,
-                                                      double *__restrict__ partial, const int *__restrict__ done) {
+                                                      double *__restrict__ partial, const int *__restrict__ done, PeerAR ar) {
   static_assert(32 % U == 0, "a batch must not straddle the 32 offsets a warp holds");
   __shared__ double red[32];
   if (done && *done) return;
@@ -264,6 +266,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_spmv_sell(int64_t nrows, const
   if (partial) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+    if (ar.enabled) ar_publish(ar, partial, (int)gridDim.x, 1, red);          // fused all-reduce: producer side
   }
 }
 
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(C::kWarps * 32, 1)
 k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *__restrict__ scol,
                 const int32_t *__restrict__ sdelta_al, const double *__restrict__ sval, const double *__restrict__ x,
                 double *__restrict__ y, double sigma, const double *__restrict__ rowscale, const double *__restrict__ w,
-                double *__restrict__ partial, int npartial, const int *__restrict__ done) {
+                double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar) {
   constexpr int kSellChunk = C::kChunk, kSellStages = C::kStages, kSellWarps = C::kWarps;
   constexpr size_t kSellStageBytes = C::kStageBytes;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -419,6 +422,7 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
     if (threadIdx.x == 0) partial[blockIdx.x] = dot;
     for (int i = blockIdx.x + (int)gridDim.x * (1 + (int)threadIdx.x); i < npartial; i += gridDim.x * blockDim.x)
       partial[i] = 0.0;                                                      // the consumers sum npartial entries
+    if (ar.enabled) ar_publish(ar, partial, npartial, 1, red);               // fused all-reduce: producer side
   }
 }
 
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell_bsr(int64_t nrows, const i
                                                           const int32_t *__restrict__ scol, const double *__restrict__ sval,
                                                           const double *__restrict__ x, double *__restrict__ y, double sigma,
                                                           const double *__restrict__ rowscale, const double *__restrict__ w,
-                                                          double *__restrict__ partial, const int *__restrict__ done) {
+                                                          double *__restrict__ partial, const int *__restrict__ done, PeerAR ar) {
   constexpr int B = NDOF * NDOF;
   __shared__ double red[32];
   if (done && *done) return;
@@ -479,6 +483,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell_bsr(int64_t nrows, const i
   if (partial) {
     dot = block_sum(dot, red);
     if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+    if (ar.enabled) ar_publish(ar, partial, (int)gridDim.x, 1, red);          // fused all-reduce: producer side
   }
 }
 
@@ -541,10 +546,10 @@ static int pick_lanes(const efv_system *s) {
 
 template <int NDOF>
 static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
-                          const double *w, double *partial, const int *done) {
+                          const double *w, double *partial, const int *done, const PeerAR &ar) {
 #define EFV_SPMV_CASE(LL, UU)                                                                                          \
   EFV_LAUNCH((k_spmv<NDOF, LL, UU>), grid, kBlock, 0, s->n_owned, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, \
-             w, partial, done)
+             w, partial, done, ar)
   const char *envu = getenv("EFV_SPMV_UNROLL");
   const int lanes = pick_lanes(s);
   int unroll = envu ? atoi(envu) : 0;
@@ -566,11 +571,11 @@ static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, d
 #undef EFV_SPMV_CASE
 }
 static void launch_spmv(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
-                        const double *w, double *partial, const int *done) {
+                        const double *w, double *partial, const int *done, const PeerAR &ar = PeerAR()) {
   KrylovWork *kw = s->kw;
   if (kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned) {
-#define EFV_SELL_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done
-#define EFV_SELL1_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done
+#define EFV_SELL_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done, ar
+#define EFV_SELL1_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done, ar
     const char *ek = getenv("EFV_SELL_KERNEL");
     if (s->ndof == 1 && !(ek && strcmp(ek, "reg") == 0)) {
 #define EFV_SELL_TMA(CH, ST, W)                                                                                       \
@@ -582,7 +587,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
       configured = true;                                                                                               \
     }                                                                                                                  \
     EFV_LAUNCH(k_spmv_sell_tma<C>, num_sms(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,            \
-               kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, grid, done);                      \
+               kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, grid, done, ar);                      \
   } while (0)
       const char *ec = getenv("EFV_SELL_TMA");
       switch (ec ? atoi(ec) : 0) {
@@ -619,10 +624,10 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
     return;
   }
   switch (s->ndof) {
-    case 1: launch_spmv_l<1>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
-    case 2: launch_spmv_l<2>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
-    case 3: launch_spmv_l<3>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
-    case 4: launch_spmv_l<4>(s, grid, x, y, sigma, rowscale, w, partial, done); break;
+    case 1: launch_spmv_l<1>(s, grid, x, y, sigma, rowscale, w, partial, done, ar); break;
+    case 2: launch_spmv_l<2>(s, grid, x, y, sigma, rowscale, w, partial, done, ar); break;
+    case 3: launch_spmv_l<3>(s, grid, x, y, sigma, rowscale, w, partial, done, ar); break;
+    case 4: launch_spmv_l<4>(s, grid, x, y, sigma, rowscale, w, partial, done, ar); break;
     default: throw Error("unsupported ndof");
   }
 }
@@ -706,10 +711,12 @@ __global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, con
                                                           const double *__restrict__ p, const double *__restrict__ Ap,
                                                           const double *__restrict__ dinv, double *__restrict__ x,
                                                           double *__restrict__ r, double *__restrict__ partial, int Gout,
-                                                          const int *__restrict__ flags) {
+                                                          const int *__restrict__ flags, PeerAR ar_in, PeerAR ar_out) {
   __shared__ double red[32];
   if (flags[0]) return;
-  double pAp = sum_partials(pAp_partial, G, red);
+  double pAp;
+  if (ar_in.enabled) { ar_wait(ar_in); pAp = ar_value(ar_in, 0); }            // fused all-reduce: consumer side
+  else pAp = sum_partials(pAp_partial, G, red);
   double alpha = sc[it & 1] / pAp;
   double rz = 0, rr = 0;
   // 16-byte accesses (buffers come from the pool: 256-byte aligned); the odd tail entry is done by one thread
@@ -736,16 +743,18 @@ __global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, con
   }
   rz = block_sum(rz, red); if (threadIdx.x == 0) partial[blockIdx.x] = rz;
   rr = block_sum(rr, red); if (threadIdx.x == 0) partial[Gout + blockIdx.x] = rr;
+  if (ar_out.enabled) ar_publish(ar_out, partial, Gout, 2, red);
 }
 // beta = rz_new / rz_old ; p = dinv r + beta p ; block 0 publishes the scalars and the convergence flag
 __global__ void __launch_bounds__(kBlock) k_pcg_update_p(int64_t n, int it, double *__restrict__ sc,
                                                          const double *__restrict__ partial, int G,
                                                          const double *__restrict__ r, const double *__restrict__ dinv,
-                                                         double *__restrict__ p, int *__restrict__ flags) {
+                                                         double *__restrict__ p, int *__restrict__ flags, PeerAR ar_in) {
   __shared__ double red[32];
   if (flags[0]) return;
-  double rz_new = sum_partials(partial, G, red);
-  double rr = sum_partials(partial + G, G, red);
+  double rz_new, rr;
+  if (ar_in.enabled) { ar_wait(ar_in); rz_new = ar_value(ar_in, 0); rr = ar_value(ar_in, 1); }
+  else { rz_new = sum_partials(partial, G, red); rr = sum_partials(partial + G, G, red); }
   double beta = rz_new / sc[it & 1];
   const int64_t n2 = n >> 1;
   const double2 *r2 = reinterpret_cast<const double2 *>(r), *d2 = reinterpret_cast<const double2 *>(dinv);
@@ -792,16 +801,29 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   const int check_every = 32;
   int it = 0;
   bool done = false;
+  const char *efuse = getenv("EFV_FUSED_ALLREDUCE");
+  const bool fused = comm_active() && comm_peer_active() && !(efuse && atoi(efuse) == 0);
+  unsigned *counter = reinterpret_cast<unsigned *>(w->flags.p + 3);        // zeroed with the flags above
   while (!done && it < maxit) {
     int batch_end = std::min(maxit, it + check_every);
     for (; it < batch_end; ++it) {
       halo_exchange(s, w->p.p);
+      if (fused) {
+        // the two all-reduces of the iteration ride on the kernels: the last block of the producer publishes to every
+        // rank's peer region, the blocks of the consumer wait for all ranks (peer.cuh)
+        const PeerAR ar1 = comm_peer_ar(counter), ar2 = comm_peer_ar(counter);
+        launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, P + 3 * G, w->flags.p, ar1);
+        EFV_LAUNCH(k_pcg_update_xr, G, kBlock, 0, n, it, w->sc.p, P + 3 * G, G, w->p.p, w->Ap.p, w->dinv.p, s->x.p, w->r.p, P, G,
+                   w->flags.p, ar1, ar2);
+        EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, P, G, w->r.p, w->dinv.p, w->p.p, w->flags.p, ar2);
+        continue;
+      }
       launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, P + 3 * G, w->flags.p);
       const double *c1 = consolidate(w, P + 3 * G, 1, 1, &Gc);
       EFV_LAUNCH(k_pcg_update_xr, G, kBlock, 0, n, it, w->sc.p, c1, Gc, w->p.p, w->Ap.p, w->dinv.p, s->x.p, w->r.p, P, G,
-                 w->flags.p);
+                 w->flags.p, PeerAR(), PeerAR());
       const double *c2 = consolidate(w, P, 2, 2, &Gc);
-      EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, c2, Gc, w->r.p, w->dinv.p, w->p.p, w->flags.p);
+      EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, c2, Gc, w->r.p, w->dinv.p, w->p.p, w->flags.p, PeerAR());
     }
     EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
     EFV_CUDA(cudaStreamSynchronize(stream()));
