@@ -76,6 +76,7 @@ __device__ __forceinline__ void ar_wait(const PeerAR &ar) {
     long long spins = 0;
     while ((int32_t)(*f - ar.seq) < 0) {
       if (++spins > kSpinLimit) { atomicExch(peer_error(self), 1); break; }
+      __nanosleep(200);                              // thousands of blocks poll the same line: back off
     }
   }
   __syncthreads();
