@@ -23,6 +23,9 @@ void set_last_error(const std::string &msg);
   do { if (!(cond)) throw efv::Error(std::string(msg)); } while (0)
 
 cudaStream_t stream();          // the one stream of the library
+// device -> host copy that returns when the data is in `host`; large copies into pageable memory are pipelined through
+// two pinned bounce buffers (a pageable cudaMemcpy D2H runs at ~3.5 GB/s on this platform, pinned at > 20 GB/s)
+void download_bytes(void *host, const void *dev, size_t bytes);
 void count_launch(int n = 1);   // bookkeeping for efv_kernel_launch_count
 int num_sms();
 
@@ -57,10 +60,7 @@ template <typename T> struct DBuf {
     if (n < count) alloc(count);
     if (count) EFV_CUDA(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, stream()));
   }
-  void download(T *host, size_t count) const {
-    if (count) EFV_CUDA(cudaMemcpyAsync(host, p, count * sizeof(T), cudaMemcpyDeviceToHost, stream()));
-    EFV_CUDA(cudaStreamSynchronize(stream()));
-  }
+  void download(T *host, size_t count) const { download_bytes(host, p, count * sizeof(T)); }
   size_t bytes() const { return n * sizeof(T); }
 };
 

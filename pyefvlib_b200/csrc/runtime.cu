@@ -1,6 +1,8 @@
 // runtime.cu -- process-level state (device, stream, last error, launch counter) and the device-wide scan.
 #include "common.cuh"
+#include <algorithm>
 #include <atomic>
+#include <cstring>
 #include <mutex>
 
 namespace efv {
@@ -45,6 +47,44 @@ cudaStream_t stream() { ensure_init(); return g_stream; }
 int num_sms() { ensure_init(); return g_num_sms; }
 void count_launch(int n) { g_launches += n; }
 int64_t launch_count() { return g_launches.load(); }
+
+// ---- device -> host copies ----------------------------------------------------------------------------------------
+constexpr size_t kBounceBytes = 8u << 20;
+static char *g_bounce[2] = {nullptr, nullptr};
+static cudaEvent_t g_bounce_ev[2] = {nullptr, nullptr};
+
+void download_bytes(void *host, const void *dev, size_t bytes) {
+  cudaStream_t st = stream();
+  bool pinned = false;
+  if (bytes >= 2 * kBounceBytes) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+  }
+  if (bytes < 2 * kBounceBytes || pinned) {
+    if (bytes) EFV_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+    EFV_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  if (!g_bounce[0]) {
+    for (int k = 0; k < 2; ++k) {
+      EFV_CUDA(cudaMallocHost((void **)&g_bounce[k], kBounceBytes));
+      EFV_CUDA(cudaEventCreateWithFlags(&g_bounce_ev[k], cudaEventDisableTiming));
+    }
+  }
+  const size_t nchunks = (bytes + kBounceBytes - 1) / kBounceBytes;
+  auto chunk_size = [&](size_t k) { return std::min(kBounceBytes, bytes - k * kBounceBytes); };
+  for (size_t k = 0; k <= nchunks; ++k) {
+    if (k < nchunks) {            // buffer k&1 was drained two rounds ago
+      EFV_CUDA(cudaMemcpyAsync(g_bounce[k & 1], (const char *)dev + k * kBounceBytes, chunk_size(k), cudaMemcpyDeviceToHost, st));
+      EFV_CUDA(cudaEventRecord(g_bounce_ev[k & 1], st));
+    }
+    if (k > 0) {                  // drain the previous chunk while the next one is in flight
+      EFV_CUDA(cudaEventSynchronize(g_bounce_ev[(k - 1) & 1]));
+      memcpy((char *)host + (k - 1) * kBounceBytes, g_bounce[(k - 1) & 1], chunk_size(k - 1));
+    }
+  }
+}
 
 // ---- exclusive scan int32 -> int64 -------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
