@@ -470,14 +470,15 @@ struct TileSmem {
 extern __shared__ __align__(16) unsigned char tile_smem[];
 template <class Tab, int L>
 __device__ __forceinline__ void heat_pair_row(const MeshView &m, const GeomView &g, const SysView &s, const double *__restrict__ props,
-                                              int64_t e, bool uniform, int idx, int cap, int slab_off, int posb_off, int mmax) {
+                                              int64_t e, bool uniform, int idx, int cap, int slab_off, int posb_off, int mmax,
+                                              bool single_region) {
   // idx = compact position of the pair inside its (shape, local vertex) bucket: consecutive over the lanes of a warp
   constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE;
   const int64_t gi = uniform ? e : m.group_index(e);
   int64_t n = g.n[CODE];
   // keep the SoA strides out of loop-invariant hoisting: 36 precomputed 64-bit plane offsets would not fit in registers
   asm volatile("" : "+l"(n));
-  const double *pr = props + 3 * m.region[e];
+  const double *pr = single_region ? props : props + 3 * m.region[e];     // one region: no dependent load before the props
   const double cond = pr[0];
   const double *St = g.St[CODE] + gi;
   double t[NVF][D];
@@ -524,12 +525,12 @@ __device__ __forceinline__ void heat_pair_row(const MeshView &m, const GeomView 
 template <class Tab, int UCODE>
 __device__ __forceinline__ void heat_pair_shape(int l, const MeshView &m, const GeomView &g, const SysView &s,
                                                 const double *__restrict__ props, int64_t e, int idx, int cap, int slab_off,
-                                                int posb_off, int mmax) {
+                                                int posb_off, int mmax, bool single_region) {
   if constexpr (UCODE < 0 || UCODE == Tab::CODE) {
     constexpr bool U = UCODE >= 0;
     switch (l) {
 #define EFV_PAIR_CASE(LL) \
-  case LL: if constexpr (Tab::M > LL) heat_pair_row<Tab, LL>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+  case LL: if constexpr (Tab::M > LL) heat_pair_row<Tab, LL>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax, single_region); break;
       EFV_PAIR_CASE(0) EFV_PAIR_CASE(1) EFV_PAIR_CASE(2) EFV_PAIR_CASE(3)
       EFV_PAIR_CASE(4) EFV_PAIR_CASE(5) EFV_PAIR_CASE(6) EFV_PAIR_CASE(7)
 #undef EFV_PAIR_CASE
@@ -542,6 +543,7 @@ template <int UCODE>
 __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
                                                                 const __grid_constant__ SysView s, const double *__restrict__ props,
                                                                 int transient, int max_row_len, int R, int cap, int mmax, int dir_mode,
+                                                                int single_region_i,
                                                                 const uint8_t *__restrict__ dflag, const uint8_t *__restrict__ rmark,
                                                                 const double *__restrict__ dval,
                                                                 double *__restrict__ gen_out, double *__restrict__ acc_out,
@@ -560,18 +562,52 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
   const int grp = tid / kAsmGroup, gl = tid % kAsmGroup;
   const unsigned gmask = 0xffu << ((tid & 31) / kAsmGroup * kAsmGroup);
   const int64_t ntiles = (s.nV + R - 1) / R;
+  const bool single_region = single_region_i != 0;
+  // The per-tile chain of dependent global loads (row range -> incidence entries -> geometry -> row pointers) is what
+  // the kernel waits on, so the head of the chain is fetched one tile ahead: while a tile is in its pair / row phases,
+  // the incidence boundaries and the first 256 packed pairs of the block's NEXT tile are already in flight.
+  int64_t cP0 = 0, cP1 = 0, c_rp = 0;
+  uint32_t c_pk = 0;
+  if ((int64_t)blockIdx.x < ntiles) {
+    const int64_t v0 = (int64_t)blockIdx.x * R;
+    const int rows = (int)min((int64_t)R, s.nV - v0);
+    cP0 = m.inc_ptr[v0];
+    cP1 = m.inc_ptr[v0 + rows];
+    if (tid <= rows) c_rp = m.inc_ptr[v0 + tid];
+    if (tid < cP1 - cP0) c_pk = m.inc[cP0 + tid];
+  }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t v0 = tile * R;
     const int rows = (int)min((int64_t)R, s.nV - v0);
-    const int64_t P0 = m.inc_ptr[v0];
-    if (tid <= rows) rp[tid] = (int)(m.inc_ptr[v0 + tid] - P0);
+    const int64_t P0 = cP0;
+    const int np = (int)(cP1 - cP0);
+    // next tile of this block: boundaries now, packed pairs before the row phase (they need nP0)
+    const int64_t ntile = tile + gridDim.x;
+    int64_t nP0 = 0, nP1 = 0, n_rp = 0;
+    if (ntile < ntiles) {
+      const int64_t v0n = ntile * R;
+      const int rowsn = (int)min((int64_t)R, s.nV - v0n);
+      nP0 = m.inc_ptr[v0n];
+      nP1 = m.inc_ptr[v0n + rowsn];
+      if (tid <= rowsn) n_rp = m.inc_ptr[v0n + tid];
+    }
+    // row-phase operands of this tile: requested now, consumed after the pair phase
+    int64_t r0 = 0;
+    int len = 0, dslot = 0;
+    bool marked = false;
+    if (grp < rows) {
+      r0 = s.gptr[v0 + grp];
+      len = (int)(s.gptr[v0 + grp + 1] - r0);
+      dslot = s.diag_slot[v0 + grp];
+      marked = dir_mode >= 0 && rmark[v0 + grp];
+    }
+    if (tid <= rows) rp[tid] = (int)(c_rp - P0);
     if (tid < 64) cnt[tid] = 0;
     for (int i = tid; i < rows * max_row_len; i += kTileThreads) T_ROWACC[i] = 0.0;
     __syncthreads();
-    const int np = rp[rows];
     // ---- bucket the tile's pairs by (shape, local vertex) ------------------------------------------------------------
     for (int i = tid; i < np; i += kTileThreads) {
-      const uint32_t pk = m.inc[P0 + i];
+      const uint32_t pk = (i < kTileThreads) ? c_pk : m.inc[P0 + i];
       const int code = (UCODE >= 0) ? UCODE : m.code(inc_elem(pk));
       const int key = code * 8 + inc_local(pk);
       const int rank = atomicAdd(&cnt[key], 1);          // the rank only decides which thread computes the pair and where
@@ -618,16 +654,18 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
       const int l = key & 7;
       const int idx = cbase[key] + (slot - base[key]);
       switch (key >> 3) {
-        case 0: heat_pair_shape<TriangleTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        case 1: heat_pair_shape<QuadrilateralTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        case 2: heat_pair_shape<TetrahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        case 3: heat_pair_shape<HexahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        case 4: heat_pair_shape<PrismTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        default: heat_pair_shape<PyramidTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 0: heat_pair_shape<TriangleTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
+        case 1: heat_pair_shape<QuadrilateralTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
+        case 2: heat_pair_shape<TetrahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
+        case 3: heat_pair_shape<HexahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
+        case 4: heat_pair_shape<PrismTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
+        default: heat_pair_shape<PyramidTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
       }
     }
     __syncthreads();
     // ---- row phase: 8-lane group per row, pairs in ascending (local vertex, element) order ----------------------------
+    uint32_t n_pk = 0;
+    if (tid < nP1 - nP0) n_pk = m.inc[nP0 + tid];          // next tile's pairs: in flight during the row phase
     if (grp < rows) {
       const int64_t v = v0 + grp;
       double *row = T_ROWACC + grp * max_row_len;
@@ -641,15 +679,13 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
         }
         if (gl == 0) { gen += T_SLAB[mmax * cap + c]; accv += T_SLAB[(mmax + 1) * cap + c]; }
       }
-      const int64_t r0 = s.gptr[v];
-      const int len = (int)(s.gptr[v + 1] - r0);
       if (gl == 0) {
-        if (transient) row[s.diag_slot[v] - r0] += accv;       // heat_transfer.py:62-67
+        if (transient) row[dslot - r0] += accv;                // heat_transfer.py:62-67
         gen_out[v] = gen;
         acc_out[v] = accv;
       }
       __syncwarp(gmask);
-      if (dir_mode < 0 || !rmark[v]) {                           // no Dirichlet DOF among the columns: plain copy
+      if (!marked) {                                             // no Dirichlet DOF among the columns: plain copy
         for (int t = gl; t < len; t += kAsmGroup) s.vals[r0 + t] = row[t];
         if (dir_mode == 1 && gl == 0) elim_out[v] = 0.0;
       } else {
@@ -670,6 +706,7 @@ __global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_con
       }
     }
     __syncthreads();
+    cP0 = nP0; cP1 = nP1; c_rp = n_rp; c_pk = n_pk;
   }
 #undef T_ROWACC
 #undef T_SLAB
@@ -707,8 +744,8 @@ static bool launch_heat_tiles(efv_system *s, const double *dprops, int transient
   EFV_CUDA(cudaFuncSetAttribute(k_heat_tiles<UCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t ntiles = div_up(s->n_owned, R);
   EFV_LAUNCH(k_heat_tiles<UCODE>, grid_for(ntiles * kTileThreads, kTileThreads, 8), kTileThreads, smem, mv, gv, sv, dprops,
-             transient, s->max_row_len, R, cap, mmax, s->fuse_mode, s->dir_flag.p, s->row_mark.p, s->dir_value.p, s->gen.p, s->acc.p,
-             s->elim.p);
+             transient, s->max_row_len, R, cap, mmax, s->fuse_mode, m->n_regions == 1 ? 1 : 0, s->dir_flag.p, s->row_mark.p,
+             s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
   return true;
 }
 
