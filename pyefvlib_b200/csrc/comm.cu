@@ -107,8 +107,10 @@ PeerAR comm_peer_ar(unsigned *counter) {
 }
 
 // op: 0 sum, 1 max.  narr <= 4 arrays of G partials each.
-__global__ void k_allreduce_peer(const double *__restrict__ partial, int G, int narr, double *__restrict__ out, PeerPtrs peers,
-                                 int me, int nranks, uint32_t seq, int op) {
+// inplace != nullptr: additionally rewrite the partial arrays as (global value, 0, 0, ...) so that kernels which re-sum
+// G partials read the all-reduced scalar without knowing about ranks (BiCGStab)
+__global__ void k_allreduce_peer(const double *partial, int G, int narr, double *__restrict__ out, PeerPtrs peers,
+                                 int me, int nranks, uint32_t seq, int op, double *inplace) {
   __shared__ double red[32];
   __shared__ double mine[4];
   for (int a = 0; a < narr; ++a) {
@@ -147,8 +149,12 @@ __global__ void k_allreduce_peer(const double *__restrict__ partial, int G, int 
       const double v = *reinterpret_cast<volatile double *>(peer_slot(self, parity, r) + threadIdx.x);
       acc = (op == 0) ? acc + v : fmax(acc, v);
     }
-    out[threadIdx.x] = acc;
+    if (out) out[threadIdx.x] = acc;
+    if (inplace) inplace[(size_t)threadIdx.x * G] = acc;
   }
+  if (inplace)
+    for (int i = threadIdx.x; i < narr * G; i += blockDim.x)
+      if (i % G != 0) inplace[i] = 0.0;
 }
 
 void comm_peer_export(char *out64) {
@@ -183,7 +189,36 @@ void comm_allreduce_partials(const double *partial, int G, int narr, double *out
   EFV_REQUIRE(comm_peer_active(), "peer collectives are not initialised");
   EFV_REQUIRE(narr >= 1 && narr <= 4, "at most 4 scalars per all-reduce");
   g_peer.seq++;
-  EFV_LAUNCH(k_allreduce_peer, 1, 256, 0, partial, G, narr, out, g_peer.all, g_rank, g_nranks, g_peer.seq, op);
+  EFV_LAUNCH(k_allreduce_peer, 1, 256, 0, partial, G, narr, out, g_peer.all, g_rank, g_nranks, g_peer.seq, op, (double *)nullptr);
+}
+__global__ void k_fold_partials(double *partial, int G, int narr, double *__restrict__ out, int scatter) {
+  __shared__ double red[32];
+  if (!scatter) {
+    for (int a = 0; a < narr; ++a) {
+      double v = 0.0;
+      for (int i = threadIdx.x; i < G; i += blockDim.x) v += partial[(size_t)a * G + i];
+      v = block_sum(v, red);
+      if (threadIdx.x == 0) out[a] = v;
+      __syncthreads();
+    }
+  } else {
+    for (int i = threadIdx.x; i < narr * G; i += blockDim.x) partial[i] = (i % G == 0) ? out[i / G] : 0.0;
+  }
+}
+// sum every one of the `narr` arrays of G partials over the ranks and leave (sum, 0, ..., 0) in its place
+void comm_allreduce_partials_inplace(double *partial, int G, int narr) {
+  if (!comm_active()) return;
+  EFV_REQUIRE(narr >= 1 && narr <= 4, "at most 4 scalars per all-reduce");
+  if (comm_peer_active()) {
+    g_peer.seq++;
+    EFV_LAUNCH(k_allreduce_peer, 1, 256, 0, partial, G, narr, (double *)nullptr, g_peer.all, g_rank, g_nranks, g_peer.seq, 0, partial);
+    return;
+  }
+  static DBuf<double> tmp;
+  if (!tmp.n) tmp.alloc(4);
+  EFV_LAUNCH(k_fold_partials, 1, 256, 0, partial, G, narr, tmp.p, 0);
+  EFV_NCCL(g_nccl.AllReduce(tmp.p, tmp.p, (size_t)narr, kNcclFloat64, kNcclSum, g_comm, stream()));
+  EFV_LAUNCH(k_fold_partials, 1, 256, 0, partial, G, narr, tmp.p, 1);
 }
 int comm_peer_error() {
   if (!g_peer.local) return 0;

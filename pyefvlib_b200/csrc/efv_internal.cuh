@@ -182,6 +182,7 @@ void comm_peer_export(char *out64);
 void comm_peer_import(const char *handles);
 bool comm_peer_active();
 void comm_allreduce_partials(const double *partial, int G, int narr, double *out, int op);
+void comm_allreduce_partials_inplace(double *partial, int G, int narr);
 int comm_peer_error();
 void halo_stage_export(efv_system *s, char *out64);
 void halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_off, const int *remote_slot);

@@ -964,20 +964,26 @@ __global__ void k_bi_scalars(int it, int G, const double *__restrict__ partial, 
 
 void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres) {
   EFV_REQUIRE(s->vals.n, "no values assembled");
-  EFV_REQUIRE(!comm_active(), "BiCGStab is single-GPU in this version (the partitioned path implements PCG)");
   ensure_vectors(s);
   KrylovWork *w = work(s);
-  const int64_t n = s->rows;
-  if (!w->r.n) { w->r.alloc(n); w->p.alloc(n); w->Ap.alloc(n); w->dinv.alloc(n); }
-  if (!w->rhat.n) { w->rhat.alloc(n); w->v.alloc(n); w->sv.alloc(n); w->t.alloc(n); }
+  // Partitioned runs: vector kernels cover the owned entries, the ghosts of the SpMV operands are refreshed by a halo
+  // exchange, and every set of per-block partials is all-reduced IN PLACE (sum, 0, 0, ...) so that the kernels below,
+  // which re-sum G partials, see the global scalars unchanged.
+  const int64_t n = s->n_owned * s->ndof;
+  const int64_t nalloc = s->rows;
+  if (!w->r.n) { w->r.alloc(nalloc); w->p.alloc(nalloc); w->Ap.alloc(nalloc); w->dinv.alloc(nalloc); }
+  if (!w->rhat.n) { w->rhat.alloc(nalloc); w->v.alloc(nalloc); w->sv.alloc(nalloc); w->t.alloc(nalloc); }
   const int G = w->grid;
   double *P = w->partial.p;
+  auto global_sums = [&](double *part, int narr) { comm_allreduce_partials_inplace(part, G, narr); };
   EFV_CUDA(cudaEventRecord(w->e0, stream()));
   sell_prepare(s, w);
-  EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->nV, s->ndof, s->diag_slot.p, s->vals.p, 1.0, w->dinv.p);
+  EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->n_owned, s->ndof, s->diag_slot.p, s->vals.p, 1.0, w->dinv.p);
   EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
+  halo_exchange(s, s->x.p);
   launch_spmv(s, G, s->x.p, w->Ap.p, 1.0, w->dinv.p, nullptr, nullptr, nullptr);
   EFV_LAUNCH(k_bi_init, G, kBlock, 0, n, s->b.p, w->Ap.p, w->dinv.p, w->r.p, w->rhat.p, w->p.p, w->v.p, P);
+  global_sums(P, 2);
   EFV_LAUNCH(k_bi_init_scalars, 1, kBlock, 0, G, P, w->sc.p, w->flags.p, rtol);
   const int check_every = 16;
   int it = 0;
@@ -987,12 +993,17 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
     for (; it < batch_end; ++it) {
       EFV_LAUNCH(k_bi_p, G, kBlock, 0, n, w->sc.p, w->r.p, w->v.p, w->p.p, w->rhat.p, w->flags.p);
       EFV_LAUNCH(k_bi_clear_restart, 1, 1, 0, w->flags.p);
+      halo_exchange(s, w->p.p);
       launch_spmv(s, G, w->p.p, w->v.p, 1.0, w->dinv.p, w->rhat.p, P + 2 * G, w->flags.p);          // v = D^-1 A p, (rhat,v)
+      global_sums(P + 2 * G, 1);
       EFV_LAUNCH(k_bi_s, G, kBlock, 0, n, w->sc.p, P + 2 * G, G, w->r.p, w->v.p, w->sv.p, w->flags.p);
+      halo_exchange(s, w->sv.p);
       launch_spmv(s, G, w->sv.p, w->t.p, 1.0, w->dinv.p, w->sv.p, P + 2 * G, w->flags.p);           // t = D^-1 A s, (t,s)
       EFV_LAUNCH(k_bi_tt, G, kBlock, 0, n, w->t.p, P + 3 * G, w->flags.p);
+      global_sums(P + 2 * G, 2);                                                                    // (t,s) and (t,t)
       EFV_LAUNCH(k_bi_xr, G, kBlock, 0, n, w->sc.p, P + 2 * G, P + 3 * G, G, w->p.p, w->sv.p, w->t.p, w->rhat.p, s->x.p,
                  w->r.p, P, w->flags.p);
+      global_sums(P, 2);                                                                            // (rhat,r) and (r,r)
       EFV_LAUNCH(k_bi_scalars, 1, kBlock, 0, it, G, P, P + 2 * G, P + 3 * G, w->sc.p, w->flags.p);
     }
     EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
@@ -1006,6 +1017,7 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
   float ms = 0;
   EFV_CUDA(cudaEventElapsedTime(&ms, w->e0, w->e1));
   s->t_solve_ms = ms;
+  if (comm_peer_active()) EFV_REQUIRE(comm_peer_error() == 0, "peer-memory collective timed out (a rank did not arrive)");
   if (iters) *iters = w->h_flags[1];
   if (relres) *relres = (w->h_sc[3] > 0) ? std::sqrt(w->h_sc[4] / w->h_sc[3]) : 0.0;
 }
