@@ -487,6 +487,135 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell_bsr(int64_t nrows, const i
   }
 }
 
+// TMA-staged block version: a chunk = E consecutive entries of a slice = E * NDOF^2 value columns, contiguous in the
+// block-SELL layout.  The offsets of a slice are read once per 32 entries with a coalesced load (their start is not
+// 16-byte aligned at entry granularity, so they do not ride on the bulk copy).
+template <int NDOF, int E, int ST, int W> struct SellBsrTma {
+  static constexpr int kB = NDOF * NDOF;
+  static constexpr size_t kStageBytes = (size_t)E * kB * 32 * sizeof(double);
+  static constexpr size_t kSmem = (size_t)W * ST * kStageBytes + (size_t)W * ST * 8 + 32 * 8;
+};
+template <int NDOF, int E, int ST, int W>
+__global__ void __launch_bounds__(W * 32, 1)
+k_spmv_sell_bsr_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *__restrict__ scol,
+                    const int32_t *__restrict__ sdelta_al, const double *__restrict__ sval, const double *__restrict__ x,
+                    double *__restrict__ y, double sigma, const double *__restrict__ rowscale, const double *__restrict__ w,
+                    double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar) {
+  using C = SellBsrTma<NDOF, E, ST, W>;
+  constexpr int B = C::kB;
+  extern __shared__ __align__(128) unsigned char smem[];
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double *vbuf = reinterpret_cast<double *>(smem) + (size_t)wid * ST * E * B * 32;
+  unsigned char *tail = smem + (size_t)W * ST * C::kStageBytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tail) + wid * ST;
+  double *red = reinterpret_cast<double *>(tail + W * ST * 8);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < ST; ++i) mbar_init(smem_u32(bars + i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  const int64_t nslices = (nrows + 31) >> 5;
+  const int64_t per = (nslices + (int64_t)gridDim.x * W - 1) / ((int64_t)gridDim.x * W);
+  const int64_t s_begin = min(nslices, ((int64_t)blockIdx.x * W + wid) * per);
+  const int64_t s_end = min(nslices, s_begin + per);
+  struct Cursor { int64_t s, base, h0, h1, o0; int k, width; };
+  auto fetch = [&](Cursor &c) {
+    if (c.s >= s_end) return;
+    if (c.s >= c.base + 32) {
+      c.base = c.s;
+      c.h0 = off[min(c.s + lane, nslices)];
+      c.h1 = off[min(c.s + lane + 1, nslices)];
+    }
+    const int j = (int)(c.s - c.base);
+    c.o0 = __shfl_sync(0xffffffffu, c.h0, j);
+    c.width = (int)(__shfl_sync(0xffffffffu, c.h1, j) - c.o0);
+  };
+  Cursor pc{s_begin, s_begin - 32, 0, 0, 0, 0, 0}, cc = pc;
+  fetch(pc);
+  fetch(cc);
+  unsigned issued = 0, consumed = 0;
+  auto issue = [&]() {
+    const int n = min(E, pc.width - pc.k);
+    const unsigned st = issued % ST;
+    if (lane == 0) {
+      const uint32_t bar = smem_u32(bars + st);
+      const uint32_t vbytes = (uint32_t)(n > 0 ? n : 0) * B * 256u;
+      mbar_expect_tx(bar, vbytes);
+      if (n > 0) bulk_g2s(smem_u32(vbuf + (size_t)st * E * B * 32), sval + (pc.o0 + pc.k) * B * 32, vbytes, bar, policy);
+    }
+    ++issued;
+    pc.k += E;
+    if (pc.k >= pc.width) { ++pc.s; pc.k = 0; fetch(pc); }
+  };
+#pragma unroll 1
+  for (int i = 0; i < ST - 1 && pc.s < s_end; ++i) issue();
+  double dot = 0.0, acc[NDOF];
+#pragma unroll
+  for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
+  int myd = 0;
+#pragma unroll 1
+  while (cc.s < s_end) {
+    if (pc.s < s_end) issue();
+    if ((cc.k & 31) == 0)                                  // offsets of the next 32 entries of this slice
+      myd = (cc.k + lane < cc.width) ? __ldg(sdelta_al + sell_delta_pos(cc.o0, cc.s) + cc.k + lane) : 0;
+    const unsigned st = consumed % ST;
+    mbar_wait(smem_u32(bars + st), (consumed / ST) & 1u);
+    const int n = min(E, cc.width - cc.k);
+    const double *sv = vbuf + (size_t)st * E * B * 32 + lane;
+    const int vi = (int)(cc.s * 32 + lane);
+    int idx[E];
+#pragma unroll
+    for (int u = 0; u < E; ++u) {                          // indices first, gathers second (see k_spmv_sell_tma)
+      const int d = __shfl_sync(0xffffffffu, myd, (cc.k + u) & 31);
+      idx[u] = vi + d;
+      if (u < n && d == kNoDelta) idx[u] = __ldcs(scol + (cc.o0 + cc.k + u) * 32 + lane);
+    }
+    double xv[E][NDOF];
+#pragma unroll
+    for (int u = 0; u < E; ++u)
+#pragma unroll
+      for (int j = 0; j < NDOF; ++j) xv[u][j] = (u < n) ? __ldg(x + (int64_t)idx[u] * NDOF + j) : 0.0;
+#pragma unroll
+    for (int u = 0; u < E; ++u)
+      if (u < n) {
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+          for (int j = 0; j < NDOF; ++j) acc[i] += sv[(u * B + i * NDOF + j) * 32] * xv[u][j];
+      }
+    __syncwarp();
+    ++consumed;
+    cc.k += E;
+    if (cc.k >= cc.width) {
+      const int64_t v = cc.s * 32 + lane;
+      if (v < nrows) {
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i) {
+          double yi = sigma * acc[i];
+          if (rowscale) yi *= rowscale[v * NDOF + i];
+          y[v * NDOF + i] = yi;
+          if (w) dot += w[v * NDOF + i] * yi;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
+      ++cc.s;
+      cc.k = 0;
+      fetch(cc);
+    }
+  }
+  if (partial) {
+    dot = block_sum(dot, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = dot;
+    for (int i = blockIdx.x + (int)gridDim.x * (1 + (int)threadIdx.x); i < npartial; i += gridDim.x * blockDim.x) partial[i] = 0.0;
+    if (ar.enabled) ar_publish(ar, partial, npartial, 1, red);
+  }
+}
+
 // (re)build the SELL copy if the values changed; returns whether the SELL path should be used
 static bool sell_prepare(efv_system *s, KrylovWork *w) {
   const char *fmt = getenv("EFV_SPMV_FORMAT");
@@ -524,7 +653,7 @@ static bool sell_prepare(efv_system *s, KrylovWork *w) {
   }
   if (!w->sell_ok) return false;
   const char *cmp = getenv("EFV_SELL_DELTA");
-  const int compress = (s->ndof == 1 && !(cmp && atoi(cmp) == 0)) ? 1 : 0;      // block kernels read the indices
+  const int compress = !(cmp && atoi(cmp) == 0) ? 1 : 0;
   const int values_only = (w->sell_indexed && w->sell_compress == compress) ? 1 : 0;
   EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->nV, s->ndof * s->ndof, compress, values_only,
              s->gptr.p, s->gcol.p, s->vals.p, w->sell_off.p, w->sell_cols.p, w->sell_delta.p, w->sell_vals.p);
@@ -612,6 +741,23 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
         case 8 * 16 + 6: EFV_LAUNCH((k_spmv_sell<8, 6>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
         default: EFV_LAUNCH((k_spmv_sell<8, 4>), grid, kBlock, 0, EFV_SELL1_ARGS); break;
       }
+    } else if (s->ndof == 3 && !(ek && strcmp(ek, "reg") == 0)) {
+      // measured: 3x3 blocks (C3) 5.64 -> 5.11 s; 4x4 blocks with one entry per chunk (C4) 7 % slower per iteration
+      // than the register-staged kernel, which therefore keeps ndof = 2 and 4
+#define EFV_BSR_TMA(ND, EE)                                                                                                 \
+  do {                                                                                                                      \
+    using C = SellBsrTma<ND, EE, 2, 20>;                                                                                    \
+    static bool configured = false;                                                                                         \
+    if (!configured) {                                                                                                      \
+      EFV_CUDA(cudaFuncSetAttribute((k_spmv_sell_bsr_tma<ND, EE, 2, 20>), cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                    (int)C::kSmem));                                                                        \
+      configured = true;                                                                                                    \
+    }                                                                                                                       \
+    EFV_LAUNCH((k_spmv_sell_bsr_tma<ND, EE, 2, 20>), num_sms(), 20 * 32, C::kSmem, s->n_owned, kw->sell_off.p,              \
+               kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, grid, done, ar);      \
+  } while (0)
+      EFV_BSR_TMA(3, 2);
+#undef EFV_BSR_TMA
     } else if (s->ndof == 2) {
       EFV_LAUNCH((k_spmv_sell_bsr<2, 4>), grid, kBlock, 0, EFV_SELL_ARGS);
     } else if (s->ndof == 3) {
