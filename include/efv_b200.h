@@ -23,7 +23,8 @@ extern "C" {
 typedef struct efv_mesh efv_mesh;       /* device mesh: vertices, elements, boundaries, incidence, geometry   */
 typedef struct efv_system efv_system;   /* linear system on a mesh: CSR graph, slot map, values, vectors, Krylov */
 
-/* shape codes [ref: PyEFVLib/Shape.py:7,35,63,98 ; Grid.py:41] */
+/* shape codes [ref: PyEFVLib/Shape.py:7,35,63,98,141,187 ; Grid.py:41]; 3-D vertex counts 4/8/6/5 = tetrahedron/
+ * hexahedron/prism/pyramid, 2-D 3/4 = triangle/quadrilateral */
 enum { EFV_TRIANGLE = 0, EFV_QUADRILATERAL = 1, EFV_TETRAHEDRON = 2, EFV_HEXAHEDRON = 3, EFV_PRISM = 4, EFV_PYRAMID = 5 };
 /* Dirichlet application modes */
 enum { EFV_DIRICHLET_ROWS = 0,       /* reference form: row <- e_i^T, b_i = g  [ref: apps/heat_transfer.py:70-76,122-126] */
@@ -63,7 +64,7 @@ int64_t efv_mesh_num_facets(const efv_mesh *m);
 int64_t efv_mesh_num_outer_faces(const efv_mesh *m);                 /* = sum of facet vertex counts */
 int64_t efv_mesh_group_size(const efv_mesh *m, int shape_code);      /* elements of one shape */
 /* one-time geometry pass (north_star kernel 1): per inner face the global derivatives G = inv(D^T X) D^T
- * [ref: InnerFace.py:23-25, Element.py:69-71], Jacobian inverse, area vector [ref: Shape.py:29-33,57-61,84-96,
+ * [ref: InnerFace.py:23-25, Element.py:69-71], Jacobian inverse, area vector [ref: Shape.py:29-33,57-61,84-96,162-185,208-247,
  * 119-139]; per element the sub-control volumes [ref: Element.py:39-48].  Stored on the device as SoA;
  * exported per shape group (elements of one shape in grid order), element by element, face by face:
  *   G    : per face d x m doubles (row-major),  Jinv : per face d x d,  S : per face 3,  vol : per element m,
