@@ -61,6 +61,36 @@ def test_owned_rows_are_complete():
         assert abs(Al[:part.n_owned] - sub).max() <= 1e-13 * abs(A).max()
 
 
+@pytest.mark.parametrize("fixture", ["heat_Prisms_3d", "heat_Pyrams_3d", "heat_eight_sphere"])
+def test_owned_rows_are_complete_on_bundled_meshes(fixture):
+    """Same property on the reference's prism, pyramid and unstructured tetrahedron meshes (ragged boundary facets,
+    5/6-vertex elements): the generic partitioner keeps every element incident to an owned vertex."""
+    from tests import util
+    z = util.load(fixture)
+    g = util.product_grid(z)
+    og = util.oracle_grid(z)
+    nV = g.numberOfVertices
+    R, C, V = O.heat_interior_coo(og, HEAT_PROPS, True, 1e-2)
+    A = sp.csr_matrix((V, (R, C)), shape=(nV, nV))
+    world = 2
+    seen = np.zeros(nV, dtype=int)
+    for rank in range(world):
+        part = efd.partition_grid(g, rank, world, efd.block_ranges(nV, world))
+        lgd = part.grid.gridData
+        ol = O.OracleGrid(O.OracleGridData(3, np.asarray(lgd.verticesCoordinates, dtype=float).reshape(-1, 3).tolist(),
+                                           [list(map(int, c)) for c in lgd.elementsConnectivities], lgd.regionsNames,
+                                           [list(map(int, r)) for r in lgd.regionsElementsIndexes], lgd.boundariesNames,
+                                           [list(map(int, r)) for r in lgd.boundariesIndexes],
+                                           [list(map(int, c)) for c in lgd.boundariesConnectivities]))
+        R, C, V = O.heat_interior_coo(ol, HEAT_PROPS, True, 1e-2)
+        Al = sp.csr_matrix((V, (R, C)), shape=(ol.numberOfVertices,) * 2)
+        l2g = part.local_to_global
+        seen[l2g[:part.n_owned]] += 1
+        sub = A[l2g[:part.n_owned]][:, l2g]
+        assert abs(Al[:part.n_owned] - sub).max() <= 1e-13 * abs(A).max()
+    assert (seen == 1).all()                       # every vertex is owned exactly once
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
