@@ -150,3 +150,40 @@ def test_fixed_stress_app(tag):
         assert util.rel_l2(out["saver"].fields["p"][k], z["p"][k]) <= 1e-7
         u = np.concatenate([out["saver"].fields[v][k] for v in variables[:d]])
         assert util.rel_l2(u, z["u"][k]) <= 1e-7
+
+
+@pytest.mark.parametrize("tag,saverType", [("Prisms_3d", "default"), ("Pyrams_3d", "stream")])
+def test_heat_app_writes_vtu_results(tag, saverType, tmp_path):
+    """App run with an output path on the prism / pyramid meshes: `extension="vtu"` writes the last field like the
+    reference's VtuSaver, `saverType="stream"` one file per saved step; the written numbers are the reference's fields."""
+    import os
+    import xml.etree.ElementTree as ET
+    from pyefvlib_b200.apps.heat_transfer import heatTransfer
+    z = util.load("heat_" + tag)
+    c = HEAT_CASES[tag]
+    grid = util.product_grid(z)
+    names = [b.name for b in grid.boundaries]
+    steps = len(z["heatT_fields"])
+    pd = P.ProblemData(meshFilePath=grid, outputFilePath=str(tmp_path),
+                       numericalSettings=P.NumericalSettings(timeStep=float(z["heatT_dt"]), finalTime=None, tolerance=None,
+                                                             maxNumberOfIterations=steps - 1),
+                       propertyData=P.PropertyData(c["props"]),
+                       boundaryConditions=P.BoundaryConditions(bc_dict({"temperature": c["bcs"]}, names, ["temperature"])))
+    s = heatTransfer(pd, extension="vtu", saverType=saverType, transient=True, verbosity=False)
+    assert s.saver.finalized
+
+    def point_data(path):
+        piece = ET.parse(path).getroot().find("UnstructuredGrid").find("Piece")
+        assert int(piece.get("NumberOfCells")) == grid.numberOfElements
+        types = np.array(piece.find("Cells").findall("DataArray")[2].text.split(), dtype=int)
+        assert (types == (13 if tag.startswith("Prisms") else 14)).all()
+        return np.array(piece.find("PointData").find("DataArray").text.split(), dtype=np.float64)
+
+    if saverType == "default":
+        assert util.rel_l2(point_data(s.saver.outputPath), z["heatT_fields"][-1]) <= 1e-8
+    else:
+        sets = ET.parse(s.saver.outputPath).getroot().find("Collection").findall("DataSet")
+        assert len(sets) == steps + 1                                 # initial field + one per step
+        for k in range(steps):
+            data = point_data(os.path.join(str(tmp_path), sets[k + 1].get("file")))
+            assert util.rel_l2(data, z["heatT_fields"][k]) <= 1e-8
