@@ -46,7 +46,7 @@ def write_msh(path, z):
     for i, c in enumerate(d["coords"]):
         lines.append(f"{i + 1} {float(c[0])!r} {float(c[1])!r} {float(c[2])!r}")
     lines += ["$EndNodes", "$Elements"]
-    code = {2: 1, 3: 2, 4: 3 if dim == 2 else 4, 8: 5}
+    code = {2: 1, 3: 2, 4: 3 if dim == 2 else 4, 8: 5, 6: 6, 5: 7}          # gmsh: 6 = prism, 7 = pyramid
     elems = []
     for bt, idx in zip(btags, d["bidx"]):
         for i in idx:
@@ -62,7 +62,7 @@ def write_msh(path, z):
         f.write("\n".join(lines))
 
 
-@pytest.mark.parametrize("tag", ["Square", "test_mixed", "Hexas3x3x3_we", "eight_sphere"])
+@pytest.mark.parametrize("tag", ["Square", "test_mixed", "Hexas3x3x3_we", "eight_sphere", "Prisms_3d", "Pyrams_3d"])
 def test_msh_reader_matches_oracle_reader(tag, tmp_path):
     z = util.load("heat_" + tag)
     path = str(tmp_path / "m.msh")
