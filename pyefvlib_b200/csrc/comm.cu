@@ -214,11 +214,11 @@ void comm_allreduce_partials_inplace(double *partial, int G, int narr) {
     EFV_LAUNCH(k_allreduce_peer, 1, 256, 0, partial, G, narr, (double *)nullptr, g_peer.all, g_rank, g_nranks, g_peer.seq, 0, partial);
     return;
   }
-  static DBuf<double> tmp;
-  if (!tmp.n) tmp.alloc(4);
-  EFV_LAUNCH(k_fold_partials, 1, 256, 0, partial, G, narr, tmp.p, 0);
-  EFV_NCCL(g_nccl.AllReduce(tmp.p, tmp.p, (size_t)narr, kNcclFloat64, kNcclSum, g_comm, stream()));
-  EFV_LAUNCH(k_fold_partials, 1, 256, 0, partial, G, narr, tmp.p, 1);
+  static double *tmp = nullptr;                      // process lifetime (no static destructor touching CUDA at exit)
+  if (!tmp) EFV_CUDA(cudaMalloc((void **)&tmp, 4 * sizeof(double)));
+  EFV_LAUNCH(k_fold_partials, 1, 256, 0, partial, G, narr, tmp, 0);
+  EFV_NCCL(g_nccl.AllReduce(tmp, tmp, (size_t)narr, kNcclFloat64, kNcclSum, g_comm, stream()));
+  EFV_LAUNCH(k_fold_partials, 1, 256, 0, partial, G, narr, tmp, 1);
 }
 int comm_peer_error() {
   if (!g_peer.local) return 0;
