@@ -38,7 +38,10 @@ int efv_set_device(int device);
 int efv_device_count(int *count);
 void *efv_get_stream(void);            /* the cudaStream_t every kernel of this library is launched on */
 int efv_synchronize(void);
-int64_t efv_kernel_launch_count(void); /* kernels launched by this library since load (bench: gpu_launches) */
+int64_t efv_kernel_launch_count(void);
+/* whole-field host<->device copies made through efv_vec_upload / efv_vec_download since the process started (a device-resident
+ * time loop downloads a field only when a saver asks for it) */
+int efv_field_copy_counters(int64_t *uploads, int64_t *upload_bytes, int64_t *downloads, int64_t *download_bytes); /* kernels launched by this library since load (bench: gpu_launches) */
 
 /* ---- mesh  [ref: PyEFVLib/GridData.py:5-24 setters; Grid.py:18-65 build] ---------------------------------
  * coords: nV x 3 doubles; elements: CSR-like (elem_ptr[nE+1] into conn, vertex ids 0-based) in grid order;
@@ -155,16 +158,20 @@ int efv_fs_update(efv_system *biot, efv_system *mass, efv_system *geo, double *d
  * neighbour rank, which owned vertices to send and which slice of the ghost block to receive.  PCG then exchanges the
  * halo of the search direction before every SpMV and all-reduces its dot products.                                   */
 int efv_comm_unique_id(const char *nccl_library_path, char *out128);
-int efv_comm_init(const char *nccl_library_path, int rank, int nranks, const char *id128);
+int efv_comm_init(const char *nccl_library_path, int rank, int nranks, const char *id128);   /* id128 NULL: peer-memory only, no NCCL */
 int efv_comm_destroy(void);
 /* peer-memory collectives over NVLink (CUDA IPC): every rank exports a 64-byte handle of its scalar region, the host
  * layer all-gathers them (rank order) and hands the table back; the Krylov all-reduces then run as one kernel that stores
  * into every peer and sums in rank order.  Same for the halo: export the system's staging buffer, import the neighbours'
- * handles with the ghost offset / flag slot this rank owns inside each of them.  Without these calls NCCL is used.   */
+ * handles with the ghost offset / flag slot this rank owns inside each of them and the neighbours' ghost counts (the
+ * staging buffers are double-buffered by exchange parity).  Without these calls NCCL is used.  The host layer must take
+ * the peer path on ALL ranks or on none (pyefvlib_b200/distributed.py: init_comm).                                   */
 int efv_comm_peer_export(char *out64);
 int efv_comm_peer_import(const char *handles);
 int efv_halo_stage_export(efv_system *s, char *out64);
-int efv_halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_offsets, const int *remote_slots);
+int efv_comm_peer_release(void);   /* unmap the peers' regions: every later collective uses NCCL */
+int efv_halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_offsets, const int *remote_slots,
+                          const int64_t *remote_ghost_counts);
 int efv_system_set_owned(efv_system *s, int64_t n_owned);
 int efv_system_set_halo(efv_system *s, int n_neighbours, const int *neighbour_ranks, const int64_t *send_ptr,
                         const int32_t *send_idx, const int64_t *recv_ptr);
@@ -178,9 +185,21 @@ int efv_halo_exchange(efv_system *s, int which);
 int efv_solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres);
 int efv_solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres);
 int efv_spmv(efv_system *s, int which_in, int which_out);   /* y = A x on two of the system's vectors */
+/* Checks that never trust the solver's own recurrences: the TRUE relative residual ||B - A X||_2 / ||B||_2 recomputed with one
+ * extra SpMV (all-reduced over the ranks of a partitioned system); sum and sum of squares of the owned entries of a vector
+ * (cross-checks of N-GPU against 1-GPU runs); max |a_ij - a_ji| / max |a_ij| of the assembled operator, which tells the apps
+ * at assembly time whether CG applies [ref: the reference never needs this, it inverts: apps/heat_transfer.py:78-81]. */
+int efv_true_residual(efv_system *s, int negate, double *relres);
+int efv_vec_sums(efv_system *s, int which, double *sum, double *sum_of_squares);
+int efv_symmetry_defect(efv_system *s, double *defect);
 /* max_i |X_i - XOLD_i|  [ref: apps/heat_transfer.py:142] and X -> XOLD copy */
 int efv_max_abs_diff(efv_system *s, double *out);
 int efv_advance(efv_system *s);
+/* device-resident time loop: the field of the step just advanced (XOLD) is downloaded on a copy stream
+ * into pinned memory while the next step is assembled and solved; _end waits for the copy and returns the field (field-major).
+ * Fields are downloaded only when a saver asks for them [ref: apps/heat_transfer.py:24-34,137-138]. */
+int efv_download_xold_begin(efv_system *s);
+int efv_download_xold_end(efv_system *s, double *host);
 /* per-kernel timing of the last solve / assemble (CUDA events on the library stream), milliseconds */
 int efv_last_timings(efv_system *s, double *assemble_ms, double *solve_ms);
 

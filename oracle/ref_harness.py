@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- harness that imports the *unmodified* reference from /root/reference.
 
-Only usable in the build container (the GPU box has no /root/reference).  Used by
-oracle/make_golden.py to pin the numpy restatement (oracle/efv_oracle.py) and to generate the
-committed fixtures in tests/golden/.  Nothing in the product package imports this file.
+Imports the reference from /root/reference (build container) or from the git-ignored copy baseline/_ref that
+__graft_entry__.build() makes (travels to the GPU box).  Used by oracle/make_golden.py to pin the numpy
+restatement (oracle/efv_oracle.py) and generate the committed fixtures in tests/golden/, and by
+oracle/ref_bench.py (the CPU arm of bench.py).  Nothing in the product package imports this file.
 
 The three import shims are the ones listed in SURVEY.md Appendix C:
   * np.object alias                   (PyEFVLib/Shape.py:151,152,194,197,198)
@@ -17,7 +18,11 @@ import numpy as np
 import scipy.sparse
 import scipy.sparse.linalg
 
-REFERENCE_ROOT = "/root/reference"
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# /root/reference exists only in the build container; baseline/_ref is the git-ignored copy of its PyEFVLib/ and
+# apps/ directories that __graft_entry__.build() makes so that the reference arm of bench.py can run on the GPU box
+_CANDIDATES = [os.environ.get("EFV_REFERENCE_ROOT", ""), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "PyEFVLib"))), "/root/reference")
 
 
 def available():

@@ -17,7 +17,7 @@ c_i32p = C.POINTER(C.c_int32)
 c_f64p = C.POINTER(C.c_double)
 c_intp = C.POINTER(C.c_int)
 
-# name -> (restype, argtypes); must list every symbol of include/efv_b200.h (tests/test_abi.py checks this)
+# name -> (restype, argtypes); must list every symbol of include/efv_b200.h (tests/test_host.py checks this)
 PROTOTYPES = {
     "efv_last_error": (C.c_char_p, []),
     "efv_set_device": (C.c_int, [C.c_int]),
@@ -25,6 +25,7 @@ PROTOTYPES = {
     "efv_get_stream": (C.c_void_p, []),
     "efv_synchronize": (C.c_int, []),
     "efv_kernel_launch_count": (C.c_int64, []),
+    "efv_field_copy_counters": (C.c_int, [c_i64p, c_i64p, c_i64p, c_i64p]),
     "efv_mesh_create": (C.c_void_p, [C.c_int, C.c_int64, c_f64p, C.c_int64, c_i64p, c_i32p, c_i32p, C.c_int]),
     "efv_mesh_create_uniform": (C.c_void_p, [C.c_int, C.c_int64, c_f64p, C.c_int64, C.c_int, c_i32p, c_i32p, C.c_int]),
     "efv_mesh_set_boundaries": (C.c_int, [C.c_void_p, C.c_int, c_i64p, C.c_int64, c_i64p, c_i32p]),
@@ -73,15 +74,21 @@ PROTOTYPES = {
     "efv_comm_peer_export": (C.c_int, [C.c_char_p]),
     "efv_comm_peer_import": (C.c_int, [C.c_char_p]),
     "efv_halo_stage_export": (C.c_int, [C.c_void_p, C.c_char_p]),
-    "efv_halo_stage_import": (C.c_int, [C.c_void_p, C.c_char_p, c_i64p, c_intp]),
+    "efv_comm_peer_release": (C.c_int, []),
+    "efv_halo_stage_import": (C.c_int, [C.c_void_p, C.c_char_p, c_i64p, c_intp, c_i64p]),
     "efv_system_set_owned": (C.c_int, [C.c_void_p, C.c_int64]),
     "efv_system_set_halo": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_i64p, c_i32p, c_i64p]),
     "efv_halo_exchange": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_solve_pcg": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, c_intp, c_f64p]),
     "efv_solve_bicgstab": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_intp, c_f64p]),
     "efv_spmv": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "efv_true_residual": (C.c_int, [C.c_void_p, C.c_int, c_f64p]),
+    "efv_vec_sums": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_f64p]),
+    "efv_symmetry_defect": (C.c_int, [C.c_void_p, c_f64p]),
     "efv_max_abs_diff": (C.c_int, [C.c_void_p, c_f64p]),
     "efv_advance": (C.c_int, [C.c_void_p]),
+    "efv_download_xold_begin": (C.c_int, [C.c_void_p]),
+    "efv_download_xold_end": (C.c_int, [C.c_void_p, c_f64p]),
     "efv_last_timings": (C.c_int, [C.c_void_p, c_f64p, c_f64p]),
 }
 
@@ -103,7 +110,7 @@ def load():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name, None)
             if fn is None:
-                continue        # not yet implemented symbols are reported by tests/test_abi.py
+                continue        # not yet implemented symbols are reported by tests/test_host.py
             fn.restype = res
             fn.argtypes = args
         _lib = lib

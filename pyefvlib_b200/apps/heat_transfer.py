@@ -20,13 +20,38 @@ class HeatTransferSolver(Solver):
 
     def init(self):
         self.system = DeviceSystem(self.grid, 1)
-        self.temperatureField = np.repeat(0.0, self.grid.numberOfVertices)
-        self.prevTemperatureField = np.asarray(self.problemData.initialValues["temperature"], dtype=np.float64)
-        self.system.upload(VEC_XOLD, self.prevTemperatureField)
-        self.system.upload(VEC_X, self.prevTemperatureField)          # initial guess of the first solve
-        self.saver.save("temperature", self.prevTemperatureField, self.currentTime)
+        self._T = None                                                # host copy of the current field (downloaded on demand)
+        self._Tprev = np.asarray(self.problemData.initialValues["temperature"], dtype=np.float64)
+        self.system.upload(VEC_XOLD, self._Tprev)
+        self.system.upload(VEC_X, self._Tprev)                        # initial guess of the first solve
+        if self.saver.wants_fields:
+            self.saver.save("temperature", self._Tprev, self.currentTime)
         self.difference = 0.0
         self._matrix_mode = None
+        self._symmetric = True
+        self._pending_save = None                                     # time stamp of the field being downloaded asynchronously
+
+    # Fields live in HBM.  The attributes of the reference (heat_transfer.py:17-19,135) are
+    # host arrays; here they are downloaded when somebody reads them.
+    @property
+    def temperatureField(self):
+        if self._T is None:
+            self._T = self.system.download(VEC_X)
+        return self._T
+
+    @temperatureField.setter
+    def temperatureField(self, value):
+        self._T = value
+
+    @property
+    def prevTemperatureField(self):
+        if self._Tprev is None:
+            self._Tprev = self.system.download(VEC_XOLD)
+        return self._Tprev
+
+    @prevTemperatureField.setter
+    def prevTemperatureField(self, value):
+        self._Tprev = value
 
     def mainloop(self):
         self.assembleMatrix()
@@ -35,11 +60,14 @@ class HeatTransferSolver(Solver):
             self.solveLinearSystem()
             self.printIterationData()
             self.currentTime += self.timeStep
-            self.saveIterationResults()
-            self.checkConvergence()
-            self.prevTemperatureField = self.temperatureField
+            self.checkConvergence()              # needs X and XOLD: before the advance (the reference checks after saving)
             self.system.advance()
+            self._Tprev = self._T                # host copies, if anybody downloaded them
+            self.saveIterationResults()
             self.iteration += 1
+        self._drain_save()
+        if not self.saver.wants_fields:          # savers that keep no history get the final field, once
+            self.saver.save("temperature", self.temperatureField, self.currentTime)
 
     # -- boundary conditions in the reference's visiting order ----------------------------------------------------
     def _send_boundary_conditions(self):
@@ -59,6 +87,9 @@ class HeatTransferSolver(Solver):
         self.system.assemble_dirichlet_mode(mode)          # Dirichlet rows/columns handled inside the assembly kernel
         self.system.heat_assemble(props, self.timeStep, self.transient)
         self._matrix_mode = mode
+        # CG or BiCGStab is decided here, from the assembled operator (general quadrilaterals / hexahedra give a
+        # non-symmetric EbFVM matrix), not after a failed CG run
+        self._symmetric = mode == DIRICHLET_SYMMETRIC and (self.linearSolver != "auto" or self.system.symmetry_defect() <= 1e-12)
 
     @property
     def matrix(self):
@@ -96,24 +127,39 @@ class HeatTransferSolver(Solver):
     def solveLinearSystem(self):
         solver = self.linearSolver
         if solver == "auto":
-            solver = "pcg" if self._matrix_mode == DIRICHLET_SYMMETRIC else "bicgstab"
+            solver = "pcg" if self._symmetric else "bicgstab"
         if solver == "pcg":
             iters, relres = self.system.solve_pcg(self.rtol, self.maxLinearIterations)
-            if not relres <= self.rtol:          # non-symmetric operator (general quads/hexes): fall over to BiCGStab
+            if not relres <= self.rtol:          # CG broke down (x is its last good iterate): finish with BiCGStab
                 iters2, relres = self.system.solve_bicgstab(self.rtol, self.maxLinearIterations)
                 iters += iters2
         else:
             iters, relres = self.system.solve_bicgstab(self.rtol, self.maxLinearIterations)
+        if not relres <= self.rtol:
+            raise Exception(f"linear solver stalled at relative residual {relres:.2e} after {iters} iterations")
         self.linearIterations.append(iters)
         self.linearResidual = relres
-        self.temperatureField = self.system.download(VEC_X)
+        self._T = None                           # the new field stays on the device until somebody asks for it
+
+    def _drain_save(self):
+        if self._pending_save is not None:
+            self.saver.save("temperature", self.system.download_xold_end(), self._pending_save)
+            self._pending_save = None
 
     def saveIterationResults(self):
-        self.saver.save("temperature", self.temperatureField, self.currentTime)
+        """Called right after the advance: XOLD holds this step's field and stays constant during the next step, so it is
+        downloaded on the copy stream while the next step runs; the saver receives it one step later (same order, same
+        time stamps as heat_transfer.py:137-138)."""
+        if not self.saver.wants_fields:
+            return
+        self._drain_save()
+        self.system.download_xold_begin()
+        self._pending_save = self.currentTime
 
     def checkConvergence(self):
         self.converged = False
-        self.difference = self.system.max_abs_diff()                               # heat_transfer.py:142
+        if self.tolerance is not None or self.verbosity:                           # one scalar read back; skipped when nobody uses it
+            self.difference = self.system.max_abs_diff()                           # heat_transfer.py:142
         if self.problemData.finalTime is not None and self.currentTime > self.problemData.finalTime:
             self.converged = True
             return

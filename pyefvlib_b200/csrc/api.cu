@@ -7,6 +7,7 @@ namespace efv {
 const std::string &last_error();
 void set_device(int device);
 int64_t launch_count();
+void field_copy_counters(int64_t *out4);
 }  // namespace efv
 
 #define EFV_API_BEGIN try {
@@ -51,6 +52,16 @@ int efv_synchronize(void) {
   EFV_API_END
 }
 int64_t efv_kernel_launch_count(void) { return efv::launch_count(); }
+int efv_field_copy_counters(int64_t *uploads, int64_t *upload_bytes, int64_t *downloads, int64_t *download_bytes) {
+  EFV_API_BEGIN
+  int64_t c[4];
+  efv::field_copy_counters(c);
+  if (uploads) *uploads = c[0];
+  if (upload_bytes) *upload_bytes = c[1];
+  if (downloads) *downloads = c[2];
+  if (download_bytes) *download_bytes = c[3];
+  EFV_API_END
+}
 
 // ---- mesh ----------------------------------------------------------------------------------------------------------
 static efv_mesh *mesh_create_impl(int dim, int64_t nV, const double *coords, int64_t nE, const int64_t *elem_ptr, int uniform_m,
@@ -208,6 +219,9 @@ int efv_system_set_values(efv_system *s, const double *data) {
 void efv_system_destroy(efv_system *s) {
   if (!s) return;
   efv::krylov_free(s);
+  efv::halo_release(s->halo);
+  if (s->dl_stream) { cudaStreamSynchronize(s->dl_stream); cudaStreamDestroy(s->dl_stream); cudaEventDestroy(s->dl_ready); cudaEventDestroy(s->dl_done); }
+  if (s->dl_host) cudaFreeHost(s->dl_host);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   delete s;
@@ -358,7 +372,7 @@ int efv_comm_unique_id(const char *nccl_library_path, char *out128) {
 }
 int efv_comm_init(const char *nccl_library_path, int rank, int nranks, const char *id128) {
   EFV_API_BEGIN
-  EFV_REQUIRE(id128 && nranks >= 1 && rank >= 0 && rank < nranks, "bad communicator arguments");
+  EFV_REQUIRE(nranks >= 1 && nranks <= 1024 && rank >= 0 && rank < nranks, "bad communicator arguments");
   efv::comm_init(nccl_library_path, rank, nranks, id128);
   EFV_API_END
 }
@@ -379,16 +393,22 @@ int efv_comm_peer_import(const char *handles) {
   efv::comm_peer_import(handles);
   EFV_API_END
 }
+int efv_comm_peer_release(void) {
+  EFV_API_BEGIN
+  efv::comm_peer_release();
+  EFV_API_END
+}
 int efv_halo_stage_export(efv_system *s, char *out64) {
   EFV_API_BEGIN
   EFV_REQUIRE(s && out64, "null argument");
-  efv::halo_stage_export(s, out64);
+  efv::halo_stage_export(s->halo, out64);
   EFV_API_END
 }
-int efv_halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_offsets, const int *remote_slots) {
+int efv_halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_offsets, const int *remote_slots,
+                          const int64_t *remote_ghosts) {
   EFV_API_BEGIN
-  EFV_REQUIRE(s && handles && remote_offsets && remote_slots, "null argument");
-  efv::halo_stage_import(s, handles, remote_offsets, remote_slots);
+  EFV_REQUIRE(s && handles && remote_offsets && remote_slots && remote_ghosts, "null argument");
+  efv::halo_stage_import(s->halo, handles, remote_offsets, remote_slots, remote_ghosts);
   EFV_API_END
 }
 int efv_system_set_owned(efv_system *s, int64_t n_owned) {
@@ -433,16 +453,70 @@ int efv_spmv(efv_system *s, int which_in, int which_out) {
   efv::spmv(s, pick_vec(s, which_in)->p, pick_vec(s, which_out)->p);
   EFV_API_END
 }
+int efv_true_residual(efv_system *s, int negate, double *relres) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && relres, "null argument");
+  *relres = efv::true_relres(s, negate);
+  EFV_API_END
+}
+int efv_vec_sums(efv_system *s, int which, double *sum, double *sum_of_squares) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null argument");
+  efv::ensure_vectors(s);
+  efv::vec_sums(s, pick_vec(s, which)->p, sum, sum_of_squares);
+  EFV_API_END
+}
+int efv_symmetry_defect(efv_system *s, double *defect) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && defect, "null argument");
+  *defect = efv::symmetry_defect(s);
+  EFV_API_END
+}
 int efv_max_abs_diff(efv_system *s, double *out) {
   EFV_API_BEGIN
   EFV_REQUIRE(s && out, "null argument");
   *out = efv::max_abs_diff(s);
   EFV_API_END
 }
+// XOLD is constant from efv_advance until the next efv_advance, so its download can overlap the next time step: the copy
+// runs on its own stream behind an event of the library stream, into a pinned buffer owned by the system
+int efv_download_xold_begin(efv_system *s) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(!s->dl_pending, "a field download is already in flight");
+  efv::ensure_vectors(s);
+  if (!s->dl_stream) {
+    EFV_CUDA(cudaStreamCreateWithFlags(&s->dl_stream, cudaStreamNonBlocking));
+    EFV_CUDA(cudaEventCreateWithFlags(&s->dl_ready, cudaEventDisableTiming));
+    EFV_CUDA(cudaEventCreateWithFlags(&s->dl_done, cudaEventDisableTiming));
+    EFV_CUDA(cudaMallocHost((void **)&s->dl_host, s->rows * sizeof(double)));
+  }
+  EFV_CUDA(cudaEventRecord(s->dl_ready, efv::stream()));
+  EFV_CUDA(cudaStreamWaitEvent(s->dl_stream, s->dl_ready, 0));
+  EFV_CUDA(cudaMemcpyAsync(s->dl_host, s->xold.p, s->rows * sizeof(double), cudaMemcpyDeviceToHost, s->dl_stream));
+  EFV_CUDA(cudaEventRecord(s->dl_done, s->dl_stream));
+  s->dl_pending = true;
+  efv::count_field_copy(1, s->rows * sizeof(double));
+  EFV_API_END
+}
+int efv_download_xold_end(efv_system *s, double *host) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && host, "null argument");
+  EFV_REQUIRE(s->dl_pending, "no field download in flight");
+  EFV_CUDA(cudaEventSynchronize(s->dl_done));
+  s->dl_pending = false;
+  const int64_t nV = s->nV;
+  if (s->ndof == 1) memcpy(host, s->dl_host, s->rows * sizeof(double));
+  else
+    for (int64_t v = 0; v < nV; ++v)
+      for (int f = 0; f < s->ndof; ++f) host[(int64_t)f * nV + v] = s->dl_host[v * s->ndof + f];   // field-major at the ABI
+  EFV_API_END
+}
 int efv_advance(efv_system *s) {
   EFV_API_BEGIN
   EFV_REQUIRE(s, "null system");
   efv::ensure_vectors(s);
+  if (s->dl_pending) EFV_CUDA(cudaStreamWaitEvent(efv::stream(), s->dl_done, 0));     // XOLD is still being read by the copy stream
   EFV_CUDA(cudaMemcpyAsync(s->xold.p, s->x.p, s->rows * sizeof(double), cudaMemcpyDeviceToDevice, efv::stream()));
   EFV_API_END
 }

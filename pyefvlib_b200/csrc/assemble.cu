@@ -1736,6 +1736,7 @@ __global__ void k_field_to_vertex_major(int64_t nV, int ndof, const double *__re
 }
 void vec_upload(efv_system *s, DBuf<double> &dst, const double *host) {
   if (!dst.n) dst.alloc(s->rows);
+  count_field_copy(0, s->rows * sizeof(double));
   if (s->ndof == 1) { dst.upload(host, s->rows); EFV_CUDA(cudaStreamSynchronize(stream())); return; }
   DBuf<double> tmp;
   tmp.upload(host, s->rows);
@@ -1744,6 +1745,7 @@ void vec_upload(efv_system *s, DBuf<double> &dst, const double *host) {
 }
 void vec_download(const efv_system *s, const DBuf<double> &src, double *host) {
   EFV_REQUIRE(src.n, "vector not allocated");
+  count_field_copy(1, s->rows * sizeof(double));
   if (s->ndof == 1) { src.download(host, s->rows); return; }
   DBuf<double> tmp(s->rows);
   EFV_LAUNCH(k_field_to_vertex_major, grid_for(s->rows, 256), 256, 0, s->nV, s->ndof, src.p, tmp.p, 1);

@@ -9,6 +9,10 @@
 
 namespace efv {
 
+constexpr int kMaxHaloNbr = kMaxRanks - 1;
+constexpr size_t kHaloFlagBytes = 2 * kMaxRanks * sizeof(uint32_t) + 128;     // two parity sets of per-neighbour flags
+struct HaloPush { double *dst[kMaxHaloNbr]; int64_t begin[kMaxHaloNbr + 1]; uint32_t *flag[kMaxHaloNbr]; int n; };
+
 typedef struct { char internal[128]; } NcclUniqueId;
 typedef void *NcclComm;
 enum { kNcclSum = 0, kNcclMax = 2, kNcclFloat64 = 8 };
@@ -65,21 +69,33 @@ void comm_unique_id(const char *nccl_path, char *out128) {
   EFV_NCCL(g_nccl.GetUniqueId(&id));
   memcpy(out128, id.internal, 128);
 }
+static bool g_comm_on = false;
+// id128 == nullptr: peer-memory-only communicator (no NCCL; every collective must then run over the CUDA-IPC peer
+// regions).  This is what lets two ranks share ONE GPU (NCCL refuses duplicate devices), used by the 1-GPU parity test.
 void comm_init(const char *nccl_path, int rank, int nranks, const char *id128) {
-  load_nccl(nccl_path);
-  EFV_REQUIRE(!g_comm, "communicator already initialised");
-  NcclUniqueId id;
-  memcpy(id.internal, id128, 128);
+  EFV_REQUIRE(!g_comm_on, "communicator already initialised");
   (void)stream();
-  EFV_NCCL(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
+  if (id128) {
+    load_nccl(nccl_path);
+    NcclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    EFV_NCCL(g_nccl.CommInitRank(&g_comm, nranks, id, rank));
+  }
   g_rank = rank;
   g_nranks = nranks;
+  g_comm_on = true;
 }
+void comm_peer_release();
 void comm_destroy() {
+  comm_peer_release();
   if (g_comm) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
-  g_rank = 0; g_nranks = 1;
+  g_rank = 0; g_nranks = 1; g_comm_on = false;
 }
-bool comm_active() { return g_comm != nullptr && g_nranks > 1; }
+bool comm_active() { return g_comm_on && g_nranks > 1; }
+static void require_nccl(const char *what) {
+  if (!g_comm) throw Error(std::string(what) + " needs NCCL, but the communicator was created in peer-memory-only mode "
+                           "(or the peer regions could not be mapped): set EFV_COMM=nccl with one GPU per rank");
+}
 int comm_rank() { return g_rank; }
 int comm_size() { return g_nranks; }
 
@@ -89,7 +105,7 @@ int comm_size() { return g_nranks; }
 struct PeerRegion {
   bool active = false;
   char *local = nullptr;
-  PeerPtrs all;
+  PeerPtrs all = {};
   uint32_t seq = 0;
 };
 static PeerRegion g_peer;
@@ -134,13 +150,7 @@ __global__ void k_allreduce_peer(const double *partial, int G, int narr, double 
     *peer_flag(dst, parity, me) = seq;
   }
   char *self = peers.p[me];
-  if (threadIdx.x < nranks) {
-    volatile uint32_t *f = peer_flag(self, parity, threadIdx.x);
-    long long spins = 0;
-    while ((int32_t)(*f - seq) < 0) {
-      if (++spins > kSpinLimit) { atomicExch(peer_error(self), 1); break; }
-    }
-  }
+  if (threadIdx.x < nranks) peer_wait_flag(peer_flag(self, parity, threadIdx.x), seq, peer_error(self), 1);
   __syncthreads();
   __threadfence_system();
   if (threadIdx.x < narr) {
@@ -171,16 +181,32 @@ void comm_peer_export(char *out64) {
 }
 void comm_peer_import(const char *handles) {
   EFV_REQUIRE(g_peer.local, "export the peer region first");
+  for (int r = 0; r < g_nranks; ++r) g_peer.all.p[r] = nullptr;
   for (int r = 0; r < g_nranks; ++r) {
     if (r == g_rank) { g_peer.all.p[r] = g_peer.local; continue; }
     cudaIpcMemHandle_t h;
     memcpy(&h, handles + 64 * (size_t)r, 64);
     void *ptr = nullptr;
-    EFV_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {                      // another node / no peer access: the caller falls back to NCCL on all ranks
+      cudaGetLastError();
+      comm_peer_release();
+      throw Error(std::string("cudaIpcOpenMemHandle failed for rank ") + std::to_string(r) + ": " + cudaGetErrorString(e));
+    }
     g_peer.all.p[r] = (char *)ptr;
   }
   g_peer.active = true;
   g_peer.seq = 0;
+}
+// unmap the peers' regions and stop using peer-memory collectives (the local region stays allocated: cheap, and other
+// ranks may still have it mapped)
+void comm_peer_release() {
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (r != g_rank && g_peer.all.p[r]) cudaIpcCloseMemHandle(g_peer.all.p[r]);
+    g_peer.all.p[r] = nullptr;
+  }
+  cudaGetLastError();
+  g_peer.active = false;
 }
 bool comm_peer_active() { return g_peer.active && comm_active(); }
 
@@ -214,28 +240,33 @@ void comm_allreduce_partials_inplace(double *partial, int G, int narr) {
     EFV_LAUNCH(k_allreduce_peer, 1, 256, 0, partial, G, narr, (double *)nullptr, g_peer.all, g_rank, g_nranks, g_peer.seq, 0, partial);
     return;
   }
+  require_nccl("all-reduce without peer regions");
   static double *tmp = nullptr;                      // process lifetime (no static destructor touching CUDA at exit)
   if (!tmp) EFV_CUDA(cudaMalloc((void **)&tmp, 4 * sizeof(double)));
   EFV_LAUNCH(k_fold_partials, 1, 256, 0, partial, G, narr, tmp, 0);
   EFV_NCCL(g_nccl.AllReduce(tmp, tmp, (size_t)narr, kNcclFloat64, kNcclSum, g_comm, stream()));
   EFV_LAUNCH(k_fold_partials, 1, 256, 0, partial, G, narr, tmp, 1);
 }
+// error word of the peer waits (1: all-reduce, 2: halo); reading it clears it, so one failed solve does not poison the next
 int comm_peer_error() {
   if (!g_peer.local) return 0;
   int e = 0;
   EFV_CUDA(cudaMemcpyAsync(&e, g_peer.local + kSlotBytes + kFlagBytes, sizeof(int), cudaMemcpyDeviceToHost, stream()));
   EFV_CUDA(cudaStreamSynchronize(stream()));
+  if (e) EFV_CUDA(cudaMemsetAsync(g_peer.local + kSlotBytes + kFlagBytes, 0, sizeof(int), stream()));
   return e;
 }
 
 void comm_allreduce_sum(double *dev, int count) {
   if (!comm_active()) return;
   if (comm_peer_active() && count <= 4) { comm_allreduce_partials(dev, 1, count, dev, 0); return; }
+  require_nccl("all-reduce without peer regions");
   EFV_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclSum, g_comm, stream()));
 }
 void comm_allreduce_max(double *dev, int count) {
   if (!comm_active()) return;
   if (comm_peer_active() && count <= 4) { comm_allreduce_partials(dev, 1, count, dev, 1); return; }
+  require_nccl("all-reduce without peer regions");
   EFV_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclMax, g_comm, stream()));
 }
 
@@ -253,26 +284,30 @@ __global__ void k_pack(const int32_t *__restrict__ idx, int64_t n, int ndof, con
 void halo_set(efv_system *s, int n_nbr, const int *nbr, const int64_t *send_ptr, const int32_t *send_idx,
               const int64_t *recv_ptr) {
   Halo &h = s->halo;
+  EFV_REQUIRE(n_nbr <= kMaxHaloNbr, "a rank can have at most 15 halo neighbours");
   h.nbr.assign(nbr, nbr + n_nbr);
   h.send_ptr.assign(send_ptr, send_ptr + n_nbr + 1);
   h.recv_ptr.assign(recv_ptr, recv_ptr + n_nbr + 1);
   EFV_REQUIRE(h.recv_ptr[n_nbr] == s->nV - s->n_owned, "halo receive lists must cover the ghost vertices");
   for (int64_t k = 0; k < h.send_ptr[n_nbr]; ++k)
     EFV_REQUIRE(send_idx[k] >= 0 && send_idx[k] < s->n_owned, "halo send index is not an owned vertex");
+  h.n_owned = s->n_owned;
+  h.n_ghost = s->nV - s->n_owned;
+  h.cap_ndof = s->ndof;
   h.send_idx.upload(send_idx, h.send_ptr[n_nbr]);
   h.send_buf.alloc((size_t)h.send_ptr[n_nbr] * s->ndof);
   EFV_CUDA(cudaStreamSynchronize(stream()));
   h.active = true;
 }
 
-// peer-memory halo: every rank owns a staging buffer [64-byte flag block | ghost values]; neighbours store their
-// boundary values straight into it over NVLink and then raise the flag of their slot; the owner waits for the flags and
-// copies the values behind its owned entries.  The all-reduces of the Krylov iteration order successive exchanges, so
-// one staging buffer per system suffices.
-constexpr size_t kHaloFlagBytes = 256;
-struct HaloPush { double *dst[8]; int64_t begin[9]; uint32_t *flag[8]; int n; };
-
-__global__ void k_halo_push(HaloPush hp, const int32_t *__restrict__ idx, int ndof, const double *__restrict__ vec) {
+// peer-memory halo: every rank owns a staging buffer [flag block | ghost values (parity 0) | ghost values (parity 1)];
+// neighbours store their interface values straight into it over NVLink and then raise the flag of their slot; the
+// owner waits for the flags and copies the values behind its owned entries.  Buffers and flags are double-buffered
+// by the parity of the exchange number: a neighbour can run at most one exchange ahead (its exchange k needs my push
+// k), so its push k+1 lands in the other buffer while I may still be copying k, and k+2 cannot be pushed before my
+// push k+1, which is stream-ordered after my copy of k.  Exchanges therefore need no collective between them.
+__global__ void k_halo_push(HaloPush hp, const int32_t *__restrict__ idx, int ndof, const double *__restrict__ vec, uint32_t seq,
+                            unsigned *__restrict__ ticket) {
   const int64_t total = hp.begin[hp.n] * ndof;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t k = i / ndof;
@@ -281,49 +316,51 @@ __global__ void k_halo_push(HaloPush hp, const int32_t *__restrict__ idx, int nd
     while (k >= hp.begin[nb + 1]) ++nb;
     hp.dst[nb][(k - hp.begin[nb]) * ndof + f] = vec[(int64_t)idx[k] * ndof + f];
   }
+  // the last block to finish raises the flags (all stores of all blocks are then visible system-wide)
+  __shared__ int s_last;
   __threadfence_system();
-}
-__global__ void k_halo_flag(HaloPush hp, uint32_t seq) {
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
   __threadfence_system();
   if (threadIdx.x < hp.n) *reinterpret_cast<volatile uint32_t *>(hp.flag[threadIdx.x]) = seq;
+  if (threadIdx.x == 0) *ticket = 0u;
 }
-__global__ void k_halo_wait_copy(const char *__restrict__ stage, int n_nbr, uint32_t seq, int64_t count, double *__restrict__ dst,
-                                 int *__restrict__ err) {
-  if (threadIdx.x < n_nbr) {
-    volatile const uint32_t *f = reinterpret_cast<volatile const uint32_t *>(stage) + threadIdx.x;
-    long long spins = 0;
-    while ((int32_t)(*f - seq) < 0) {
-      if (++spins > kSpinLimit) { atomicExch(err, 2); break; }
-    }
-  }
+__global__ void k_halo_wait_copy(const char *__restrict__ stage, const double *__restrict__ src, int n_nbr, uint32_t seq, int64_t count,
+                                 double *__restrict__ dst, int *__restrict__ err) {
+  if (threadIdx.x < n_nbr)
+    peer_wait_flag(reinterpret_cast<volatile const uint32_t *>(stage) + (seq & 1u) * kMaxRanks + threadIdx.x, seq, err, 2);
   __syncthreads();
   __threadfence_system();
-  const volatile double *src = reinterpret_cast<const volatile double *>(stage + kHaloFlagBytes);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  const volatile double *vsrc = src;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) dst[i] = vsrc[i];
 }
 
-void halo_stage_export(efv_system *s, char *out64) {
-  Halo &h = s->halo;
+static size_t halo_stage_bytes(const Halo &h) { return kHaloFlagBytes + 2 * (size_t)h.n_ghost * h.cap_ndof * sizeof(double) + 64; }
+
+void halo_stage_export(Halo &h, char *out64) {
   EFV_REQUIRE(h.active, "register the halo first");
-  const size_t bytes = kHaloFlagBytes + (size_t)(s->nV - s->n_owned) * s->ndof * sizeof(double) + 64;
   if (!h.stage) {
-    EFV_CUDA(cudaMalloc((void **)&h.stage, bytes));
-    EFV_CUDA(cudaMemset(h.stage, 0, bytes));
+    EFV_CUDA(cudaMalloc((void **)&h.stage, halo_stage_bytes(h)));
+    EFV_CUDA(cudaMemset(h.stage, 0, halo_stage_bytes(h)));
+    EFV_CUDA(cudaMalloc((void **)&h.ticket, sizeof(unsigned)));
+    EFV_CUDA(cudaMemset(h.ticket, 0, sizeof(unsigned)));
   }
   cudaIpcMemHandle_t hd;
   EFV_CUDA(cudaIpcGetMemHandle(&hd, h.stage));
   memcpy(out64, &hd, 64);
 }
 // handles: one per neighbour (same order as the neighbour list); remote_off[i]: first ghost slot (in vertices) of
-// neighbour i's staging area that belongs to this rank; remote_slot[i]: which flag of neighbour i this rank raises
-void halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_off, const int *remote_slot) {
-  Halo &h = s->halo;
+// neighbour i's staging area that belongs to this rank; remote_slot[i]: which flag of neighbour i this rank raises;
+// remote_ghosts[i]: number of ghost vertices of neighbour i (= the stride between its two parity buffers)
+void halo_stage_import(Halo &h, const char *handles, const int64_t *remote_off, const int *remote_slot, const int64_t *remote_ghosts) {
   EFV_REQUIRE(h.stage, "export the staging buffer first");
   const int n = (int)h.nbr.size();
-  EFV_REQUIRE(n <= 8, "peer halo supports at most 8 neighbours per rank");
   h.remote.assign(n, nullptr);
   h.remote_off.assign(remote_off, remote_off + n);
   h.remote_slot.assign(remote_slot, remote_slot + n);
+  h.remote_ghosts.assign(remote_ghosts, remote_ghosts + n);
   for (int i = 0; i < n; ++i) {
     cudaIpcMemHandle_t hd;
     memcpy(&hd, handles + 64 * (size_t)i, 64);
@@ -334,38 +371,51 @@ void halo_stage_import(efv_system *s, const char *handles, const int64_t *remote
   h.peer = true;
   h.seq = 0;
 }
+void halo_release(Halo &h) {
+  for (char *r : h.remote) if (r) cudaIpcCloseMemHandle(r);
+  h.remote.clear();
+  if (h.stage) cudaFree(h.stage);
+  if (h.ticket) cudaFree(h.ticket);
+  h.stage = nullptr; h.ticket = nullptr; h.peer = false; h.active = false;
+  cudaGetLastError();
+}
 
-// ghost entries of `vec` <- owner ranks' values
-void halo_exchange(efv_system *s, double *vec) {
-  Halo &h = s->halo;
+// ghost entries of `vec` (ndof values per vertex, ndof <= the capacity the halo was registered with) <- owners' values
+void halo_exchange(Halo &h, double *vec, int ndof) {
   if (!h.active || !comm_active()) return;
+  EFV_REQUIRE(ndof <= h.cap_ndof, "halo exchange wider than the registered capacity");
   const int n_nbr = (int)h.nbr.size();
   const int64_t n_send = h.send_ptr[n_nbr];
   if (h.peer && comm_peer_active()) {
     h.seq++;
+    const uint32_t par = h.seq & 1u;
     HaloPush hp;
     hp.n = n_nbr;
     for (int i = 0; i < n_nbr; ++i) {
-      hp.dst[i] = reinterpret_cast<double *>(h.remote[i] + kHaloFlagBytes) + h.remote_off[i] * s->ndof;
-      hp.flag[i] = reinterpret_cast<uint32_t *>(h.remote[i]) + h.remote_slot[i];
+      hp.dst[i] = reinterpret_cast<double *>(h.remote[i] + kHaloFlagBytes) + (size_t)par * h.remote_ghosts[i] * h.cap_ndof +
+                  h.remote_off[i] * ndof;
+      hp.flag[i] = reinterpret_cast<uint32_t *>(h.remote[i]) + par * kMaxRanks + h.remote_slot[i];
       hp.begin[i] = h.send_ptr[i];
     }
     hp.begin[n_nbr] = n_send;
-    if (n_send) EFV_LAUNCH(k_halo_push, grid_for(n_send * s->ndof, 256, 2), 256, 0, hp, h.send_idx.p, s->ndof, vec);
-    EFV_LAUNCH(k_halo_flag, 1, 32, 0, hp, h.seq);
-    const int64_t count = (s->nV - s->n_owned) * s->ndof;
-    EFV_LAUNCH(k_halo_wait_copy, grid_for(count, 256, 1), 256, 0, h.stage, n_nbr, h.seq, count, vec + s->n_owned * s->ndof,
+    EFV_LAUNCH(k_halo_push, grid_for(std::max<int64_t>(n_send * ndof, 1), 256, 2), 256, 0, hp, h.send_idx.p, ndof, vec, h.seq, h.ticket);
+    const int64_t count = h.n_ghost * ndof;
+    const double *src = reinterpret_cast<const double *>(h.stage + kHaloFlagBytes) + (size_t)par * h.n_ghost * h.cap_ndof;
+    EFV_LAUNCH(k_halo_wait_copy, grid_for(count, 256, 1), 256, 0, h.stage, src, n_nbr, h.seq, count, vec + h.n_owned * ndof,
                reinterpret_cast<int *>(g_peer.local + kSlotBytes + kFlagBytes));
     return;
   }
-  if (n_send) EFV_LAUNCH(k_pack, grid_for(n_send * s->ndof, 256), 256, 0, h.send_idx.p, n_send, s->ndof, vec, h.send_buf.p);
+  require_nccl("halo exchange without peer staging buffers");
+  if ((size_t)n_send * ndof > h.send_buf.n) h.send_buf.alloc((size_t)n_send * ndof);
+  if (n_send) EFV_LAUNCH(k_pack, grid_for(n_send * ndof, 256), 256, 0, h.send_idx.p, n_send, ndof, vec, h.send_buf.p);
   EFV_NCCL(g_nccl.GroupStart());
   for (int i = 0; i < n_nbr; ++i) {
-    const int64_t ns = (h.send_ptr[i + 1] - h.send_ptr[i]) * s->ndof, nr = (h.recv_ptr[i + 1] - h.recv_ptr[i]) * s->ndof;
-    if (ns) EFV_NCCL(g_nccl.Send(h.send_buf.p + h.send_ptr[i] * s->ndof, (size_t)ns, kNcclFloat64, h.nbr[i], g_comm, stream()));
-    if (nr) EFV_NCCL(g_nccl.Recv(vec + (s->n_owned + h.recv_ptr[i]) * s->ndof, (size_t)nr, kNcclFloat64, h.nbr[i], g_comm, stream()));
+    const int64_t ns = (h.send_ptr[i + 1] - h.send_ptr[i]) * ndof, nr = (h.recv_ptr[i + 1] - h.recv_ptr[i]) * ndof;
+    if (ns) EFV_NCCL(g_nccl.Send(h.send_buf.p + h.send_ptr[i] * ndof, (size_t)ns, kNcclFloat64, h.nbr[i], g_comm, stream()));
+    if (nr) EFV_NCCL(g_nccl.Recv(vec + (h.n_owned + h.recv_ptr[i]) * ndof, (size_t)nr, kNcclFloat64, h.nbr[i], g_comm, stream()));
   }
   EFV_NCCL(g_nccl.GroupEnd());
 }
+void halo_exchange(efv_system *s, double *vec) { halo_exchange(s->halo, vec, s->ndof); }
 
 }  // namespace efv

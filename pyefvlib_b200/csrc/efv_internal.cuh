@@ -83,11 +83,14 @@ struct Halo {
   std::vector<int64_t> recv_ptr;        // per neighbour range into the ghost block (ghosts are grouped by owner)
   DBuf<int32_t> send_idx;               // local ids of owned vertices to send
   DBuf<double> send_buf;
-  // peer-memory path (CUDA IPC): own staging buffer [flags | ghost values] and the neighbours' mapped buffers
+  int64_t n_owned = 0, n_ghost = 0;     // vector layout: [owned | ghosts grouped by owner]
+  int cap_ndof = 1;                     // widest exchange (values per vertex) the buffers are sized for
+  // peer-memory path (CUDA IPC): own staging buffer [flags | ghost values x 2 parities] and the neighbours' mapped buffers
   bool peer = false;
   char *stage = nullptr;
+  unsigned *ticket = nullptr;           // block counter of the push kernel (last block raises the flags)
   std::vector<char *> remote;
-  std::vector<int64_t> remote_off;
+  std::vector<int64_t> remote_off, remote_ghosts;
   std::vector<int> remote_slot;
   uint32_t seq = 0;
 };
@@ -130,6 +133,11 @@ struct efv_system {
   efv::DBuf<double> scratch;            // local element matrices of the two-phase assembly, component-major
   efv::DBuf<uint8_t> tmap_off;          // transposed slot map: per CSR entry the offset of its contribution list in the row block
   efv::DBuf<uint32_t> tmap_idx;         // contributions: element | (l*M + j) << 26
+  // asynchronous field download: XOLD -> pinned staging buffer on a copy stream, overlapped with the next step
+  double *dl_host = nullptr;
+  cudaStream_t dl_stream = nullptr;
+  cudaEvent_t dl_ready = nullptr, dl_done = nullptr;
+  bool dl_pending = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // assembly timing (read lazily: no host sync in the hot path)
   bool assemble_timed = false;
 };
@@ -169,6 +177,9 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
 void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres);
 void spmv(efv_system *s, const double *x, double *y);
 double max_abs_diff(efv_system *s);
+double true_relres(efv_system *s, int negate);
+void vec_sums(efv_system *s, const double *vec, double *sum, double *sumsq);
+double symmetry_defect(efv_system *s);
 // comm.cu
 void comm_unique_id(const char *nccl_path, char *out128);
 void comm_init(const char *nccl_path, int rank, int nranks, const char *id128);
@@ -184,8 +195,11 @@ bool comm_peer_active();
 void comm_allreduce_partials(const double *partial, int G, int narr, double *out, int op);
 void comm_allreduce_partials_inplace(double *partial, int G, int narr);
 int comm_peer_error();
-void halo_stage_export(efv_system *s, char *out64);
-void halo_stage_import(efv_system *s, const char *handles, const int64_t *remote_off, const int *remote_slot);
+void halo_stage_export(Halo &h, char *out64);
+void halo_stage_import(Halo &h, const char *handles, const int64_t *remote_off, const int *remote_slot, const int64_t *remote_ghosts);
+void halo_release(Halo &h);
+void halo_exchange(Halo &h, double *vec, int ndof);
+void comm_peer_release();
 void halo_set(efv_system *s, int n_nbr, const int *nbr, const int64_t *send_ptr, const int32_t *send_idx, const int64_t *recv_ptr);
 void halo_exchange(efv_system *s, double *vec);
 }  // namespace efv

@@ -10,6 +10,7 @@
 // apps/stress_equilibrium.py:170-173, apps/geomechanics.py:140,254).
 #include "views.cuh"
 #include "peer.cuh"
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -662,6 +663,14 @@ static bool sell_prepare(efv_system *s, KrylovWork *w) {
   return true;
 }
 
+// persistent SpMV kernels launch one block per SM; EFV_SPMV_BLOCKS overrides that (test hook: with a handful of blocks
+// every warp walks many slices of a SMALL matrix, which exercises the slice-offset refresh and the mbarrier phase wrap
+// that otherwise only occur beyond ~3.6 M rows)
+static int spmv_blocks() {
+  const char *e = getenv("EFV_SPMV_BLOCKS");
+  const int b = e ? atoi(e) : 0;
+  return b > 0 ? std::min(b, num_sms()) : num_sms();
+}
 static int pick_lanes(const efv_system *s) {
   const char *env = getenv("EFV_SPMV_LANES");
   if (env) { int l = atoi(env); if (l == 2 || l == 4 || l == 8 || l == 16 || l == 32) return l; }
@@ -715,7 +724,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
       EFV_CUDA(cudaFuncSetAttribute(k_spmv_sell_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));  \
       configured = true;                                                                                               \
     }                                                                                                                  \
-    EFV_LAUNCH(k_spmv_sell_tma<C>, num_sms(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,            \
+    EFV_LAUNCH(k_spmv_sell_tma<C>, spmv_blocks(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,            \
                kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, grid, done, ar);                      \
   } while (0)
       const char *ec = getenv("EFV_SELL_TMA");
@@ -753,7 +762,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
                                     (int)C::kSmem));                                                                        \
       configured = true;                                                                                                    \
     }                                                                                                                       \
-    EFV_LAUNCH((k_spmv_sell_bsr_tma<ND, EE, 2, 20>), num_sms(), 20 * 32, C::kSmem, s->n_owned, kw->sell_off.p,              \
+    EFV_LAUNCH((k_spmv_sell_bsr_tma<ND, EE, 2, 20>), spmv_blocks(), 20 * 32, C::kSmem, s->n_owned, kw->sell_off.p,              \
                kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, grid, done, ar);      \
   } while (0)
       EFV_BSR_TMA(3, 2);
@@ -794,8 +803,11 @@ __global__ void k_reduce_partials(const double *__restrict__ partial, int G, int
   }
 }
 // returns the (pointer, length) pair the consumer kernels should use for `narr` consecutive partial arrays
-static const double *consolidate(KrylovWork *w, const double *partial, int narr, int slot, int *Gout) {
-  if (!comm_active()) { *Gout = w->grid; return partial; }
+// a partitioned system in a multi-rank job (a plain system created next to it keeps solving alone)
+static bool is_dist(const efv_system *s) { return comm_active() && s->halo.active; }
+static const double *consolidate(efv_system *s, const double *partial, int narr, int slot, int *Gout) {
+  KrylovWork *w = s->kw;
+  if (!is_dist(s)) { *Gout = w->grid; return partial; }
   double *out = w->sc.p + 32 + 4 * slot;
   if (comm_peer_active()) {
     comm_allreduce_partials(partial, w->grid, narr, out, 0);     // one launch: fold partials + all-reduce over peer memory
@@ -863,6 +875,7 @@ __global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, con
   double pAp;
   if (ar_in.enabled) { ar_wait(ar_in); pAp = ar_value(ar_in, 0); }            // fused all-reduce: consumer side
   else pAp = sum_partials(pAp_partial, G, red);
+  if (!(pAp > 0.0) || !(pAp < 1e300)) return;        // not SPD / non-finite: k_pcg_update_p raises the breakdown flag, x stays as it is
   double alpha = sc[it & 1] / pAp;
   double rz = 0, rr = 0;
   // 16-byte accesses (buffers come from the pool: 256-byte aligned); the odd tail entry is done by one thread
@@ -895,9 +908,17 @@ __global__ void __launch_bounds__(kBlock) k_pcg_update_xr(int64_t n, int it, con
 __global__ void __launch_bounds__(kBlock) k_pcg_update_p(int64_t n, int it, double *__restrict__ sc,
                                                          const double *__restrict__ partial, int G,
                                                          const double *__restrict__ r, const double *__restrict__ dinv,
-                                                         double *__restrict__ p, int *__restrict__ flags, PeerAR ar_in) {
+                                                         double *__restrict__ p, int *__restrict__ flags, PeerAR ar_in,
+                                                         const double *__restrict__ pAp_partial, int GpAp) {
   __shared__ double red[32];
   if (flags[0]) return;
+  if (pAp_partial) {
+    const double pAp = sum_partials(pAp_partial, GpAp, red);
+    if (!(pAp > 0.0) || !(pAp < 1e300)) {            // same test as k_pcg_update_xr, which left x and r untouched
+      if (blockIdx.x == 0 && threadIdx.x == 0) { flags[2] = 1; flags[0] = 1; }
+      return;
+    }
+  }
   double rz_new, rr;
   if (ar_in.enabled) { ar_wait(ar_in); rz_new = ar_value(ar_in, 0); rr = ar_value(ar_in, 1); }
   else { rz_new = sum_partials(partial, G, red); rr = sum_partials(partial + G, G, red); }
@@ -942,7 +963,7 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   halo_exchange(s, s->x.p);
   launch_spmv(s, G, s->x.p, w->Ap.p, sigma, nullptr, nullptr, nullptr, nullptr);
   EFV_LAUNCH(k_pcg_init, G, kBlock, 0, n, s->b.p, w->Ap.p, w->dinv.p, sigma, w->r.p, w->p.p, P);
-  const double *c0 = consolidate(w, P, 3, 0, &Gc);
+  const double *c0 = consolidate(s, P, 3, 0, &Gc);
   EFV_LAUNCH(k_pcg_init_scalars, 1, kBlock, 0, Gc, c0, w->sc.p, w->flags.p, rtol);
   const int check_every = 32;
   int it = 0;
@@ -950,7 +971,7 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   const char *efuse = getenv("EFV_FUSED_ALLREDUCE");
   // opt-in: measured neutral at N=2 (135.6 vs 135.9 ms/step) and 10 % slower at N=8 (146.8 vs 133.4 ms/step at C2 weak),
   // where every block of the consumer polls the flags the peers are writing over NVLink
-  const bool fused = comm_active() && comm_peer_active() && efuse && atoi(efuse) == 1;
+  const bool fused = is_dist(s) && comm_peer_active() && efuse && atoi(efuse) == 1;
   unsigned *counter = reinterpret_cast<unsigned *>(w->flags.p + 3);        // zeroed with the flags above
   while (!done && it < maxit) {
     int batch_end = std::min(maxit, it + check_every);
@@ -963,15 +984,17 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
         launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, P + 3 * G, w->flags.p, ar1);
         EFV_LAUNCH(k_pcg_update_xr, G, kBlock, 0, n, it, w->sc.p, P + 3 * G, G, w->p.p, w->Ap.p, w->dinv.p, s->x.p, w->r.p, P, G,
                    w->flags.p, ar1, ar2);
-        EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, P, G, w->r.p, w->dinv.p, w->p.p, w->flags.p, ar2);
+        EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, P, G, w->r.p, w->dinv.p, w->p.p, w->flags.p, ar2, (const double *)nullptr, 0);
         continue;
       }
       launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, P + 3 * G, w->flags.p);
-      const double *c1 = consolidate(w, P + 3 * G, 1, 1, &Gc);
+      int Gc1 = G;
+      const double *c1 = consolidate(s, P + 3 * G, 1, 1, &Gc1);
+      Gc = Gc1;
       EFV_LAUNCH(k_pcg_update_xr, G, kBlock, 0, n, it, w->sc.p, c1, Gc, w->p.p, w->Ap.p, w->dinv.p, s->x.p, w->r.p, P, G,
                  w->flags.p, PeerAR(), PeerAR());
-      const double *c2 = consolidate(w, P, 2, 2, &Gc);
-      EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, c2, Gc, w->r.p, w->dinv.p, w->p.p, w->flags.p, PeerAR());
+      const double *c2 = consolidate(s, P, 2, 2, &Gc);
+      EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, c2, Gc, w->r.p, w->dinv.p, w->p.p, w->flags.p, PeerAR(), c1, Gc1);
     }
     EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
     EFV_CUDA(cudaStreamSynchronize(stream()));
@@ -984,9 +1007,11 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   float ms = 0;
   EFV_CUDA(cudaEventElapsedTime(&ms, w->e0, w->e1));
   s->t_solve_ms = ms;
-  if (comm_peer_active()) EFV_REQUIRE(comm_peer_error() == 0, "peer-memory collective timed out (a rank did not arrive)");
+  if (is_dist(s) && comm_peer_active()) EFV_REQUIRE(comm_peer_error() == 0, "peer-memory collective timed out (a rank did not arrive)");
   if (iters) *iters = w->h_flags[1];
-  if (relres) *relres = (w->h_sc[2] > 0) ? std::sqrt(w->h_sc[3] / w->h_sc[2]) : 0.0;
+  // breakdown (p.Ap <= 0 or a non-finite scalar: the operator is not SPD): x is the last good iterate, the residual is
+  // reported as NaN so that callers never mistake it for convergence
+  if (relres) *relres = w->h_flags[2] ? NAN : ((w->h_sc[2] > 0) ? std::sqrt(w->h_sc[3] / w->h_sc[2]) : 0.0);
 }
 
 // ---- BiCGStab on the row-scaled system D^-1 A x = D^-1 b ---------------------------------------
@@ -1121,7 +1146,7 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
   if (!w->rhat.n) { w->rhat.alloc(nalloc); w->v.alloc(nalloc); w->sv.alloc(nalloc); w->t.alloc(nalloc); }
   const int G = w->grid;
   double *P = w->partial.p;
-  auto global_sums = [&](double *part, int narr) { comm_allreduce_partials_inplace(part, G, narr); };
+  auto global_sums = [&](double *part, int narr) { if (is_dist(s)) comm_allreduce_partials_inplace(part, G, narr); };
   EFV_CUDA(cudaEventRecord(w->e0, stream()));
   sell_prepare(s, w);
   EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->n_owned, s->ndof, s->diag_slot.p, s->vals.p, 1.0, w->dinv.p);
@@ -1163,9 +1188,111 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
   float ms = 0;
   EFV_CUDA(cudaEventElapsedTime(&ms, w->e0, w->e1));
   s->t_solve_ms = ms;
-  if (comm_peer_active()) EFV_REQUIRE(comm_peer_error() == 0, "peer-memory collective timed out (a rank did not arrive)");
+  if (is_dist(s) && comm_peer_active()) EFV_REQUIRE(comm_peer_error() == 0, "peer-memory collective timed out (a rank did not arrive)");
   if (iters) *iters = w->h_flags[1];
   if (relres) *relres = (w->h_sc[3] > 0) ? std::sqrt(w->h_sc[4] / w->h_sc[3]) : 0.0;
+}
+
+__global__ void k_max_final(int G, const double *__restrict__ partial, double *__restrict__ out);
+// ---- true residual ||b - A x|| / ||b|| with one extra SpMV (never the recurrence residual), checksums -------------------------
+__global__ void __launch_bounds__(kBlock) k_resid_norms(int64_t n, const double *__restrict__ b, const double *__restrict__ y,
+                                                        double sigma, double *__restrict__ partial) {
+  __shared__ double red[32];
+  double rr = 0, bb = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bi = sigma * b[i], ri = bi - y[i];
+    rr += ri * ri; bb += bi * bi;
+  }
+  const int G = gridDim.x;
+  rr = block_sum(rr, red); if (threadIdx.x == 0) partial[blockIdx.x] = rr;
+  bb = block_sum(bb, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = bb;
+}
+__global__ void __launch_bounds__(kBlock) k_sums(int64_t n, const double *__restrict__ a, double *__restrict__ partial) {
+  __shared__ double red[32];
+  double s1 = 0, s2 = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = a[i];
+    s1 += v; s2 += v * v;
+  }
+  const int G = gridDim.x;
+  s1 = block_sum(s1, red); if (threadIdx.x == 0) partial[blockIdx.x] = s1;
+  s2 = block_sum(s2, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = s2;
+}
+// two global sums (over the owned entries of all ranks) from two arrays of G per-block partials
+static void two_global_sums(efv_system *s, double *out2) {
+  KrylovWork *w = s->kw;
+  double *dev = w->sc.p + 48;
+  EFV_LAUNCH(k_reduce_partials, 1, kBlock, 0, w->partial.p, w->grid, 2, dev);
+  if (is_dist(s)) comm_allreduce_sum(dev, 2);
+  EFV_CUDA(cudaMemcpyAsync(out2, dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+}
+double true_relres(efv_system *s, int negate) {
+  EFV_REQUIRE(s->vals.n, "no values assembled");
+  ensure_vectors(s);
+  KrylovWork *w = work(s);
+  if (!w->Ap.n) { w->r.alloc(s->rows); w->p.alloc(s->rows); w->Ap.alloc(s->rows); w->dinv.alloc(s->rows); }
+  const double sigma = negate ? -1.0 : 1.0;
+  sell_prepare(s, w);
+  halo_exchange(s, s->x.p);
+  launch_spmv(s, w->grid, s->x.p, w->Ap.p, sigma, nullptr, nullptr, nullptr, nullptr);
+  EFV_LAUNCH(k_resid_norms, w->grid, kBlock, 0, s->n_owned * s->ndof, s->b.p, w->Ap.p, sigma, w->partial.p);
+  double h[2];
+  two_global_sums(s, h);
+  return h[1] > 0 ? std::sqrt(h[0] / h[1]) : std::sqrt(h[0]);
+}
+void vec_sums(efv_system *s, const double *vec, double *sum, double *sumsq) {
+  KrylovWork *w = work(s);
+  EFV_LAUNCH(k_sums, w->grid, kBlock, 0, s->n_owned * s->ndof, vec, w->partial.p);
+  double h[2];
+  two_global_sums(s, h);
+  if (sum) *sum = h[0];
+  if (sumsq) *sumsq = h[1];
+}
+// max_ij |a_ij - a_ji| / max_ij |a_ij| over the owned scalar entries (column inside the owned block), by binary search
+// of the transposed entry: tells the apps at assembly time whether CG applies (general quadrilaterals / hexahedra give
+// a non-symmetric EbFVM operator)
+__global__ void __launch_bounds__(kBlock) k_symmetry(int64_t n_owned, int ndof, const int64_t *__restrict__ gptr,
+                                                     const int32_t *__restrict__ gcol, const double *__restrict__ vals,
+                                                     double *__restrict__ partial) {
+  __shared__ double red[32];
+  double dmax = 0.0, amax = 0.0;
+  const int B = ndof * ndof;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_owned; v += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t t = gptr[v]; t < gptr[v + 1]; ++t) {
+      const int64_t c = gcol[t];
+      for (int q = 0; q < B; ++q) amax = fmax(amax, fabs(vals[t * B + q]));
+      if (c >= n_owned || c <= v) continue;
+      int64_t lo = gptr[c], hi = gptr[c + 1] - 1, pos = -1;
+      while (lo <= hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int32_t cm = gcol[mid];
+        if (cm == v) { pos = mid; break; }
+        if (cm < v) lo = mid + 1; else hi = mid - 1;
+      }
+      for (int i = 0; i < ndof; ++i)
+        for (int j = 0; j < ndof; ++j) {
+          const double a = vals[t * B + i * ndof + j];
+          const double at = pos >= 0 ? vals[pos * B + j * ndof + i] : 0.0;
+          dmax = fmax(dmax, fabs(a - at));
+        }
+    }
+  }
+  const int G = gridDim.x;
+  dmax = block_max(dmax, red); if (threadIdx.x == 0) partial[blockIdx.x] = dmax;
+  amax = block_max(amax, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = amax;
+}
+double symmetry_defect(efv_system *s) {
+  EFV_REQUIRE(s->vals.n, "no values assembled");
+  KrylovWork *w = work(s);
+  EFV_LAUNCH(k_symmetry, w->grid, kBlock, 0, s->n_owned, s->ndof, s->gptr.p, s->gcol.p, s->vals.p, w->partial.p);
+  EFV_LAUNCH(k_max_final, 1, kBlock, 0, w->grid, w->partial.p, w->sc.p + 48);
+  EFV_LAUNCH(k_max_final, 1, kBlock, 0, w->grid, w->partial.p + w->grid, w->sc.p + 49);
+  if (is_dist(s)) comm_allreduce_max(w->sc.p + 48, 2);
+  double h[2];
+  EFV_CUDA(cudaMemcpyAsync(h, w->sc.p + 48, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+  return h[1] > 0 ? h[0] / h[1] : 0.0;
 }
 
 // ---- max |x - xold| (heat_transfer.py:142) ----------------------------------------------------------------------------------
@@ -1190,7 +1317,7 @@ double max_abs_diff(efv_system *s) {
   KrylovWork *w = work(s);
   EFV_LAUNCH(k_max_abs_diff, w->grid, kBlock, 0, s->n_owned * s->ndof, s->x.p, s->xold.p, w->partial.p);
   EFV_LAUNCH(k_max_final, 1, kBlock, 0, w->grid, w->partial.p, w->sc.p + 15);
-  comm_allreduce_max(w->sc.p + 15, 1);
+  if (is_dist(s)) comm_allreduce_max(w->sc.p + 15, 1);
   double out = 0;
   EFV_CUDA(cudaMemcpyAsync(&out, w->sc.p + 15, sizeof(double), cudaMemcpyDeviceToHost, stream()));
   EFV_CUDA(cudaStreamSynchronize(stream()));

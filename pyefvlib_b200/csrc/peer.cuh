@@ -19,7 +19,31 @@ constexpr int kMaxRanks = 16;
 constexpr size_t kSlotBytes = 2 * kMaxRanks * 4 * sizeof(double);
 constexpr size_t kFlagBytes = 2 * kMaxRanks * sizeof(uint32_t);
 constexpr size_t kPeerBytes = kSlotBytes + kFlagBytes + 64;
-constexpr long long kSpinLimit = 1LL << 24;     // ~ seconds; a rank that never arrives turns into an error, not a hang
+// A rank that never arrives turns into an error, not a hang: spin waits give up after kPeerTimeoutNs of WALL time
+// (%globaltimer), generous enough for ordinary rank skew (a peer writing output files, lazy module loads, uneven
+// assembly, two ranks time-sliced on one GPU).  After a timeout the error word stays set until the host has reported it
+// (comm_peer_error() clears it), and every later wait returns at once, so the solve ends instead of timing out again.
+constexpr unsigned long long kPeerTimeoutNs = 60ULL * 1000000000ULL;
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wait until *f >= seq (wrap-safe); returns false on timeout / earlier error (err set to `code`)
+__device__ __forceinline__ bool peer_wait_flag(volatile const uint32_t *f, uint32_t seq, int *err, int code) {
+  if ((int32_t)(*f - seq) >= 0) return true;
+  if (*reinterpret_cast<volatile int *>(err) != 0) return false;
+  const unsigned long long t0 = global_ns();
+  unsigned spins = 0;
+  while ((int32_t)(*f - seq) < 0) {
+    __nanosleep(100);
+    if ((++spins & 1023u) == 0u) {
+      if (*reinterpret_cast<volatile int *>(err) != 0) return false;
+      if (global_ns() - t0 > kPeerTimeoutNs) { atomicExch(err, code); return false; }
+    }
+  }
+  return true;
+}
 
 struct PeerPtrs { char *p[kMaxRanks]; };
 
@@ -72,12 +96,7 @@ __device__ __forceinline__ void ar_publish(const PeerAR &ar, const double *parti
 __device__ __forceinline__ void ar_wait(const PeerAR &ar) {
   char *self = ar.peers.p[ar.me];
   if ((int)threadIdx.x < ar.nranks) {
-    volatile uint32_t *f = peer_flag(self, ar.seq & 1, threadIdx.x);
-    long long spins = 0;
-    while ((int32_t)(*f - ar.seq) < 0) {
-      if (++spins > kSpinLimit) { atomicExch(peer_error(self), 1); break; }
-      __nanosleep(200);                              // thousands of blocks poll the same line: back off
-    }
+    peer_wait_flag(peer_flag(self, ar.seq & 1, threadIdx.x), ar.seq, peer_error(self), 1);
   }
   __syncthreads();
   __threadfence_system();

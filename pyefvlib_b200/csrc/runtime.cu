@@ -46,6 +46,12 @@ void set_device(int device) {
 cudaStream_t stream() { ensure_init(); return g_stream; }
 int num_sms() { ensure_init(); return g_num_sms; }
 void count_launch(int n) { g_launches += n; }
+static std::atomic<int64_t> g_field_copies[2]{{0}, {0}}, g_field_bytes[2]{{0}, {0}};
+void count_field_copy(int d2h, size_t bytes) { g_field_copies[d2h ? 1 : 0] += 1; g_field_bytes[d2h ? 1 : 0] += (int64_t)bytes; }
+void field_copy_counters(int64_t *out4) {
+  out4[0] = g_field_copies[0].load(); out4[1] = g_field_bytes[0].load();
+  out4[2] = g_field_copies[1].load(); out4[3] = g_field_bytes[1].load();
+}
 int64_t launch_count() { return g_launches.load(); }
 
 // ---- device -> host copies ----------------------------------------------------------------------------------------

@@ -7,6 +7,13 @@ import scipy.sparse as sp
 from . import _lib
 from . import shapes as _shapes
 
+def field_copy_counters():
+    """dict(uploads, upload_bytes, downloads, download_bytes): whole-field copies since the process started."""
+    c = [C.c_int64(0) for _ in range(4)]
+    _lib.check(_lib.load().efv_field_copy_counters(*[C.byref(x) for x in c]))
+    return dict(uploads=c[0].value, upload_bytes=c[1].value, downloads=c[2].value, download_bytes=c[3].value)
+
+
 DIRICHLET_ROWS, DIRICHLET_SYMMETRIC = 0, 1
 VEC_X, VEC_B, VEC_XOLD = 0, 1, 2
 
@@ -209,6 +216,32 @@ class DeviceSystem:
 
     def advance(self):
         _lib.check(_lib.load().efv_advance(self.handle))
+
+    def download_xold_begin(self):
+        """Start the asynchronous download of XOLD (the field of the step just advanced) on the copy stream."""
+        _lib.check(_lib.load().efv_download_xold_begin(self.handle))
+
+    def download_xold_end(self):
+        out = np.empty(self.rows)
+        _lib.check(_lib.load().efv_download_xold_end(self.handle, out.ctypes.data_as(_lib.c_f64p)))
+        return out
+
+    def true_residual(self, negate=False):
+        """||B - A X|| / ||B|| recomputed with one extra SpMV (not the solver's recurrence residual)."""
+        out = C.c_double(0.0)
+        _lib.check(_lib.load().efv_true_residual(self.handle, int(bool(negate)), C.byref(out)))
+        return out.value
+
+    def vec_sums(self, which):
+        """(sum, sum of squares) of the owned entries, all-reduced over the ranks of a partitioned system."""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        _lib.check(_lib.load().efv_vec_sums(self.handle, int(which), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def symmetry_defect(self):
+        out = C.c_double(0.0)
+        _lib.check(_lib.load().efv_symmetry_defect(self.handle, C.byref(out)))
+        return out.value
 
     def timings(self):
         a, s = C.c_double(0.0), C.c_double(0.0)

@@ -175,12 +175,17 @@ def nccl_library_path():
 
 
 _comm_ready = False
+_peer_ok = False
 
 
-def init_comm():
-    """Create the library's NCCL communicator; the unique id travels through torch.distributed."""
-    global _comm_ready
+def init_comm(use_nccl=True):
+    """Create the library's communicator.  With NCCL (default) the unique id travels through torch.distributed; with
+    `use_nccl=False` the communicator is peer-memory only (CUDA IPC), which also works for several ranks on ONE GPU.
+    The peer-memory path (EFV_COMM=peer, the default) is taken only if EVERY rank is on the same host and managed to
+    map every other rank's region; otherwise all ranks fall back to NCCL together."""
+    global _comm_ready, _peer_ok
     import ctypes as C
+    import socket
     import torch.distributed as dist
     from . import _lib
     if _comm_ready:
@@ -188,19 +193,39 @@ def init_comm():
     L = _lib.load()
     rank, world = dist.get_rank(), dist.get_world_size()
     path = nccl_library_path().encode()
-    buf = C.create_string_buffer(128)
-    if rank == 0:
-        _lib.check(L.efv_comm_unique_id(path, buf))
-    box = [bytes(buf.raw)]
-    dist.broadcast_object_list(box, src=0)
-    _lib.check(L.efv_comm_init(path, rank, world, box[0]))
-    if os.environ.get("EFV_COMM", "peer") == "peer" and world <= 16:
-        # scalar all-reduce region of every rank, mapped everywhere through CUDA IPC
-        mine = C.create_string_buffer(64)
-        _lib.check(L.efv_comm_peer_export(mine))
-        table = [None] * world
-        dist.all_gather_object(table, bytes(mine.raw))
-        _lib.check(L.efv_comm_peer_import(b"".join(table)))
+    if use_nccl:
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _lib.check(L.efv_comm_unique_id(path, buf))
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        _lib.check(L.efv_comm_init(path, rank, world, box[0]))
+    else:
+        _lib.check(L.efv_comm_init(None, rank, world, None))
+    want_peer = os.environ.get("EFV_COMM", "peer") == "peer" and world <= 16
+    # every rank takes part in the same collectives below, whatever it decides locally
+    mine = C.create_string_buffer(64)
+    ok = want_peer
+    if want_peer:
+        try:
+            _lib.check(L.efv_comm_peer_export(mine))
+        except _lib.EfvError:
+            ok = False
+    table = [None] * world
+    dist.all_gather_object(table, (socket.gethostname(), ok, bytes(mine.raw)))
+    ok = all(t[1] for t in table) and len({t[0] for t in table}) == 1
+    if ok:
+        try:
+            _lib.check(L.efv_comm_peer_import(b"".join(t[2] for t in table)))
+        except _lib.EfvError:
+            ok = False
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    _peer_ok = all(flags)
+    if not _peer_ok:
+        _lib.check(L.efv_comm_peer_release())
+        if not use_nccl:
+            raise _lib.EfvError("peer-memory communicator requested without NCCL, but the ranks cannot map each other's memory")
     _comm_ready = True
 
 
@@ -218,18 +243,20 @@ def make_system(part, ndof=1):
     rp = np.asarray(part.recv_ptr, dtype=np.int64)
     _lib.check(L.efv_system_set_halo(s.handle, len(nb), nb.ctypes.data_as(_lib.c_intp), sp.ctypes.data_as(_lib.c_i64p),
                                      si.ctypes.data_as(_lib.c_i32p), rp.ctypes.data_as(_lib.c_i64p)))
-    if os.environ.get("EFV_COMM", "peer") == "peer" and part.world <= 16 and len(nb) <= 8:
+    if _peer_ok:                      # a global decision (init_comm): every rank runs the collective below or none does
         import torch.distributed as dist
-        # staging buffers: everybody publishes (handle, {neighbour: (ghost offset, flag slot) it reserves for that neighbour})
+        # staging buffers: everybody publishes (handle, ghost count, {neighbour: (ghost offset, flag slot) reserved for it})
         mine = C.create_string_buffer(64)
         _lib.check(L.efv_halo_stage_export(s.handle, mine))
         info = {int(q): (int(part.recv_ptr[i]), i) for i, q in enumerate(part.nbr)}
         table = [None] * part.world
-        dist.all_gather_object(table, (bytes(mine.raw), info))
+        dist.all_gather_object(table, (bytes(mine.raw), int(part.n_ghost), info))
         handles = b"".join(table[int(q)][0] for q in part.nbr)
-        offs = np.array([table[int(q)][1][part.rank][0] for q in part.nbr], dtype=np.int64)
-        slots = np.array([table[int(q)][1][part.rank][1] for q in part.nbr], dtype=np.int32)
-        _lib.check(L.efv_halo_stage_import(s.handle, handles, offs.ctypes.data_as(_lib.c_i64p), slots.ctypes.data_as(_lib.c_intp)))
+        offs = np.array([table[int(q)][2][part.rank][0] for q in part.nbr], dtype=np.int64)
+        slots = np.array([table[int(q)][2][part.rank][1] for q in part.nbr], dtype=np.int32)
+        ghosts = np.array([table[int(q)][1] for q in part.nbr], dtype=np.int64)
+        _lib.check(L.efv_halo_stage_import(s.handle, handles, offs.ctypes.data_as(_lib.c_i64p), slots.ctypes.data_as(_lib.c_intp),
+                                           ghosts.ctypes.data_as(_lib.c_i64p)))
     return s
 
 

@@ -12,6 +12,7 @@ import numpy as np
 class Saver:
     """Buffers every saved field like PyEFVLib/Saver.py:16-22; CSV output like CsvSaver.py:9-41.
     (Output formatting is outside the hot path; only the in-memory `fields` contract matters to the apps.)"""
+    wants_fields = True          # the time loop downloads a field from the device only for savers that ask for it
 
     def __init__(self, grid, outputPath, basePath, extension="csv", fileName="Results", **kwargs):
         self.grid, self.fileName, self.extension, self.basePath = grid, fileName, extension, basePath
@@ -44,7 +45,9 @@ CsvSaver = Saver
 
 
 class NullSaver(Saver):
-    """Keeps only the latest field (large meshes: the reference's keep-everything buffer would not fit)."""
+    """Keeps only the latest field (large meshes: the reference's keep-everything buffer would not fit).  The time loop
+    does not download anything for it; the solver hands it the final field once, when the run ends."""
+    wants_fields = False
 
     def save(self, fieldName, fieldValues, currentTime):
         self.fields[fieldName] = np.asarray(fieldValues)[None, :]
@@ -85,8 +88,11 @@ class Solver:
         elif self.extension == "vtu":
             from .savers import VtuSaver
             self.saver = VtuSaver(self.grid, self.outputPath, self.problemData.libraryPath)
-        else:
+        elif self.extension == "csv":
             self.saver = Saver(self.grid, self.outputPath, self.problemData.libraryPath, extension=self.extension)
+        else:
+            raise Exception(f"Output extension '{self.extension}' is not supported by the GPU backend (csv, vtu, or saverType "
+                            "'stream' / 'none'); the reference's xdmf / vtm writers need meshio")
         self.numberOfVertices = self.grid.numberOfVertices
         self.dimension = self.grid.dimension
         self.currentTime = 0.0

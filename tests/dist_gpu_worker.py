@@ -23,10 +23,20 @@ def main():
     kind = sys.argv[1] if len(sys.argv) > 1 else "hex"
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # EFV_TEST_SHARED_GPU=1: every rank runs on cuda:0 (a 1-GPU box).  NCCL refuses duplicate devices, so the library's
+    # communicator is created in peer-memory-only mode (CUDA IPC between the processes) and torch uses gloo.
+    shared = os.environ.get("EFV_TEST_SHARED_GPU", "0") == "1"
+    if shared:
+        local_rank = 0
     torch.cuda.set_device(local_rank)
     _lib.check(_lib.load().efv_set_device(local_rank))
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    efd.init_comm()
+    if shared:
+        dist.init_process_group("gloo")
+        efd.init_comm(use_nccl=False)
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        efd.init_comm()
+    tdev = "cpu" if shared else "cuda"
     part = efd.structured_part(n, kind, rank, world, perturb=0.0)
     s = efd.make_system(part, 1)
     props = np.array([[1.0, 1.0, 1.0, 100.0]])
@@ -59,7 +69,7 @@ def main():
     assert relres <= 1e-10, (iters, relres)
     x = s.download(VEC_X)[:part.n_owned]
     err = np.array([np.sum((x - xref[own]) ** 2), np.sum(xref[own] ** 2)])
-    t = torch.tensor(err, device="cuda", dtype=torch.float64)
+    t = torch.tensor(err, device=tdev, dtype=torch.float64)
     dist.all_reduce(t)
     rel = float(torch.sqrt(t[0] / t[1]).item())
     assert rel <= 1e-8, rel
@@ -73,7 +83,7 @@ def main():
     assert rr_b <= 1e-10, (it_b, rr_b)
     xb = s.download(VEC_X)[:part.n_owned]
     err = np.array([np.sum((xb - xref[own]) ** 2), np.sum(xref[own] ** 2)])
-    t = torch.tensor(err, device="cuda", dtype=torch.float64)
+    t = torch.tensor(err, device=tdev, dtype=torch.float64)
     dist.all_reduce(t)
     rel_b = float(torch.sqrt(t[0] / t[1]).item())
     assert rel_b <= 1e-8, rel_b
@@ -109,12 +119,12 @@ def main():
     assert rr_e <= 1e-10, (it_e, rr_e)
     xl = se.download(VEC_X).reshape(3, nl)[:, :part.n_owned]
     xg = xe.reshape(3, nV)[:, own]
-    t = torch.tensor([np.sum((xl - xg) ** 2), np.sum(xg ** 2)], device="cuda", dtype=torch.float64)
+    t = torch.tensor([np.sum((xl - xg) ** 2), np.sum(xg ** 2)], device=tdev, dtype=torch.float64)
     dist.all_reduce(t)
     rel_e = float(torch.sqrt(t[0] / t[1]).item())
     assert rel_e <= 1e-8, rel_e
     if rank == 0:
-        print(f"DIST_OK world={world} kind={kind} n={n} iters={iters} relres={relres:.2e} rel_l2={rel:.2e} "
+        print(f"DIST_OK world={world} shared_gpu={int(shared)} kind={kind} n={n} iters={iters} relres={relres:.2e} rel_l2={rel:.2e} "
               f"elasticity iters={it_e} rel_l2={rel_e:.2e}")
     dist.barrier()
     _lib.load().efv_comm_destroy()

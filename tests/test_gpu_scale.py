@@ -1,0 +1,192 @@
+"""Parity at bench scale.  The fixtures of tests/golden stop at a few thousand rows, where every persistent SpMV warp
+owns at most one slice and every assembly block one tile; these tests drive the SAME kernels the benchmark runs
+through their multi-slice / multi-tile paths (slice-offset refresh, mbarrier phase wrap, tile prefetch loop) and
+compare with scipy on the exported CSR and with the oracle's own matrix and solution."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import pyefvlib_b200 as P
+import pyefvlib_b200.device as D
+from tests import util
+from tests.cases import BC3D, HEAT_PROPS, STRESS_PROPS, _s3
+
+pytestmark = pytest.mark.gpu
+PROPS1 = np.array([[1.0, 1.0, 1.0, 100.0]])
+DT = 1e-2
+
+
+class env:
+    """Temporarily set environment switches of the CUDA library (it reads them with getenv at launch time)."""
+
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        for k, v in self.kv.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = str(v)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def heat_bcs(system, grid):
+    system.bc_clear()
+    for b in grid.boundaries:
+        kind, val = BC3D[b.name]
+        if kind == "neumann":
+            system.bc_neumann(b.handle, 0, val, 1.0)
+    for b in grid.boundaries:
+        kind, val = BC3D[b.name]
+        if kind == "dirichlet":
+            system.bc_dirichlet(b.verticesIndexes, np.full(len(b.verticesIndexes), val))
+
+
+def heat_system(n, kind="hex", perturb=0.0):
+    grid = P.Grid(P.structured_grid_data(n, kind, perturb))
+    s = D.DeviceSystem(grid, 1)
+    heat_bcs(s, grid)
+    s.assemble_dirichlet_mode(D.DIRICHLET_SYMMETRIC)
+    s.heat_assemble(PROPS1, DT, True)
+    return grid, s
+
+
+def spmv_error(s, A, x, scale):
+    s.upload(D.VEC_X, x)
+    s.spmv(D.VEC_X, D.VEC_B)
+    return float(np.abs(s.download(D.VEC_B) - A @ x).max() / scale)
+
+
+SPMV_VARIANTS = [
+    ("tma+delta", dict(EFV_SPMV_FORMAT=None, EFV_SELL_KERNEL=None, EFV_SELL_DELTA=None)),
+    ("tma", dict(EFV_SPMV_FORMAT=None, EFV_SELL_KERNEL=None, EFV_SELL_DELTA=0)),
+    ("reg+delta", dict(EFV_SPMV_FORMAT=None, EFV_SELL_KERNEL="reg", EFV_SELL_DELTA=None)),
+    ("reg", dict(EFV_SPMV_FORMAT=None, EFV_SELL_KERNEL="reg", EFV_SELL_DELTA=0)),
+    ("csr", dict(EFV_SPMV_FORMAT="csr", EFV_SELL_KERNEL=None, EFV_SELL_DELTA=None)),
+]
+
+
+def test_spmv_paths_at_bench_scale_hex():
+    """n = 160: 4.1 M rows = 128 k slices, i.e. > 32 slices for each of the 148 x 24 persistent warps of k_spmv_sell_tma:
+    the slice-offset refresh and the mbarrier phase wrap run.  Every SpMV path against scipy on the exported CSR."""
+    n = 160
+    grid, s = heat_system(n)
+    A = s.to_scipy()
+    assert A.shape[0] == n ** 3 and A.nnz == (3 * n - 2) ** 3
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(A.shape[0])
+    scale = float((abs(A) @ np.abs(x)).max())
+    for name, kv in SPMV_VARIANTS:
+        with env(**kv):
+            s.heat_assemble(PROPS1, DT, True)          # new values version: the solver-side copy is rebuilt for this variant
+            err = spmv_error(s, A, x, scale)
+        assert err <= 1e-13, (name, err)
+    # the solve on top of it: true residual recomputed from b - A x, on the host, with the exported matrix
+    s.heat_assemble(PROPS1, DT, True)
+    s.upload(D.VEC_XOLD, np.zeros(s.rows)); s.upload(D.VEC_X, np.zeros(s.rows))
+    s.build_rhs(True)
+    b = s.download(D.VEC_B)
+    it, rr = s.solve_pcg(1e-10, 5000)
+    xs = s.download(D.VEC_X)
+    host = float(np.linalg.norm(b - A @ xs) / np.linalg.norm(b))
+    dev = s.true_residual()
+    assert rr <= 1e-10 and host <= 2e-10 and abs(dev - host) <= 1e-12, (it, rr, host, dev)
+
+
+@pytest.mark.parametrize("blocks", [1, 3])
+def test_spmv_many_slices_per_warp_small(blocks):
+    """Same code paths on a small matrix: with 1 or 3 persistent blocks every warp walks dozens to hundreds of slices
+    (perturbed mesh: part of the columns is incompressible, so compressed and indexed chunks alternate)."""
+    grid, s = heat_system(44, perturb=0.2)
+    A = s.to_scipy()
+    x = np.random.default_rng(3).standard_normal(A.shape[0])
+    scale = float((abs(A) @ np.abs(x)).max())
+    with env(EFV_SPMV_BLOCKS=blocks):
+        for name, kv in SPMV_VARIANTS[:2]:
+            with env(**kv):
+                s.heat_assemble(PROPS1, DT, True)
+                assert spmv_error(s, A, x, scale) <= 1e-13, name
+
+
+@pytest.mark.parametrize("blocks", [0, 2])
+def test_block_spmv_tets_elasticity(blocks):
+    """3x3-block TMA kernel (k_spmv_sell_bsr_tma) and the register-staged block kernel on a tetrahedral elasticity
+    operator; with 2 persistent blocks each warp owns > 32 slices."""
+    grid = P.Grid(P.structured_grid_data(36, "tet"))
+    s = D.DeviceSystem(grid, 3)
+    props = np.array([[STRESS_PROPS["Body"][k] for k in ("ShearModulus", "PoissonsRatio", "Density", "Gravity")]])
+    s.assemble_dirichlet_mode(-1)
+    s.elasticity_assemble(props, False)
+    A = s.to_scipy()
+    x = np.random.default_rng(5).standard_normal(A.shape[0])
+    scale = float((abs(A) @ np.abs(x)).max())
+    for kern in (None, "reg"):
+        with env(EFV_SPMV_BLOCKS=blocks or None, EFV_SELL_KERNEL=kern):
+            s.elasticity_assemble(props, False)
+            assert spmv_error(s, A, x, scale) <= 1e-13, kern
+    with env(EFV_SPMV_FORMAT="csr"):
+        assert spmv_error(s, A, x, scale) <= 1e-13
+
+
+@pytest.mark.parametrize("n", [64, 96])
+def test_heat_matrix_and_solution_vs_oracle_large(n):
+    """Assembly through many tiles per block (k_heat_tiles' prefetch loop) and the solve, against the ORACLE's matrix
+    and scipy's solution of it (rtol 1e-13): values <= 1e-12 row-relative, solution <= 1e-8 relative L2."""
+    from oracle import efv_oracle as O
+    og = O.OracleGrid(O.structured_grid_data(n, "hex"))
+    Aref = sp.csr_matrix(O.heat_matrix(og, HEAT_PROPS, BC3D, transient=True, dt=DT))
+    bref = O.heat_rhs(og, HEAT_PROPS, BC3D, transient=True, dt=DT, Told=np.zeros(og.numberOfVertices))
+    grid = P.Grid(P.structured_grid_data(n, "hex"))
+    s = D.DeviceSystem(grid, 1)
+    heat_bcs(s, grid)
+    s.assemble_dirichlet_mode(D.DIRICHLET_ROWS)
+    s.heat_assemble(PROPS1, DT, True)
+    assert util.row_rel_matrix_error(s.to_scipy(), Aref) <= 1e-12
+    s.upload(D.VEC_XOLD, np.zeros(s.rows)); s.upload(D.VEC_X, np.zeros(s.rows))
+    s.build_rhs(True)
+    assert util.rel_max(s.download(D.VEC_B), bref) <= 1e-12
+    # solve on the symmetric form (what the apps and the benchmark do)
+    s.assemble_dirichlet_mode(D.DIRICHLET_SYMMETRIC)
+    s.heat_assemble(PROPS1, DT, True)
+    s.build_rhs(True)
+    it, rr = s.solve_pcg(1e-10, 5000)
+    x = s.download(D.VEC_X)
+    xref, info = spla.bicgstab(Aref, bref, rtol=1e-13, M=sp.diags(1.0 / Aref.diagonal()), maxiter=5000)
+    assert info == 0 and np.linalg.norm(bref - Aref @ xref) <= 1e-12 * np.linalg.norm(bref)
+    assert rr <= 1e-10 and util.rel_l2(x, xref) <= 1e-8, (it, rr, util.rel_l2(x, xref))
+    assert np.linalg.norm(bref - Aref @ x) <= 2e-10 * np.linalg.norm(bref)        # true residual on the reference operator
+
+
+def test_device_resident_time_loop_downloads_nothing():
+    """with saverType='none' a multi-step run makes no field download before the end (one, when the
+    final field is handed over); with the default saver the per-step downloads are asynchronous and still complete."""
+    from pyefvlib_b200.apps.heat_transfer import HeatTransferSolver
+    grid = P.Grid(P.structured_grid_data(20, "hex"))
+    bcs = {"temperature": dict({"InitialValue": 0.0}, **{name: {"condition": P.Dirichlet if kind == "dirichlet" else P.Neumann,
+                                                                "type": P.Constant, "value": val} for name, (kind, val) in BC3D.items()})}
+
+    def run(saverType):
+        pd = P.ProblemData(grid, P.PropertyData(HEAT_PROPS), P.BoundaryConditions(bcs),
+                           P.NumericalSettings(timeStep=DT, finalTime=None, tolerance=None, maxNumberOfIterations=5))
+        c0 = D.field_copy_counters()
+        s = HeatTransferSolver(pd, saverType=saverType, transient=True, verbosity=False)
+        s.settings(); s.init(); s.mainloop()
+        c1 = D.field_copy_counters()
+        return s, c1["downloads"] - c0["downloads"]
+    s_none, d_none = run("none")
+    assert s_none.iteration == 6 and d_none == 1                       # only the final hand-over
+    s_all, d_all = run("default")
+    assert d_all == 6 and len(s_all.saver.fields["temperature"]) == 7    # initial field + 6 steps, one async download each
+    assert util.rel_l2(s_all.saver.fields["temperature"][-1], s_none.temperatureField) <= 1e-12
+    assert np.allclose(s_all.saver.timeSteps, DT * np.arange(7))
