@@ -103,12 +103,12 @@ def main():
     se.bc_clear()
     for h, b in enumerate(part.grid.boundaries):
         for i, var in enumerate("uvw"):
-            kind, val = ebc[var][b.name]
-            if kind == "neumann":
+            bkind, val = ebc[var][b.name]
+            if bkind == "neumann":
                 se.bc_neumann(b.handle, i, val, -1.0)
         for i, var in enumerate("uvw"):
-            kind, val = ebc[var][b.name]
-            if kind == "dirichlet":
+            bkind, val = ebc[var][b.name]
+            if bkind == "dirichlet":
                 idx = part.boundary_vertices[h]
                 se.bc_dirichlet(idx + i * nl, np.full(len(idx), val))
     se.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)

@@ -164,8 +164,15 @@ def test_heat_matrix_and_solution_vs_oracle_large(n):
     x = s.download(D.VEC_X)
     xref, info = spla.bicgstab(Aref, bref, rtol=1e-13, M=sp.diags(1.0 / Aref.diagonal()), maxiter=5000)
     assert info == 0 and np.linalg.norm(bref - Aref @ xref) <= 1e-12 * np.linalg.norm(bref)
-    assert rr <= 1e-10 and util.rel_l2(x, xref) <= 1e-8, (it, rr, util.rel_l2(x, xref))
+    assert rr <= 1e-10
     assert np.linalg.norm(bref - Aref @ x) <= 2e-10 * np.linalg.norm(bref)        # true residual on the reference operator
+    # error <= cond(A) x residual: at 1e-10 the Jacobi-PCG field is 2e-8 away from the direct solution on these meshes
+    # (measured, n = 64), within 1e-8 once the residual is pushed two more digits -- the kernels are exact, the
+    # stopping rule decides the error
+    assert util.rel_l2(x, xref) <= 1e-7, (it, rr, util.rel_l2(x, xref))
+    it2, rr2 = s.solve_pcg(1e-12, 5000)
+    x = s.download(D.VEC_X)
+    assert rr2 <= 1e-12 and util.rel_l2(x, xref) <= 1e-8, (it2, rr2, util.rel_l2(x, xref))
 
 
 def test_device_resident_time_loop_downloads_nothing():
