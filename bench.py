@@ -194,13 +194,14 @@ def hot_path_step(system, grid, props):
     return iters, relres
 
 
-def same_config_run(n, cpu):
+def same_config_run(n, cpu, precond="jacobi"):
     """The GPU arm at exactly the size of the CPU sample (one `same_config: true` comparison; at this size the GPU step is
     launch-latency bound, which is why the headline config is not this one)."""
     import pyefvlib_b200 as P
     from pyefvlib_b200.device import DeviceSystem, VEC_X, VEC_XOLD
     grid = P.Grid(P.structured_grid_data(n, "hex"))
     system = DeviceSystem(grid, 1)
+    system.set_preconditioner(precond)
     props = np.array([[1.0, 1.0, 1.0, 100.0]])
     system.upload(VEC_XOLD, np.zeros(system.rows)); system.upload(VEC_X, np.zeros(system.rows))
     for _ in range(3):
@@ -269,6 +270,7 @@ def run_gpu(args):
     e1.record(stream)
     mesh.build_geometry()                    # kernel 1
     system = DeviceSystem(grid, 1)           # kernel 2
+    system.set_preconditioner(args.precond)
     e2.record(stream)
     torch.cuda.synchronize()
     upload_ms, setup_ms = e0.elapsed_time(e1), e1.elapsed_time(e2)
@@ -382,7 +384,7 @@ def run_gpu(args):
                                                                 "type": P.Constant, "value": val} for name, (kind, val) in BC3D.items()})}))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        solver = HeatTransferSolver(pd, saverType="none", transient=True, verbosity=False, rtol=RTOL)
+        solver = HeatTransferSolver(pd, saverType="none", transient=True, verbosity=False, rtol=RTOL, preconditioner=args.precond)
         solver.solve()
         Tfinal = solver.temperatureField
         _lib.check(L.efv_synchronize())
@@ -454,6 +456,7 @@ def main():
     ap.add_argument("--n", type=int, default=216, help="vertices per side of the structured mesh (216 = C2)")
     ap.add_argument("--cpu-n", type=int, default=0, help="vertices per side of the bounded CPU sample (0: chosen from the time budget)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"], help="preconditioner of the CG solve")
     ap.add_argument("--steady", action="store_true", help="(N>1 leg) steady problem instead of one transient step")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2: configs[1] (N>1: weak scaling, one C2 block per GPU); c5: configs[4] 368^3 strong scaling")

@@ -183,6 +183,18 @@ int efv_halo_exchange(efv_system *s, int which);
  * stop when ||r||_2 <= rtol * ||b||_2.  scale: multiply the system by -1 internally (elasticity) so that CG
  * sees an SPD operator.  Outputs: iterations done and final relative residual.                             */
 int efv_solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres);
+/* Preconditioner of efv_solve_pcg: 0 = Jacobi (default), 1 = aggregation multigrid (plain aggregation in ~8-vertex aggregates,
+ * Galerkin coarse operators, Chebyshev-smoothed V-cycle built from the SpMV kernels; csrc/amg.cu).  The hierarchy is symbolic
+ * per pattern and re-summed after every assembly.  efv_system_set_lattice tells the system that its owned vertices are
+ * numbered i + nx (j + ny k) on an nx x ny x nz lattice (structured meshes and their slabs): aggregates are then 2x2x2 blocks
+ * computed arithmetically on the device; otherwise they come from three rounds of pairwise matching on the graph.
+ * efv_amg_info reports the hierarchy (levels, rows / nnz / Chebyshev bound per level, time of the last numeric set-up). */
+int efv_system_set_preconditioner(efv_system *s, int kind);
+int efv_system_set_lattice(efv_system *s, int nx, int ny, int nz);
+int efv_amg_info(efv_system *s, int capacity, int *levels, int64_t *rows, int64_t *nnz, double *lmax, double *numeric_ms);
+/* one level on the host (any pointer may be NULL): block-CSR pattern over the level's rows, values (ndof x ndof blocks, row-major
+ * inside a block), aggregate of every row (not on the coarsest level) -- lets the tests rebuild P^T A P with scipy */
+int efv_amg_level_export(efv_system *s, int level, int64_t *gptr, int32_t *gcol, double *vals, int32_t *aggregates);
 int efv_solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres);
 int efv_spmv(efv_system *s, int which_in, int which_out);   /* y = A x on two of the system's vectors */
 /* Checks that never trust the solver's own recurrences: the TRUE relative residual ||B - A X||_2 / ||B||_2 recomputed with one

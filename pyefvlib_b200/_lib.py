@@ -80,6 +80,10 @@ PROTOTYPES = {
     "efv_system_set_halo": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_i64p, c_i32p, c_i64p]),
     "efv_halo_exchange": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_solve_pcg": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, c_intp, c_f64p]),
+    "efv_system_set_preconditioner": (C.c_int, [C.c_void_p, C.c_int]),
+    "efv_system_set_lattice": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "efv_amg_level_export": (C.c_int, [C.c_void_p, C.c_int, c_i64p, c_i32p, c_f64p, c_i32p]),
+    "efv_amg_info": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_i64p, c_i64p, c_f64p, c_f64p]),
     "efv_solve_bicgstab": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_intp, c_f64p]),
     "efv_spmv": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "efv_true_residual": (C.c_int, [C.c_void_p, C.c_int, c_f64p]),

@@ -13,13 +13,18 @@ PROPERTY_NAMES = ["Conductivity", "Density", "HeatCapacity", "HeatGeneration"]
 
 
 class HeatTransferSolver(Solver):
-    def __init__(self, workspaceDirectory, rtol=1e-10, maxLinearIterations=20000, linearSolver="auto", **kwargs):
+    def __init__(self, workspaceDirectory, rtol=1e-10, maxLinearIterations=20000, linearSolver="auto", preconditioner="auto", **kwargs):
         Solver.__init__(self, workspaceDirectory, **kwargs)
         self.rtol, self.maxLinearIterations, self.linearSolver = rtol, maxLinearIterations, linearSolver
+        self.preconditioner = preconditioner          # of the CG solve: "jacobi", "amg", or "auto" (multigrid from 50 000 rows up)
         self.linearIterations = []
 
     def init(self):
         self.system = DeviceSystem(self.grid, 1)
+        pc = self.preconditioner
+        if pc == "auto":
+            pc = "amg" if self.system.rows >= 50000 else "jacobi"
+        self.system.set_preconditioner(pc)
         self._T = None                                                # host copy of the current field (downloaded on demand)
         self._Tprev = np.asarray(self.problemData.initialValues["temperature"], dtype=np.float64)
         self.system.upload(VEC_XOLD, self._Tprev)

@@ -1,0 +1,797 @@
+// amg.cu -- aggregation multigrid preconditioner for the CG solver (replaces the Jacobi diagonal where the iteration
+// count, not the bandwidth, decides the time to solution: SURVEY.md section 7.2-1; the reference inverts the matrix
+// instead, apps/heat_transfer.py:78-81).
+//
+// Hierarchy.  Level 0 is the assembled system.  Level l+1 is the Galerkin operator of PLAIN aggregation,
+// A_c[I][J] = sum of a_ij over i in aggregate I, j in aggregate J (blocks are summed entry-wise for ndof > 1, i.e. the
+// coarse space of a vertex aggregate is one value per DOF).  Aggregates hold ~8 vertices: 2x2x2 blocks computed
+// arithmetically when the system knows that its vertices are numbered like a lattice (efv_system_set_lattice; the
+// synthetic meshes and their slabs), otherwise three rounds of pairwise matching on the graph (host, once per pattern).
+// Aggregates never cross ranks, so the transfer operators and the Galerkin sums need no communication.
+//
+// Everything structural is computed once per pattern (symbolic): members of every aggregate, the sorted coarse CSR
+// pattern, and for every coarse entry the ascending list of fine entries that sum into it.  The numeric set-up that
+// runs after every assembly is then one gather-sum kernel per level (fixed order: bit-reproducible, no float atomics),
+// the inverse diagonal, the Gershgorin bound of D^-1 A (the Chebyshev interval) and a dense inverse of the coarsest
+// operator (<= 256 rows).
+//
+// Cycle.  V(2,2) with Chebyshev smoothing on [lmax/8, lmax] and an over-corrected coarse-grid update (x += s P e_c,
+// s = 1.8 for scalar problems: plain aggregation under-estimates the correction, Braess 1995).  Every smoothing step
+// and every residual is ONE SpMV launch of krylov.cu with a fused epilogue (SpmvEpi): 4 matrix passes per level and
+// cycle + 3 short vector kernels (first direction, restriction, prolongation).  The cycle is a fixed symmetric
+// linear operator, so plain CG applies.  Measured iteration counts are in DESIGN.md.
+#include "krylov.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+namespace efv {
+
+constexpr int kMaxDeg = 4;
+constexpr int kCoarsestRows = 256;     // scalar rows of the dense coarsest solve
+constexpr int kMaxLevels = 24;
+
+struct AmgLevel {
+  efv_system *sys = nullptr;           // level 0: the caller's system; coarser levels: pattern + values owned here
+  bool owns_sys = false;
+  int64_t n = 0, ng = 0;               // owned / ghost block rows
+  int lat[3] = {0, 0, 0};              // lattice extents of the owned rows (0: unknown)
+  DBuf<double> dinv, x, b, r, d0, d1, res;
+  DBuf<double> coef;                   // kMaxDeg steps x (1/theta, c1, c2, -) followed by (lmax, -, -, -)
+  // transfer to the next level
+  int64_t nc = 0;
+  DBuf<int32_t> agg;                   // aggregate (coarse row) of every owned row
+  DBuf<int64_t> mem_ptr;               // members of every aggregate, ascending
+  DBuf<int32_t> mem;
+  DBuf<int64_t> cl_ptr;                // per coarse entry: the fine entries summed into it, ascending
+  DBuf<int32_t> cl;
+};
+
+struct AmgHierarchy {
+  std::vector<AmgLevel *> lv;
+  uint64_t numeric_version = 0;
+  double numeric_sigma = 0.0;
+  int deg = 2;
+  double ratio = 8.0, scale = 1.8;
+  int64_t nd = 0;                      // scalar rows of the coarsest level
+  DBuf<double> dense;                  // nd x 2 nd work matrix; the inverse is its right half
+  double t_numeric_ms = 0.0;
+  bool numeric_timed = false;
+  ~AmgHierarchy() {
+    for (AmgLevel *L : lv) {
+      if (L->owns_sys && L->sys) { krylov_free(L->sys); delete L->sys; }
+      delete L;
+    }
+  }
+};
+
+// ---- symbolic: aggregates -----------------------------------------------------------------------------------------------
+__global__ void k_agg_lattice(int64_t n, int nx, int ny, int cx, int cy, int32_t *__restrict__ agg) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(v % nx), j = (int)((v / nx) % ny);
+    const int64_t k = v / ((int64_t)nx * ny);
+    agg[v] = (int32_t)((i >> 1) + (int64_t)cx * ((j >> 1) + (int64_t)cy * (k >> 1)));
+  }
+}
+
+// pairwise matching on the host (general meshes; once per pattern): `passes` rounds, every round pairs each unmatched
+// vertex with its unmatched neighbour of smallest degree and then contracts the graph
+static std::vector<int32_t> host_aggregate(int64_t n, const std::vector<int64_t> &ptr0, const std::vector<int32_t> &col0, int passes,
+                                           int64_t *n_coarse) {
+  std::vector<int32_t> map(n);
+  std::iota(map.begin(), map.end(), 0);
+  std::vector<int64_t> ptr = ptr0;
+  std::vector<int32_t> col = col0;
+  int64_t m = n;
+  for (int pass = 0; pass < passes && m > 1; ++pass) {
+    std::vector<int32_t> id(m, -1);
+    int32_t next = 0;
+    for (int64_t v = 0; v < m; ++v) {
+      if (id[v] >= 0) continue;
+      int64_t best = -1, best_deg = INT64_MAX;
+      for (int64_t t = ptr[v]; t < ptr[v + 1]; ++t) {
+        const int64_t u = col[t];
+        if (u == v || u >= m || id[u] >= 0) continue;
+        const int64_t deg = ptr[u + 1] - ptr[u];
+        if (deg < best_deg) { best_deg = deg; best = u; }
+      }
+      id[v] = next;
+      if (best >= 0) id[best] = next;
+      ++next;
+    }
+    // contract
+    std::vector<std::vector<int32_t>> rows(next);
+    for (int64_t v = 0; v < m; ++v)
+      for (int64_t t = ptr[v]; t < ptr[v + 1]; ++t)
+        if (col[t] < m) rows[id[v]].push_back(id[col[t]]);
+    std::vector<int64_t> nptr(next + 1, 0);
+    std::vector<int32_t> ncol;
+    for (int32_t a = 0; a < next; ++a) {
+      auto &r = rows[a];
+      std::sort(r.begin(), r.end());
+      r.erase(std::unique(r.begin(), r.end()), r.end());
+      nptr[a + 1] = nptr[a] + (int64_t)r.size();
+      ncol.insert(ncol.end(), r.begin(), r.end());
+    }
+    for (int64_t v = 0; v < n; ++v) map[v] = id[map[v]];
+    ptr.swap(nptr);
+    col.swap(ncol);
+    m = next;
+  }
+  *n_coarse = m;
+  return map;
+}
+
+// ---- symbolic: members, coarse pattern, gather lists ------------------------------------------------------------------------
+__global__ void k_count_members(int64_t n, const int32_t *__restrict__ agg, int32_t *__restrict__ cnt) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) atomicAdd(cnt + agg[v], 1);
+}
+__global__ void k_fill_members(int64_t n, const int32_t *__restrict__ agg, const int64_t *__restrict__ ptr, int32_t *__restrict__ cursor,
+                               int32_t *__restrict__ mem) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t a = agg[v];
+    mem[ptr[a] + atomicAdd(cursor + a, 1)] = (int32_t)v;
+  }
+}
+// ascending order inside every list (the fill order above depends on the schedule; the sorted lists do not)
+__global__ void k_sort_lists(int64_t nlists, const int64_t *__restrict__ ptr, int32_t *__restrict__ items) {
+  for (int64_t a = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; a < nlists; a += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p0 = ptr[a], p1 = ptr[a + 1];
+    for (int64_t i = p0 + 1; i < p1; ++i) {
+      const int32_t key = items[i];
+      int64_t j = i - 1;
+      while (j >= p0 && items[j] > key) { items[j + 1] = items[j]; --j; }
+      items[j + 1] = key;
+    }
+  }
+}
+
+constexpr int kCWarps = 4;
+constexpr int kCMaxCand = 2048;
+// one warp per coarse row: candidates = aggregates of the columns of the member rows; distinct values in ascending order
+template <bool FILL>
+__global__ void __launch_bounds__(kCWarps * 32) k_coarse_rows(int64_t nc, int64_t n_owned_fine, const int64_t *__restrict__ mem_ptr,
+                                                              const int32_t *__restrict__ mem, const int64_t *__restrict__ gptr,
+                                                              const int32_t *__restrict__ gcol, const int32_t *__restrict__ agg_all,
+                                                              int32_t *__restrict__ rowlen, const int64_t *__restrict__ cptr,
+                                                              int32_t *__restrict__ ccol, int32_t *__restrict__ cdiag,
+                                                              int *__restrict__ error_flag) {
+  __shared__ int32_t cand_s[kCWarps][kCMaxCand];
+  __shared__ uint8_t first_s[kCWarps][kCMaxCand];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int32_t *cand = cand_s[warp];
+  uint8_t *first = first_s[warp];
+  for (int64_t I = (int64_t)blockIdx.x * kCWarps + warp; I < nc; I += (int64_t)gridDim.x * kCWarps) {
+    int n = 0;
+    bool overflow = false;
+    for (int64_t q = mem_ptr[I]; q < mem_ptr[I + 1] && !overflow; ++q) {
+      const int64_t v = mem[q];
+      const int64_t r0 = gptr[v];
+      const int len = (int)(gptr[v + 1] - r0);
+      if (n + len > kCMaxCand) { overflow = true; break; }
+      for (int k = lane; k < len; k += 32) cand[n + k] = agg_all[gcol[r0 + k]];
+      n += len;
+    }
+    if (overflow) { if (lane == 0) atomicExch(error_flag, 1); continue; }
+    __syncwarp();
+    int count = 0;
+    for (int i = lane; i < n; i += 32) {
+      const int32_t c = cand[i];
+      bool is_first = true;
+      for (int t = 0; t < i; ++t) is_first &= (cand[t] != c);
+      first[i] = is_first;
+      count += is_first;
+    }
+    __syncwarp();
+    if (!FILL) {
+      for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
+      if (lane == 0) rowlen[I] = count;
+    } else {
+      for (int i = lane; i < n; i += 32) {
+        if (!first[i]) continue;
+        const int32_t c = cand[i];
+        int rank = 0;
+        for (int t = 0; t < n; ++t) rank += (first[t] && cand[t] < c);
+        ccol[cptr[I] + rank] = c;
+        if (c == (int32_t)I) cdiag[I] = (int32_t)(cptr[I] + rank);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__device__ __forceinline__ int64_t coarse_slot(const int64_t *__restrict__ cptr, const int32_t *__restrict__ ccol, int32_t I, int32_t J) {
+  int64_t lo = cptr[I], hi = cptr[I + 1] - 1;
+  while (lo <= hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int32_t c = ccol[mid];
+    if (c == J) return mid;
+    if (c < J) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+// pass 0: count the fine entries of every coarse entry; pass 1: fill the lists through a cursor
+template <int PASS>
+__global__ void k_gather_lists(int64_t n_owned, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
+                               const int32_t *__restrict__ agg_all, const int64_t *__restrict__ cptr, const int32_t *__restrict__ ccol,
+                               int32_t *__restrict__ cnt, const int64_t *__restrict__ cl_ptr, int32_t *__restrict__ cl,
+                               int *__restrict__ error_flag) {
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_owned; v += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t I = agg_all[v];
+    for (int64_t t = gptr[v]; t < gptr[v + 1]; ++t) {
+      const int64_t e = coarse_slot(cptr, ccol, I, agg_all[gcol[t]]);
+      if (e < 0) { atomicExch(error_flag, 2); continue; }
+      if (PASS == 0) atomicAdd(cnt + e, 1);
+      else cl[cl_ptr[e] + atomicAdd(cnt + e, 1)] = (int32_t)t;
+    }
+  }
+}
+
+// ---- numeric ------------------------------------------------------------------------------------------------------------------
+// coarse value = sum of its fine values in ascending entry order (one thread per coarse entry and block component)
+__global__ void k_galerkin(int64_t cnnz, int B, const int64_t *__restrict__ cl_ptr, const int32_t *__restrict__ cl,
+                           const double *__restrict__ fine, double *__restrict__ coarse) {
+  const int64_t total = cnnz * B;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i / B;
+    const int q = (int)(i % B);
+    double acc = 0.0;
+    for (int64_t k = cl_ptr[e]; k < cl_ptr[e + 1]; ++k) acc += fine[(int64_t)cl[k] * B + q];
+    coarse[i] = acc;
+  }
+}
+// dinv = 1 / (sigma a_ii) per scalar row and the Gershgorin bound max_i sum_j |a_ij| / |a_ii| of D^-1 A: a group of 8
+// lanes per block row
+__global__ void __launch_bounds__(256) k_diag_gershgorin(int64_t n_owned, int ndof, const int64_t *__restrict__ gptr,
+                                                         const int32_t *__restrict__ gcol, const double *__restrict__ vals,
+                                                         const int32_t *__restrict__ diag_slot, double sigma,
+                                                         double *__restrict__ dinv, double *__restrict__ partial) {
+  __shared__ double red[32];
+  const int gl = threadIdx.x & 7;
+  const int B = ndof * ndof;
+  double worst = 0.0;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < n_owned; base += (int64_t)gridDim.x * 32) {
+    const int64_t v = base + (threadIdx.x >> 3);
+    const bool valid = v < n_owned;
+    const int64_t r0 = valid ? gptr[v] : 0, r1 = valid ? gptr[v + 1] : 0;
+    double sum[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t t = r0 + gl; t < r1; t += 8)
+      for (int i = 0; i < ndof; ++i)
+        for (int j = 0; j < ndof; ++j) sum[i] += fabs(vals[t * B + i * ndof + j]);
+    for (int i = 0; i < ndof; ++i) {
+      double sv = sum[i];
+      for (int o = 4; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+      if (valid && gl == 0) {
+        const double d = vals[(int64_t)diag_slot[v] * B + i * ndof + i];
+        dinv[v * ndof + i] = (d != 0.0) ? 1.0 / (sigma * d) : 1.0;
+        if (d != 0.0) worst = fmax(worst, sv / fabs(d));
+      }
+    }
+  }
+  worst = block_max(worst, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = worst;
+}
+// Chebyshev coefficients of the interval [lmax / ratio, lmax] (one thread; partial: per-block maxima of the bound)
+__global__ void k_cheb_coef(const double *__restrict__ partial, int G, double ratio, double *__restrict__ coef) {
+  __shared__ double red[32];
+  double m = 0.0;
+  for (int i = threadIdx.x; i < G; i += blockDim.x) m = fmax(m, partial[i]);
+  m = block_max(m, red);
+  if (threadIdx.x == 0) {
+    const double lmax = (m > 0.0) ? m : 1.0, lmin = lmax / ratio;
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma1 = theta / delta;
+    double rho = 1.0 / sigma1;
+    coef[0] = 1.0 / theta; coef[1] = 0.0; coef[2] = 0.0; coef[3] = 0.0;
+    for (int k = 1; k < kMaxDeg; ++k) {
+      const double rho_new = 1.0 / (2.0 * sigma1 - rho);
+      coef[4 * k + 0] = 1.0 / theta;
+      coef[4 * k + 1] = rho_new * rho;
+      coef[4 * k + 2] = 2.0 * rho_new / delta;
+      coef[4 * k + 3] = 0.0;
+      rho = rho_new;
+    }
+    coef[4 * kMaxDeg] = lmax;
+  }
+}
+// dense copy [sigma A | I] of the coarsest operator, then Gauss-Jordan without pivoting (SPD) in one block
+__global__ void k_dense_fill(int64_t n, int ndof, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
+                             const double *__restrict__ vals, double sigma, double *__restrict__ M) {
+  const int64_t N = n * ndof;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N * 2 * N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (2 * N), c = i % (2 * N);
+    M[i] = (c == r + N) ? 1.0 : 0.0;
+  }
+  // (second launch fills the entries: see amg_numeric)
+}
+__global__ void k_dense_entries(int64_t n, int ndof, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
+                                const double *__restrict__ vals, double sigma, double *__restrict__ M) {
+  const int64_t N = n * ndof;
+  const int B = ndof * ndof;
+  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t t = gptr[v]; t < gptr[v + 1]; ++t) {
+      const int64_t c = gcol[t];
+      if (c >= n) continue;
+      for (int i = 0; i < ndof; ++i)
+        for (int j = 0; j < ndof; ++j) M[(v * ndof + i) * 2 * N + c * ndof + j] = sigma * vals[t * B + i * ndof + j];
+    }
+}
+__global__ void __launch_bounds__(1024) k_gauss_jordan(int N, double *__restrict__ M) {
+  __shared__ double col[kCoarsestRows];
+  __shared__ double pivot_inv;
+  const int W = 2 * N;
+  for (int k = 0; k < N; ++k) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) col[i] = M[(int64_t)i * W + k];
+    if (threadIdx.x == 0) {
+      double p = M[(int64_t)k * W + k];
+      if (!(fabs(p) > 1e-300)) p = 1.0;            // singular coarse operator (pure Neumann): keep the row as it is
+      pivot_inv = 1.0 / p;
+    }
+    __syncthreads();
+    const double pinv = pivot_inv;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) M[(int64_t)k * W + j] *= pinv;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < N * W; idx += blockDim.x) {
+      const int i = idx / W, j = idx % W;
+      if (i != k) M[(int64_t)i * W + j] -= col[i] * M[(int64_t)k * W + j];
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_dense_solve(int N, const double *__restrict__ M, const double *__restrict__ b,
+                                                     double *__restrict__ x, const int *__restrict__ done) {
+  if (done && *done) return;
+  __shared__ double bs[kCoarsestRows];
+  for (int i = threadIdx.x; i < N; i += blockDim.x) bs[i] = b[i];
+  __syncthreads();
+  const int W = 2 * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double acc = 0.0;
+    for (int j = 0; j < N; ++j) acc += M[(int64_t)i * W + N + j] * bs[j];
+    x[i] = acc;
+  }
+}
+
+// ---- cycle kernels ----------------------------------------------------------------------------------------------------------------
+// first Chebyshev direction from a zero initial guess: d0 = dinv b / theta (deg == 1: that is already the smoothed x)
+__global__ void __launch_bounds__(256) k_first_direction(int64_t n, const double *__restrict__ b, const double *__restrict__ dinv,
+                                                         const double *__restrict__ coef, double *__restrict__ d0,
+                                                         const int *__restrict__ done) {
+  if (done && *done) return;
+  const double it = coef[0];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d0[i] = dinv[i] * b[i] * it;
+}
+// b_c[I] = sum of res over the members of I (ascending member order); optionally also the first direction of the coarse level
+__global__ void __launch_bounds__(256) k_restrict(int64_t nc, int ndof, const int64_t *__restrict__ mem_ptr, const int32_t *__restrict__ mem,
+                                                  const double *__restrict__ res, double *__restrict__ bc,
+                                                  const double *__restrict__ dinv_c, const double *__restrict__ coef_c,
+                                                  double *__restrict__ d0_c, const int *__restrict__ done) {
+  if (done && *done) return;
+  const int64_t total = nc * ndof;
+  const double it = d0_c ? coef_c[0] : 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t I = i / ndof;
+    const int f = (int)(i % ndof);
+    double acc = 0.0;
+    for (int64_t q = mem_ptr[I]; q < mem_ptr[I + 1]; ++q) acc += res[(int64_t)mem[q] * ndof + f];
+    bc[i] = acc;
+    if (d0_c) d0_c[i] = dinv_c[i] * acc * it;
+  }
+}
+// x += scale * x_c[aggregate]
+__global__ void __launch_bounds__(256) k_prolong(int64_t n, int ndof, const int32_t *__restrict__ agg, const double *__restrict__ xc,
+                                                 double scale, double *__restrict__ x, const int *__restrict__ done) {
+  if (done && *done) return;
+  const int64_t total = n * ndof;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / ndof;
+    const int f = (int)(i % ndof);
+    x[i] += scale * xc[(int64_t)agg[v] * ndof + f];
+  }
+}
+__global__ void __launch_bounds__(256) k_axpy1(int64_t n, const double *__restrict__ d, double *__restrict__ x, const int *__restrict__ done) {
+  if (done && *done) return;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += d[i];
+}
+
+// ---- set-up ----------------------------------------------------------------------------------------------------------------------------
+static void level_vectors(AmgLevel *L, bool top) {
+  const size_t len = (size_t)(L->n + L->ng) * L->sys->ndof;
+  L->dinv.alloc(len); L->r.alloc(len); L->d0.alloc(len); L->d1.alloc(len); L->res.alloc(len);
+  L->d0.zero(); L->d1.zero(); L->res.zero();
+  if (!top) { L->x.alloc(len); L->b.alloc(len); L->x.zero(); L->b.zero(); }
+  L->coef.alloc(4 * (kMaxDeg + 1));
+}
+
+static void build_transfer(AmgLevel *F, AmgLevel *C) {
+  efv_system *fs = F->sys;
+  const int64_t n = F->n;
+  EFV_REQUIRE(F->ng == 0, "the multigrid hierarchy of a partitioned system is built by amg_dist (ghost aggregates)");
+  // 1. aggregates of the owned rows
+  F->agg.alloc(n + F->ng);
+  int64_t nc = 0;
+  if (F->lat[0] > 0) {
+    const int nx = F->lat[0], ny = F->lat[1], nz = F->lat[2];
+    const int cx = (nx + 1) / 2, cy = (ny + 1) / 2, cz = (nz + 1) / 2;
+    EFV_LAUNCH(k_agg_lattice, grid_for(n, 256), 256, 0, n, nx, ny, cx, cy, F->agg.p);
+    nc = (int64_t)cx * cy * cz;
+    C->lat[0] = cx; C->lat[1] = cy; C->lat[2] = cz;
+  } else {
+    std::vector<int64_t> ptr(n + 1);
+    fs->gptr.download(ptr.data(), n + 1);
+    std::vector<int32_t> col(ptr[n]);
+    fs->gcol.download(col.data(), ptr[n]);
+    const int passes = (fs->mesh && fs->mesh->dim == 2) ? 2 : 3;
+    std::vector<int32_t> map = host_aggregate(n, ptr, col, passes, &nc);
+    F->agg.upload(map.data(), n);
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+  }
+  F->nc = nc;
+  // 2. members of every aggregate
+  DBuf<int32_t> cnt(nc);
+  cnt.zero();
+  EFV_LAUNCH(k_count_members, grid_for(n, 256), 256, 0, n, F->agg.p, cnt.p);
+  F->mem_ptr.alloc(nc + 1);
+  const int64_t total = exclusive_scan_i32_to_i64(cnt.p, F->mem_ptr.p, nc);
+  EFV_REQUIRE(total == n, "aggregation lost rows");
+  F->mem.alloc(n);
+  cnt.zero();
+  EFV_LAUNCH(k_fill_members, grid_for(n, 256), 256, 0, n, F->agg.p, F->mem_ptr.p, cnt.p, F->mem.p);
+  EFV_LAUNCH(k_sort_lists, grid_for(nc, 128), 128, 0, nc, F->mem_ptr.p, F->mem.p);
+  // 3. coarse pattern
+  efv_system *cs = new efv_system();
+  C->sys = cs; C->owns_sys = true;
+  cs->mesh = nullptr; cs->ndof = fs->ndof; cs->nV = cs->n_owned = nc; cs->rows = nc * fs->ndof;
+  DBuf<int32_t> rowlen(nc);
+  DBuf<int> err(1);
+  err.zero();
+  const int grid = grid_for(nc * 32, kCWarps * 32, 8);
+  EFV_LAUNCH(k_coarse_rows<false>, grid, kCWarps * 32, 0, nc, n, F->mem_ptr.p, F->mem.p, fs->gptr.p, fs->gcol.p, F->agg.p, rowlen.p,
+             (const int64_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, err.p);
+  cs->gptr.alloc(nc + 1);
+  cs->nnzg = exclusive_scan_i32_to_i64(rowlen.p, cs->gptr.p, nc);
+  EFV_REQUIRE(cs->nnzg < (int64_t(1) << 31), "coarse nnz exceeds int32 range");
+  cs->gcol.alloc(cs->nnzg);
+  cs->diag_slot.alloc(nc);
+  EFV_LAUNCH(k_coarse_rows<true>, grid, kCWarps * 32, 0, nc, n, F->mem_ptr.p, F->mem.p, fs->gptr.p, fs->gcol.p, F->agg.p, (int32_t *)nullptr,
+             cs->gptr.p, cs->gcol.p, cs->diag_slot.p, err.p);
+  cs->vals.alloc((size_t)cs->nnzg * fs->ndof * fs->ndof);
+  // 4. gather lists: coarse entry <- fine entries
+  DBuf<int32_t> ccnt(cs->nnzg);
+  ccnt.zero();
+  EFV_LAUNCH((k_gather_lists<0>), grid_for(n, 128), 128, 0, n, fs->gptr.p, fs->gcol.p, F->agg.p, cs->gptr.p, cs->gcol.p, ccnt.p,
+             (const int64_t *)nullptr, (int32_t *)nullptr, err.p);
+  F->cl_ptr.alloc(cs->nnzg + 1);
+  int64_t fine_nnz_owned = 0;
+  {
+    int64_t ends[2] = {0, 0};
+    EFV_CUDA(cudaMemcpyAsync(&ends[1], fs->gptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream()));
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+    fine_nnz_owned = ends[1];
+  }
+  const int64_t listed = exclusive_scan_i32_to_i64(ccnt.p, F->cl_ptr.p, cs->nnzg);
+  int herr = 0;
+  err.download(&herr, 1);
+  EFV_REQUIRE(herr == 0, herr == 1 ? "an aggregate has more than 2048 candidate columns" : "coarse pattern misses an entry");
+  EFV_REQUIRE(listed == fine_nnz_owned, "gather lists do not cover the fine entries");
+  F->cl.alloc(listed);
+  ccnt.zero();
+  EFV_LAUNCH((k_gather_lists<1>), grid_for(n, 128), 128, 0, n, fs->gptr.p, fs->gcol.p, F->agg.p, cs->gptr.p, cs->gcol.p, ccnt.p,
+             F->cl_ptr.p, F->cl.p, err.p);
+  EFV_LAUNCH(k_sort_lists, grid_for(cs->nnzg, 128), 128, 0, cs->nnzg, F->cl_ptr.p, F->cl.p);
+  C->n = nc; C->ng = 0;
+}
+
+AmgHierarchy *amg_symbolic(efv_system *s) {
+  AmgHierarchy *H = new AmgHierarchy();
+  try {
+    const char *e;
+    if ((e = getenv("EFV_AMG_DEGREE"))) H->deg = std::max(1, std::min(kMaxDeg, atoi(e)));
+    if ((e = getenv("EFV_AMG_RATIO"))) H->ratio = std::max(1.5, atof(e));
+    H->scale = s->ndof == 1 ? 1.8 : 1.3;
+    if ((e = getenv("EFV_AMG_SCALE"))) H->scale = atof(e);
+    AmgLevel *L = new AmgLevel();
+    L->sys = s; L->n = s->n_owned; L->ng = s->nV - s->n_owned;
+    for (int k = 0; k < 3; ++k) L->lat[k] = s->lattice[k];
+    H->lv.push_back(L);
+    while ((int)H->lv.size() < kMaxLevels) {
+      AmgLevel *F = H->lv.back();
+      if (F->n * s->ndof <= kCoarsestRows) break;
+      AmgLevel *C = new AmgLevel();
+      H->lv.push_back(C);
+      build_transfer(F, C);
+      EFV_REQUIRE(C->n < F->n, "aggregation did not coarsen the operator");
+    }
+    AmgLevel *last = H->lv.back();
+    EFV_REQUIRE(last->n * s->ndof <= kCoarsestRows, "hierarchy too deep");
+    H->nd = last->n * s->ndof;
+    H->dense.alloc((size_t)H->nd * 2 * H->nd);
+    for (size_t l = 0; l < H->lv.size(); ++l) level_vectors(H->lv[l], l == 0);
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+    return H;
+  } catch (...) {
+    delete H;
+    throw;
+  }
+}
+void amg_free(AmgHierarchy *H) { delete H; }
+
+// numeric set-up for the current values of the system (and sign convention sigma)
+void amg_numeric(AmgHierarchy *H, double sigma) {
+  efv_system *s = H->lv[0]->sys;
+  if (H->numeric_version == s->vals_version && H->numeric_sigma == sigma) return;
+  KrylovWork *w0 = work(s);
+  EFV_CUDA(cudaEventRecord(w0->e0, stream()));
+  for (size_t l = 0; l < H->lv.size(); ++l) {
+    AmgLevel *L = H->lv[l];
+    efv_system *ls = L->sys;
+    KrylovWork *w = work(ls);
+    if (l > 0) {
+      AmgLevel *F = H->lv[l - 1];
+      const int B = ls->ndof * ls->ndof;
+      EFV_LAUNCH(k_galerkin, grid_for(ls->nnzg * B, 256), 256, 0, ls->nnzg, B, F->cl_ptr.p, F->cl.p, F->sys->vals.p, ls->vals.p);
+      ls->vals_version++;
+    }
+    if (l + 1 < H->lv.size()) {
+      EFV_LAUNCH(k_diag_gershgorin, w->grid, 256, 0, L->n, ls->ndof, ls->gptr.p, ls->gcol.p, ls->vals.p, ls->diag_slot.p, sigma, L->dinv.p,
+                 w->partial.p);
+      EFV_LAUNCH(k_cheb_coef, 1, 256, 0, w->partial.p, w->grid, H->ratio, L->coef.p);
+      sell_prepare(ls, w);
+    } else {
+      const int64_t N = H->nd;
+      EFV_LAUNCH(k_dense_fill, grid_for(N * 2 * N, 256), 256, 0, L->n, ls->ndof, ls->gptr.p, ls->gcol.p, ls->vals.p, sigma, H->dense.p);
+      EFV_LAUNCH(k_dense_entries, grid_for(L->n, 64), 64, 0, L->n, ls->ndof, ls->gptr.p, ls->gcol.p, ls->vals.p, sigma, H->dense.p);
+      EFV_LAUNCH(k_gauss_jordan, 1, 1024, 0, (int)N, H->dense.p);
+    }
+  }
+  EFV_CUDA(cudaEventRecord(w0->e1, stream()));
+  H->numeric_timed = true;
+  H->numeric_version = s->vals_version;
+  H->numeric_sigma = sigma;
+}
+
+// ---- cycle ------------------------------------------------------------------------------------------------------------------------------
+// z = M b on level l (b, z: level vectors; on level 0 the caller's).  rz_partial (level 0 only): per-block partials of b . z,
+// produced by the epilogue of the last smoothing step.
+static void cycle(AmgHierarchy *H, size_t l, const double *b, double *x, double sigma, double *rz_partial, const int *done,
+                  bool first_direction_ready) {
+  AmgLevel *L = H->lv[l];
+  efv_system *ls = L->sys;
+  KrylovWork *w = work(ls);
+  const int G = w->grid;
+  const int64_t len = L->n * ls->ndof;
+  if (l + 1 == H->lv.size()) {
+    EFV_LAUNCH(k_dense_solve, 1, 256, 0, (int)H->nd, H->dense.p, b, x, done);
+    return;
+  }
+  const int deg = H->deg;
+  auto cheb = [&](int step, const double *din, double *dout, int flags, bool last, const double *dotw, double *partial) {
+    SpmvEpi e;
+    e.mode = last ? kEpiChebLast : kEpiChebMid;
+    e.flags = flags; e.sigma = sigma;
+    e.b = b; e.dinv = L->dinv.p; e.r_in = L->r.p; e.r_out = L->r.p; e.d_in = din; e.d_out = dout; e.x = x;
+    e.coef = L->coef.p + 4 * step; e.w = dotw;
+    halo_exchange(ls, const_cast<double *>(din));
+    launch_spmv(ls, G, din, e, partial, done);
+  };
+  // pre-smoothing from x = 0
+  if (!first_direction_ready)     // (coarse levels: written by the restriction kernel)
+    EFV_LAUNCH(k_first_direction, grid_for(len, 256, 8), 256, 0, len, b, L->dinv.p, L->coef.p, deg == 1 ? x : L->d0.p, done);
+  double *din = L->d0.p, *dout = L->d1.p;
+  for (int k = 1; k < deg; ++k) {
+    cheb(k, din, dout, k == 1 ? (kEpiXZero | kEpiRFromB) : 0, k == deg - 1, nullptr, nullptr);
+    std::swap(din, dout);
+  }
+  // residual, restriction (+ first direction of the next level), coarse solve, over-corrected prolongation
+  {
+    SpmvEpi e;
+    e.mode = kEpiResid; e.sigma = sigma; e.b = b; e.y = L->res.p;
+    halo_exchange(ls, x);
+    launch_spmv(ls, G, x, e, nullptr, done);
+  }
+  AmgLevel *C = H->lv[l + 1];
+  const bool c_smooths = l + 2 < H->lv.size();
+  EFV_LAUNCH(k_restrict, grid_for(C->n * ls->ndof, 256, 8), 256, 0, C->n, ls->ndof, L->mem_ptr.p, L->mem.p, L->res.p, C->b.p,
+             c_smooths ? C->dinv.p : (const double *)nullptr, c_smooths ? C->coef.p : (const double *)nullptr,
+             c_smooths ? (H->deg == 1 ? C->x.p : C->d0.p) : (double *)nullptr, done);
+  cycle(H, l + 1, C->b.p, C->x.p, sigma, nullptr, done, true);
+  EFV_LAUNCH(k_prolong, grid_for(len, 256, 8), 256, 0, L->n, ls->ndof, L->agg.p, C->x.p, H->scale, x, done);
+  // post-smoothing
+  {
+    SpmvEpi e;
+    e.mode = kEpiChebFirst; e.sigma = sigma; e.b = b; e.dinv = L->dinv.p; e.r_out = L->r.p; e.d_out = L->d0.p; e.coef = L->coef.p;
+    halo_exchange(ls, x);
+    launch_spmv(ls, G, x, e, nullptr, done);
+  }
+  if (deg == 1) {
+    EFV_LAUNCH(k_axpy1, grid_for(len, 256, 8), 256, 0, len, L->d0.p, x, done);
+    EFV_REQUIRE(!rz_partial, "degree-1 smoothing has no fused r.z (use degree >= 2)");
+    return;
+  }
+  din = L->d0.p; dout = L->d1.p;
+  for (int k = 1; k < deg; ++k) {
+    const bool last = k == deg - 1;
+    cheb(k, din, dout, 0, last, last && rz_partial ? b : nullptr, last ? rz_partial : nullptr);
+    std::swap(din, dout);
+  }
+}
+
+// ---- CG preconditioned by the cycle ----------------------------------------------------------------------------------------------------
+// r = sigma b - y; partials [0] r.r [1] b.b
+__global__ void __launch_bounds__(256) k_mg_init(int64_t n, const double *__restrict__ b, const double *__restrict__ y, double sigma,
+                                                 double *__restrict__ r, double *__restrict__ partial) {
+  __shared__ double red[32];
+  double rr = 0, bb = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double bi = sigma * b[i], ri = bi - y[i];
+    r[i] = ri;
+    rr += ri * ri; bb += bi * bi;
+  }
+  const int G = gridDim.x;
+  rr = block_sum(rr, red); if (threadIdx.x == 0) partial[blockIdx.x] = rr;
+  bb = block_sum(bb, red); if (threadIdx.x == 0) partial[G + blockIdx.x] = bb;
+}
+// sc: [0] rz, [2] b.b, [3] r.r, [4] rtol^2; flags: [0] done [1] iterations [2] breakdown
+__global__ void k_mg_init_scalars(int G, const double *__restrict__ partial, double *__restrict__ sc, int *__restrict__ flags, double rtol) {
+  __shared__ double red[32];
+  const double rr = sum_partials(partial, G, red);
+  const double bb = sum_partials(partial + G, G, red);
+  if (threadIdx.x == 0) {
+    sc[0] = 0.0; sc[2] = bb; sc[3] = rr; sc[4] = rtol * rtol;
+    flags[0] = (rr <= rtol * rtol * bb) ? 1 : 0;
+    flags[1] = 0; flags[2] = 0;
+  }
+}
+// first direction: p = z, rz = r.z
+__global__ void __launch_bounds__(256) k_mg_first_p(int64_t n, const double *__restrict__ z, double *__restrict__ p,
+                                                    const double *__restrict__ rz_partial, int G, double *__restrict__ sc,
+                                                    const int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  const double rz = sum_partials(rz_partial, G, red);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = z[i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc[0] = rz;
+}
+// alpha = rz / p.Ap; x += alpha p; r -= alpha Ap; partial r.r
+__global__ void __launch_bounds__(256) k_mg_xr(int64_t n, const double *__restrict__ sc, const double *__restrict__ pAp_partial, int G,
+                                               const double *__restrict__ p, const double *__restrict__ Ap, double *__restrict__ x,
+                                               double *__restrict__ r, double *__restrict__ partial, const int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  const double pAp = sum_partials(pAp_partial, G, red);
+  if (!(pAp > 0.0) || !(pAp < 1e300)) return;                 // k_mg_check raises the breakdown flag
+  const double alpha = sc[0] / pAp;
+  double rr = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * Ap[i];
+    r[i] = ri;
+    rr += ri * ri;
+  }
+  rr = block_sum(rr, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = rr;
+}
+// one block: convergence / breakdown decision right after the update, so that a converged solve skips the last cycle
+__global__ void k_mg_check(int it, const double *__restrict__ pAp_partial, int Gp, const double *__restrict__ rr_partial, int Gr,
+                           double *__restrict__ sc, int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  const double pAp = sum_partials(pAp_partial, Gp, red);
+  const double rr = sum_partials(rr_partial, Gr, red);
+  if (threadIdx.x == 0) {
+    if (!(pAp > 0.0) || !(pAp < 1e300) || !(sc[0] > 0.0)) { flags[2] = 1; flags[0] = 1; return; }
+    sc[3] = rr;
+    flags[1] = it + 1;
+    if (!(rr > sc[4] * sc[2])) flags[0] = 1;
+  }
+}
+// beta = rz_new / rz; p = z + beta p
+__global__ void __launch_bounds__(256) k_mg_p(int64_t n, double *__restrict__ sc, const double *__restrict__ rz_partial, int G,
+                                              const double *__restrict__ z, double *__restrict__ p, const int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  const double rz_new = sum_partials(rz_partial, G, red);
+  const double beta = rz_new / sc[0];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = z[i] + beta * p[i];
+  // sc[0] is read by every block above and overwritten by the NEXT kernel in the stream (k_mg_store_rz)
+}
+__global__ void k_mg_store_rz(const double *__restrict__ rz_partial, int G, double *__restrict__ sc, const int *__restrict__ flags) {
+  __shared__ double red[32];
+  if (flags[0]) return;
+  const double rz = sum_partials(rz_partial, G, red);
+  if (threadIdx.x == 0) sc[0] = rz;
+}
+
+void solve_pcg_amg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres) {
+  EFV_REQUIRE(s->vals.n, "no values assembled");
+  EFV_REQUIRE(!is_dist(s), "the multigrid preconditioner of a partitioned system is not available in this build path");
+  ensure_vectors(s);
+  KrylovWork *w = work(s);
+  const int64_t n = s->n_owned * s->ndof;
+  if (!w->r.n) { w->r.alloc(s->rows); w->p.alloc(s->rows); w->Ap.alloc(s->rows); w->dinv.alloc(s->rows); }
+  if (!w->v.n) { w->v.alloc(s->rows); w->v.zero(); }                 // z
+  const double sigma = negate ? -1.0 : 1.0;
+  if (!s->amg) s->amg = amg_symbolic(s);
+  AmgHierarchy *H = s->amg;
+  const int G = w->grid;
+  double *P = w->partial.p;                                          // [0,G) r.r  [G,2G) b.b / r.z  [3G,4G) p.Ap
+  cudaEvent_t t0, t1;
+  EFV_CUDA(cudaEventCreate(&t0));
+  EFV_CUDA(cudaEventCreate(&t1));
+  EFV_CUDA(cudaEventRecord(t0, stream()));
+  sell_prepare(s, w);
+  amg_numeric(H, sigma);
+  EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
+  launch_spmv(s, G, s->x.p, plain_epi(w->Ap.p, sigma, nullptr, nullptr), nullptr, nullptr);
+  EFV_LAUNCH(k_mg_init, G, 256, 0, n, s->b.p, w->Ap.p, sigma, w->r.p, P);
+  EFV_LAUNCH(k_mg_init_scalars, 1, 256, 0, G, P, w->sc.p, w->flags.p, rtol);
+  double *z = w->v.p;
+  cycle(H, 0, w->r.p, z, sigma, P + G, w->flags.p, false);
+  EFV_LAUNCH(k_mg_first_p, G, 256, 0, n, z, w->p.p, P + G, G, w->sc.p, w->flags.p);
+  int it = 0;
+  bool done = false;
+  const int check_every = (n > 200000) ? 1 : 4;
+  while (!done && it < maxit) {
+    const int batch_end = std::min(maxit, it + check_every);
+    for (; it < batch_end; ++it) {
+      launch_spmv(s, G, w->p.p, plain_epi(w->Ap.p, sigma, nullptr, w->p.p), P + 3 * G, w->flags.p);
+      EFV_LAUNCH(k_mg_xr, G, 256, 0, n, w->sc.p, P + 3 * G, G, w->p.p, w->Ap.p, s->x.p, w->r.p, P, w->flags.p);
+      EFV_LAUNCH(k_mg_check, 1, 256, 0, it, P + 3 * G, G, P, G, w->sc.p, w->flags.p);
+      cycle(H, 0, w->r.p, z, sigma, P + G, w->flags.p, false);
+      EFV_LAUNCH(k_mg_p, G, 256, 0, n, w->sc.p, P + G, G, z, w->p.p, w->flags.p);
+      EFV_LAUNCH(k_mg_store_rz, 1, 256, 0, P + G, G, w->sc.p, w->flags.p);
+    }
+    EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+    done = w->h_flags[0] != 0;
+  }
+  EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaMemcpyAsync(w->h_sc, w->sc.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaEventRecord(t1, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+  float ms = 0;
+  EFV_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+  s->t_solve_ms = ms;
+  if (H->numeric_timed) {
+    EFV_CUDA(cudaEventElapsedTime(&ms, w->e0, w->e1));
+    H->t_numeric_ms = ms;
+    H->numeric_timed = false;
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  if (iters) *iters = w->h_flags[1];
+  if (relres) *relres = w->h_flags[2] ? NAN : ((w->h_sc[2] > 0) ? std::sqrt(w->h_sc[3] / w->h_sc[2]) : 0.0);
+}
+
+// diagnostics for tests / DESIGN.md: levels, rows and nnz per level, Chebyshev bound per level, last numeric set-up time
+int amg_info(efv_system *s, int64_t *rows, int64_t *nnz, double *lmax, int cap, double *numeric_ms) {
+  if (!s->amg) return 0;
+  AmgHierarchy *H = s->amg;
+  const int nl = (int)H->lv.size();
+  for (int l = 0; l < nl && l < cap; ++l) {
+    rows[l] = H->lv[l]->n * H->lv[l]->sys->ndof;
+    nnz[l] = H->lv[l]->sys->nnzg * H->lv[l]->sys->ndof * H->lv[l]->sys->ndof;
+    double v = 0.0;
+    if (l + 1 < nl) EFV_CUDA(cudaMemcpyAsync(&v, H->lv[l]->coef.p + 4 * kMaxDeg, sizeof(double), cudaMemcpyDeviceToHost, stream()));
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+    lmax[l] = v;
+  }
+  if (numeric_ms) *numeric_ms = H->t_numeric_ms;
+  return nl;
+}
+
+// one level of the hierarchy on the host (tests): pattern, values, aggregate of every owned row (level < last)
+void amg_level_export(efv_system *s, int level, int64_t *gptr, int32_t *gcol, double *vals, int32_t *agg) {
+  EFV_REQUIRE(s->amg, "no multigrid hierarchy (solve once with the multigrid preconditioner first)");
+  AmgHierarchy *H = s->amg;
+  EFV_REQUIRE(level >= 0 && level < (int)H->lv.size(), "level out of range");
+  AmgLevel *L = H->lv[level];
+  efv_system *ls = L->sys;
+  if (gptr) ls->gptr.download(gptr, L->n + 1);
+  if (gcol) ls->gcol.download(gcol, ls->nnzg);
+  if (vals) ls->vals.download(vals, (size_t)ls->nnzg * ls->ndof * ls->ndof);
+  if (agg) { EFV_REQUIRE(L->agg.n, "the coarsest level has no aggregates"); L->agg.download(agg, L->n); }
+}
+
+}  // namespace efv

@@ -218,6 +218,7 @@ int efv_system_set_values(efv_system *s, const double *data) {
 }
 void efv_system_destroy(efv_system *s) {
   if (!s) return;
+  if (s->amg) efv::amg_free(s->amg);
   efv::krylov_free(s);
   efv::halo_release(s->halo);
   if (s->dl_stream) { cudaStreamSynchronize(s->dl_stream); cudaStreamDestroy(s->dl_stream); cudaEventDestroy(s->dl_ready); cudaEventDestroy(s->dl_done); }
@@ -436,7 +437,35 @@ int efv_halo_exchange(efv_system *s, int which) {
 int efv_solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres) {
   EFV_API_BEGIN
   EFV_REQUIRE(s, "null system");
-  efv::solve_pcg(s, rtol, maxit, negate, iters, relres);
+  if (s->precond == 1) efv::solve_pcg_amg(s, rtol, maxit, negate, iters, relres);
+  else efv::solve_pcg(s, rtol, maxit, negate, iters, relres);
+  EFV_API_END
+}
+int efv_system_set_preconditioner(efv_system *s, int kind) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(kind == 0 || kind == 1, "preconditioner: 0 = Jacobi, 1 = aggregation multigrid");
+  s->precond = kind;
+  EFV_API_END
+}
+int efv_system_set_lattice(efv_system *s, int nx, int ny, int nz) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  EFV_REQUIRE(nx > 0 && ny > 0 && nz > 0 && (int64_t)nx * ny * nz == s->n_owned, "lattice extents must multiply to the owned vertex count");
+  EFV_REQUIRE(!s->amg, "set the lattice before the first preconditioned solve");
+  s->lattice[0] = nx; s->lattice[1] = ny; s->lattice[2] = nz;
+  EFV_API_END
+}
+int efv_amg_level_export(efv_system *s, int level, int64_t *gptr, int32_t *gcol, double *vals, int32_t *aggregates) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s, "null system");
+  efv::amg_level_export(s, level, gptr, gcol, vals, aggregates);
+  EFV_API_END
+}
+int efv_amg_info(efv_system *s, int capacity, int *levels, int64_t *rows, int64_t *nnz, double *lmax, double *numeric_ms) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && levels && rows && nnz && lmax, "null argument");
+  *levels = efv::amg_info(s, rows, nnz, lmax, capacity, numeric_ms);
   EFV_API_END
 }
 int efv_solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres) {

@@ -7,10 +7,10 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall)
 mkdir -p "$HERE/_obj"
 pids=()
-for f in runtime mesh geometry csr assemble krylov comm api; do
+for f in runtime mesh geometry csr assemble krylov amg comm api; do
   "$NVCC" "${FLAGS[@]}" "$@" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/_obj/{runtime,mesh,geometry,csr,assemble,krylov,comm,api}.o -lcudart -ldl
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/_obj/{runtime,mesh,geometry,csr,assemble,krylov,amg,comm,api}.o -lcudart -ldl
 echo "built $OUT"

@@ -75,6 +75,7 @@ struct efv_mesh {
 
 namespace efv {
 struct KrylovWork;
+struct AmgHierarchy;
 // owned/ghost exchange lists of a vertex-block partition
 struct Halo {
   bool active = false;
@@ -128,6 +129,9 @@ struct efv_system {
   int physics = 0;
   // Krylov workspace
   efv::KrylovWork *kw = nullptr;
+  efv::AmgHierarchy *amg = nullptr;    // aggregation multigrid hierarchy (built at the first preconditioned solve)
+  int precond = 0;                     // 0: Jacobi, 1: aggregation multigrid (efv_system_set_preconditioner)
+  int lattice[3] = {0, 0, 0};          // owned vertices are numbered i + nx (j + ny k) on an nx x ny x nz lattice (0: unknown)
   double t_assemble_ms = 0, t_solve_ms = 0, t_spmv_ms = 0;
   efv::DBuf<double> props_dev;
   efv::DBuf<double> scratch;            // local element matrices of the two-phase assembly, component-major
@@ -176,6 +180,10 @@ void krylov_free(efv_system *s);
 void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres);
 void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *relres);
 void spmv(efv_system *s, const double *x, double *y);
+void solve_pcg_amg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres);
+void amg_free(AmgHierarchy *H);
+void amg_level_export(efv_system *s, int level, int64_t *gptr, int32_t *gcol, double *vals, int32_t *agg);
+int amg_info(efv_system *s, int64_t *rows, int64_t *nnz, double *lmax, int cap, double *numeric_ms);
 double max_abs_diff(efv_system *s);
 double true_relres(efv_system *s, int negate);
 void vec_sums(efv_system *s, const double *vec, double *sum, double *sumsq);

@@ -8,8 +8,7 @@
 // round trip and no float atomics; the host only polls a `done` flag every few dozen iterations.
 // These solvers replace the reference's explicit inverses (apps/heat_transfer.py:78-81,134-135,
 // apps/stress_equilibrium.py:170-173, apps/geomechanics.py:140,254).
-#include "views.cuh"
-#include "peer.cuh"
+#include "krylov.cuh"
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -18,31 +17,7 @@
 
 namespace efv {
 
-constexpr int kBlock = 256;
-
-struct KrylovWork {
-  int64_t n = 0;
-  int grid = 0;
-  DBuf<double> r, p, Ap, dinv, rhat, v, sv, t, phat, shat;
-  DBuf<double> partial;     // 4 * grid
-  DBuf<double> sc;          // device scalars
-  DBuf<int> flags;          // [0] done, [1] iterations, [2] breakdown
-  // sliced-ELL copy of a scalar matrix for the solver (slices of 32 rows, column-major inside a slice)
-  DBuf<int64_t> sell_off;   // nslices+1, in units of 32-entry columns
-  DBuf<int32_t> sell_cols;
-  DBuf<int32_t> sell_delta; // one per 32-entry column: common (column - row) offset, or kNoDelta
-  DBuf<double> sell_vals;
-  int64_t sell_slices = 0, sell_rows = 0;
-  uint64_t sell_version = 0;
-  bool sell_ok = false, sell_use = false;
-  bool sell_indexed = false;  // columns / offsets of the current pattern are in place (values-only refills)
-  int sell_compress = -1;
-  int *h_flags = nullptr;   // pinned
-  double *h_sc = nullptr;   // pinned
-  cudaEvent_t ev = nullptr, e0 = nullptr, e1 = nullptr;
-};
-
-static KrylovWork *work(efv_system *s) {
+KrylovWork *work(efv_system *s) {
   if (!s->kw) {
     KrylovWork *w = new KrylovWork();
     w->n = s->rows;
@@ -71,17 +46,60 @@ void krylov_free(efv_system *s) {
   s->kw = nullptr;
 }
 
-// fixed-order sum of `count` partials, identical in every block
-__device__ __forceinline__ double sum_partials(const double *__restrict__ part, int count, double *red) {
-  double a = 0.0;
-  for (int i = threadIdx.x; i < count; i += blockDim.x) a += part[i];
-  a = block_sum(a, red);
-  __shared__ double bc;
-  if (threadIdx.x == 0) bc = a;
-  __syncthreads();
-  double r = bc;
-  __syncthreads();
-  return r;
+// ---- SpMV epilogue ---------------------------------------------------------------------------------------------------------
+// Every SpMV kernel ends a row with epi_apply(row entry, (A v)_entry).  Besides the plain product the epilogue fuses the
+// row-wise part of what follows the product, so that a Chebyshev smoothing step or a residual costs ONE pass over the
+// matrix and no separate vector kernels (amg.cu):
+//   kEpiPlain     y = sigma A v (* rowscale);                                   dot += w . y
+//   kEpiResid     y = b - sigma A v
+//   kEpiChebFirst r = dinv (b - sigma A v);  d_out = r / theta                  (v = current iterate x, left untouched)
+//   kEpiChebMid   r = r_in - dinv sigma A v; d_out = c1 d_in + c2 r;  x += d_in (v = d_in, the previous direction)
+//   kEpiChebLast  as Mid, but x += d_in + d_new and nothing else is written;    dot += w . x
+// kEpiXZero: x is known to be zero (pre-smoothing), it is not read; kEpiRFromB: r_in = dinv b is formed on the fly.
+// The scalars 1/theta, c1, c2 of the step are read from device memory (coef), computed on the device from the
+// Gershgorin bound of the level, so that no host round trip sits between the assembly and the solve.
+__device__ __forceinline__ double epi_apply(const SpmvEpi &e, int64_t i, double acc) {
+  const double av = e.sigma * acc;
+  switch (e.mode) {
+    case kEpiPlain: {
+      double yi = av;
+      if (e.rowscale) yi *= e.rowscale[i];
+      e.y[i] = yi;
+      return e.w ? e.w[i] * yi : 0.0;
+    }
+    case kEpiResid: {
+      const double yi = e.b[i] - av;
+      e.y[i] = yi;
+      return e.w ? e.w[i] * yi : 0.0;
+    }
+    case kEpiChebFirst: {
+      const double r = e.dinv[i] * (e.b[i] - av);
+      e.r_out[i] = r;
+      e.d_out[i] = r * e.coef[0];
+      return 0.0;
+    }
+    default: {
+      const double di = e.dinv[i];
+      const double r = ((e.flags & kEpiRFromB) ? di * e.b[i] : e.r_in[i]) - di * av;
+      const double dprev = e.d_in[i];
+      const double dn = e.coef[1] * dprev + e.coef[2] * r;
+      const double x0 = (e.flags & kEpiXZero) ? 0.0 : e.x[i];
+      if (e.mode == kEpiChebMid) {
+        e.r_out[i] = r;
+        e.d_out[i] = dn;
+        e.x[i] = x0 + dprev;
+        return 0.0;
+      }
+      const double xi = x0 + dprev + dn;
+      e.x[i] = xi;
+      return e.w ? e.w[i] * xi : 0.0;
+    }
+  }
+}
+SpmvEpi plain_epi(double *y, double sigma, const double *rowscale, const double *w) {
+  SpmvEpi e;
+  e.y = y; e.sigma = sigma; e.rowscale = rowscale; e.w = w;
+  return e;
 }
 
 // ---- SpMV: y = sigma * A x  (optionally y *= rowscale), partial[blockIdx] = sum_i w_i * y_i -------------------------
@@ -91,8 +109,7 @@ __device__ __forceinline__ double sum_partials(const double *__restrict__ part, 
 template <int NDOF, int L, int U>
 __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__restrict__ gptr,
                                                  const int32_t *__restrict__ gcol, const double *__restrict__ vals,
-                                                 const double *__restrict__ x, double *__restrict__ y, double sigma,
-                                                 const double *__restrict__ rowscale, const double *__restrict__ w,
+                                                 const double *__restrict__ x, SpmvEpi epi,
                                                  double *__restrict__ partial, const int *__restrict__ done, PeerAR ar) {
   __shared__ double red[32];
   if (done && *done) return;
@@ -138,12 +155,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(int64_t nV, const int64_t *__re
     for (int i = 0; i < NDOF; ++i) acc[i] = group_sum<L>(acc[i]);
     if (valid && gl == 0) {
 #pragma unroll
-      for (int i = 0; i < NDOF; ++i) {
-        double yi = sigma * acc[i];
-        if (rowscale) yi *= rowscale[v * NDOF + i];
-        y[v * NDOF + i] = yi;
-        if (w) dot += w[v * NDOF + i] * yi;
-      }
+      for (int i = 0; i < NDOF; ++i) dot += epi_apply(epi, v * NDOF + i, acc[i]);
     }
   }
   if (partial) {
@@ -220,8 +232,7 @@ template <int U, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_spmv_sell(int64_t nrows, const int64_t *__restrict__ off,
                                                       const int32_t *__restrict__ scol, const int32_t *__restrict__ sdelta,
                                                       const double *__restrict__ sval,
-                                                      const double *__restrict__ x, double *__restrict__ y, double sigma,
-                                                      const double *__restrict__ rowscale, const double *__restrict__ w,
+                                                      const double *__restrict__ x, SpmvEpi epi,
                                                       double *__restrict__ partial, const int *__restrict__ done, PeerAR ar) {
   static_assert(32 % U == 0, "a batch must not straddle the 32 offsets a warp holds");
   __shared__ double red[32];
@@ -257,12 +268,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_spmv_sell(int64_t nrows, const
       }
     }
     const int64_t v = slice * 32 + lane;
-    if (v < nrows) {
-      double yi = sigma * acc;
-      if (rowscale) yi *= rowscale[v];
-      y[v] = yi;
-      if (w) dot += w[v] * yi;
-    }
+    if (v < nrows) dot += epi_apply(epi, v, acc);
   }
   if (partial) {
     dot = block_sum(dot, red);
@@ -309,8 +315,7 @@ template <class C>
 __global__ void __launch_bounds__(C::kWarps * 32, 1)
 k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *__restrict__ scol,
                 const int32_t *__restrict__ sdelta_al, const double *__restrict__ sval, const double *__restrict__ x,
-                double *__restrict__ y, double sigma, const double *__restrict__ rowscale, const double *__restrict__ w,
-                double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar) {
+                SpmvEpi epi, double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar) {
   constexpr int kSellChunk = C::kChunk, kSellStages = C::kStages, kSellWarps = C::kWarps;
   constexpr size_t kSellStageBytes = C::kStageBytes;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -406,12 +411,7 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
     cc.k += kSellChunk;
     if (cc.k >= cc.width) {
       const int64_t v = cc.s * 32 + lane;
-      if (v < nrows) {
-        double yi = sigma * acc;
-        if (rowscale) yi *= rowscale[v];
-        y[v] = yi;
-        if (w) dot += w[v] * yi;
-      }
+      if (v < nrows) dot += epi_apply(epi, v, acc);
       acc = 0.0;
       ++cc.s;
       cc.k = 0;
@@ -431,8 +431,7 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
 template <int NDOF, int U>
 __global__ void __launch_bounds__(kBlock) k_spmv_sell_bsr(int64_t nrows, const int64_t *__restrict__ off,
                                                           const int32_t *__restrict__ scol, const double *__restrict__ sval,
-                                                          const double *__restrict__ x, double *__restrict__ y, double sigma,
-                                                          const double *__restrict__ rowscale, const double *__restrict__ w,
+                                                          const double *__restrict__ x, SpmvEpi epi,
                                                           double *__restrict__ partial, const int *__restrict__ done, PeerAR ar) {
   constexpr int B = NDOF * NDOF;
   __shared__ double red[32];
@@ -473,12 +472,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_sell_bsr(int64_t nrows, const i
     const int64_t v = slice * 32 + lane;
     if (v < nrows) {
 #pragma unroll
-      for (int i = 0; i < NDOF; ++i) {
-        double yi = sigma * acc[i];
-        if (rowscale) yi *= rowscale[v * NDOF + i];
-        y[v * NDOF + i] = yi;
-        if (w) dot += w[v * NDOF + i] * yi;
-      }
+      for (int i = 0; i < NDOF; ++i) dot += epi_apply(epi, v * NDOF + i, acc[i]);
     }
   }
   if (partial) {
@@ -500,8 +494,7 @@ template <int NDOF, int E, int ST, int W>
 __global__ void __launch_bounds__(W * 32, 1)
 k_spmv_sell_bsr_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *__restrict__ scol,
                     const int32_t *__restrict__ sdelta_al, const double *__restrict__ sval, const double *__restrict__ x,
-                    double *__restrict__ y, double sigma, const double *__restrict__ rowscale, const double *__restrict__ w,
-                    double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar) {
+                    SpmvEpi epi, double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar) {
   using C = SellBsrTma<NDOF, E, ST, W>;
   constexpr int B = C::kB;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -595,12 +588,7 @@ k_spmv_sell_bsr_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_
       const int64_t v = cc.s * 32 + lane;
       if (v < nrows) {
 #pragma unroll
-        for (int i = 0; i < NDOF; ++i) {
-          double yi = sigma * acc[i];
-          if (rowscale) yi *= rowscale[v * NDOF + i];
-          y[v * NDOF + i] = yi;
-          if (w) dot += w[v * NDOF + i] * yi;
-        }
+        for (int i = 0; i < NDOF; ++i) dot += epi_apply(epi, v * NDOF + i, acc[i]);
       }
 #pragma unroll
       for (int i = 0; i < NDOF; ++i) acc[i] = 0.0;
@@ -618,7 +606,7 @@ k_spmv_sell_bsr_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_
 }
 
 // (re)build the SELL copy if the values changed; returns whether the SELL path should be used
-static bool sell_prepare(efv_system *s, KrylovWork *w) {
+bool sell_prepare(efv_system *s, KrylovWork *w) {
   const char *fmt = getenv("EFV_SPMV_FORMAT");
   if (fmt && strcmp(fmt, "csr") == 0) { w->sell_use = false; return false; }
   w->sell_use = true;
@@ -683,11 +671,10 @@ static int pick_lanes(const efv_system *s) {
 }
 
 template <int NDOF>
-static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
-                          const double *w, double *partial, const int *done, const PeerAR &ar) {
+static void launch_spmv_l(efv_system *s, int grid, const double *x, const SpmvEpi &epi, double *partial, const int *done,
+                          const PeerAR &ar) {
 #define EFV_SPMV_CASE(LL, UU)                                                                                          \
-  EFV_LAUNCH((k_spmv<NDOF, LL, UU>), grid, kBlock, 0, s->n_owned, s->gptr.p, s->gcol.p, s->vals.p, x, y, sigma, rowscale, \
-             w, partial, done, ar)
+  EFV_LAUNCH((k_spmv<NDOF, LL, UU>), grid, kBlock, 0, s->n_owned, s->gptr.p, s->gcol.p, s->vals.p, x, epi, partial, done, ar)
   const char *envu = getenv("EFV_SPMV_UNROLL");
   const int lanes = pick_lanes(s);
   int unroll = envu ? atoi(envu) : 0;
@@ -708,12 +695,12 @@ static void launch_spmv_l(efv_system *s, int grid, const double *x, double *y, d
   }
 #undef EFV_SPMV_CASE
 }
-static void launch_spmv(efv_system *s, int grid, const double *x, double *y, double sigma, const double *rowscale,
-                        const double *w, double *partial, const int *done, const PeerAR &ar = PeerAR()) {
+void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi, double *partial, const int *done,
+                 const PeerAR &ar) {
   KrylovWork *kw = s->kw;
   if (kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned) {
-#define EFV_SELL_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done, ar
-#define EFV_SELL1_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, done, ar
+#define EFV_SELL_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, epi, partial, done, ar
+#define EFV_SELL1_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, done, ar
     const char *ek = getenv("EFV_SELL_KERNEL");
     if (s->ndof == 1 && !(ek && strcmp(ek, "reg") == 0)) {
 #define EFV_SELL_TMA(CH, ST, W)                                                                                       \
@@ -725,7 +712,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
       configured = true;                                                                                               \
     }                                                                                                                  \
     EFV_LAUNCH(k_spmv_sell_tma<C>, spmv_blocks(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,            \
-               kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, grid, done, ar);                      \
+               kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar);                                        \
   } while (0)
       const char *ec = getenv("EFV_SELL_TMA");
       switch (ec ? atoi(ec) : 0) {
@@ -763,7 +750,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
       configured = true;                                                                                                    \
     }                                                                                                                       \
     EFV_LAUNCH((k_spmv_sell_bsr_tma<ND, EE, 2, 20>), spmv_blocks(), 20 * 32, C::kSmem, s->n_owned, kw->sell_off.p,              \
-               kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, y, sigma, rowscale, w, partial, grid, done, ar);      \
+               kw->sell_cols.p, kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar);                        \
   } while (0)
       EFV_BSR_TMA(3, 2);
 #undef EFV_BSR_TMA
@@ -779,10 +766,10 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
     return;
   }
   switch (s->ndof) {
-    case 1: launch_spmv_l<1>(s, grid, x, y, sigma, rowscale, w, partial, done, ar); break;
-    case 2: launch_spmv_l<2>(s, grid, x, y, sigma, rowscale, w, partial, done, ar); break;
-    case 3: launch_spmv_l<3>(s, grid, x, y, sigma, rowscale, w, partial, done, ar); break;
-    case 4: launch_spmv_l<4>(s, grid, x, y, sigma, rowscale, w, partial, done, ar); break;
+    case 1: launch_spmv_l<1>(s, grid, x, epi, partial, done, ar); break;
+    case 2: launch_spmv_l<2>(s, grid, x, epi, partial, done, ar); break;
+    case 3: launch_spmv_l<3>(s, grid, x, epi, partial, done, ar); break;
+    case 4: launch_spmv_l<4>(s, grid, x, epi, partial, done, ar); break;
     default: throw Error("unsupported ndof");
   }
 }
@@ -790,7 +777,7 @@ static void launch_spmv(efv_system *s, int grid, const double *x, double *y, dou
 void spmv(efv_system *s, const double *x, double *y) {
   EFV_REQUIRE(s->vals.n, "no values assembled");
   sell_prepare(s, work(s));
-  launch_spmv(s, num_sms() * 8, x, y, 1.0, nullptr, nullptr, nullptr, nullptr);
+  launch_spmv(s, num_sms() * 8, x, plain_epi(y, 1.0, nullptr, nullptr), nullptr, nullptr);
 }
 
 // multi-GPU: collapse `narr` partial arrays of length G into narr scalars (then all-reduced over the ranks); the
@@ -804,8 +791,8 @@ __global__ void k_reduce_partials(const double *__restrict__ partial, int G, int
 }
 // returns the (pointer, length) pair the consumer kernels should use for `narr` consecutive partial arrays
 // a partitioned system in a multi-rank job (a plain system created next to it keeps solving alone)
-static bool is_dist(const efv_system *s) { return comm_active() && s->halo.active; }
-static const double *consolidate(efv_system *s, const double *partial, int narr, int slot, int *Gout) {
+bool is_dist(const efv_system *s) { return comm_active() && s->halo.active; }
+const double *consolidate(efv_system *s, const double *partial, int narr, int slot, int *Gout) {
   KrylovWork *w = s->kw;
   if (!is_dist(s)) { *Gout = w->grid; return partial; }
   double *out = w->sc.p + 32 + 4 * slot;
@@ -961,7 +948,7 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->n_owned, s->ndof, s->diag_slot.p, s->vals.p, sigma, w->dinv.p);
   EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
   halo_exchange(s, s->x.p);
-  launch_spmv(s, G, s->x.p, w->Ap.p, sigma, nullptr, nullptr, nullptr, nullptr);
+  launch_spmv(s, G, s->x.p, plain_epi(w->Ap.p, sigma, nullptr, nullptr), nullptr, nullptr);
   EFV_LAUNCH(k_pcg_init, G, kBlock, 0, n, s->b.p, w->Ap.p, w->dinv.p, sigma, w->r.p, w->p.p, P);
   const double *c0 = consolidate(s, P, 3, 0, &Gc);
   EFV_LAUNCH(k_pcg_init_scalars, 1, kBlock, 0, Gc, c0, w->sc.p, w->flags.p, rtol);
@@ -981,13 +968,13 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
         // the two all-reduces of the iteration ride on the kernels: the last block of the producer publishes to every
         // rank's peer region, the blocks of the consumer wait for all ranks (peer.cuh)
         const PeerAR ar1 = comm_peer_ar(counter), ar2 = comm_peer_ar(counter);
-        launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, P + 3 * G, w->flags.p, ar1);
+        launch_spmv(s, G, w->p.p, plain_epi(w->Ap.p, sigma, nullptr, w->p.p), P + 3 * G, w->flags.p, ar1);
         EFV_LAUNCH(k_pcg_update_xr, G, kBlock, 0, n, it, w->sc.p, P + 3 * G, G, w->p.p, w->Ap.p, w->dinv.p, s->x.p, w->r.p, P, G,
                    w->flags.p, ar1, ar2);
         EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, P, G, w->r.p, w->dinv.p, w->p.p, w->flags.p, ar2, (const double *)nullptr, 0);
         continue;
       }
-      launch_spmv(s, G, w->p.p, w->Ap.p, sigma, nullptr, w->p.p, P + 3 * G, w->flags.p);
+      launch_spmv(s, G, w->p.p, plain_epi(w->Ap.p, sigma, nullptr, w->p.p), P + 3 * G, w->flags.p);
       int Gc1 = G;
       const double *c1 = consolidate(s, P + 3 * G, 1, 1, &Gc1);
       Gc = Gc1;
@@ -1152,7 +1139,7 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
   EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->n_owned, s->ndof, s->diag_slot.p, s->vals.p, 1.0, w->dinv.p);
   EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
   halo_exchange(s, s->x.p);
-  launch_spmv(s, G, s->x.p, w->Ap.p, 1.0, w->dinv.p, nullptr, nullptr, nullptr);
+  launch_spmv(s, G, s->x.p, plain_epi(w->Ap.p, 1.0, w->dinv.p, nullptr), nullptr, nullptr);
   EFV_LAUNCH(k_bi_init, G, kBlock, 0, n, s->b.p, w->Ap.p, w->dinv.p, w->r.p, w->rhat.p, w->p.p, w->v.p, P);
   global_sums(P, 2);
   EFV_LAUNCH(k_bi_init_scalars, 1, kBlock, 0, G, P, w->sc.p, w->flags.p, rtol);
@@ -1165,11 +1152,11 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
       EFV_LAUNCH(k_bi_p, G, kBlock, 0, n, w->sc.p, w->r.p, w->v.p, w->p.p, w->rhat.p, w->flags.p);
       EFV_LAUNCH(k_bi_clear_restart, 1, 1, 0, w->flags.p);
       halo_exchange(s, w->p.p);
-      launch_spmv(s, G, w->p.p, w->v.p, 1.0, w->dinv.p, w->rhat.p, P + 2 * G, w->flags.p);          // v = D^-1 A p, (rhat,v)
+      launch_spmv(s, G, w->p.p, plain_epi(w->v.p, 1.0, w->dinv.p, w->rhat.p), P + 2 * G, w->flags.p);          // v = D^-1 A p, (rhat,v)
       global_sums(P + 2 * G, 1);
       EFV_LAUNCH(k_bi_s, G, kBlock, 0, n, w->sc.p, P + 2 * G, G, w->r.p, w->v.p, w->sv.p, w->flags.p);
       halo_exchange(s, w->sv.p);
-      launch_spmv(s, G, w->sv.p, w->t.p, 1.0, w->dinv.p, w->sv.p, P + 2 * G, w->flags.p);           // t = D^-1 A s, (t,s)
+      launch_spmv(s, G, w->sv.p, plain_epi(w->t.p, 1.0, w->dinv.p, w->sv.p), P + 2 * G, w->flags.p);           // t = D^-1 A s, (t,s)
       EFV_LAUNCH(k_bi_tt, G, kBlock, 0, n, w->t.p, P + 3 * G, w->flags.p);
       global_sums(P + 2 * G, 2);                                                                    // (t,s) and (t,t)
       EFV_LAUNCH(k_bi_xr, G, kBlock, 0, n, w->sc.p, P + 2 * G, P + 3 * G, G, w->p.p, w->sv.p, w->t.p, w->rhat.p, s->x.p,
@@ -1235,7 +1222,7 @@ double true_relres(efv_system *s, int negate) {
   const double sigma = negate ? -1.0 : 1.0;
   sell_prepare(s, w);
   halo_exchange(s, s->x.p);
-  launch_spmv(s, w->grid, s->x.p, w->Ap.p, sigma, nullptr, nullptr, nullptr, nullptr);
+  launch_spmv(s, w->grid, s->x.p, plain_epi(w->Ap.p, sigma, nullptr, nullptr), nullptr, nullptr);
   EFV_LAUNCH(k_resid_norms, w->grid, kBlock, 0, s->n_owned * s->ndof, s->b.p, w->Ap.p, sigma, w->partial.p);
   double h[2];
   two_global_sums(s, h);

@@ -15,6 +15,7 @@ def field_copy_counters():
 
 
 DIRICHLET_ROWS, DIRICHLET_SYMMETRIC = 0, 1
+PRECOND_JACOBI, PRECOND_AMG = 0, 1
 VEC_X, VEC_B, VEC_XOLD = 0, 1, 2
 
 
@@ -108,6 +109,9 @@ class DeviceSystem:
         self.rows = L.efv_system_rows(self.handle)
         self.nnz = L.efv_system_nnz(self.handle)
         self.graph_nnz = L.efv_system_graph_nnz(self.handle)
+        lat = getattr(grid, "lattice", None)
+        if lat is not None and int(np.prod(lat)) == grid.numberOfVertices:       # structured numbering: 2x2x2 aggregates on the device
+            self.set_lattice(*lat)
 
     def __del__(self):
         try:
@@ -194,6 +198,38 @@ class DeviceSystem:
 
     def build_rhs(self, transient=False):
         _lib.check(_lib.load().efv_build_rhs(self.handle, int(bool(transient))))
+
+    # -- preconditioner ------------------------------------------------------------------------------------------
+    def set_preconditioner(self, kind):
+        """PRECOND_JACOBI (default) or PRECOND_AMG (aggregation multigrid, csrc/amg.cu) for solve_pcg."""
+        kind = {"jacobi": PRECOND_JACOBI, "amg": PRECOND_AMG}.get(kind, kind)
+        _lib.check(_lib.load().efv_system_set_preconditioner(self.handle, int(kind)))
+
+    def set_lattice(self, nx, ny, nz):
+        _lib.check(_lib.load().efv_system_set_lattice(self.handle, int(nx), int(ny), int(nz)))
+
+    def amg_info(self):
+        cap = 32
+        n = C.c_int(0)
+        rows = np.zeros(cap, dtype=np.int64); nnz = np.zeros(cap, dtype=np.int64); lmax = np.zeros(cap); ms = C.c_double(0.0)
+        _lib.check(_lib.load().efv_amg_info(self.handle, cap, C.byref(n), rows.ctypes.data_as(_lib.c_i64p), nnz.ctypes.data_as(_lib.c_i64p),
+                                            lmax.ctypes.data_as(_lib.c_f64p), C.byref(ms)))
+        k = n.value
+        return dict(levels=k, rows=rows[:k].tolist(), nnz=nnz[:k].tolist(), lmax=lmax[:k].tolist(), numeric_ms=ms.value)
+
+    def amg_level(self, level, with_aggregates=True):
+        """(block CSR as scipy BSR-expanded CSR in vertex-major scalar numbering, aggregates) of one hierarchy level."""
+        info = self.amg_info()
+        nd = self.ndof
+        nrow = info["rows"][level] // nd
+        nblk = info["nnz"][level] // (nd * nd)
+        gptr = np.empty(nrow + 1, dtype=np.int64); gcol = np.empty(nblk, dtype=np.int32); vals = np.empty(nblk * nd * nd)
+        agg = np.empty(nrow, dtype=np.int32) if (with_aggregates and level + 1 < info["levels"]) else None
+        _lib.check(_lib.load().efv_amg_level_export(self.handle, level, gptr.ctypes.data_as(_lib.c_i64p), gcol.ctypes.data_as(_lib.c_i32p),
+                                                    vals.ctypes.data_as(_lib.c_f64p),
+                                                    agg.ctypes.data_as(_lib.c_i32p) if agg is not None else None))
+        A = sp.bsr_matrix((vals.reshape(nblk, nd, nd), gcol, gptr), shape=(nrow * nd, nrow * nd)).tocsr()
+        return A, agg
 
     # -- solve ---------------------------------------------------------------------------------------------------
     def solve_pcg(self, rtol=1e-10, maxit=10000, negate=False):

@@ -229,6 +229,7 @@ class Grid:
         if not isinstance(gridData, GridData):
             raise Exception("Grid argument must be of class GridData")                   # Grid.py:12-13
         self.gridData = gridData
+        self.lattice = getattr(gridData, "lattice", None)
         self.dimension = int(gridData.dimension)
         self.coords = np.ascontiguousarray(np.asarray(gridData.verticesCoordinates, dtype=np.float64).reshape(-1, 3))
         self.numberOfVertices = len(self.coords)
@@ -431,6 +432,7 @@ def structured_grid_data(n, kind="hex", perturb=0.0, nz=None):
     gd.setRegions(["Body"], [np.arange(len(conn), dtype=np.int64)])
     gd.setBoundaries(list(BOUNDARY_NAMES_3D), [np.arange(starts[h], starts[h + 1], dtype=np.int64) for h in range(6)], bconn)
     gd.setShapes([[]] * 7)
+    gd.lattice = (n, n, nz or n)          # vertex id = i + n j + n^2 k: lets the multigrid preconditioner aggregate arithmetically
     return gd
 
 
