@@ -47,6 +47,9 @@ struct AmgLevel {
   DBuf<int32_t> mem;
   DBuf<int64_t> cl_ptr;                // per coarse entry: the fine entries summed into it, ascending
   DBuf<int32_t> cl;
+  // partitioned runs: for every ghost row of THIS level its owner rank and its row number there (levels >= 1)
+  std::vector<int> ghost_rank;
+  std::vector<int64_t> ghost_owner_local;
 };
 
 struct AmgHierarchy {
@@ -55,8 +58,14 @@ struct AmgHierarchy {
   double numeric_sigma = 0.0;
   int deg = 2;
   double ratio = 8.0, scale = 1.8;
-  int64_t nd = 0;                      // scalar rows of the coarsest level
+  int64_t nd = 0;                      // scalar rows of the coarsest level (all ranks together)
   DBuf<double> dense;                  // nd x 2 nd work matrix; the inverse is its right half
+  // partitioned runs: the coarsest operator is gathered on every rank and inverted redundantly
+  bool dist = false;
+  int64_t nd_off = 0, nd_local = 0;    // first scalar row / scalar rows of this rank inside the gathered coarsest system
+  GatherStage *stage = nullptr;
+  DBuf<int32_t> colmap;                // coarsest level: local column -> global row of the gathered system
+  DBuf<double> bfull, dense_local;
   double t_numeric_ms = 0.0;
   bool numeric_timed = false;
   ~AmgHierarchy() {
@@ -64,6 +73,7 @@ struct AmgHierarchy {
       if (L->owns_sys && L->sys) { krylov_free(L->sys); delete L->sys; }
       delete L;
     }
+    if (stage) gather_stage_destroy(stage);
   }
 };
 
@@ -146,6 +156,10 @@ __global__ void k_sort_lists(int64_t nlists, const int64_t *__restrict__ ptr, in
       items[j + 1] = key;
     }
   }
+}
+
+__global__ void k_i32_to_f64(int64_t n, const int32_t *__restrict__ a, double *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (double)a[i];
 }
 
 constexpr int kCWarps = 4;
@@ -295,24 +309,24 @@ __global__ void k_cheb_coef(const double *__restrict__ partial, int G, double ra
     coef[4 * kMaxDeg] = lmax;
   }
 }
-// dense copy [sigma A | I] of the coarsest operator, then Gauss-Jordan without pivoting (SPD) in one block
-__global__ void k_dense_fill(int64_t n, int ndof, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
-                             const double *__restrict__ vals, double sigma, double *__restrict__ M) {
-  const int64_t N = n * ndof;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N * 2 * N; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / (2 * N), c = i % (2 * N);
+// dense copy [sigma A | I] of the coarsest operator (rows [row0, row0 + nrows) of the N x 2N system; M holds those rows
+// only), then Gauss-Jordan without pivoting (SPD) in one block
+__global__ void k_dense_fill(int64_t nrows, int64_t row0, int64_t N, double *__restrict__ M) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nrows * 2 * N; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row0 + i / (2 * N), c = i % (2 * N);
     M[i] = (c == r + N) ? 1.0 : 0.0;
   }
-  // (second launch fills the entries: see amg_numeric)
 }
+// colmap: local block column -> block row of the gathered system (nullptr: identity, ghosts skipped)
 __global__ void k_dense_entries(int64_t n, int ndof, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
-                                const double *__restrict__ vals, double sigma, double *__restrict__ M) {
-  const int64_t N = n * ndof;
+                                const double *__restrict__ vals, double sigma, const int32_t *__restrict__ colmap, int64_t row0, int64_t N,
+                                double *__restrict__ M) {
   const int B = ndof * ndof;
   for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n; v += (int64_t)gridDim.x * blockDim.x)
     for (int64_t t = gptr[v]; t < gptr[v + 1]; ++t) {
-      const int64_t c = gcol[t];
-      if (c >= n) continue;
+      int64_t c = gcol[t];
+      if (colmap) c = colmap[c];
+      else if (c >= n) continue;
       for (int i = 0; i < ndof; ++i)
         for (int j = 0; j < ndof; ++j) M[(v * ndof + i) * 2 * N + c * ndof + j] = sigma * vals[t * B + i * ndof + j];
     }
@@ -339,16 +353,17 @@ __global__ void __launch_bounds__(1024) k_gauss_jordan(int N, double *__restrict
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(256) k_dense_solve(int N, const double *__restrict__ M, const double *__restrict__ b,
+// x[0, nrows) = rows [row0, row0 + nrows) of the inverse times the full right-hand side b[0, N)
+__global__ void __launch_bounds__(256) k_dense_solve(int N, int row0, int nrows, const double *__restrict__ M, const double *__restrict__ b,
                                                      double *__restrict__ x, const int *__restrict__ done) {
   if (done && *done) return;
   __shared__ double bs[kCoarsestRows];
   for (int i = threadIdx.x; i < N; i += blockDim.x) bs[i] = b[i];
   __syncthreads();
   const int W = 2 * N;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
     double acc = 0.0;
-    for (int j = 0; j < N; ++j) acc += M[(int64_t)i * W + N + j] * bs[j];
+    for (int j = 0; j < N; ++j) acc += M[(int64_t)(row0 + i) * W + N + j] * bs[j];
     x[i] = acc;
   }
 }
@@ -390,6 +405,17 @@ __global__ void __launch_bounds__(256) k_prolong(int64_t n, int ndof, const int3
     x[i] += scale * xc[(int64_t)agg[v] * ndof + f];
   }
 }
+// b . x of a short vector in one block: partial[0] = sum, partial[1..G) = 0 (the consumers sum G entries)
+__global__ void __launch_bounds__(256) k_dot_partial(int64_t n, const double *__restrict__ b, const double *__restrict__ x,
+                                                     double *__restrict__ partial, int G, const int *__restrict__ done) {
+  __shared__ double red[32];
+  if (done && *done) return;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += b[i] * x[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partial[0] = acc;
+  for (int i = 1 + threadIdx.x; i < G; i += blockDim.x) partial[i] = 0.0;
+}
 __global__ void __launch_bounds__(256) k_axpy1(int64_t n, const double *__restrict__ d, double *__restrict__ x, const int *__restrict__ done) {
   if (done && *done) return;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] += d[i];
@@ -407,7 +433,6 @@ static void level_vectors(AmgLevel *L, bool top) {
 static void build_transfer(AmgLevel *F, AmgLevel *C) {
   efv_system *fs = F->sys;
   const int64_t n = F->n;
-  EFV_REQUIRE(F->ng == 0, "the multigrid hierarchy of a partitioned system is built by amg_dist (ghost aggregates)");
   // 1. aggregates of the owned rows
   F->agg.alloc(n + F->ng);
   int64_t nc = 0;
@@ -428,6 +453,50 @@ static void build_transfer(AmgLevel *F, AmgLevel *C) {
     EFV_CUDA(cudaStreamSynchronize(stream()));
   }
   F->nc = nc;
+  // 1b. partitioned level: aggregates of the ghost rows (they live on the neighbours) and the halo of the coarse level.
+  // Every rank sends the aggregate number of its interface rows through the level's halo; the distinct numbers received
+  // from neighbour q, ascending, become the ghost rows of the coarse level (same order as q derives for its send list).
+  const bool dist = F->ng > 0 || (fs->halo.active && comm_active());
+  int64_t ncg = 0;
+  std::vector<int> c_nbr;
+  std::vector<int64_t> c_send_ptr(1, 0), c_recv_ptr(1, 0);
+  std::vector<int32_t> c_send_idx;
+  if (dist) {
+    Halo &fh = fs->halo;
+    EFV_REQUIRE(fh.active && fh.peer && comm_peer_active(), "the multigrid preconditioner of a partitioned system needs the peer-memory halo (EFV_COMM=peer)");
+    const int64_t ng = F->ng;
+    DBuf<double> aggd(n + ng);
+    EFV_LAUNCH(k_i32_to_f64, grid_for(n, 256), 256, 0, n, F->agg.p, aggd.p);
+    halo_exchange(fh, aggd.p, 1);
+    std::vector<double> gh(ng);
+    std::vector<int32_t> own(n);
+    if (ng) EFV_CUDA(cudaMemcpyAsync(gh.data(), aggd.p + n, ng * sizeof(double), cudaMemcpyDeviceToHost, stream()));
+    EFV_CUDA(cudaMemcpyAsync(own.data(), F->agg.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream()));
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+    std::vector<int32_t> ghost_agg(ng);
+    const int nn = (int)fh.nbr.size();
+    for (int i = 0; i < nn; ++i) {
+      std::vector<int64_t> ids;
+      for (int64_t k = fh.recv_ptr[i]; k < fh.recv_ptr[i + 1]; ++k) ids.push_back((int64_t)gh[k]);
+      std::vector<int64_t> u = ids;
+      std::sort(u.begin(), u.end());
+      u.erase(std::unique(u.begin(), u.end()), u.end());
+      for (int64_t k = fh.recv_ptr[i]; k < fh.recv_ptr[i + 1]; ++k)
+        ghost_agg[k] = (int32_t)(nc + ncg + (std::lower_bound(u.begin(), u.end(), ids[k - fh.recv_ptr[i]]) - u.begin()));
+      std::vector<int32_t> snd;
+      for (int64_t k = fh.send_ptr[i]; k < fh.send_ptr[i + 1]; ++k) snd.push_back(own[fh.send_idx_host[k]]);
+      std::sort(snd.begin(), snd.end());
+      snd.erase(std::unique(snd.begin(), snd.end()), snd.end());
+      c_nbr.push_back(fh.nbr[i]);
+      c_send_idx.insert(c_send_idx.end(), snd.begin(), snd.end());
+      c_send_ptr.push_back((int64_t)c_send_idx.size());
+      for (int64_t id : u) { C->ghost_rank.push_back(fh.nbr[i]); C->ghost_owner_local.push_back(id); }
+      ncg += (int64_t)u.size();
+      c_recv_ptr.push_back(ncg);
+    }
+    if (ng) EFV_CUDA(cudaMemcpyAsync(F->agg.p + n, ghost_agg.data(), ng * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+  }
   // 2. members of every aggregate
   DBuf<int32_t> cnt(nc);
   cnt.zero();
@@ -442,7 +511,7 @@ static void build_transfer(AmgLevel *F, AmgLevel *C) {
   // 3. coarse pattern
   efv_system *cs = new efv_system();
   C->sys = cs; C->owns_sys = true;
-  cs->mesh = nullptr; cs->ndof = fs->ndof; cs->nV = cs->n_owned = nc; cs->rows = nc * fs->ndof;
+  cs->mesh = nullptr; cs->ndof = fs->ndof; cs->nV = nc + ncg; cs->n_owned = nc; cs->rows = (nc + ncg) * fs->ndof;
   DBuf<int32_t> rowlen(nc);
   DBuf<int> err(1);
   err.zero();
@@ -480,7 +549,18 @@ static void build_transfer(AmgLevel *F, AmgLevel *C) {
   EFV_LAUNCH((k_gather_lists<1>), grid_for(n, 128), 128, 0, n, fs->gptr.p, fs->gcol.p, F->agg.p, cs->gptr.p, cs->gcol.p, ccnt.p,
              F->cl_ptr.p, F->cl.p, err.p);
   EFV_LAUNCH(k_sort_lists, grid_for(cs->nnzg, 128), 128, 0, cs->nnzg, F->cl_ptr.p, F->cl.p);
-  C->n = nc; C->ng = 0;
+  C->n = nc; C->ng = ncg;
+  if (dist) {                                   // halo of the coarse level + its peer staging buffers
+    Halo &h = cs->halo;
+    h.nbr = c_nbr; h.send_ptr = c_send_ptr; h.recv_ptr = c_recv_ptr;
+    h.n_owned = nc; h.n_ghost = ncg; h.cap_ndof = cs->ndof;
+    h.send_idx_host = c_send_idx;
+    h.send_idx.upload(c_send_idx.data(), c_send_idx.size());
+    h.send_buf.alloc(std::max<size_t>(c_send_idx.size() * cs->ndof, 1));
+    EFV_CUDA(cudaStreamSynchronize(stream()));
+    h.active = true;
+    halo_connect_peer(h);
+  }
 }
 
 AmgHierarchy *amg_symbolic(efv_system *s) {
@@ -495,18 +575,46 @@ AmgHierarchy *amg_symbolic(efv_system *s) {
     L->sys = s; L->n = s->n_owned; L->ng = s->nV - s->n_owned;
     for (int k = 0; k < 3; ++k) L->lat[k] = s->lattice[k];
     H->lv.push_back(L);
+    H->dist = is_dist(s);
+    const int nranks = H->dist ? comm_size() : 1;
+    std::vector<int64_t> counts(nranks, 0);
+    auto global_rows = [&](int64_t mine) {          // block rows of a level over all ranks (collective: every rank, every level)
+      if (!H->dist) { counts[0] = mine; return mine; }
+      comm_allgather_i64(mine, counts.data());
+      int64_t t = 0;
+      for (int64_t c : counts) t += c;
+      return t;
+    };
+    int64_t glob = global_rows(L->n);
     while ((int)H->lv.size() < kMaxLevels) {
       AmgLevel *F = H->lv.back();
-      if (F->n * s->ndof <= kCoarsestRows) break;
+      if (glob * s->ndof <= kCoarsestRows) break;
       AmgLevel *C = new AmgLevel();
       H->lv.push_back(C);
       build_transfer(F, C);
-      EFV_REQUIRE(C->n < F->n, "aggregation did not coarsen the operator");
+      const int64_t cglob = global_rows(C->n);
+      EFV_REQUIRE(cglob < glob, "aggregation did not coarsen the operator");
+      glob = cglob;
     }
     AmgLevel *last = H->lv.back();
-    EFV_REQUIRE(last->n * s->ndof <= kCoarsestRows, "hierarchy too deep");
-    H->nd = last->n * s->ndof;
+    EFV_REQUIRE(glob * s->ndof <= kCoarsestRows, "hierarchy too deep");
+    EFV_REQUIRE(!H->dist || H->lv.size() >= 2, "a partitioned system of <= 256 rows needs no multigrid (use the Jacobi preconditioner)");
+    H->nd = glob * s->ndof;
     H->dense.alloc((size_t)H->nd * 2 * H->nd);
+    if (H->dist) {
+      // gathered coarsest system: rank r's rows come after those of ranks < r; ghost columns map through (owner, row there)
+      std::vector<int64_t> off(nranks + 1, 0);
+      for (int r = 0; r < nranks; ++r) off[r + 1] = off[r] + counts[r];
+      H->nd_off = off[comm_rank()] * s->ndof;
+      H->nd_local = last->n * s->ndof;
+      std::vector<int32_t> cm(last->n + last->ng);
+      for (int64_t v = 0; v < last->n; ++v) cm[v] = (int32_t)(off[comm_rank()] + v);
+      for (int64_t g = 0; g < last->ng; ++g) cm[last->n + g] = (int32_t)(off[last->ghost_rank[g]] + last->ghost_owner_local[g]);
+      H->colmap.upload(cm.data(), cm.size());
+      H->bfull.alloc(H->nd);
+      H->dense_local.alloc((size_t)std::max<int64_t>(H->nd_local, 1) * 2 * H->nd);
+      H->stage = gather_stage_create((size_t)H->nd * 2 * H->nd);
+    }
     for (size_t l = 0; l < H->lv.size(); ++l) level_vectors(H->lv[l], l == 0);
     EFV_CUDA(cudaStreamSynchronize(stream()));
     return H;
@@ -536,12 +644,25 @@ void amg_numeric(AmgHierarchy *H, double sigma) {
     if (l + 1 < H->lv.size()) {
       EFV_LAUNCH(k_diag_gershgorin, w->grid, 256, 0, L->n, ls->ndof, ls->gptr.p, ls->gcol.p, ls->vals.p, ls->diag_slot.p, sigma, L->dinv.p,
                  w->partial.p);
-      EFV_LAUNCH(k_cheb_coef, 1, 256, 0, w->partial.p, w->grid, H->ratio, L->coef.p);
+      if (H->dist) {          // one interval for all ranks: the smoother must be the same polynomial everywhere
+        comm_allreduce_partials(w->partial.p, w->grid, 1, w->sc.p + 50, 1);
+        EFV_LAUNCH(k_cheb_coef, 1, 256, 0, w->sc.p + 50, 1, H->ratio, L->coef.p);
+      } else {
+        EFV_LAUNCH(k_cheb_coef, 1, 256, 0, w->partial.p, w->grid, H->ratio, L->coef.p);
+      }
       sell_prepare(ls, w);
     } else {
       const int64_t N = H->nd;
-      EFV_LAUNCH(k_dense_fill, grid_for(N * 2 * N, 256), 256, 0, L->n, ls->ndof, ls->gptr.p, ls->gcol.p, ls->vals.p, sigma, H->dense.p);
-      EFV_LAUNCH(k_dense_entries, grid_for(L->n, 64), 64, 0, L->n, ls->ndof, ls->gptr.p, ls->gcol.p, ls->vals.p, sigma, H->dense.p);
+      if (!H->dist) {
+        EFV_LAUNCH(k_dense_fill, grid_for(N * 2 * N, 256), 256, 0, N, (int64_t)0, N, H->dense.p);
+        EFV_LAUNCH(k_dense_entries, grid_for(L->n, 64), 64, 0, L->n, ls->ndof, ls->gptr.p, ls->gcol.p, ls->vals.p, sigma, (const int32_t *)nullptr,
+                   (int64_t)0, N, H->dense.p);
+      } else {                // my rows of [sigma A | I] in gathered numbering, then every rank receives every block of rows
+        EFV_LAUNCH(k_dense_fill, grid_for(std::max<int64_t>(H->nd_local, 1) * 2 * N, 256), 256, 0, H->nd_local, H->nd_off, N, H->dense_local.p);
+        EFV_LAUNCH(k_dense_entries, grid_for(std::max<int64_t>(L->n, 1), 64), 64, 0, L->n, ls->ndof, ls->gptr.p, ls->gcol.p, ls->vals.p, sigma,
+                   H->colmap.p, H->nd_off, N, H->dense_local.p);
+        gather_all(H->stage, H->nd_off * 2 * N, H->nd_local * 2 * N, N * 2 * N, H->dense_local.p, H->dense.p, nullptr);
+      }
       EFV_LAUNCH(k_gauss_jordan, 1, 1024, 0, (int)N, H->dense.p);
     }
   }
@@ -562,7 +683,13 @@ static void cycle(AmgHierarchy *H, size_t l, const double *b, double *x, double 
   const int G = w->grid;
   const int64_t len = L->n * ls->ndof;
   if (l + 1 == H->lv.size()) {
-    EFV_LAUNCH(k_dense_solve, 1, 256, 0, (int)H->nd, H->dense.p, b, x, done);
+    if (H->dist) {
+      gather_all(H->stage, H->nd_off, H->nd_local, H->nd, b, H->bfull.p, done);
+      EFV_LAUNCH(k_dense_solve, 1, 256, 0, (int)H->nd, (int)H->nd_off, (int)H->nd_local, H->dense.p, H->bfull.p, x, done);
+    } else {
+      EFV_LAUNCH(k_dense_solve, 1, 256, 0, (int)H->nd, 0, (int)H->nd, H->dense.p, b, x, done);
+    }
+    if (rz_partial) EFV_LAUNCH(k_dot_partial, 1, 256, 0, len, b, x, rz_partial, G, done);      // single-level hierarchy (<= 256 rows)
     return;
   }
   const int deg = H->deg;
@@ -705,7 +832,6 @@ __global__ void k_mg_store_rz(const double *__restrict__ rz_partial, int G, doub
 
 void solve_pcg_amg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres) {
   EFV_REQUIRE(s->vals.n, "no values assembled");
-  EFV_REQUIRE(!is_dist(s), "the multigrid preconditioner of a partitioned system is not available in this build path");
   ensure_vectors(s);
   KrylovWork *w = work(s);
   const int64_t n = s->n_owned * s->ndof;
@@ -723,24 +849,32 @@ void solve_pcg_amg(efv_system *s, double rtol, int maxit, int negate, int *iters
   sell_prepare(s, w);
   amg_numeric(H, sigma);
   EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
+  int Gc = G, Gp = G, Gr = G, Gz = G;               // partitioned runs: the partials are all-reduced into single scalars
+  halo_exchange(s, s->x.p);
   launch_spmv(s, G, s->x.p, plain_epi(w->Ap.p, sigma, nullptr, nullptr), nullptr, nullptr);
   EFV_LAUNCH(k_mg_init, G, 256, 0, n, s->b.p, w->Ap.p, sigma, w->r.p, P);
-  EFV_LAUNCH(k_mg_init_scalars, 1, 256, 0, G, P, w->sc.p, w->flags.p, rtol);
+  const double *c0 = consolidate(s, P, 2, 0, &Gc);
+  EFV_LAUNCH(k_mg_init_scalars, 1, 256, 0, Gc, c0, w->sc.p, w->flags.p, rtol);
   double *z = w->v.p;
   cycle(H, 0, w->r.p, z, sigma, P + G, w->flags.p, false);
-  EFV_LAUNCH(k_mg_first_p, G, 256, 0, n, z, w->p.p, P + G, G, w->sc.p, w->flags.p);
+  const double *cz = consolidate(s, P + G, 1, 3, &Gz);
+  EFV_LAUNCH(k_mg_first_p, G, 256, 0, n, z, w->p.p, cz, Gz, w->sc.p, w->flags.p);
   int it = 0;
   bool done = false;
   const int check_every = (n > 200000) ? 1 : 4;
   while (!done && it < maxit) {
     const int batch_end = std::min(maxit, it + check_every);
     for (; it < batch_end; ++it) {
+      halo_exchange(s, w->p.p);
       launch_spmv(s, G, w->p.p, plain_epi(w->Ap.p, sigma, nullptr, w->p.p), P + 3 * G, w->flags.p);
-      EFV_LAUNCH(k_mg_xr, G, 256, 0, n, w->sc.p, P + 3 * G, G, w->p.p, w->Ap.p, s->x.p, w->r.p, P, w->flags.p);
-      EFV_LAUNCH(k_mg_check, 1, 256, 0, it, P + 3 * G, G, P, G, w->sc.p, w->flags.p);
+      const double *cp = consolidate(s, P + 3 * G, 1, 1, &Gp);
+      EFV_LAUNCH(k_mg_xr, G, 256, 0, n, w->sc.p, cp, Gp, w->p.p, w->Ap.p, s->x.p, w->r.p, P, w->flags.p);
+      const double *cr = consolidate(s, P, 1, 2, &Gr);
+      EFV_LAUNCH(k_mg_check, 1, 256, 0, it, cp, Gp, cr, Gr, w->sc.p, w->flags.p);
       cycle(H, 0, w->r.p, z, sigma, P + G, w->flags.p, false);
-      EFV_LAUNCH(k_mg_p, G, 256, 0, n, w->sc.p, P + G, G, z, w->p.p, w->flags.p);
-      EFV_LAUNCH(k_mg_store_rz, 1, 256, 0, P + G, G, w->sc.p, w->flags.p);
+      const double *cz2 = consolidate(s, P + G, 1, 3, &Gz);
+      EFV_LAUNCH(k_mg_p, G, 256, 0, n, w->sc.p, cz2, Gz, z, w->p.p, w->flags.p);
+      EFV_LAUNCH(k_mg_store_rz, 1, 256, 0, cz2, Gz, w->sc.p, w->flags.p);
     }
     EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
     EFV_CUDA(cudaStreamSynchronize(stream()));
@@ -760,6 +894,7 @@ void solve_pcg_amg(efv_system *s, double rtol, int maxit, int negate, int *iters
   }
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
+  if (is_dist(s) && comm_peer_active()) EFV_REQUIRE(comm_peer_error() == 0, "peer-memory collective timed out (a rank did not arrive)");
   if (iters) *iters = w->h_flags[1];
   if (relres) *relres = w->h_flags[2] ? NAN : ((w->h_sc[2] > 0) ? std::sqrt(w->h_sc[3] / w->h_sc[2]) : 0.0);
 }

@@ -4,6 +4,7 @@
 // NCCL instance.  Everything runs on the library stream.
 #include "views.cuh"
 #include "peer.cuh"
+#include <algorithm>
 #include <dlfcn.h>
 #include <cstring>
 
@@ -270,6 +271,168 @@ void comm_allreduce_max(double *dev, int count) {
   EFV_NCCL(g_nccl.AllReduce(dev, dev, (size_t)count, kNcclFloat64, kNcclMax, g_comm, stream()));
 }
 
+// ---- mailbox: small host-driven point-to-point messages over the peer regions --------------------------------------------
+// Used at set-up time only (IPC handles and offsets of per-level halo buffers, row counts), where torch.distributed is
+// out of reach of the C library and NCCL may be absent (ranks sharing a GPU).  Collective in COUNT: every rank must call
+// comm_mail_exchange the same number of times (possibly with no peers), because the boxes are sequence-numbered.
+struct MailMsg { unsigned long long w[kMailBytes / 8]; };
+static uint32_t g_mail_seq = 0;
+__global__ void k_mail_send(char *dst, int me, MailMsg msg, uint32_t seq) {
+  unsigned long long *box = reinterpret_cast<unsigned long long *>(dst + kMailOffset + ((size_t)(seq & 1u) * kMaxRanks + me) * kMailBytes);
+  if (threadIdx.x < kMailBytes / 8) box[threadIdx.x] = msg.w[threadIdx.x];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t *>(dst + kMailFlagOffset + ((size_t)(seq & 1u) * kMaxRanks + me) * sizeof(uint32_t)) = seq;
+}
+__global__ void k_mail_recv(char *self, int from, uint32_t seq, unsigned long long *__restrict__ out) {
+  if (threadIdx.x == 0)
+    peer_wait_flag(reinterpret_cast<volatile const uint32_t *>(self + kMailFlagOffset + ((size_t)(seq & 1u) * kMaxRanks + from) * sizeof(uint32_t)), seq,
+                   peer_error(self), 3);
+  __syncthreads();
+  __threadfence_system();
+  const volatile unsigned long long *box =
+      reinterpret_cast<const volatile unsigned long long *>(self + kMailOffset + ((size_t)(seq & 1u) * kMaxRanks + from) * kMailBytes);
+  if (threadIdx.x < kMailBytes / 8) out[threadIdx.x] = box[threadIdx.x];
+}
+// send one kMailBytes message to every rank of `peers` and receive one from each (recv: npeers * kMailBytes, peer order)
+void comm_mail_exchange(int npeers, const int *peers, const char *send, char *recv) {
+  EFV_REQUIRE(comm_peer_active(), "the mailbox needs the peer-memory regions");
+  g_mail_seq++;
+  DBuf<unsigned long long> tmp((size_t)std::max(npeers, 1) * (kMailBytes / 8));
+  for (int i = 0; i < npeers; ++i) {
+    MailMsg m;
+    memcpy(m.w, send + (size_t)i * kMailBytes, kMailBytes);
+    EFV_LAUNCH(k_mail_send, 1, 32, 0, g_peer.all.p[peers[i]], g_rank, m, g_mail_seq);
+  }
+  for (int i = 0; i < npeers; ++i) EFV_LAUNCH(k_mail_recv, 1, 32, 0, g_peer.local, peers[i], g_mail_seq, tmp.p + (size_t)i * (kMailBytes / 8));
+  if (npeers) EFV_CUDA(cudaMemcpyAsync(recv, tmp.p, (size_t)npeers * kMailBytes, cudaMemcpyDeviceToHost, stream()));
+  EFV_CUDA(cudaStreamSynchronize(stream()));
+  EFV_REQUIRE(comm_peer_error() == 0, "mailbox exchange timed out (a rank did not arrive)");
+}
+// one int64 per rank, gathered on every rank
+void comm_allgather_i64(int64_t mine, int64_t *all) {
+  std::vector<int> peers;
+  for (int r = 0; r < g_nranks; ++r) if (r != g_rank) peers.push_back(r);
+  std::vector<char> send(peers.size() * kMailBytes, 0), recv(peers.size() * kMailBytes, 0);
+  for (size_t i = 0; i < peers.size(); ++i) memcpy(send.data() + i * kMailBytes, &mine, sizeof(int64_t));
+  comm_mail_exchange((int)peers.size(), peers.data(), send.data(), recv.data());
+  all[g_rank] = mine;
+  for (size_t i = 0; i < peers.size(); ++i) memcpy(&all[peers[i]], recv.data() + i * kMailBytes, sizeof(int64_t));
+}
+
+// ---- gather stage: every rank's slice of a short vector on every rank (coarsest multigrid level) ---------------------------
+// Buffer of every rank: [flags 2 x kMaxRanks | data parity 0 | data parity 1], mapped by all ranks through CUDA IPC.
+constexpr size_t kGatherFlagBytes = 2 * kMaxRanks * sizeof(uint32_t) + 128;
+struct GatherPtrs { char *p[kMaxRanks]; };
+__global__ void k_gather_push(GatherPtrs all, int nranks, int me, size_t cap, int64_t offset, int64_t count, const double *__restrict__ src,
+                              uint32_t seq, unsigned *__restrict__ ticket, const int *__restrict__ done) {
+  // `done` is deliberately NOT honoured for the flags: peers that are still iterating would wait for them
+  const size_t par = seq & 1u;
+  const bool skip = done && *done;
+  if (!skip)
+    for (int r = 0; r < nranks; ++r) {
+      double *dst = reinterpret_cast<double *>(all.p[r] + kGatherFlagBytes) + par * cap + offset;
+      for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+  __shared__ int s_last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < nranks) *reinterpret_cast<volatile uint32_t *>(all.p[threadIdx.x] + (par * kMaxRanks + me) * sizeof(uint32_t)) = seq;
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+__global__ void k_gather_wait_copy(const char *__restrict__ self, int nranks, size_t cap, int64_t count, uint32_t seq, double *__restrict__ dst,
+                                   int *__restrict__ err) {
+  const size_t par = seq & 1u;
+  if ((int)threadIdx.x < nranks) peer_wait_flag(reinterpret_cast<volatile const uint32_t *>(self) + par * kMaxRanks + threadIdx.x, seq, err, 4);
+  __syncthreads();
+  __threadfence_system();
+  const volatile double *src = reinterpret_cast<const volatile double *>(self + kGatherFlagBytes) + par * cap;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+struct GatherStage {
+  char *local = nullptr;
+  GatherPtrs all = {};
+  size_t cap = 0;
+  unsigned *ticket = nullptr;
+  uint32_t seq = 0;
+};
+GatherStage *gather_stage_create(size_t cap_doubles) {
+  EFV_REQUIRE(comm_peer_active(), "the gather stage needs the peer-memory regions");
+  GatherStage *g = new GatherStage();
+  g->cap = cap_doubles;
+  const size_t bytes = kGatherFlagBytes + 2 * cap_doubles * sizeof(double) + 64;
+  EFV_CUDA(cudaMalloc((void **)&g->local, bytes));
+  EFV_CUDA(cudaMemset(g->local, 0, bytes));
+  EFV_CUDA(cudaMalloc((void **)&g->ticket, sizeof(unsigned)));
+  EFV_CUDA(cudaMemset(g->ticket, 0, sizeof(unsigned)));
+  cudaIpcMemHandle_t mine;
+  EFV_CUDA(cudaIpcGetMemHandle(&mine, g->local));
+  std::vector<int> peers;
+  for (int r = 0; r < g_nranks; ++r) if (r != g_rank) peers.push_back(r);
+  std::vector<char> send(peers.size() * kMailBytes, 0), recv(peers.size() * kMailBytes, 0);
+  for (size_t i = 0; i < peers.size(); ++i) memcpy(send.data() + i * kMailBytes, &mine, 64);
+  comm_mail_exchange((int)peers.size(), peers.data(), send.data(), recv.data());
+  g->all.p[g_rank] = g->local;
+  for (size_t i = 0; i < peers.size(); ++i) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, recv.data() + i * kMailBytes, 64);
+    void *ptr = nullptr;
+    EFV_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    g->all.p[peers[i]] = (char *)ptr;
+  }
+  return g;
+}
+void gather_stage_destroy(GatherStage *g) {
+  if (!g) return;
+  for (int r = 0; r < kMaxRanks; ++r) if (r != g_rank && g->all.p[r]) cudaIpcCloseMemHandle(g->all.p[r]);
+  if (g->local) cudaFree(g->local);
+  if (g->ticket) cudaFree(g->ticket);
+  cudaGetLastError();
+  delete g;
+}
+// dst[0, total) <- concatenation over ranks of their (offset, count) slices of src; `done`: the push of a finished solve
+// still raises its flags (see k_gather_push)
+void gather_all(GatherStage *g, int64_t offset, int64_t count, int64_t total, const double *src, double *dst, const int *done) {
+  EFV_REQUIRE((size_t)total <= g->cap, "gather larger than the stage");
+  g->seq++;
+  EFV_LAUNCH(k_gather_push, grid_for(std::max<int64_t>(count, 1), 256, 1), 256, 0, g->all, g_nranks, g_rank, g->cap, offset, count, src, g->seq,
+             g->ticket, done);
+  EFV_LAUNCH(k_gather_wait_copy, grid_for(total, 256, 1), 256, 0, g->local, g_nranks, g->cap, total, g->seq, dst,
+             reinterpret_cast<int *>(g_peer.local + kSlotBytes + kFlagBytes));
+}
+
+// connect the peer staging buffers of a halo whose lists are already registered (C-side version of what the host layer
+// does for the finest level with all_gather_object): neighbours swap (IPC handle, ghost count, offset, flag slot)
+void halo_connect_peer(Halo &h) {
+  EFV_REQUIRE(h.active, "register the halo first");
+  const int n = (int)h.nbr.size();
+  char mine[64];
+  halo_stage_export(h, mine);
+  std::vector<char> send((size_t)std::max(n, 1) * kMailBytes, 0), recv((size_t)std::max(n, 1) * kMailBytes, 0);
+  for (int i = 0; i < n; ++i) {
+    char *m = send.data() + (size_t)i * kMailBytes;
+    memcpy(m, mine, 64);
+    const int64_t info[3] = {h.n_ghost, h.recv_ptr[i], (int64_t)i};      // my ghost count; where neighbour i's values go; its flag slot
+    memcpy(m + 64, info, sizeof(info));
+  }
+  comm_mail_exchange(n, h.nbr.data(), send.data(), recv.data());
+  std::vector<char> handles((size_t)std::max(n, 1) * 64);
+  std::vector<int64_t> off(n), ghosts(n);
+  std::vector<int> slot(n);
+  for (int i = 0; i < n; ++i) {
+    const char *m = recv.data() + (size_t)i * kMailBytes;
+    memcpy(handles.data() + (size_t)i * 64, m, 64);
+    int64_t info[3];
+    memcpy(info, m + 64, sizeof(info));
+    ghosts[i] = info[0]; off[i] = info[1]; slot[i] = (int)info[2];
+  }
+  halo_stage_import(h, handles.data(), off.data(), slot.data(), ghosts.data());
+}
+
 // ---- halo exchange ----------------------------------------------------------------------------------------------------
 __global__ void k_pack(const int32_t *__restrict__ idx, int64_t n, int ndof, const double *__restrict__ vec,
                        double *__restrict__ buf) {
@@ -295,6 +458,7 @@ void halo_set(efv_system *s, int n_nbr, const int *nbr, const int64_t *send_ptr,
   h.n_ghost = s->nV - s->n_owned;
   h.cap_ndof = s->ndof;
   h.send_idx.upload(send_idx, h.send_ptr[n_nbr]);
+  h.send_idx_host.assign(send_idx, send_idx + h.send_ptr[n_nbr]);
   h.send_buf.alloc((size_t)h.send_ptr[n_nbr] * s->ndof);
   EFV_CUDA(cudaStreamSynchronize(stream()));
   h.active = true;

@@ -83,6 +83,7 @@ struct Halo {
   std::vector<int64_t> send_ptr;        // per neighbour range into send_idx
   std::vector<int64_t> recv_ptr;        // per neighbour range into the ghost block (ghosts are grouped by owner)
   DBuf<int32_t> send_idx;               // local ids of owned vertices to send
+  std::vector<int32_t> send_idx_host;   // host copy (coarse-level halos of the multigrid hierarchy are derived from it)
   DBuf<double> send_buf;
   int64_t n_owned = 0, n_ghost = 0;     // vector layout: [owned | ghosts grouped by owner]
   int cap_ndof = 1;                     // widest exchange (values per vertex) the buffers are sized for
@@ -208,6 +209,13 @@ void halo_stage_import(Halo &h, const char *handles, const int64_t *remote_off, 
 void halo_release(Halo &h);
 void halo_exchange(Halo &h, double *vec, int ndof);
 void comm_peer_release();
+void comm_mail_exchange(int npeers, const int *peers, const char *send, char *recv);
+void comm_allgather_i64(int64_t mine, int64_t *all);
+struct GatherStage;
+GatherStage *gather_stage_create(size_t cap_doubles);
+void gather_stage_destroy(GatherStage *g);
+void gather_all(GatherStage *g, int64_t offset, int64_t count, int64_t total, const double *src, double *dst, const int *done);
+void halo_connect_peer(Halo &h);
 void halo_set(efv_system *s, int n_nbr, const int *nbr, const int64_t *send_ptr, const int32_t *send_idx, const int64_t *recv_ptr);
 void halo_exchange(efv_system *s, double *vec);
 }  // namespace efv

@@ -18,7 +18,11 @@ namespace efv {
 constexpr int kMaxRanks = 16;
 constexpr size_t kSlotBytes = 2 * kMaxRanks * 4 * sizeof(double);
 constexpr size_t kFlagBytes = 2 * kMaxRanks * sizeof(uint32_t);
-constexpr size_t kPeerBytes = kSlotBytes + kFlagBytes + 64;
+// small host-driven messages between ranks (set-up of per-level halos, counts): one 256-byte box per (parity, sender)
+constexpr size_t kMailBytes = 256;
+constexpr size_t kMailOffset = kSlotBytes + kFlagBytes + 64;
+constexpr size_t kMailFlagOffset = kMailOffset + 2 * kMaxRanks * kMailBytes;
+constexpr size_t kPeerBytes = kMailFlagOffset + 2 * kMaxRanks * sizeof(uint32_t) + 64;
 // A rank that never arrives turns into an error, not a hang: spin waits give up after kPeerTimeoutNs of WALL time
 // (%globaltimer), generous enough for ordinary rank skew (a peer writing output files, lazy module loads, uneven
 // assembly, two ranks time-sliced on one GPU).  After a timeout the error word stays set until the host has reported it

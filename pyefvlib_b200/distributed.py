@@ -37,6 +37,7 @@ class LocalPart:
         self.send_lists = send_lists              # per neighbour: local ids of owned vertices it needs (global order)
         self.recv_ptr = np.asarray(recv_ptr, dtype=np.int64)   # per neighbour slice of the ghost block
         self.boundary_vertices = boundary_vertices   # per boundary: local ids (owned and ghost) lying on it
+        self.lattice = None                          # (nx, ny, nz) when the OWNED vertices are numbered like a lattice
 
     @property
     def n_ghost(self):
@@ -155,7 +156,9 @@ def structured_part(n, kind, rank, world, perturb=0.0, nz=None):
     if len(above):
         nbr.append(rank + 1); send_lists.append(np.arange(n_owned - n2, n_owned, dtype=np.int32)); recv.append(recv[-1] + len(above))
     grid = _make_local_grid(3, coords, conn_local, ["Body"], np.zeros(len(conn_local), dtype=np.int32), _grid.BOUNDARY_NAMES_3D, facets_local)
-    return LocalPart(rank, world, ranges, grid, n_owned, l2g, nbr, send_lists, recv, bverts)
+    part = LocalPart(rank, world, ranges, grid, n_owned, l2g, nbr, send_lists, recv, bverts)
+    part.lattice = (n, n, k1 - k0)            # the owned vertices are numbered like an n x n x (owned planes) lattice
+    return part
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -237,6 +240,8 @@ def make_system(part, ndof=1):
     s = DeviceSystem(part.grid, ndof)
     L = _lib.load()
     _lib.check(L.efv_system_set_owned(s.handle, part.n_owned))
+    if part.lattice is not None:
+        s.set_lattice(*part.lattice)
     nb = np.asarray(part.nbr, dtype=np.int32)
     sp = np.concatenate([[0], np.cumsum([len(x) for x in part.send_lists])]).astype(np.int64)
     si = np.concatenate(part.send_lists).astype(np.int32) if part.send_lists else np.zeros(0, dtype=np.int32)

@@ -73,6 +73,18 @@ def main():
     dist.all_reduce(t)
     rel = float(torch.sqrt(t[0] / t[1]).item())
     assert rel <= 1e-8, rel
+    # 2a. the same solve with the aggregation multigrid preconditioner (ghost aggregates, per-level halos, gathered coarsest level)
+    s.set_preconditioner("amg")
+    s.upload(VEC_X, Told_global[l2g])
+    it_a, rr_a = s.solve_pcg(1e-10, 500)
+    assert rr_a <= 1e-10 and s.true_residual() <= 2e-10, (it_a, rr_a)
+    xa = s.download(VEC_X)[:part.n_owned]
+    err = np.array([np.sum((xa - xref[own]) ** 2), np.sum(xref[own] ** 2)])
+    t = torch.tensor(err, device=tdev, dtype=torch.float64)
+    dist.all_reduce(t)
+    rel_a = float(torch.sqrt(t[0] / t[1]).item())
+    assert rel_a <= 1e-8 and it_a < iters, (rel_a, it_a, iters)
+    s.set_preconditioner("jacobi")
     # 2b. distributed BiCGStab on the reference (row-replaced, non-symmetric) form: halo before both SpMVs of an
     #     iteration, per-block partials all-reduced in place
     s.assemble_dirichlet_mode(DIRICHLET_ROWS)
@@ -117,6 +129,10 @@ def main():
     se.upload(VEC_X, np.zeros(se.rows))
     it_e, rr_e = se.solve_pcg(1e-10, 50000, negate=True)
     assert rr_e <= 1e-10, (it_e, rr_e)
+    se.set_preconditioner("amg")
+    se.upload(VEC_X, np.zeros(se.rows))
+    it_ea, rr_ea = se.solve_pcg(1e-10, 5000, negate=True)
+    assert rr_ea <= 1e-10 and it_ea < it_e, (it_ea, it_e, rr_ea)
     xl = se.download(VEC_X).reshape(3, nl)[:, :part.n_owned]
     xg = xe.reshape(3, nV)[:, own]
     t = torch.tensor([np.sum((xl - xg) ** 2), np.sum(xg ** 2)], device=tdev, dtype=torch.float64)
@@ -125,7 +141,7 @@ def main():
     assert rel_e <= 1e-8, rel_e
     if rank == 0:
         print(f"DIST_OK world={world} shared_gpu={int(shared)} kind={kind} n={n} iters={iters} relres={relres:.2e} rel_l2={rel:.2e} "
-              f"elasticity iters={it_e} rel_l2={rel_e:.2e}")
+              f"amg iters={it_a} rel_l2={rel_a:.2e} elasticity iters={it_e} (amg {it_ea}) rel_l2={rel_e:.2e}")
     dist.barrier()
     _lib.load().efv_comm_destroy()
     dist.destroy_process_group()
