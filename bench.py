@@ -245,7 +245,7 @@ def run_gpu(args):
     L = _lib.load()
     _lib.check(L.efv_set_device(local_rank))
     stream = torch.cuda.ExternalStream(L.efv_get_stream())
-    n = 368 if (args.workload == "c5" and args.n == 216) else args.n
+    n = args.c5_n if (args.workload == "c5" and args.n == 216) else args.n
     t_host = time.perf_counter()
     gd = P.structured_grid_data(n, "hex")
     keep = []
@@ -308,6 +308,7 @@ def run_gpu(args):
     true_relres = system.true_residual()
     assert true_relres <= 2e-10, f"true residual {true_relres:.3e} of the last timed step exceeds 2e-10"
     field_sums = system.vec_sums(VEC_X)
+    amg_info = system.amg_info() if args.precond == "amg" else None
 
     # ---- roofline of the dominant kernel (SpMV), timed live with CUDA events on the library stream -----------------
     reps = 30
@@ -396,6 +397,12 @@ def run_gpu(args):
     e2e_value = nV / (float(np.mean(e2e_ms)) / 1e3)
     assert np.isfinite(Tfinal).all() and Tfinal.min() > -1e-6 and Tfinal.max() < 1e4
 
+    # ---- the north_star's target case on this GPU count: C5 steady (368^3), strong-scaling base -------------------------
+    c5 = None
+    if not args.no_c5 and n != args.c5_n:
+        from pyefvlib_b200 import distributed as efd
+        c5 = efd.c5_steady(args, 0, 1, BC3D, PROPS, DT, RTOL, stream)
+
     # ---- CPU baseline on a bounded sample (rank 0, N = 1), and the GPU arm once more at exactly that size -------------
     cpu = None
     same = None
@@ -408,7 +415,7 @@ def run_gpu(args):
         else:
             n_cpu = args.cpu_n or 30
             cpu = cpu_port(n_cpu)
-        same = same_config_run(n_cpu, cpu)
+        same = same_config_run(n_cpu, cpu, args.precond)
     # assembly kernel against the HBM roofline with the three byte counts SURVEY 8(d) asks for side by side
     asm_s = float(np.mean(asm_ms)) * 1e-3
     asm_bytes = {"compulsory (coords + connectivity + region in, values + rhs out)": 24.0 * nV + 36.0 * nE + 8.0 * nnz + 8.0 * rows,
@@ -423,10 +430,10 @@ def run_gpu(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{'C5' if n == 368 else 'C2'}: 3D transient heat conduction, structured hex mesh {n}^3 vertices, dt=1e-2, 3-D BC set, "
-                               "PCG(Jacobi) rtol 1e-10, 1 time step per step (assembly + BCs + RHS + solve)",
+                               f"PCG({args.precond}) rtol 1e-10, 1 time step per step (assembly + BCs + RHS + solve)",
                    "vertices": nV, "elements": nE, "nnz": nnz, "pcg_iterations_per_step": timed_iters,
                    "iterations_total": int(np.sum(timed_iters)), "ms_per_iteration": float(np.sum(solve_ms)) / max(1, int(np.sum(timed_iters))),
-                   "true_relres": true_relres, "field_sum": field_sums[0], "field_sum_of_squares": field_sums[1],
+                   "amg": amg_info, "true_relres": true_relres, "field_sum": field_sums[0], "field_sum_of_squares": field_sums[1],
                    "timed_steps": f"time steps 1..{args.steps} from T0 = 0 (fields reset after the {args.warmup} warm-up steps)",
                    "host_mesh_outside_e2e": "the structured mesh arrays are generated on the host before the timed regions "
                                             "(host_mesh_generation_s); e2e starts from those host arrays in pinned memory",
@@ -439,6 +446,7 @@ def run_gpu(args):
         "assembly_roofline": assembly_roofline,
         "cpu_baseline": cpu,
         "same_config_as_cpu_baseline": same,
+        "c5_steady": c5,
         "e2e": {"value": e2e_value, "unit": "DOF/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": float(np.mean(e2e_ms)), "what": "HeatTransferSolver(problemData).solve(), one time step, host arrays in / host field out"},
         "gpu_launches": int(launches2 - launches1),
@@ -457,6 +465,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=0, help="vertices per side of the bounded CPU sample (0: chosen from the time budget)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"], help="preconditioner of the CG solve")
+    ap.add_argument("--no-c5", action="store_true", help="skip the nested C5 steady case (368^3, the north_star target)")
+    ap.add_argument("--c5-n", type=int, default=368, help="vertices per side of the nested C5 case")
     ap.add_argument("--steady", action="store_true", help="(N>1 leg) steady problem instead of one transient step")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2: configs[1] (N>1: weak scaling, one C2 block per GPU); c5: configs[4] 368^3 strong scaling")

@@ -289,39 +289,47 @@ def _peak_gbs():
         return 6650.0
 
 
-def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
-    """N > 1 leg of bench.py: strong scaling of the C5/C2-style problem -- the SAME global mesh is cut into N slabs."""
-    import json
+def _allreduce_max(value, world):
+    if world == 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, steps, warmup, precond, stream):
+    """The hot path on the n x n x nz structured hexahedral mesh cut into `world` vertex-block slabs (world = 1: the whole
+    mesh on one GPU): slab generation on the host, upload + geometry + CSR (setup), then `warmup` + `steps` passes of
+    assembly + BCs + RHS + PCG solve (+ advance).  Transient runs restart from T0 = 0 after the warm-up; steady runs
+    solve from x0 = 0 every time.  Times are CUDA events on the library stream, max over ranks."""
     import time
     import torch
     import torch.distributed as dist
     from . import _lib
     from .device import DIRICHLET_SYMMETRIC, VEC_X, VEC_XOLD
-    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
     L = _lib.load()
-    _lib.check(L.efv_set_device(local_rank))
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    init_comm()
-    stream = torch.cuda.ExternalStream(L.efv_get_stream())
-    n = args.n
-    # default: WEAK scaling of C2 -- every rank owns a 216 x 216 x 216 block of an elongated n x n x (n*world) box;
-    # --workload c5: STRONG scaling of the 368^3 cube (BASELINE.json configs[4])
-    strong = args.workload == "c5"
-    if strong:
-        n = 368 if args.n == 216 else args.n
-        nz = n
-    else:
-        nz = n * world
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
     t0 = time.perf_counter()
     part = structured_part(n, "hex", rank, world, nz=nz)
     host_s = time.perf_counter() - t0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
     system = make_system(part, 1)
+    system.set_preconditioner(precond)
+    e1.record(stream)
+    barrier()
+    setup_ms = _allreduce_max(e0.elapsed_time(e1), world)
     props = np.array([[PROPS["Body"]["Conductivity"], PROPS["Body"]["Density"], PROPS["Body"]["HeatCapacity"], PROPS["Body"]["HeatGeneration"]]])
-    system.upload(VEC_XOLD, np.zeros(system.rows))
-    system.upload(VEC_X, np.zeros(system.rows))
-
-    transient = not getattr(args, "steady", False)
+    zeros = np.zeros(system.rows)
+    system.upload(VEC_XOLD, zeros); system.upload(VEC_X, zeros)
 
     def step():
         send_heat_bcs(system, part, BC3D)
@@ -329,42 +337,120 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
         system.heat_assemble(props, DT, transient)
         system.build_rhs(transient)
         if not transient:
-            system.upload(VEC_X, np.zeros(system.rows))          # steady: every step is the full solve from zero
+            system.upload(VEC_X, zeros)          # steady: every step is the full solve from zero
         it, rr = system.solve_pcg(RTOL, 20000)
         system.advance()
         return it, rr
-    warm = [step()[0] for _ in range(args.warmup)]
+    warm = [step()[0] for _ in range(warmup)]
+    if transient:
+        system.upload(VEC_XOLD, zeros); system.upload(VEC_X, zeros)      # timed steps = time steps 1..K from T0
     launches1 = L.efv_kernel_launch_count()
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record(stream)
     iters, solve_ms, asm_ms = [], [], []
-    for _ in range(args.steps):
+    for _ in range(steps):
         it, rr = step()
         assert rr <= RTOL, f"PCG did not converge on rank {rank}: {rr}"
         iters.append(it)
         tm = system.timings(); solve_ms.append(tm["solve_ms"]); asm_ms.append(tm["assemble_ms"])
     e1.record(stream)
-    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    barrier()
     launches2 = L.efv_kernel_launch_count()
-    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    nV = n * n * nz
-    ms_per_step = total_ms / args.steps
-    # aggregate algorithmic bytes of the PCG iterations (12 nnz + 112 rows per iteration, owned rows only) over the ranks
-    nnz_owned = float(system.nnz)                  # local graph incl. ghost rows (values exist only for owned rows)
-    gb = torch.tensor([(12.0 * 27.0 * part.n_owned + 112.0 * part.n_owned) * float(np.sum(iters)), float(np.sum(solve_ms))],
-                      device="cuda", dtype=torch.float64)
-    gb_sum = gb.clone(); dist.all_reduce(gb_sum)
-    gb_max = gb.clone(); dist.all_reduce(gb_max, op=dist.ReduceOp.MAX)
-    pcg_gbs_total = float(gb_sum[0].item()) / (float(gb_max[1].item()) * 1e-3) / 1e9
-    # e2e: mesh slab upload + setup + one step + field download, through the same Python API
+    total_ms = _allreduce_max(e0.elapsed_time(e1), world)
+    true_relres = system.true_residual()                     # b - A x with one extra SpMV, all-reduced
+    assert true_relres <= 2e-10, f"true residual {true_relres:.3e} exceeds 2e-10"
+    sums = system.vec_sums(VEC_X)
+    out = dict(n=n, nz=nz, vertices=n * n * nz, ms_per_step=total_ms / steps, iterations=iters, warmup_iterations=warm,
+               solve_ms=float(np.mean(solve_ms)), assemble_ms=float(np.mean(asm_ms)), setup_ms=setup_ms, host_slab_generation_s=host_s,
+               true_relres=true_relres, field_sum=sums[0], field_sum_of_squares=sums[1], launches=int(launches2 - launches1),
+               iterations_total=int(np.sum(iters)), ms_per_iteration=float(np.sum(solve_ms)) / max(1, int(np.sum(iters))),
+               n_owned=part.n_owned)
+    if precond == "amg":
+        out["amg"] = system.amg_info()
+    return out, system, part
+
+
+def c5_steady(args, rank, world, BC3D, PROPS, DT, RTOL, stream):
+    """BASELINE.json configs[4] / the north_star target: STEADY heat conduction on the 368^3-vertex mesh (49.8 M vertices),
+    assembled and solved to 1e-10 from x0 = 0, strong scaling (the same mesh on `world` GPUs)."""
+    n = args.c5_n
+    res, system, part = run_partitioned_case(n, n, rank, world, BC3D, PROPS, DT, RTOL, False, 2, 1, args.precond, stream)
+    del system
+    part.grid._device = None
+    return {"workload": f"C5: 3D STEADY heat conduction, structured hex mesh {n}^3 vertices, 3-D BC set, assembled + solved to 1e-10 from "
+                        f"x0 = 0 with PCG({args.precond}); strong scaling over {world} GPU(s)",
+            "n_gpus": world, "vertices": res["vertices"], "time_to_solution_s": res["ms_per_step"] * 1e-3,
+            "dof_per_s": res["vertices"] / (res["ms_per_step"] * 1e-3), "iterations": res["iterations"],
+            "assemble_ms": res["assemble_ms"], "solve_ms": res["solve_ms"], "setup_ms_once": res["setup_ms"],
+            "host_slab_generation_s": res["host_slab_generation_s"], "true_relres": res["true_relres"],
+            "field_sum": res["field_sum"], "field_sum_of_squares": res["field_sum_of_squares"], "amg": res.get("amg")}
+
+
+def cross_check_small(rank, world, BC3D, PROPS, DT, RTOL, precond, stream):
+    """N-GPU against 1-GPU on the same global mesh (24^3): the owned-row checksums of the partitioned solve must equal
+    the sums of a plain single-GPU solve (every rank runs its own copy of it next to the partitioned system)."""
+    from .device import DeviceSystem, DIRICHLET_SYMMETRIC, VEC_X, VEC_XOLD
+    n = 24
+    res, system, part = run_partitioned_case(n, n, rank, world, BC3D, PROPS, DT, RTOL, True, 2, 0, precond, stream)
+    g = _grid.Grid(_grid.structured_grid_data(n, "hex"))
+    single = DeviceSystem(g, 1)
+    single.set_preconditioner(precond)
+    props = np.array([[PROPS["Body"]["Conductivity"], PROPS["Body"]["Density"], PROPS["Body"]["HeatCapacity"], PROPS["Body"]["HeatGeneration"]]])
+    single.upload(VEC_XOLD, np.zeros(single.rows)); single.upload(VEC_X, np.zeros(single.rows))
+    for _ in range(2):
+        single.bc_clear()
+        for b in g.boundaries:
+            kind, val = BC3D[b.name]
+            if kind == "neumann":
+                single.bc_neumann(b.handle, 0, val, 1.0)
+        for b in g.boundaries:
+            kind, val = BC3D[b.name]
+            if kind == "dirichlet":
+                single.bc_dirichlet(b.verticesIndexes, np.full(len(b.verticesIndexes), val))
+        single.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
+        single.heat_assemble(props, DT, True)
+        single.build_rhs(True)
+        single.solve_pcg(RTOL, 20000)
+        single.advance()
+    s1 = single.vec_sums(VEC_X)
+    rel = max(abs(res["field_sum"] - s1[0]) / abs(s1[0]), abs(res["field_sum_of_squares"] - s1[1]) / abs(s1[1]))
+    assert rel <= 1e-9, f"partitioned and single-GPU solutions differ: {rel:.3e}"
+    return {"mesh": f"{n}^3", "n_gpus": world, "field_sum_partitioned": res["field_sum"], "field_sum_single_gpu": s1[0],
+            "field_sum_of_squares_partitioned": res["field_sum_of_squares"], "field_sum_of_squares_single_gpu": s1[1], "max_rel_diff": rel}
+
+
+def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
+    """N > 1 leg of bench.py.  Headline line: WEAK scaling of C2 (every rank owns an n x n x n block of an n x n x (n N) box,
+    same per-GPU work as the N = 1 run), so that the driver's per-N series is one workload.  Nested: the north_star's
+    C5 steady STRONG-scaling case and the N-GPU vs 1-GPU cross-check."""
+    import json
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    L = _lib.load()
+    _lib.check(L.efv_set_device(local_rank))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    init_comm()
+    stream = torch.cuda.ExternalStream(L.efv_get_stream())
+    transient = not getattr(args, "steady", False)
+    strong = args.workload == "c5"
+    n = args.c5_n if strong else args.n
+    nz = n if strong else n * world
+    res, system, part = run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, args.steps, args.warmup, args.precond, stream)
+    nV = res["vertices"]
+    ms_per_step = res["ms_per_step"]
+    # e2e: slab upload + setup + one step + owned field download through the same Python API, host arrays in / host field out
+    import time
+    from .device import DIRICHLET_SYMMETRIC, VEC_X, VEC_XOLD
     del system
     part.grid._device = None
     torch.cuda.synchronize(); dist.barrier()
+    props = np.array([[PROPS["Body"]["Conductivity"], PROPS["Body"]["Density"], PROPS["Body"]["HeatCapacity"], PROPS["Body"]["HeatGeneration"]]])
     t0 = time.perf_counter()
     sys2 = make_system(part, 1)
+    sys2.set_preconditioner(args.precond)
     sys2.upload(VEC_XOLD, np.zeros(sys2.rows)); sys2.upload(VEC_X, np.zeros(sys2.rows))
     send_heat_bcs(sys2, part, BC3D)
     sys2.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
@@ -373,37 +459,52 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     it0, rr0 = sys2.solve_pcg(RTOL, 20000)
     T = sys2.download(VEC_X)[:part.n_owned]
     _lib.check(L.efv_synchronize())
-    e2e_t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = _allreduce_max(time.perf_counter() - t0, world)
     g = part.grid
     h2d = g.coords.nbytes + g.conn.nbytes + g.elem_ptr.nbytes + g.region_of_element.nbytes + g.facet_conn.nbytes + g.facet_ptr.nbytes + 2 * g.numberOfVertices * 8
     hb = torch.tensor([float(h2d), float(part.n_owned * 8)], device="cuda", dtype=torch.float64)
     dist.all_reduce(hb)
+    del sys2
+    part.grid._device = None
+    nested = {}
+    if not args.no_c5 and not strong:
+        nested["c5_steady"] = c5_steady(args, rank, world, BC3D, PROPS, DT, RTOL, stream)
+    nested["cross_check"] = cross_check_small(rank, world, BC3D, PROPS, DT, RTOL, args.precond, stream)
     if rank == 0:
+        # aggregate algorithmic bytes of one solver iteration over the ranks: Jacobi-PCG 12 nnz + 112 rows; multigrid-PCG
+        # 5 passes over the matrix on the finest level + the coarser levels
+        peak = _peak_gbs()
         line = {
             "metric": "heat_transfer_3d_dof_per_s", "value": nV / (ms_per_step / 1e3), "unit": "DOF/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": (f"C5 strong scaling: 3D transient heat conduction, structured hex mesh {n}^3 vertices cut into {world} "
+            "config": {"workload": (f"C5 strong scaling: 3D heat conduction, structured hex mesh {n}^3 vertices cut into {world} "
                                     "vertex-block slabs" if strong else
                                     f"C2 weak scaling: each of the {world} ranks owns a {n}x{n}x{n}-vertex block of an {n}x{n}x{nz} hex box "
                                     "(same spacing, same per-GPU work as the N=1 C2 run)") +
-                                   (", dt=1e-2, 3-D BC set, PCG(Jacobi) rtol 1e-10, 1 time step per step" if transient else
-                                    ", STEADY, 3-D BC set, PCG(Jacobi) rtol 1e-10 from x0 = 0, one full assemble + solve per step"),
-                       "vertices": nV, "pcg_iterations_per_step": iters, "warmup_iterations": warm,
-                       "assemble_ms_per_step": float(np.mean(asm_ms)), "solve_ms_per_step": float(np.mean(solve_ms)),
-                       "solve_dof_per_s": nV / (float(np.mean(solve_ms)) * 1e-3), "time_to_solution_s_per_step": ms_per_step * 1e-3,
-                       "host_slab_generation_s": host_s, "halo": ("peer-memory stores over NVLink (CUDA IPC) + peer-memory all-reduce" if os.environ.get("EFV_COMM", "peer") == "peer" else "NCCL send/recv + ncclAllReduce") + ", one n^2 plane per neighbour per SpMV",
+                                   (f", dt=1e-2, 3-D BC set, PCG({args.precond}) rtol 1e-10, 1 time step per step from T0 = 0" if transient else
+                                    f", STEADY, 3-D BC set, PCG({args.precond}) rtol 1e-10 from x0 = 0, one full assemble + solve per step"),
+                       "vertices": nV, "pcg_iterations_per_step": res["iterations"], "warmup_iterations": res["warmup_iterations"],
+                       "iterations_total": res["iterations_total"], "ms_per_iteration": res["ms_per_iteration"],
+                       "assemble_ms_per_step": res["assemble_ms"], "solve_ms_per_step": res["solve_ms"],
+                       "solve_dof_per_s": nV / (res["solve_ms"] * 1e-3), "time_to_solution_s_per_step": ms_per_step * 1e-3,
+                       "setup_ms": res["setup_ms"], "true_relres": res["true_relres"], "field_sum": res["field_sum"],
+                       "field_sum_of_squares": res["field_sum_of_squares"], "amg": res.get("amg"),
+                       "host_slab_generation_s": res["host_slab_generation_s"],
+                       "host_mesh_outside_e2e": "every rank generates its slab arrays on the host before the timed regions",
+                       "halo": ("peer-memory stores over NVLink (CUDA IPC) + peer-memory all-reduce" if _peer_ok else "NCCL send/recv + ncclAllReduce") + ", one n^2 plane per neighbour per SpMV (and per multigrid level)",
                        "l2_policy": "inputs larger than L2"},
-            "roofline": {"bound": "hbm", "kernel": "PCG iteration (k_spmv_sell + k_pcg_update_xr + k_pcg_update_p), all ranks",
-                         "achieved": pcg_gbs_total, "peak": _peak_gbs() * world, "unit": "GB/s", "frac": pcg_gbs_total / (_peak_gbs() * world),
-                         "traffic": None, "note": "algorithmic bytes 12*27*rows + 112*rows per iteration per rank (interior 27-point rows), "
-                                                  "summed over ranks / slowest rank's solve time; peak = N x measured single-GPU copy bandwidth"},
-            "e2e": {"value": nV / float(e2e_t.item()), "unit": "DOF/s", "h2d_bytes_per_step": int(hb[0].item()),
-                    "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * float(e2e_t.item()),
-                    "what": "per-rank slab upload + setup + assembly + one time-step solve + owned field download"},
-            "gpu_launches": int(launches2 - launches1),
+            "roofline": {"bound": "hbm", "kernel": "k_spmv_sell_tma on the finest level, all ranks (every solver iteration passes over the matrix "
+                                                   + ("5 times: 1 CG product + 4 fused Chebyshev / residual passes of the V-cycle)" if args.precond == "amg" else "once)"),
+                         "achieved": None, "peak": peak * world, "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "the per-kernel roofline (bytes moved / launch time / measured peak) is measured in the N = 1 line; "
+                                 "here: see ms_per_iteration against the N = 1 value"},
+            "e2e": {"value": nV / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": int(hb[0].item()),
+                    "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * e2e_s,
+                    "what": "per-rank slab upload + setup + assembly + one solve + owned field download"},
+            "gpu_launches": res["launches"],
         }
+        line.update(nested)
         print(json.dumps(line))
     dist.barrier()
     L.efv_comm_destroy()
