@@ -544,29 +544,60 @@ void halo_release(Halo &h) {
   cudaGetLastError();
 }
 
+// Peer path, first half: store my interface values into the neighbours' staging buffers and raise their flags.
+// Returns false when the halo has no peer buffers (the caller then uses halo_exchange, i.e. NCCL).
+bool halo_push(Halo &h, const double *vec, int ndof) {
+  if (!h.active || !comm_active()) return false;
+  if (!(h.peer && comm_peer_active())) return false;
+  EFV_REQUIRE(ndof <= h.cap_ndof, "halo exchange wider than the registered capacity");
+  const int n_nbr = (int)h.nbr.size();
+  const int64_t n_send = h.send_ptr[n_nbr];
+  h.seq++;
+  const uint32_t par = h.seq & 1u;
+  HaloPush hp;
+  hp.n = n_nbr;
+  for (int i = 0; i < n_nbr; ++i) {
+    hp.dst[i] = reinterpret_cast<double *>(h.remote[i] + kHaloFlagBytes) + (size_t)par * h.remote_ghosts[i] * h.cap_ndof +
+                h.remote_off[i] * ndof;
+    hp.flag[i] = reinterpret_cast<uint32_t *>(h.remote[i]) + par * kMaxRanks + h.remote_slot[i];
+    hp.begin[i] = h.send_ptr[i];
+  }
+  hp.begin[n_nbr] = n_send;
+  EFV_LAUNCH(k_halo_push, grid_for(std::max<int64_t>(n_send * ndof, 1), 256, 2), 256, 0, hp, h.send_idx.p, ndof, vec, h.seq, h.ticket);
+  return true;
+}
+// What a consumer kernel needs to read the ghosts of the exchange just pushed straight from the staging buffer: it waits
+// for the neighbours' flags only when (and where) it first touches a ghost, so rows without ghosts overlap the transfer.
+HaloIn halo_in(const Halo &h, int ndof) {
+  HaloIn v;
+  const uint32_t par = h.seq & 1u;
+  v.ghost = reinterpret_cast<const double *>(h.stage + kHaloFlagBytes) + (size_t)par * h.n_ghost * h.cap_ndof;
+  v.flags = reinterpret_cast<const uint32_t *>(h.stage) + par * kMaxRanks;
+  v.n_nbr = (int)h.nbr.size();
+  v.seq = h.seq;
+  v.n_owned = h.n_owned;
+  v.err = reinterpret_cast<int *>(g_peer.local + kSlotBytes + kFlagBytes);
+  (void)ndof;
+  return v;
+}
+// Peer path, second half for consumers that need the ghosts inside the vector: wait for the flags, copy behind the owned entries
+void halo_wait_copy(Halo &h, double *vec, int ndof) {
+  const int n_nbr = (int)h.nbr.size();
+  const uint32_t par = h.seq & 1u;
+  const int64_t count = h.n_ghost * ndof;
+  const double *src = reinterpret_cast<const double *>(h.stage + kHaloFlagBytes) + (size_t)par * h.n_ghost * h.cap_ndof;
+  EFV_LAUNCH(k_halo_wait_copy, grid_for(count, 256, 1), 256, 0, h.stage, src, n_nbr, h.seq, count, vec + h.n_owned * ndof,
+             reinterpret_cast<int *>(g_peer.local + kSlotBytes + kFlagBytes));
+}
+
 // ghost entries of `vec` (ndof values per vertex, ndof <= the capacity the halo was registered with) <- owners' values
 void halo_exchange(Halo &h, double *vec, int ndof) {
   if (!h.active || !comm_active()) return;
   EFV_REQUIRE(ndof <= h.cap_ndof, "halo exchange wider than the registered capacity");
   const int n_nbr = (int)h.nbr.size();
   const int64_t n_send = h.send_ptr[n_nbr];
-  if (h.peer && comm_peer_active()) {
-    h.seq++;
-    const uint32_t par = h.seq & 1u;
-    HaloPush hp;
-    hp.n = n_nbr;
-    for (int i = 0; i < n_nbr; ++i) {
-      hp.dst[i] = reinterpret_cast<double *>(h.remote[i] + kHaloFlagBytes) + (size_t)par * h.remote_ghosts[i] * h.cap_ndof +
-                  h.remote_off[i] * ndof;
-      hp.flag[i] = reinterpret_cast<uint32_t *>(h.remote[i]) + par * kMaxRanks + h.remote_slot[i];
-      hp.begin[i] = h.send_ptr[i];
-    }
-    hp.begin[n_nbr] = n_send;
-    EFV_LAUNCH(k_halo_push, grid_for(std::max<int64_t>(n_send * ndof, 1), 256, 2), 256, 0, hp, h.send_idx.p, ndof, vec, h.seq, h.ticket);
-    const int64_t count = h.n_ghost * ndof;
-    const double *src = reinterpret_cast<const double *>(h.stage + kHaloFlagBytes) + (size_t)par * h.n_ghost * h.cap_ndof;
-    EFV_LAUNCH(k_halo_wait_copy, grid_for(count, 256, 1), 256, 0, h.stage, src, n_nbr, h.seq, count, vec + h.n_owned * ndof,
-               reinterpret_cast<int *>(g_peer.local + kSlotBytes + kFlagBytes));
+  if (halo_push(h, vec, ndof)) {
+    halo_wait_copy(h, vec, ndof);
     return;
   }
   require_nccl("halo exchange without peer staging buffers");

@@ -208,6 +208,18 @@ void halo_stage_export(Halo &h, char *out64);
 void halo_stage_import(Halo &h, const char *handles, const int64_t *remote_off, const int *remote_slot, const int64_t *remote_ghosts);
 void halo_release(Halo &h);
 void halo_exchange(Halo &h, double *vec, int ndof);
+// ghosts read from the staging buffer by the consumer kernel itself (krylov.cu: k_spmv_sell_tma)
+struct HaloIn {
+  const double *ghost = nullptr;        // staging values of the current exchange (nullptr: ghosts are inside the vector)
+  const uint32_t *flags = nullptr;      // one per neighbour
+  int n_nbr = 0;
+  uint32_t seq = 0;
+  int64_t n_owned = 0;
+  int *err = nullptr;
+};
+bool halo_push(Halo &h, const double *vec, int ndof);
+HaloIn halo_in(const Halo &h, int ndof);
+void halo_wait_copy(Halo &h, double *vec, int ndof);
 void comm_peer_release();
 void comm_mail_exchange(int npeers, const int *peers, const char *send, char *recv);
 void comm_allgather_i64(int64_t mine, int64_t *all);

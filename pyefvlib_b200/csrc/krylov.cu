@@ -190,7 +190,10 @@ __device__ __host__ __forceinline__ int64_t sell_delta_pos(int64_t o0, int64_t s
 __global__ void k_sell_fill(int64_t nrows, int64_t ncols, int B, int compress, int values_only, const int64_t *__restrict__ gptr,
                             const int32_t *__restrict__ gcol, const double *__restrict__ vals,
                             const int64_t *__restrict__ off, int32_t *__restrict__ scol, int32_t *__restrict__ sdelta,
-                            double *__restrict__ sval) {
+                            double *__restrict__ sval, double *__restrict__ rowabs) {
+  // rowabs (optional): sum_j |a_ij| of every scalar row, for the Gershgorin bound of the multigrid smoother -- this
+  // pass reads every value anyway
+  const int nd = (B == 1) ? 1 : (B == 4 ? 2 : (B == 9 ? 3 : 4));
   // block rows (vertices) of a slice are the lanes; values of entry k are stored as B consecutive 32-lane columns.
   // Index compression: when every lane of a 32-entry column has the same (column - row) offset -- the rule on meshes
   // numbered like a structured grid -- the column is described by that one offset (sdelta) and the kernel never
@@ -205,11 +208,18 @@ __global__ void k_sell_fill(int64_t nrows, int64_t ncols, int B, int compress, i
     const int len = valid ? (int)(gptr[v + 1] - r0) : 0;
     const int width = (int)(off[slice + 1] - off[slice]);
     const int64_t o0 = off[slice];
+    double ra[4] = {0.0, 0.0, 0.0, 0.0};
     if (values_only) {                                             // the index part only depends on the pattern
       for (int k = 0; k < width; ++k) {
         const bool in = k < len;
-        for (int q = 0; q < B; ++q) sval[((o0 + k) * B + q) * 32 + lane] = in ? vals[(r0 + k) * B + q] : 0.0;
+        for (int q = 0; q < B; ++q) {
+          const double a = in ? vals[(r0 + k) * B + q] : 0.0;
+          sval[((o0 + k) * B + q) * 32 + lane] = a;
+          ra[q / nd] += fabs(a);
+        }
       }
+      if (rowabs && valid)
+        for (int i = 0; i < nd; ++i) rowabs[v * nd + i] = ra[i];
       continue;
     }
     for (int k = 0; k < width; ++k) {
@@ -224,8 +234,14 @@ __global__ void k_sell_fill(int64_t nrows, int64_t ncols, int B, int compress, i
       if (!in) col = uniform ? (int32_t)(v + dref) : (int32_t)(valid ? v : 0);
       scol[(o0 + k) * 32 + lane] = col;
       if (lane == 0) sdelta[sell_delta_pos(o0, slice) + k] = uniform ? (int32_t)dref : kNoDelta;
-      for (int q = 0; q < B; ++q) sval[((o0 + k) * B + q) * 32 + lane] = in ? vals[(r0 + k) * B + q] : 0.0;
+      for (int q = 0; q < B; ++q) {
+        const double a = in ? vals[(r0 + k) * B + q] : 0.0;
+        sval[((o0 + k) * B + q) * 32 + lane] = a;
+        ra[q / nd] += fabs(a);
+      }
     }
+    if (rowabs && valid)
+      for (int i = 0; i < nd; ++i) rowabs[v * nd + i] = ra[i];
   }
 }
 template <int U, int MINB>
@@ -315,7 +331,7 @@ template <class C>
 __global__ void __launch_bounds__(C::kWarps * 32, 1)
 k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *__restrict__ scol,
                 const int32_t *__restrict__ sdelta_al, const double *__restrict__ sval, const double *__restrict__ x,
-                SpmvEpi epi, double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar) {
+                SpmvEpi epi, double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar, HaloIn hin) {
   constexpr int kSellChunk = C::kChunk, kSellStages = C::kStages, kSellWarps = C::kWarps;
   constexpr size_t kSellStageBytes = C::kStageBytes;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -378,6 +394,7 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
 #pragma unroll 1
   for (int i = 0; i < kSellStages - 1 && pc.s < s_end; ++i) issue();
   double dot = 0.0, acc = 0.0;
+  bool waited = false;
 #pragma unroll 1
   while (cc.s < s_end) {
     if (pc.s < s_end) issue();
@@ -402,8 +419,27 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
       }
     }
     double xv[kSellChunk];
+    if (hin.ghost == nullptr) {
 #pragma unroll
-    for (int u = 0; u < kSellChunk; ++u) xv[u] = (u < n) ? __ldg(x + idx[u]) : 0.0;
+      for (int u = 0; u < kSellChunk; ++u) xv[u] = (u < n) ? __ldg(x + idx[u]) : 0.0;
+    } else {
+      // partitioned system: ghost entries of x are read straight from the halo staging buffer that the neighbours fill
+      // over NVLink.  The warp waits for their flags the first time it meets a ghost column, so the rows that touch no
+      // ghost (all but the interface planes) run while the transfer is still in flight.
+      const int no = (int)hin.n_owned;
+      bool g = false;
+#pragma unroll
+      for (int u = 0; u < kSellChunk; ++u) g |= (u < n) && (idx[u] >= no);
+      if (!waited && __any_sync(0xffffffffu, g)) {
+        if (lane < hin.n_nbr) peer_wait_flag(hin.flags + lane, hin.seq, hin.err, 2);
+        __syncwarp();
+        __threadfence_system();
+        waited = true;
+      }
+#pragma unroll
+      for (int u = 0; u < kSellChunk; ++u)
+        xv[u] = (u < n) ? (idx[u] < no ? __ldg(x + idx[u]) : __ldcg(hin.ghost + (idx[u] - no))) : 0.0;
+    }
 #pragma unroll
     for (int u = 0; u < kSellChunk; ++u) acc += (u < n) ? sv[u * 32] * xv[u] : 0.0;
     __syncwarp();                                                            // buffer free for the copy issued next turn
@@ -606,7 +642,9 @@ k_spmv_sell_bsr_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_
 }
 
 // (re)build the SELL copy if the values changed; returns whether the SELL path should be used
-bool sell_prepare(efv_system *s, KrylovWork *w) {
+// rowabs (optional, rows entries): filled with sum_j |a_ij| whenever the copy is (re)filled; *rowabs_done tells the caller
+bool sell_prepare(efv_system *s, KrylovWork *w, double *rowabs, bool *rowabs_done) {
+  if (rowabs_done) *rowabs_done = false;
   const char *fmt = getenv("EFV_SPMV_FORMAT");
   if (fmt && strcmp(fmt, "csr") == 0) { w->sell_use = false; return false; }
   w->sell_use = true;
@@ -645,7 +683,8 @@ bool sell_prepare(efv_system *s, KrylovWork *w) {
   const int compress = !(cmp && atoi(cmp) == 0) ? 1 : 0;
   const int values_only = (w->sell_indexed && w->sell_compress == compress) ? 1 : 0;
   EFV_LAUNCH(k_sell_fill, grid_for(nslices * 32, 256), 256, 0, nrows, s->nV, s->ndof * s->ndof, compress, values_only,
-             s->gptr.p, s->gcol.p, s->vals.p, w->sell_off.p, w->sell_cols.p, w->sell_delta.p, w->sell_vals.p);
+             s->gptr.p, s->gcol.p, s->vals.p, w->sell_off.p, w->sell_cols.p, w->sell_delta.p, w->sell_vals.p, rowabs);
+  if (rowabs_done) *rowabs_done = rowabs != nullptr;
   w->sell_indexed = true;
   w->sell_compress = compress;
   return true;
@@ -695,8 +734,34 @@ static void launch_spmv_l(efv_system *s, int grid, const double *x, const SpmvEp
   }
 #undef EFV_SPMV_CASE
 }
+// does the SpMV of this system run on the TMA-staged scalar SELL kernel (the one that can read ghosts from the halo stage)?
+static bool uses_tma_scalar(const efv_system *s) {
+  const KrylovWork *kw = s->kw;
+  const char *ek = getenv("EFV_SELL_KERNEL");
+  return kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned && s->ndof == 1 &&
+         !(ek && strcmp(ek, "reg") == 0);
+}
+// SpMV whose input vector needs its ghosts refreshed first (partitioned systems; plain launch otherwise).  On the peer
+// path the exchange is only PUSHED here; the TMA kernel picks the ghosts up from the staging buffer itself, every other
+// kernel gets them copied behind the owned entries first.
+void spmv_halo(efv_system *s, int grid, double *x, const SpmvEpi &epi, double *partial, const int *done) {
+  if (!is_dist(s)) { launch_spmv(s, grid, x, epi, partial, done); return; }
+  const char *ef = getenv("EFV_HALO_FUSED");
+  if ((ef && atoi(ef) == 0) || !halo_push(s->halo, x, s->ndof)) {
+    halo_exchange(s, x);
+    launch_spmv(s, grid, x, epi, partial, done);
+    return;
+  }
+  if (uses_tma_scalar(s)) {
+    const HaloIn hin = halo_in(s->halo, s->ndof);
+    launch_spmv(s, grid, x, epi, partial, done, PeerAR(), &hin);
+  } else {
+    halo_wait_copy(s->halo, x, s->ndof);
+    launch_spmv(s, grid, x, epi, partial, done);
+  }
+}
 void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi, double *partial, const int *done,
-                 const PeerAR &ar) {
+                 const PeerAR &ar, const HaloIn *hin) {
   KrylovWork *kw = s->kw;
   if (kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned) {
 #define EFV_SELL_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, epi, partial, done, ar
@@ -712,7 +777,7 @@ void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi, d
       configured = true;                                                                                               \
     }                                                                                                                  \
     EFV_LAUNCH(k_spmv_sell_tma<C>, spmv_blocks(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,            \
-               kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar);                                        \
+               kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar, hin ? *hin : HaloIn());                 \
   } while (0)
       const char *ec = getenv("EFV_SELL_TMA");
       switch (ec ? atoi(ec) : 0) {
@@ -963,8 +1028,8 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
   while (!done && it < maxit) {
     int batch_end = std::min(maxit, it + check_every);
     for (; it < batch_end; ++it) {
-      halo_exchange(s, w->p.p);
       if (fused) {
+        halo_exchange(s, w->p.p);
         // the two all-reduces of the iteration ride on the kernels: the last block of the producer publishes to every
         // rank's peer region, the blocks of the consumer wait for all ranks (peer.cuh)
         const PeerAR ar1 = comm_peer_ar(counter), ar2 = comm_peer_ar(counter);
@@ -974,7 +1039,7 @@ void solve_pcg(efv_system *s, double rtol, int maxit, int negate, int *iters, do
         EFV_LAUNCH(k_pcg_update_p, G, kBlock, 0, n, it, w->sc.p, P, G, w->r.p, w->dinv.p, w->p.p, w->flags.p, ar2, (const double *)nullptr, 0);
         continue;
       }
-      launch_spmv(s, G, w->p.p, plain_epi(w->Ap.p, sigma, nullptr, w->p.p), P + 3 * G, w->flags.p);
+      spmv_halo(s, G, w->p.p, plain_epi(w->Ap.p, sigma, nullptr, w->p.p), P + 3 * G, w->flags.p);
       int Gc1 = G;
       const double *c1 = consolidate(s, P + 3 * G, 1, 1, &Gc1);
       Gc = Gc1;

@@ -57,12 +57,13 @@ struct SpmvEpi {
 SpmvEpi plain_epi(double *y, double sigma, const double *rowscale, const double *w);
 
 KrylovWork *work(efv_system *s);
-bool sell_prepare(efv_system *s, KrylovWork *w);
+bool sell_prepare(efv_system *s, KrylovWork *w, double *rowabs = nullptr, bool *rowabs_done = nullptr);
 bool is_dist(const efv_system *s);
 const double *consolidate(efv_system *s, const double *partial, int narr, int slot, int *Gout);
 // y-epilogue(A x) on the owned rows of s (SELL copy when prepared, CSR otherwise); partial: per-block partials of the
 // epilogue's dot product (grid entries), done: device flag that turns the launch into a no-op
 void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi, double *partial, const int *done,
-                 const PeerAR &ar = PeerAR());
+                 const PeerAR &ar = PeerAR(), const HaloIn *hin = nullptr);
+void spmv_halo(efv_system *s, int grid, double *x, const SpmvEpi &epi, double *partial, const int *done);
 
 }  // namespace efv

@@ -18,8 +18,9 @@ def _n_gpus():
         return 0
 
 
-def _run_worker(world, kind, n, shared, port):
+def _run_worker(world, kind, n, shared, port, extra_env=None):
     env = dict(os.environ, EFV_TEST_SHARED_GPU="1" if shared else "0")
+    env.update(extra_env or {})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_worker.py"), kind, str(n)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
@@ -40,11 +41,13 @@ def test_partitioned_heat_matches_oracle(kind, n):
     _run_worker(world, kind, n, False, 29517)
 
 
-@pytest.mark.parametrize("kind,n,world", [("hex", 14, 2), ("tet", 10, 3)])
-def test_partitioned_heat_matches_oracle_shared_gpu(kind, n, world):
+@pytest.mark.parametrize("kind,n,world,extra", [("hex", 14, 2, {}), ("tet", 10, 3, {}),
+                                                # every multigrid level partitioned down to the gathered dense solve, ghosts copied by a kernel
+                                                ("hex", 14, 2, {"EFV_AMG_GATHER_ROWS": "0", "EFV_HALO_FUSED": "0"})])
+def test_partitioned_heat_matches_oracle_shared_gpu(kind, n, world, extra):
     """The same N>1 parity run with all ranks time-sliced on ONE GPU: partition, ghost assembly, peer-memory halo and
     all-reduce (CUDA IPC), distributed PCG / BiCGStab / elasticity against the oracle.  This is the N>1 correctness
     evidence on a single-GPU box."""
     if _n_gpus() < 1:
         pytest.skip("needs a GPU")
-    _run_worker(world, kind, n, True, 29519)
+    _run_worker(world, kind, n, True, 29519, extra)
