@@ -26,8 +26,45 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <string>
 
 namespace efv {
+
+// EFV_AMG_TIMING=1: CUDA events at the phase boundaries of the first iterations of a solve, printed per label after the solve
+// (diagnostics; the events serialise nothing, they only cost their own recording)
+struct PhaseTimer {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> label;
+  size_t used = 0;
+  void mark(const std::string &name) {
+    if (!on || used >= 4000) return;
+    if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); label.push_back(name); }
+    label[used] = name;
+    cudaEventRecord(ev[used++], stream());
+  }
+  void report(int rank, long long rows) {
+    if (!on || used < 2) { used = 0; return; }
+    cudaEventSynchronize(ev[used - 1]);
+    std::vector<std::string> order;
+    std::vector<double> sum;
+    std::vector<int> cnt;
+    for (size_t i = 1; i < used; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      size_t k = 0;
+      for (; k < order.size(); ++k) if (order[k] == label[i]) break;
+      if (k == order.size()) { order.push_back(label[i]); sum.push_back(0); cnt.push_back(0); }
+      sum[k] += ms; cnt[k]++;
+    }
+    fprintf(stderr, "[efv amg timing rank %d rows %lld]", rank, rows);
+    for (size_t k = 0; k < order.size(); ++k) fprintf(stderr, " %s=%.3fms/%d", order[k].c_str(), sum[k], cnt[k]);
+    fprintf(stderr, "\n");
+    used = 0;
+  }
+};
+static PhaseTimer g_pt;
+#define EFV_PT(name) g_pt.mark(name)
 
 constexpr int kMaxDeg = 4;
 constexpr int kCoarsestRows = 256;     // scalar rows of the dense coarsest solve
@@ -896,6 +933,7 @@ static void cycle(AmgHierarchy *H, size_t l, const double *b, double *x, double 
     e.coef = L->coef.p + 4 * step; e.w = dotw;
     spmv_halo(ls, G, const_cast<double *>(din), e, partial, done);
   };
+  const std::string tag = "L" + std::to_string(l);
   // pre-smoothing from x = 0
   if (!first_direction_ready)     // (coarse levels: written by the restriction kernel)
     EFV_LAUNCH(k_first_direction, grid_for(len, 256, 8), 256, 0, len, b, L->dinv.p, L->coef.p, deg == 1 ? x : L->d0.p, done);
@@ -904,18 +942,22 @@ static void cycle(AmgHierarchy *H, size_t l, const double *b, double *x, double 
     cheb(k, din, dout, k == 1 ? (kEpiXZero | kEpiRFromB) : 0, k == deg - 1, nullptr, nullptr);
     std::swap(din, dout);
   }
+  if (g_pt.on) EFV_PT(tag + ".pre");
   // residual, restriction (+ first direction of the next level), coarse solve, over-corrected prolongation
   {
     SpmvEpi e;
     e.mode = kEpiResid; e.sigma = sigma; e.b = b; e.y = L->res.p;
     spmv_halo(ls, G, x, e, nullptr, done);
   }
+  if (g_pt.on) EFV_PT(tag + ".resid");
   AmgLevel *C = H->lv[l + 1];
   const bool c_smooths = l + 2 < H->lv.size() && !C->gathered;
   EFV_LAUNCH(k_restrict, grid_for(C->n * ls->ndof, 256, 8), 256, 0, C->n, ls->ndof, L->mem_ptr.p, L->mem.p, L->res.p, C->b.p,
              c_smooths ? C->dinv.p : (const double *)nullptr, c_smooths ? C->coef.p : (const double *)nullptr,
              c_smooths ? (H->deg == 1 ? C->x.p : C->d0.p) : (double *)nullptr, done);
+  if (g_pt.on) EFV_PT(tag + ".restrict");
   cycle(H, l + 1, C->b.p, C->x.p, sigma, nullptr, done, true);
+  if (g_pt.on) EFV_PT(tag + ".coarse_tail");
   EFV_LAUNCH(k_prolong, grid_for(len, 256, 8), 256, 0, L->n, ls->ndof, L->agg.p, C->x.p, H->scale, x, done);
   // post-smoothing
   {
@@ -934,6 +976,7 @@ static void cycle(AmgHierarchy *H, size_t l, const double *b, double *x, double 
     cheb(k, din, dout, 0, last, last && rz_partial ? b : nullptr, last ? rz_partial : nullptr);
     std::swap(din, dout);
   }
+  if (g_pt.on) EFV_PT(tag + ".post");
 }
 
 // ---- CG preconditioned by the cycle ----------------------------------------------------------------------------------------------------
@@ -1053,23 +1096,30 @@ void solve_pcg_amg(efv_system *s, double rtol, int maxit, int negate, int *iters
   int it = 0;
   bool done = false;
   const int check_every = (n > 200000) ? 1 : 4;
+  { const char *et = getenv("EFV_AMG_TIMING"); g_pt.on = et && atoi(et) == 1; }
+  EFV_PT("start");
   while (!done && it < maxit) {
     const int batch_end = std::min(maxit, it + check_every);
     for (; it < batch_end; ++it) {
       spmv_halo(s, G, w->p.p, plain_epi(w->Ap.p, sigma, nullptr, w->p.p), P + 3 * G, w->flags.p);
+      EFV_PT("cg.spmv");
       const double *cp = consolidate(s, P + 3 * G, 1, 1, &Gp);
       EFV_LAUNCH(k_mg_xr, G, 256, 0, n, w->sc.p, cp, Gp, w->p.p, w->Ap.p, s->x.p, w->r.p, P, w->flags.p);
       const double *cr = consolidate(s, P, 1, 2, &Gr);
       EFV_LAUNCH(k_mg_check, 1, 256, 0, it, cp, Gp, cr, Gr, w->sc.p, w->flags.p);
+      EFV_PT("cg.xr_check");
       cycle(H, 0, w->r.p, z, sigma, P + G, w->flags.p, false);
       const double *cz2 = consolidate(s, P + G, 1, 3, &Gz);
       EFV_LAUNCH(k_mg_p, G, 256, 0, n, w->sc.p, cz2, Gz, z, w->p.p, w->flags.p);
       EFV_LAUNCH(k_mg_store_rz, 1, 256, 0, cz2, Gz, w->sc.p, w->flags.p);
+      EFV_PT("cg.p");
     }
     EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
     EFV_CUDA(cudaStreamSynchronize(stream()));
     done = w->h_flags[0] != 0;
+    EFV_PT("cg.poll");
   }
+  g_pt.report(comm_rank(), (long long)n);
   EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
   EFV_CUDA(cudaMemcpyAsync(w->h_sc, w->sc.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, stream()));
   EFV_CUDA(cudaEventRecord(t1, stream()));

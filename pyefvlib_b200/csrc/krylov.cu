@@ -96,6 +96,39 @@ __device__ __forceinline__ double epi_apply(const SpmvEpi &e, int64_t i, double 
     }
   }
 }
+// The same epilogue split in two for the persistent TMA kernel: the row-wise operands of a Chebyshev step are loaded when
+// the warp STARTS a slice, so that their latency hides behind the slice's gathers instead of stalling the warp at its end
+// (measured: 0.63 -> see DESIGN.md ms per fused smoothing pass at C2, against 0.44 ms for the plain product).
+struct EpiOperands { double dinv, rb, dprev, x0; };
+__device__ __forceinline__ void epi_prefetch(const SpmvEpi &e, int64_t i, EpiOperands &o) {
+  if (e.mode < kEpiChebFirst) return;
+  o.dinv = e.dinv[i];
+  if (e.mode == kEpiChebFirst) { o.rb = e.b[i]; return; }
+  o.rb = (e.flags & kEpiRFromB) ? e.b[i] : e.r_in[i];
+  o.dprev = e.d_in[i];
+  o.x0 = (e.flags & kEpiXZero) ? 0.0 : e.x[i];
+}
+__device__ __forceinline__ double epi_finish(const SpmvEpi &e, const EpiOperands &o, int64_t i, double acc) {
+  if (e.mode < kEpiChebFirst) return epi_apply(e, i, acc);
+  const double av = e.sigma * acc;
+  if (e.mode == kEpiChebFirst) {
+    const double r = o.dinv * (o.rb - av);
+    e.r_out[i] = r;
+    e.d_out[i] = r * e.coef[0];
+    return 0.0;
+  }
+  const double r = ((e.flags & kEpiRFromB) ? o.dinv * o.rb : o.rb) - o.dinv * av;
+  const double dn = e.coef[1] * o.dprev + e.coef[2] * r;
+  if (e.mode == kEpiChebMid) {
+    e.r_out[i] = r;
+    e.d_out[i] = dn;
+    e.x[i] = o.x0 + o.dprev;
+    return 0.0;
+  }
+  const double xi = o.x0 + o.dprev + dn;
+  e.x[i] = xi;
+  return e.w ? e.w[i] * xi : 0.0;
+}
 SpmvEpi plain_epi(double *y, double sigma, const double *rowscale, const double *w) {
   SpmvEpi e;
   e.y = y; e.sigma = sigma; e.rowscale = rowscale; e.w = w;
@@ -327,7 +360,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
-template <class C>
+template <class C, bool HALO>
 __global__ void __launch_bounds__(C::kWarps * 32, 1)
 k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *__restrict__ scol,
                 const int32_t *__restrict__ sdelta_al, const double *__restrict__ sval, const double *__restrict__ x,
@@ -395,9 +428,14 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
   for (int i = 0; i < kSellStages - 1 && pc.s < s_end; ++i) issue();
   double dot = 0.0, acc = 0.0;
   bool waited = false;
+  EpiOperands eo = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
   while (cc.s < s_end) {
     if (pc.s < s_end) issue();
+    if (cc.k == 0) {                                                         // new slice: start loading its epilogue operands
+      const int64_t v0 = cc.s * 32 + lane;
+      if (v0 < nrows && epi.prefetch) epi_prefetch(epi, v0, eo);
+    }
     const unsigned st = consumed % kSellStages;
     mbar_wait(smem_u32(bars + st), (consumed / kSellStages) & 1u);
     const int n = min(kSellChunk, cc.width - cc.k);
@@ -419,7 +457,7 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
       }
     }
     double xv[kSellChunk];
-    if (hin.ghost == nullptr) {
+    if (!HALO) {
 #pragma unroll
       for (int u = 0; u < kSellChunk; ++u) xv[u] = (u < n) ? __ldg(x + idx[u]) : 0.0;
     } else {
@@ -436,9 +474,15 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
         __threadfence_system();
         waited = true;
       }
+      // one load instruction for owned and ghost entries (mixing load flavours between the gathers serialises them on the
+      // scoreboard): the ghost block is addressed relative to x.  Plain cached loads are safe for the ghosts: L1 is
+      // invalidated at kernel start and no thread reads a ghost line before the flags of this exchange were seen.
+      const int64_t gofs = (hin.ghost - x) - (int64_t)no;
 #pragma unroll
-      for (int u = 0; u < kSellChunk; ++u)
-        xv[u] = (u < n) ? (idx[u] < no ? __ldg(x + idx[u]) : __ldcg(hin.ghost + (idx[u] - no))) : 0.0;
+      for (int u = 0; u < kSellChunk; ++u) {
+        const int64_t a = (int64_t)idx[u] + (idx[u] >= no ? gofs : (int64_t)0);
+        xv[u] = (u < n) ? x[a] : 0.0;
+      }
     }
 #pragma unroll
     for (int u = 0; u < kSellChunk; ++u) acc += (u < n) ? sv[u * 32] * xv[u] : 0.0;
@@ -447,7 +491,7 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
     cc.k += kSellChunk;
     if (cc.k >= cc.width) {
       const int64_t v = cc.s * 32 + lane;
-      if (v < nrows) dot += epi_apply(epi, v, acc);
+      if (v < nrows) dot += epi.prefetch ? epi_finish(epi, eo, v, acc) : epi_apply(epi, v, acc);
       acc = 0.0;
       ++cc.s;
       cc.k = 0;
@@ -671,7 +715,9 @@ bool sell_prepare(efv_system *s, KrylovWork *w, double *rowabs, bool *rowabs_don
       nnz_owned = ends[1] - ends[0];
     }
     const bool force = fmt && strcmp(fmt, "sell") == 0;
-    w->sell_ok = force || padded <= 1.2 * (double)nnz_owned;      // irregular rows: stay on CSR
+    // irregular rows: stay on CSR; so do small matrices (coarse multigrid levels), where the persistent one-block-per-SM
+    // kernels cost 10-17 us against 5 us of the plain CSR kernel
+    w->sell_ok = force || (padded <= 1.2 * (double)nnz_owned && nrows >= 32768);
     if (!w->sell_ok) { w->sell_cols.release(); w->sell_delta.release(); w->sell_vals.release(); return false; }
     w->sell_indexed = false;
     w->sell_cols.alloc((size_t)cols32 * 32);
@@ -746,8 +792,10 @@ static bool uses_tma_scalar(const efv_system *s) {
 // kernel gets them copied behind the owned entries first.
 void spmv_halo(efv_system *s, int grid, double *x, const SpmvEpi &epi, double *partial, const int *done) {
   if (!is_dist(s)) { launch_spmv(s, grid, x, epi, partial, done); return; }
+  // EFV_HALO_FUSED=1 (opt-in): measured SLOWER at N = 2 (5.11 vs 4.60 ms per multigrid-CG iteration at C2 weak): the
+  // per-gather ghost test costs more in the issue-bound main loop than the copy kernel and the exposed latency it saves
   const char *ef = getenv("EFV_HALO_FUSED");
-  if ((ef && atoi(ef) == 0) || !halo_push(s->halo, x, s->ndof)) {
+  if (!(ef && atoi(ef) == 1) || !halo_push(s->halo, x, s->ndof)) {
     halo_exchange(s, x);
     launch_spmv(s, grid, x, epi, partial, done);
     return;
@@ -760,8 +808,10 @@ void spmv_halo(efv_system *s, int grid, double *x, const SpmvEpi &epi, double *p
     launch_spmv(s, grid, x, epi, partial, done);
   }
 }
-void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi, double *partial, const int *done,
+void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi_in, double *partial, const int *done,
                  const PeerAR &ar, const HaloIn *hin) {
+  SpmvEpi epi = epi_in;
+  { static const int pf = [] { const char *e = getenv("EFV_EPI_PREFETCH"); return (e && atoi(e) == 0) ? 0 : 1; }(); epi.prefetch = pf; }
   KrylovWork *kw = s->kw;
   if (kw && kw->sell_use && kw->sell_ok && kw->sell_version == s->vals_version && kw->sell_rows == s->n_owned) {
 #define EFV_SELL_ARGS s->n_owned, kw->sell_off.p, kw->sell_cols.p, kw->sell_vals.p, x, epi, partial, done, ar
@@ -773,11 +823,16 @@ void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi, d
     using C = SellTma<CH, ST, W>;                                                                                      \
     static bool configured = false;                                                                                    \
     if (!configured) {                                                                                                 \
-      EFV_CUDA(cudaFuncSetAttribute(k_spmv_sell_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));  \
+      EFV_CUDA(cudaFuncSetAttribute((k_spmv_sell_tma<C, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));  \
+      EFV_CUDA(cudaFuncSetAttribute((k_spmv_sell_tma<C, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));   \
       configured = true;                                                                                               \
     }                                                                                                                  \
-    EFV_LAUNCH(k_spmv_sell_tma<C>, spmv_blocks(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,            \
-               kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar, hin ? *hin : HaloIn());                 \
+    if (hin)                                                                                                           \
+      EFV_LAUNCH((k_spmv_sell_tma<C, true>), spmv_blocks(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,  \
+                 kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar, *hin);                              \
+    else                                                                                                               \
+      EFV_LAUNCH((k_spmv_sell_tma<C, false>), spmv_blocks(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p, \
+                 kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar, HaloIn());                          \
   } while (0)
       const char *ec = getenv("EFV_SELL_TMA");
       switch (ec ? atoi(ec) : 0) {

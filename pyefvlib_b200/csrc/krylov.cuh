@@ -48,6 +48,7 @@ enum { kEpiXZero = 1, kEpiRFromB = 2 };
 // what a SpMV kernel does with (A v)_i at the end of a row: see epi_apply in krylov.cu
 struct SpmvEpi {
   int mode = kEpiPlain, flags = 0;
+  int prefetch = 1;                    // TMA kernel: load the row-wise operands at the start of a slice (EFV_EPI_PREFETCH=0: at its end)
   double sigma = 1.0;
   double *y = nullptr;
   const double *rowscale = nullptr, *w = nullptr;

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -27,6 +28,10 @@ static void ensure_init() {
   EFV_CUDA(cudaGetDeviceProperties(&prop, g_device));
   g_num_sms = prop.multiProcessorCount;
   EFV_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  if (const char *cc = getenv("EFV_CACHE_CONFIG")) {      // experiment: one shared-memory carveout for every kernel
+    if (strcmp(cc, "shared") == 0) cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
+    if (strcmp(cc, "l1") == 0) cudaDeviceSetCacheConfig(cudaFuncCachePreferL1);
+  }
   cudaMemPool_t pool;
   EFV_CUDA(cudaDeviceGetDefaultMemPool(&pool, g_device));
   uint64_t keep = UINT64_MAX;

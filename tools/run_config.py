@@ -33,6 +33,7 @@ if which == "c3":
             kind, val = bcs[var].get(b.name, N0)
             if kind == "dirichlet":
                 s.bc_dirichlet(b.verticesIndexes + i * nV, np.full(len(b.verticesIndexes), val))
+    s.set_preconditioner(os.environ.get("PRECOND", "amg"))
     s.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
     s.elasticity_assemble(np.array([[6.0e6, 0.4, 1800.0, 0.0]]), False)
     s.build_rhs(False)
@@ -42,7 +43,8 @@ if which == "c3":
     x = s.download(VEC_X)
     out = dict(config="C3 elasticity tets", n=n, vertices=nV, elements=grid.numberOfElements, rows=s.rows, nnz=s.nnz,
                pcg_iterations=it, relres=rr, assemble_ms=tm["assemble_ms"], solve_ms=tm["solve_ms"], setup_s=setup_s,
-               host_mesh_s=host_s, v_min=float(x[nV:2 * nV].min()), dof_per_s=s.rows / (1e-3 * (tm["assemble_ms"] + tm["solve_ms"])),
+               host_mesh_s=host_s, v_min=float(x[nV:2 * nV].min()), true_relres=s.true_residual(negate=True),
+               preconditioner=os.environ.get("PRECOND", "amg"), amg=(s.amg_info() if os.environ.get("PRECOND", "amg") == "amg" else None), dof_per_s=s.rows / (1e-3 * (tm["assemble_ms"] + tm["solve_ms"])),
                iteration_GBs=(s.graph_nnz * (72 + 4) + s.rows * 112) * it / (tm["solve_ms"] * 1e-3) / 1e9)
 else:
     props = np.array([[0.2, 6.0e9, 0.0, 0.19, 1.9e-15, 3.0303e-10, 1000.0, 2700.0, 1000.0]])     # apps/geomechanics.py:292-304
