@@ -128,6 +128,12 @@ int efv_bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, i
  * DOF adds its flux to the prescribed value (the elasticity app visits boundary by boundary, stress_equilibrium.py:119-163);
  * a later Dirichlet call overwrites it.                                                                              */
 int efv_bc_neumann(efv_system *s, int boundary, int dof, double value, double sign);
+/* variable Neumann condition: one value per OUTER FACE of the boundary, in the reference's visiting order (facet by facet,
+ * outer face by outer face); efv_boundary_outer_faces returns their number and the global number of the first one.
+ * The host layer evaluates the expression exactly where the reference does [ref: apps/heat_transfer.py:116-120 calls
+ * getValue(outerFace.handle), i.e. at the vertex whose NUMBER equals the outer face's global counter, Boundary.py:74]. */
+int64_t efv_boundary_outer_faces(const efv_mesh *m, int boundary, int64_t *first);
+int efv_bc_neumann_values(efv_system *s, int boundary, int dof, const double *values, int64_t n, double sign);
 /* how the next assembly call treats the recorded Dirichlet set: -1 leave the interior operator (apply later with
  * efv_apply_dirichlet), EFV_DIRICHLET_ROWS or EFV_DIRICHLET_SYMMETRIC applied inside the assembly kernel.          */
 int efv_assemble_dirichlet_mode(efv_system *s, int mode);

@@ -62,6 +62,8 @@ PROTOTYPES = {
     "efv_bc_clear": (C.c_int, [C.c_void_p]),
     "efv_bc_dirichlet": (C.c_int, [C.c_void_p, c_i64p, c_f64p, C.c_int64]),
     "efv_bc_neumann": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "efv_boundary_outer_faces": (C.c_int64, [C.c_void_p, C.c_int, c_i64p]),
+    "efv_bc_neumann_values": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_f64p, C.c_int64, C.c_double]),
     "efv_assemble_dirichlet_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_apply_dirichlet": (C.c_int, [C.c_void_p, C.c_int]),
     "efv_build_rhs": (C.c_int, [C.c_void_p, C.c_int]),

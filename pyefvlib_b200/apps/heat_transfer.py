@@ -80,9 +80,9 @@ class HeatTransferSolver(Solver):
         s.bc_clear()
         for bc in self.problemData.neumannBoundaries["temperature"]:         # heat_transfer.py:115-120
             if bc.expression:
-                raise Exception("Variable Neumann conditions are not supported on the GPU backend "
-                                "(the reference evaluates them with an outer-face handle, heat_transfer.py:120)")
-            s.bc_neumann(bc.boundary.handle, 0, bc.value, 1.0)
+                s.bc_neumann_expression(bc, 0, 0.0, 1.0)              # getValue(handle) without a time: t = 0 (heat_transfer.py:120)
+            else:
+                s.bc_neumann(bc.boundary.handle, 0, bc.value, 1.0)
         for bc in self.problemData.dirichletBoundaries["temperature"]:       # heat_transfer.py:70-76, 122-126
             s.bc_dirichlet(bc.boundary.verticesIndexes, bc.values_on_vertices(self.currentTime))
 

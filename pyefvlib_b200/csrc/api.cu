@@ -326,6 +326,20 @@ int efv_bc_neumann(efv_system *s, int boundary, int dof, double value, double si
   efv::bc_neumann(s, boundary, dof, value, sign);
   EFV_API_END
 }
+int64_t efv_boundary_outer_faces(const efv_mesh *m, int boundary, int64_t *first) {
+  if (!m || boundary < 0 || boundary >= m->bnd.nB) return -1;
+  if (first) *first = m->bnd.outer_ptr_host[boundary];
+  return m->bnd.outer_ptr_host[boundary + 1] - m->bnd.outer_ptr_host[boundary];
+}
+int efv_bc_neumann_values(efv_system *s, int boundary, int dof, const double *values, int64_t n, double sign) {
+  EFV_API_BEGIN
+  EFV_REQUIRE(s && values, "null argument");
+  EFV_REQUIRE(s->mesh, "this system has no mesh (created from a CSR pattern)");
+  EFV_REQUIRE(boundary >= 0 && boundary < s->mesh->bnd.nB, "bad boundary index");
+  EFV_REQUIRE(n == s->mesh->bnd.outer_ptr_host[boundary + 1] - s->mesh->bnd.outer_ptr_host[boundary], "one value per outer face of the boundary");
+  efv::bc_neumann(s, boundary, dof, 0.0, sign, values);
+  EFV_API_END
+}
 int efv_assemble_dirichlet_mode(efv_system *s, int mode) {
   EFV_API_BEGIN
   EFV_REQUIRE(s, "null system");

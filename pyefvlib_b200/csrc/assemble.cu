@@ -1371,14 +1371,14 @@ void bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int6
 // reference's facet order (heat_transfer.py:115-120) -> deterministic
 __global__ void k_neumann(int64_t nbv, const int32_t *__restrict__ bv, const int64_t *__restrict__ bvo_ptr,
                           const int64_t *__restrict__ bvo, const double *__restrict__ norm, int64_t o0, int64_t o1,
-                          int ndof, int dof, double coef, double *__restrict__ rhs, const uint8_t *__restrict__ dflag,
-                          double *__restrict__ dvalue) {
+                          int ndof, int dof, double coef, const double *__restrict__ per_face, double *__restrict__ rhs,
+                          const uint8_t *__restrict__ dflag, double *__restrict__ dvalue) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nbv; k += (int64_t)gridDim.x * blockDim.x) {
     double acc = 0.0;
     bool any = false;
     for (int64_t p = bvo_ptr[k]; p < bvo_ptr[k + 1]; ++p) {
       int64_t o = bvo[p];
-      if (o >= o0 && o < o1) { acc += coef * norm[o]; any = true; }
+      if (o >= o0 && o < o1) { acc += (per_face ? coef * per_face[o - o0] : coef) * norm[o]; any = true; }
     }
     if (any) {
       const int64_t idx = (int64_t)bv[k] * ndof + dof;
@@ -1391,16 +1391,21 @@ __global__ void k_neumann(int64_t nbv, const int32_t *__restrict__ bv, const int
   }
 }
 
-void bc_neumann(efv_system *s, int boundary, int dof, double value, double sign) {
+// values == nullptr: the constant `value` on every outer face; otherwise one value per outer face of the boundary, in the
+// reference's visiting order (facet by facet, outer face by outer face: Boundary.py:62-75)
+void bc_neumann(efv_system *s, int boundary, int dof, double value, double sign, const double *values) {
   efv_mesh *m = s->mesh;
   Boundaries &B = m->bnd;
   EFV_REQUIRE(boundary >= 0 && boundary < B.nB, "bad boundary index");
   EFV_REQUIRE(dof >= 0 && dof < s->ndof, "bad dof");
   if (!s->dir_flag.n) bc_clear(s);
-  if (value == 0.0 || B.nbv == 0) return;
-  EFV_LAUNCH(k_neumann, grid_for(B.nbv, 128), 128, 0, B.nbv, B.bv.p, B.bvo_ptr.p, B.bvo.p, B.outer_area_norm.p,
-             B.outer_ptr_host[boundary], B.outer_ptr_host[boundary + 1], s->ndof, dof, sign * value, s->static_rhs.p, s->dir_flag.p,
-             s->dir_value.p);
+  if ((!values && value == 0.0) || B.nbv == 0) return;
+  const int64_t o0 = B.outer_ptr_host[boundary], o1 = B.outer_ptr_host[boundary + 1];
+  DBuf<double> dv;
+  if (values) dv.upload(values, (size_t)(o1 - o0));
+  EFV_LAUNCH(k_neumann, grid_for(B.nbv, 128), 128, 0, B.nbv, B.bv.p, B.bvo_ptr.p, B.bvo.p, B.outer_area_norm.p, o0, o1, s->ndof, dof,
+             values ? sign : sign * value, values ? dv.p : (const double *)nullptr, s->static_rhs.p, s->dir_flag.p, s->dir_value.p);
+  if (values) EFV_CUDA(cudaStreamSynchronize(stream()));      // dv is released on return
 }
 
 // Dirichlet on the matrix: GROUP lanes per row-vertex.

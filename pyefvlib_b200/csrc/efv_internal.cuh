@@ -164,7 +164,7 @@ void elasticity_assemble(efv_system *s, const double *props_host, int gravity);
 void biot_assemble(efv_system *s, const double *props_host, double dt, const double *gvec);
 void bc_clear(efv_system *s);
 void bc_dirichlet(efv_system *s, const int64_t *rows, const double *values, int64_t n);
-void bc_neumann(efv_system *s, int boundary, int dof, double value, double sign);
+void bc_neumann(efv_system *s, int boundary, int dof, double value, double sign, const double *values = nullptr);
 void apply_dirichlet(efv_system *s, int mode);
 void build_rhs(efv_system *s, int transient);
 void ensure_vectors(efv_system *s);

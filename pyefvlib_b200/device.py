@@ -189,6 +189,18 @@ class DeviceSystem:
     def bc_neumann(self, boundary, dof, value, sign=1.0):
         _lib.check(_lib.load().efv_bc_neumann(self.handle, int(boundary), int(dof), float(value), float(sign)))
 
+    def bc_neumann_expression(self, bc, dof, time=0.0, sign=1.0):
+        """Variable Neumann condition.  The reference evaluates bc.getValue(outerFace.handle) (apps/heat_transfer.py:116-120):
+        the expression at the coordinates of the VERTEX whose number is the outer face's global counter (Boundary.py:74) --
+        reproduced as is, including its IndexError when the counter exceeds the number of vertices."""
+        first = C.c_int64(0)
+        n = _lib.load().efv_boundary_outer_faces(self.mesh.handle, int(bc.boundary.handle), C.byref(first))
+        if first.value + n > self.grid.numberOfVertices:
+            raise IndexError("index %d is out of bounds for axis 0 with size %d" % (first.value + n - 1, self.grid.numberOfVertices))
+        vals = np.array([bc.getValue(first.value + k, time) for k in range(n)], dtype=np.float64)
+        v, pv = _lib.f64(vals)
+        _lib.check(_lib.load().efv_bc_neumann_values(self.handle, int(bc.boundary.handle), int(dof), pv, n, float(sign)))
+
     def assemble_dirichlet_mode(self, mode):
         """Dirichlet treatment fused into the next assembly kernel (-1 = none)."""
         _lib.check(_lib.load().efv_assemble_dirichlet_mode(self.handle, int(mode)))

@@ -187,3 +187,26 @@ def test_heat_app_writes_vtu_results(tag, saverType, tmp_path):
         for k in range(steps):
             data = point_data(os.path.join(str(tmp_path), sets[k + 1].get("file")))
             assert util.rel_l2(data, z["heatT_fields"][k]) <= 1e-8
+
+
+def test_heat_variable_neumann_matches_reference():
+    """Expression-valued Neumann conditions: RHS and field of the UNMODIFIED reference (oracle/make_golden_variable_neumann.py),
+    including its evaluation point (the vertex numbered like the outer face's global counter, apps/heat_transfer.py:120)."""
+    from pyefvlib_b200.apps.heat_transfer import heatTransfer
+    z = util.load("heat_Square")
+    g = np.load(util.GOLDEN + "/heat_Square_variable_neumann.npz")
+    grid = util.product_grid(z)
+    expr = dict(zip([str(s) for s in g["expr_names"]], [str(s) for s in g["expr"]]))
+    bc = {"InitialValue": 0.0}
+    for b in grid.boundaries:
+        if b.name in expr:
+            bc[b.name] = {"condition": P.Neumann, "type": P.Variable, "value": expr[b.name]}
+        elif b.name == "West":
+            bc[b.name] = {"condition": P.Dirichlet, "type": P.Constant, "value": 300.0}
+        else:
+            bc[b.name] = {"condition": P.Neumann, "type": P.Constant, "value": 0.0}
+    pd = P.ProblemData(grid, P.PropertyData(HEAT_CASES["Square"]["props"]), P.BoundaryConditions({"temperature": bc}),
+                       P.NumericalSettings(timeStep=0.01, finalTime=None, tolerance=1e-6, maxNumberOfIterations=5))
+    s = heatTransfer(pd, transient=False, verbosity=False)
+    assert util.rel_max(s.independent, g["rhs"]) <= 1e-12
+    assert util.rel_l2(s.temperatureField, g["T"]) <= 1e-8

@@ -153,7 +153,7 @@ def test_mixed_mesh_elasticity_and_biot_against_oracle():
     Ab, bbv = O.biot_system(og, bp, bb, 20.0, u_old, p_old)
     assert util.row_rel_matrix_error(sb.to_scipy(), Ab) <= 1e-12
     scale = np.maximum(np.abs(bbv), abs(Ab) @ np.abs(np.concatenate([u_old, p_old])))
-    assert (np.abs(sb.download(D.VEC_B) - bbv) / np.maximum(scale, 1e-300)).max() <= 1e-11
+    assert (np.abs(sb.download(D.VEC_B) - bbv) / np.maximum(scale, 1e-300)).max() <= 1e-12
 
 
 def test_bad_connectivity_is_rejected():
