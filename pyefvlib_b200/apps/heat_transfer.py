@@ -75,14 +75,17 @@ class HeatTransferSolver(Solver):
             self.saver.save("temperature", self.temperatureField, self.currentTime)
 
     # -- boundary conditions in the reference's visiting order ----------------------------------------------------
+    def _send_neumann(self, system):
+        for bc in self.problemData.neumannBoundaries["temperature"]:         # heat_transfer.py:115-120
+            if bc.expression:
+                system.bc_neumann_expression(bc, 0, 0.0, 1.0)         # getValue(handle) without a time: t = 0 (heat_transfer.py:120)
+            else:
+                system.bc_neumann(bc.boundary.handle, 0, bc.value, 1.0)
+
     def _send_boundary_conditions(self):
         s = self.system
         s.bc_clear()
-        for bc in self.problemData.neumannBoundaries["temperature"]:         # heat_transfer.py:115-120
-            if bc.expression:
-                s.bc_neumann_expression(bc, 0, 0.0, 1.0)              # getValue(handle) without a time: t = 0 (heat_transfer.py:120)
-            else:
-                s.bc_neumann(bc.boundary.handle, 0, bc.value, 1.0)
+        self._send_neumann(s)
         for bc in self.problemData.dirichletBoundaries["temperature"]:       # heat_transfer.py:70-76, 122-126
             s.bc_dirichlet(bc.boundary.verticesIndexes, bc.values_on_vertices(self.currentTime))
 
@@ -120,8 +123,7 @@ class HeatTransferSolver(Solver):
             return self.system.download(VEC_B)
         tmp = DeviceSystem(self.grid, 1)
         tmp.heat_assemble(self.propertyData.table(PROPERTY_NAMES), self.timeStep, self.transient)
-        for bc in self.problemData.neumannBoundaries["temperature"]:
-            tmp.bc_neumann(bc.boundary.handle, 0, bc.value, 1.0)
+        self._send_neumann(tmp)
         for bc in self.problemData.dirichletBoundaries["temperature"]:
             tmp.bc_dirichlet(bc.boundary.verticesIndexes, bc.values_on_vertices(self.currentTime))
         tmp.apply_dirichlet(DIRICHLET_ROWS)

@@ -209,202 +209,6 @@ __global__ void __launch_bounds__(256) k_heat_rows(MeshView m, GeomView g, SysVi
   }
 }
 
-// ---- two-phase assembly for uniform meshes (EFV_ASSEMBLY=two_phase; measured slower than the fused row kernel) ---------------------------------------------------------
-// Phase A `k_heat_local`: one thread per element of an element batch, fully unrolled: the 12 (hex) face vectors J^-T s
-// are streamed from the SoA, the table entries are constant-bank operands, the M x M local matrix lives in registers
-// and is written, transposed through shared memory, into an element-major scratch array  Ke[e][i*M+j].
-// Phase B `k_gather_entries`: deterministic segmented reduction through the TRANSPOSED slot map (k_build_tmap, once per
-// pattern): one lane per CSR entry sums that entry's contributions in a fixed order and the warp writes the row with
-// coalesced stores (plus accumulation term and Dirichlet epilogue).  No float atomics anywhere.
-template <class Tab>
-__global__ void __launch_bounds__(128) k_heat_local(int64_t n, const int32_t *__restrict__ region, const double *__restrict__ props,
-                                                    const double *__restrict__ St, double *__restrict__ Ke) {
-  constexpr int M = Tab::M, D = Tab::DIM, NF = Tab::NF;
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t ec = e < n ? e : n - 1;                 // out-of-range threads compute a harmless duplicate
-  const double cond = props[3 * region[ec]];
-  double K[M][M];
-#pragma unroll
-  for (int i = 0; i < M; ++i)
-#pragma unroll
-    for (int j = 0; j < M; ++j) K[i][j] = 0.0;
-#pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    double t[D];
-#pragma unroll
-    for (int a = 0; a < D; ++a) t[a] = cond * St[(int64_t)(f * D + a) * n + ec];
-    const int b = Tab::nbr(f, 0), fw = Tab::nbr(f, 1);
-#pragma unroll
-    for (int j = 0; j < M; ++j) {
-      double w = 0.0;
-#pragma unroll
-      for (int a = 0; a < D; ++a) w += Tab::ifD(f, j, a) * t[a];       // k * G^T s  (heat_transfer.py:47)
-      K[b][j] -= w;                                                    // heat_transfer.py:52-54
-      K[fw][j] += w;
-    }
-  }
-  // transpose through shared memory so that the element-major (AoS) scratch  Ke[e][i*M+j]  is written with coalesced
-  // stores: phase B then gathers one 8*M-byte contiguous row segment per (element, local vertex) pair
-  extern __shared__ double tile[];
-  constexpr int LD = M * M + 1;
-  if (e < n) {
-#pragma unroll
-    for (int i = 0; i < M; ++i)
-#pragma unroll
-      for (int j = 0; j < M; ++j) tile[threadIdx.x * LD + i * M + j] = K[i][j];
-  }
-  __syncthreads();
-  const int64_t e0 = blockIdx.x * (int64_t)blockDim.x;
-  const int64_t count = min((int64_t)blockDim.x, n - e0) * (M * M);
-  for (int64_t k = threadIdx.x; k < count; k += blockDim.x) Ke[e0 * (M * M) + k] = tile[(k / (M * M)) * LD + (k % (M * M))];
-}
-
-// transposed slot map of a uniform mesh: for every CSR entry the list of its contributions (element, local row,
-// local column), in (local row, element) order.  Stored as one u32 per contribution = element | component << 26 with
-// component = l*M + j; the contributions of row v occupy [M*inc_ptr[v], M*inc_ptr[v+1]) and entry t of the row starts at
-// byte offset coff[r0 + t] inside that block.  Built once per sparsity pattern by one warp per row from the byte slot map.
-template <class Tab>
-__global__ void __launch_bounds__(256) k_build_tmap(MeshView m, SysView s, uint8_t *__restrict__ coff, uint32_t *__restrict__ cidx) {
-  constexpr int M = Tab::M;
-  const int lane = threadIdx.x & 31;
-  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; v < s.nV; v += warps) {
-    const int64_t r0 = s.gptr[v];
-    const int len = (int)(s.gptr[v + 1] - r0);
-    const int64_t p0 = m.inc_ptr[v], p1 = m.inc_ptr[v + 1];
-    for (int tb = 0; tb < len; tb += 32) {             // rows longer than 32 entries: several passes
-      const int t = tb + lane;
-      int cnt = 0;
-      if (t < len)
-        for (int64_t p = p0; p < p1; ++p) {
-          const uint32_t pk = m.inc[p];
-          const uint8_t *sp = s.slotpos + inc_elem(pk) * (int64_t)(M * M) + inc_local(pk) * M;
-#pragma unroll
-          for (int j = 0; j < M; ++j) cnt += (sp[j] == t);
-        }
-      // exclusive prefix over the lanes (+ carry of the previous pass)
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-      }
-      __shared__ int carry_s[8];
-      int *carry = &carry_s[threadIdx.x >> 5];
-      if (tb == 0 && lane == 0) *carry = 0;
-      __syncwarp();
-      const int start = *carry + incl - cnt;
-      __syncwarp();
-      if (lane == 31) *carry += incl;
-      __syncwarp();
-      if (t < len) {
-        coff[r0 + t] = (uint8_t)start;
-        int64_t w = (int64_t)M * p0 + start;
-        for (int64_t p = p0; p < p1; ++p) {
-          const uint32_t pk = m.inc[p];
-          const int64_t e = inc_elem(pk);
-          const int l = inc_local(pk);
-          const uint8_t *sp = s.slotpos + e * (int64_t)(M * M) + l * M;
-#pragma unroll
-          for (int j = 0; j < M; ++j)
-            if (sp[j] == t) cidx[w++] = (uint32_t)e | ((uint32_t)(l * M + j) << 26);
-        }
-      }
-    }
-  }
-}
-
-// lumped vectors  gen = sum vol_k q,  acc = sum vol_k rho cp / dt  in (l, element) order (heat_transfer.py:92-113)
-template <class Tab>
-__global__ void k_heat_lumped(MeshView m, int64_t nrows, int64_t n, const double *__restrict__ vol, const double *__restrict__ props,
-                              double *__restrict__ gen_out, double *__restrict__ acc_out) {
-  for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < nrows; v += (int64_t)gridDim.x * blockDim.x) {
-    double gen = 0.0, accv = 0.0;
-    for (int64_t p = m.inc_ptr[v]; p < m.inc_ptr[v + 1]; ++p) {
-      const uint32_t pk = m.inc[p];
-      const int64_t e = inc_elem(pk);
-      const double vq = vol[(int64_t)inc_local(pk) * n + e];
-      const double *pr = props + 3 * m.region[e];
-      gen += vq * pr[2];
-      accv += vq * pr[1];
-    }
-    gen_out[v] = gen;
-    acc_out[v] = accv;
-  }
-}
-
-// Phase B: one warp per CSR row, one lane per entry: sum the entry's contributions from the local matrices in the
-// fixed order of the transposed slot map, add the accumulation term on the diagonal, Dirichlet treatment, coalesced store.
-template <class Tab>
-__global__ void __launch_bounds__(256) k_gather_entries(MeshView m, SysView s, int64_t n, const double *__restrict__ Ke,
-                                                        const uint8_t *__restrict__ coff, const uint32_t *__restrict__ cidx,
-                                                        const double *__restrict__ acc, int transient, int dir_mode,
-                                                        const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
-                                                        double *__restrict__ elim_out) {
-  constexpr int M = Tab::M;
-  __shared__ double buf_s[8][256];
-  const int lane = threadIdx.x & 31;
-  double *buf = buf_s[threadIdx.x >> 5];
-  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t v = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; v < s.nV; v += warps) {
-    const int64_t r0 = s.gptr[v];
-    const int len = (int)(s.gptr[v + 1] - r0);
-    const int64_t cb = (int64_t)M * m.inc_ptr[v];
-    const int nc = (int)((int64_t)M * m.inc_ptr[v + 1] - cb);       // contributions of this row (<= 255)
-    // contribution-parallel: every lane fetches its share of the row's contributions (coalesced index loads, independent
-    // gathers => full memory-level parallelism), then the entry lanes sum their segments from shared memory
-    for (int k = lane; k < nc; k += 32) {
-      const uint32_t ci = __ldcs(cidx + cb + k);
-      buf[k] = __ldcs(Ke + (int64_t)(ci & 0x3ffffffu) * (M * M) + (ci >> 26));
-    }
-    __syncwarp();
-    const bool rowd = (dir_mode >= 0) ? dflag[v] : false;
-    double el = 0.0;
-    for (int tb = 0; tb < len; tb += 32) {
-      const int t = tb + lane;
-      if (t < len) {
-        const int b0 = coff[r0 + t];
-        const int b1 = (t + 1 < len) ? coff[r0 + t + 1] : nc;
-        double a = 0.0;
-        for (int k = b0; k < b1; ++k) a += buf[k];
-        const int c = s.gcol[r0 + t];
-        if (transient && c == v) a += acc[v];                  // heat_transfer.py:62-67
-        if (rowd) a = (c == v) ? 1.0 : 0.0;                    // heat_transfer.py:70-76
-        else if (dir_mode == 1 && dflag[c]) { el -= a * dval[c]; a = 0.0; }
-        s.vals[r0 + t] = a;
-      }
-    }
-    if (dir_mode == 1) {
-      el = warp_sum(el);
-      if (lane == 0) elim_out[v] = rowd ? 0.0 : el;
-    }
-    __syncwarp();
-  }
-}
-
-template <class Tab>
-static void launch_heat_two_phase(efv_system *s, const double *dprops, int transient) {
-  efv_mesh *m = s->mesh;
-  constexpr int M = Tab::M;
-  const int64_t n = m->nE;
-  EFV_REQUIRE(n < (int64_t(1) << 26), "two-phase assembly packs the element id into 26 bits");
-  if (s->scratch.n < (size_t)n * M * M) s->scratch.alloc((size_t)n * M * M);
-  GeomView g = geom_of(m);
-  MeshView mv = view_of(m);
-  SysView sv = sys_view(s);
-  if (!s->tmap_idx.n) {             // transposed slot map: once per sparsity pattern
-    s->tmap_off.alloc(s->nnzg);
-    s->tmap_idx.alloc((size_t)m->conn_size * M);
-    EFV_LAUNCH(k_build_tmap<Tab>, grid_for(s->n_owned * 32, 256, 8), 256, 0, mv, sv, s->tmap_off.p, s->tmap_idx.p);
-  }
-  const size_t tile_bytes = (size_t)128 * (M * M + 1) * sizeof(double);
-  EFV_CUDA(cudaFuncSetAttribute(k_heat_local<Tab>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_bytes));
-  EFV_LAUNCH(k_heat_local<Tab>, (unsigned)div_up(n, 128), 128, tile_bytes, n, m->region.p, dprops, g.St[Tab::CODE], s->scratch.p);
-  EFV_LAUNCH(k_heat_lumped<Tab>, grid_for(s->n_owned, 256), 256, 0, mv, s->n_owned, n, g.vol[Tab::CODE], dprops, s->gen.p, s->acc.p);
-  EFV_LAUNCH(k_gather_entries<Tab>, grid_for(s->n_owned * 32, 256, 8), 256, 0, mv, sv, n, s->scratch.p, s->tmap_off.p, s->tmap_idx.p,
-             s->acc.p, transient, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->elim.p);
-}
-
 template <int UCODE>
 static void launch_heat_rows(efv_system *s, const double *dprops, int transient) {
   efv_mesh *m = s->mesh;
@@ -770,20 +574,12 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
     s->marks_valid = true;
   }
   EFV_CUDA(cudaEventRecord(s->ev0, stream()));
-  // default: the fused row kernel (k_heat_rows).  EFV_ASSEMBLY=two_phase selects the element-batch kernel + segmented
-  // reduction (k_heat_local + k_local_to_csr) on uniform meshes: same values to the last bit, 10.9 ms vs 8.1 ms at C2
-  // (profiles/r01_assembly_variants.json) because the reduction phase is latency-bound.
+  // default: the pair-centric tile kernel (k_heat_tiles); EFV_ASSEMBLY=rows, and meshes whose tiles do not fit in shared
+  // memory, take the row-group kernel (k_heat_rows).  (A two-phase element-batch formulation -- local matrices to a scratch
+  // array + segmented reduction through a transposed slot map -- was measured slower on every mesh type in round 1,
+  // profiles/r01_assembly_variants.json, and is gone.)
   const char *mode = getenv("EFV_ASSEMBLY");
-  const bool fits = m->uniform_code >= 0 && m->uniform_code <= 3 && (int64_t)m->max_incidence * shape_m(m->uniform_code) <= 255 && m->nE < (int64_t(1) << 26);
-  const bool two_phase = mode && strcmp(mode, "two_phase") == 0 && fits;
-  if (two_phase) {
-    switch (m->uniform_code) {
-      case 0: launch_heat_two_phase<TriangleTab>(s, s->props_dev.p, transient); break;
-      case 1: launch_heat_two_phase<QuadrilateralTab>(s, s->props_dev.p, transient); break;
-      case 2: launch_heat_two_phase<TetrahedronTab>(s, s->props_dev.p, transient); break;
-      default: launch_heat_two_phase<HexahedronTab>(s, s->props_dev.p, transient); break;
-    }
-  } else if (!(mode && strcmp(mode, "rows") == 0) &&
+  if (!(mode && strcmp(mode, "rows") == 0) &&
              (m->uniform_code == 0   ? launch_heat_tiles<0>(s, s->props_dev.p, transient)
               : m->uniform_code == 1 ? launch_heat_tiles<1>(s, s->props_dev.p, transient)
               : m->uniform_code == 2 ? launch_heat_tiles<2>(s, s->props_dev.p, transient)

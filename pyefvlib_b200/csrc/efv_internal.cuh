@@ -135,9 +135,6 @@ struct efv_system {
   int lattice[3] = {0, 0, 0};          // owned vertices are numbered i + nx (j + ny k) on an nx x ny x nz lattice (0: unknown)
   double t_assemble_ms = 0, t_solve_ms = 0, t_spmv_ms = 0;
   efv::DBuf<double> props_dev;
-  efv::DBuf<double> scratch;            // local element matrices of the two-phase assembly, component-major
-  efv::DBuf<uint8_t> tmap_off;          // transposed slot map: per CSR entry the offset of its contribution list in the row block
-  efv::DBuf<uint32_t> tmap_idx;         // contributions: element | (l*M + j) << 26
   // asynchronous field download: XOLD -> pinned staging buffer on a copy stream, overlapped with the next step
   double *dl_host = nullptr;
   cudaStream_t dl_stream = nullptr;
