@@ -216,6 +216,20 @@ __global__ void k_sell_widths(int64_t nrows, const int64_t *__restrict__ gptr, i
     if (lane == 0) width[slice] = len;
   }
 }
+// slice has a column beyond the owned rows (a ghost of a partitioned system)
+__global__ void k_sell_ghost_flags(int64_t nrows, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol, uint8_t *__restrict__ flag) {
+  int64_t slice = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t nslices = (nrows + 31) >> 5;
+  for (; slice < nslices; slice += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+    const int64_t v = slice * 32 + lane;
+    bool g = false;
+    if (v < nrows)
+      for (int64_t t = gptr[v]; t < gptr[v + 1]; ++t) g |= gcol[t] >= nrows;
+    const unsigned any = __ballot_sync(0xffffffffu, g);
+    if (lane == 0) flag[slice] = any ? 1 : 0;
+  }
+}
 constexpr int32_t kNoDelta = INT32_MIN;
 // Offsets of slice s start at a 16-byte aligned position of the offset array so that the TMA kernel can bulk-copy
 // them: q(s) = floor4(off[s] + 3 s) leaves room for width(s) entries before q(s+1).  Array length: off[n] + 3 n + 4.
@@ -364,7 +378,10 @@ template <class C, bool HALO>
 __global__ void __launch_bounds__(C::kWarps * 32, 1)
 k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *__restrict__ scol,
                 const int32_t *__restrict__ sdelta_al, const double *__restrict__ sval, const double *__restrict__ x,
-                SpmvEpi epi, double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar, HaloIn hin) {
+                SpmvEpi epi, double *__restrict__ partial, int npartial, const int *__restrict__ done, PeerAR ar, HaloIn hin,
+                int64_t s_first, int64_t s_last) {
+  // [s_first, s_last): the slices this launch covers (s_last < 0: all).  Partitioned systems split a product into an
+  // interior launch (slices without ghost columns, started right after the halo push) and boundary launches.
   constexpr int kSellChunk = C::kChunk, kSellStages = C::kStages, kSellWarps = C::kWarps;
   constexpr size_t kSellStageBytes = C::kStageBytes;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -388,9 +405,11 @@ k_spmv_sell_tma(int64_t nrows, const int64_t *__restrict__ off, const int32_t *_
   const int64_t nslices = (nrows + 31) >> 5;
   // every warp owns a contiguous range of slices; the slice offsets are fetched 32 at a time (lane j holds slice
   // base+j's) so that neither cursor waits on a global load per slice
-  const int64_t per = (nslices + (int64_t)gridDim.x * kSellWarps - 1) / ((int64_t)gridDim.x * kSellWarps);
-  const int64_t s_begin = min(nslices, ((int64_t)blockIdx.x * kSellWarps + wid) * per);
-  const int64_t s_end = min(nslices, s_begin + per);
+  if (s_last < 0) { s_first = 0; s_last = nslices; }
+  const int64_t nsub = s_last - s_first;
+  const int64_t per = (nsub + (int64_t)gridDim.x * kSellWarps - 1) / ((int64_t)gridDim.x * kSellWarps);
+  const int64_t s_begin = s_first + min(nsub, ((int64_t)blockIdx.x * kSellWarps + wid) * per);
+  const int64_t s_end = min(s_last, s_begin + per);
   struct Cursor { int64_t s, base, h0, h1, o0; int k, width; };
   auto fetch = [&](Cursor &c) {            // (o0, width) of slice c.s
     if (c.s >= s_end) return;
@@ -733,6 +752,20 @@ bool sell_prepare(efv_system *s, KrylovWork *w, double *rowabs, bool *rowabs_don
   if (rowabs_done) *rowabs_done = rowabs != nullptr;
   w->sell_indexed = true;
   w->sell_compress = compress;
+  if (is_dist(s) && w->int_rows != nrows) {
+    // longest run of slices without ghost columns (once per pattern): the interior launch of a partitioned product
+    DBuf<uint8_t> gh(nslices);
+    EFV_LAUNCH(k_sell_ghost_flags, grid_for(nslices * 32, 256), 256, 0, nrows, s->gptr.p, s->gcol.p, gh.p);
+    std::vector<uint8_t> h(nslices);
+    gh.download(h.data(), nslices);
+    int64_t best_lo = 0, best_hi = 0, run = 0;
+    for (int64_t i = 0; i <= nslices; ++i) {
+      if (i < nslices && !h[i]) { ++run; continue; }
+      if (run > best_hi - best_lo) { best_lo = i - run; best_hi = i; }
+      run = 0;
+    }
+    w->int_lo = best_lo; w->int_hi = best_hi; w->int_rows = nrows;
+  }
   return true;
 }
 
@@ -744,6 +777,9 @@ static int spmv_blocks() {
   const int b = e ? atoi(e) : 0;
   return b > 0 ? std::min(b, num_sms()) : num_sms();
 }
+// sub-range of slices for the TMA scalar kernel (interior / boundary split of partitioned products); blocks: 0 = one per SM
+static thread_local int64_t g_sub_first = 0, g_sub_last = -1;
+static thread_local int g_sub_blocks = 0;
 static int pick_lanes(const efv_system *s) {
   const char *env = getenv("EFV_SPMV_LANES");
   if (env) { int l = atoi(env); if (l == 2 || l == 4 || l == 8 || l == 16 || l == 32) return l; }
@@ -792,8 +828,37 @@ static bool uses_tma_scalar(const efv_system *s) {
 // kernel gets them copied behind the owned entries first.
 void spmv_halo(efv_system *s, int grid, double *x, const SpmvEpi &epi, double *partial, const int *done) {
   if (!is_dist(s)) { launch_spmv(s, grid, x, epi, partial, done); return; }
-  // EFV_HALO_FUSED=1 (opt-in): measured SLOWER at N = 2 (5.11 vs 4.60 ms per multigrid-CG iteration at C2 weak): the
-  // per-gather ghost test costs more in the issue-bound main loop than the copy kernel and the exposed latency it saves
+  // Interior / boundary split (default on the TMA scalar kernel): the slices of the longest run of rows that have no
+  // ghost column are multiplied right after the halo PUSH -- while the neighbours' values are still in flight and
+  // whatever skew the ranks have is absorbed -- and the few boundary slices afterwards, by launches of the same kernel
+  // that read the ghosts from the staging buffer once the flags are up.  EFV_HALO_SPLIT=0 disables it.
+  KrylovWork *kw = s->kw;
+  static const int split_on = [] { const char *e = getenv("EFV_HALO_SPLIT"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  if (split_on && uses_tma_scalar(s) && kw->int_hi > kw->int_lo && halo_push(s->halo, x, s->ndof)) {
+    const HaloIn hin = halo_in(s->halo, s->ndof);
+    const int64_t ns = (s->n_owned + 31) >> 5;
+    const int Gb = num_sms();                                   // partial slots of one boundary launch
+    const bool lo = kw->int_lo > 0, hi = kw->int_hi < ns;
+    double *pA = partial, *pB1 = partial ? partial + (grid - 2 * Gb) : nullptr, *pB2 = partial ? partial + (grid - Gb) : nullptr;
+    g_sub_first = kw->int_lo; g_sub_last = kw->int_hi; g_sub_blocks = 0;
+    launch_spmv(s, grid - 2 * Gb, x, epi, pA, done);            // interior: no ghosts, no wait
+    auto boundary = [&](int64_t a, int64_t b, double *p, bool present) {
+      if (!present) {                                           // keep the partial slots defined (the consumers sum all of them)
+        if (p) EFV_CUDA(cudaMemsetAsync(p, 0, Gb * sizeof(double), stream()));
+        return;
+      }
+      g_sub_first = a; g_sub_last = b;
+      g_sub_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(Gb, (b - a + 23) / 24));
+      launch_spmv(s, Gb, x, epi, p, done, PeerAR(), &hin);
+    };
+    boundary(0, kw->int_lo, pB1, lo);
+    boundary(kw->int_hi, ns, pB2, hi);
+    g_sub_first = 0; g_sub_last = -1; g_sub_blocks = 0;
+    return;
+  }
+  // EFV_HALO_FUSED=1 (opt-in): the whole product in one launch that tests every gather for a ghost -- measured SLOWER at
+  // N = 2 (5.11 vs 4.60 ms per multigrid-CG iteration at C2 weak): the test costs more in the issue-bound main loop than
+  // the copy kernel and the exposed latency it saves
   const char *ef = getenv("EFV_HALO_FUSED");
   if (!(ef && atoi(ef) == 1) || !halo_push(s->halo, x, s->ndof)) {
     halo_exchange(s, x);
@@ -810,6 +875,8 @@ void spmv_halo(efv_system *s, int grid, double *x, const SpmvEpi &epi, double *p
 }
 void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi_in, double *partial, const int *done,
                  const PeerAR &ar, const HaloIn *hin) {
+  const int64_t sub_first = g_sub_first, sub_last = g_sub_last;
+  const int nblk = g_sub_blocks > 0 ? std::min(g_sub_blocks, spmv_blocks()) : spmv_blocks();
   SpmvEpi epi = epi_in;
   { static const int pf = [] { const char *e = getenv("EFV_EPI_PREFETCH"); return (e && atoi(e) == 0) ? 0 : 1; }(); epi.prefetch = pf; }
   KrylovWork *kw = s->kw;
@@ -828,11 +895,11 @@ void launch_spmv(efv_system *s, int grid, const double *x, const SpmvEpi &epi_in
       configured = true;                                                                                               \
     }                                                                                                                  \
     if (hin)                                                                                                           \
-      EFV_LAUNCH((k_spmv_sell_tma<C, true>), spmv_blocks(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,  \
-                 kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar, *hin);                              \
+      EFV_LAUNCH((k_spmv_sell_tma<C, true>), nblk, W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,          \
+                 kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar, *hin, sub_first, sub_last);         \
     else                                                                                                               \
-      EFV_LAUNCH((k_spmv_sell_tma<C, false>), spmv_blocks(), W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p, \
-                 kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar, HaloIn());                          \
+      EFV_LAUNCH((k_spmv_sell_tma<C, false>), nblk, W * 32, C::kSmem, s->n_owned, kw->sell_off.p, kw->sell_cols.p,         \
+                 kw->sell_delta.p, kw->sell_vals.p, x, epi, partial, grid, done, ar, HaloIn(), sub_first, sub_last);     \
   } while (0)
       const char *ec = getenv("EFV_SELL_TMA");
       switch (ec ? atoi(ec) : 0) {

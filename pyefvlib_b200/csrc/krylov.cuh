@@ -25,6 +25,7 @@ struct KrylovWork {
   bool sell_ok = false, sell_use = false;
   bool sell_indexed = false;  // columns / offsets of the current pattern are in place (values-only refills)
   int sell_compress = -1;
+  int64_t int_lo = 0, int_hi = 0, int_rows = -1;   // partitioned systems: longest run of slices without ghost columns
   int *h_flags = nullptr;   // pinned
   double *h_sc = nullptr;   // pinned
   cudaEvent_t ev = nullptr, e0 = nullptr, e1 = nullptr;
