@@ -828,12 +828,14 @@ static bool uses_tma_scalar(const efv_system *s) {
 // kernel gets them copied behind the owned entries first.
 void spmv_halo(efv_system *s, int grid, double *x, const SpmvEpi &epi, double *partial, const int *done) {
   if (!is_dist(s)) { launch_spmv(s, grid, x, epi, partial, done); return; }
-  // Interior / boundary split (default on the TMA scalar kernel): the slices of the longest run of rows that have no
-  // ghost column are multiplied right after the halo PUSH -- while the neighbours' values are still in flight and
-  // whatever skew the ranks have is absorbed -- and the few boundary slices afterwards, by launches of the same kernel
-  // that read the ghosts from the staging buffer once the flags are up.  EFV_HALO_SPLIT=0 disables it.
+  // Interior / boundary split (EFV_HALO_SPLIT=1, opt-in): the slices of the longest run of rows that have no ghost column
+  // are multiplied right after the halo PUSH -- while the neighbours' values are still in flight -- and the few boundary
+  // slices afterwards, by launches of the same kernel that read the ghosts from the staging buffer once the flags are up.
+  // Parity-tested (tests/test_gpu_distributed.py), but measured neutral to slightly slower than push + copy kernel at
+  // N = 2 (5.10 vs 4.99 ms per multigrid-CG iteration) and N = 8 (5.16 vs 5.07): the halo of one plane is not what the
+  // partitioned iteration waits for, and the two extra persistent launches cost what the hidden latency saves.
   KrylovWork *kw = s->kw;
-  static const int split_on = [] { const char *e = getenv("EFV_HALO_SPLIT"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  static const int split_on = [] { const char *e = getenv("EFV_HALO_SPLIT"); return (e && atoi(e) == 1) ? 1 : 0; }();
   if (split_on && uses_tma_scalar(s) && kw->int_hi > kw->int_lo && halo_push(s->halo, x, s->ndof)) {
     const HaloIn hin = halo_in(s->halo, s->ndof);
     const int64_t ns = (s->n_owned + 31) >> 5;

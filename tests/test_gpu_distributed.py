@@ -43,7 +43,7 @@ def test_partitioned_heat_matches_oracle(kind, n):
 
 @pytest.mark.parametrize("kind,n,world,extra", [("hex", 14, 2, {}), ("tet", 10, 3, {}),
                                                 # SELL / TMA kernels forced on the small mesh: interior + boundary launches of the split product
-                                                ("hex", 16, 2, {"EFV_SPMV_FORMAT": "sell"}),
+                                                ("hex", 16, 2, {"EFV_SPMV_FORMAT": "sell", "EFV_HALO_SPLIT": "1"}),
                                                 ("hex", 14, 3, {"EFV_SPMV_FORMAT": "sell", "EFV_HALO_SPLIT": "0", "EFV_HALO_FUSED": "1"}),
                                                 # every multigrid level partitioned down to the gathered dense solve, ghosts copied by a kernel
                                                 ("hex", 14, 2, {"EFV_AMG_GATHER_ROWS": "0", "EFV_HALO_FUSED": "0"})])
