@@ -114,6 +114,12 @@ struct AmgHierarchy {
   int64_t rep_row_off = 0, rep_rows = 0, rep_nnz_off = 0, rep_nnz = 0, rep_total_rows = 0, rep_total_nnz = 0;
   double t_numeric_ms = 0.0;
   bool numeric_timed = false;
+  // one CG iteration (product, update, check, V-cycle, direction) captured as a CUDA graph: ~60 launches, most of them
+  // a few microseconds long on the small levels, replayed with one launch (single-GPU systems only: the peer collectives
+  // carry per-call sequence numbers)
+  cudaGraphExec_t iter_graph = nullptr;
+  double graph_sigma = 0.0;
+  int graph_nodes = 0;
   ~AmgHierarchy() {
     for (AmgLevel *L : lv) {
       if (L->owns_sys && L->sys) { krylov_free(L->sys); delete L->sys; }
@@ -121,6 +127,7 @@ struct AmgHierarchy {
     }
     if (stage) gather_stage_destroy(stage);
     if (rep_stage) gather_stage_destroy(rep_stage);
+    if (iter_graph) cudaGraphExecDestroy(iter_graph);
   }
 };
 
@@ -1035,7 +1042,7 @@ __global__ void __launch_bounds__(256) k_mg_xr(int64_t n, const double *__restri
   if (threadIdx.x == 0) partial[blockIdx.x] = rr;
 }
 // one block: convergence / breakdown decision right after the update, so that a converged solve skips the last cycle
-__global__ void k_mg_check(int it, const double *__restrict__ pAp_partial, int Gp, const double *__restrict__ rr_partial, int Gr,
+__global__ void k_mg_check(const double *__restrict__ pAp_partial, int Gp, const double *__restrict__ rr_partial, int Gr,
                            double *__restrict__ sc, int *__restrict__ flags) {
   __shared__ double red[32];
   if (flags[0]) return;
@@ -1044,7 +1051,7 @@ __global__ void k_mg_check(int it, const double *__restrict__ pAp_partial, int G
   if (threadIdx.x == 0) {
     if (!(pAp > 0.0) || !(pAp < 1e300) || !(sc[0] > 0.0)) { flags[2] = 1; flags[0] = 1; return; }
     sc[3] = rr;
-    flags[1] = it + 1;
+    flags[1] += 1;                                    // iterations done (device-side: the iteration body is a replayed CUDA graph)
     if (!(rr > sc[4] * sc[2])) flags[0] = 1;
   }
 }
@@ -1098,21 +1105,50 @@ void solve_pcg_amg(efv_system *s, double rtol, int maxit, int negate, int *iters
   const int check_every = (n > 200000) ? 1 : 4;
   { const char *et = getenv("EFV_AMG_TIMING"); g_pt.on = et && atoi(et) == 1; }
   EFV_PT("start");
-  while (!done && it < maxit) {
-    const int batch_end = std::min(maxit, it + check_every);
-    for (; it < batch_end; ++it) {
+  auto body = [&]() {
       spmv_halo(s, G, w->p.p, plain_epi(w->Ap.p, sigma, nullptr, w->p.p), P + 3 * G, w->flags.p);
       EFV_PT("cg.spmv");
       const double *cp = consolidate(s, P + 3 * G, 1, 1, &Gp);
       EFV_LAUNCH(k_mg_xr, G, 256, 0, n, w->sc.p, cp, Gp, w->p.p, w->Ap.p, s->x.p, w->r.p, P, w->flags.p);
       const double *cr = consolidate(s, P, 1, 2, &Gr);
-      EFV_LAUNCH(k_mg_check, 1, 256, 0, it, cp, Gp, cr, Gr, w->sc.p, w->flags.p);
+      EFV_LAUNCH(k_mg_check, 1, 256, 0, cp, Gp, cr, Gr, w->sc.p, w->flags.p);
       EFV_PT("cg.xr_check");
       cycle(H, 0, w->r.p, z, sigma, P + G, w->flags.p, false);
       const double *cz2 = consolidate(s, P + G, 1, 3, &Gz);
       EFV_LAUNCH(k_mg_p, G, 256, 0, n, w->sc.p, cz2, Gz, z, w->p.p, w->flags.p);
       EFV_LAUNCH(k_mg_store_rz, 1, 256, 0, cz2, Gz, w->sc.p, w->flags.p);
       EFV_PT("cg.p");
+  };
+  static const int graph_on = [] { const char *e = getenv("EFV_AMG_GRAPH"); return (e && atoi(e) == 0) ? 0 : 1; }();
+  const bool use_graph = graph_on && !is_dist(s) && !g_pt.on;
+  if (use_graph && (!H->iter_graph || H->graph_sigma != sigma)) {
+    if (H->iter_graph) { cudaGraphExecDestroy(H->iter_graph); H->iter_graph = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const int64_t before = launch_count();
+    EFV_CUDA(cudaStreamBeginCapture(stream(), cudaStreamCaptureModeThreadLocal));
+    try {
+      body();
+    } catch (...) {
+      cudaStreamEndCapture(stream(), &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    EFV_CUDA(cudaStreamEndCapture(stream(), &graph));
+    H->graph_nodes = (int)(launch_count() - before);
+    count_launch(-H->graph_nodes);                            // nothing ran yet
+    EFV_CUDA(cudaGraphInstantiate(&H->iter_graph, graph, 0));
+    cudaGraphDestroy(graph);
+    H->graph_sigma = sigma;
+  }
+  while (!done && it < maxit) {
+    const int batch_end = std::min(maxit, it + check_every);
+    for (; it < batch_end; ++it) {
+      if (use_graph) {
+        EFV_CUDA(cudaGraphLaunch(H->iter_graph, stream()));
+        count_launch(H->graph_nodes);
+      } else {
+        body();
+      }
     }
     EFV_CUDA(cudaMemcpyAsync(w->h_flags, w->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream()));
     EFV_CUDA(cudaStreamSynchronize(stream()));

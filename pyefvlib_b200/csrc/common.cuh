@@ -27,6 +27,7 @@ cudaStream_t stream();          // the one stream of the library
 // two pinned bounce buffers (a pageable cudaMemcpy D2H runs at ~3.5 GB/s on this platform, pinned at > 20 GB/s)
 void download_bytes(void *host, const void *dev, size_t bytes);
 void count_launch(int n = 1);   // bookkeeping for efv_kernel_launch_count
+int64_t launch_count();
 void count_field_copy(int d2h, size_t bytes);   // whole-field uploads / downloads through efv_vec_upload / efv_vec_download
 int num_sms();
 
