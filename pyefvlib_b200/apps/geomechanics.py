@@ -24,7 +24,7 @@ def send_boundary_conditions(system, problemData):
             system.bc_dirichlet(bc.boundary.verticesIndexes + i * nV, bc.values_on_vertices())
 
 
-def geomechanics(problemData, rtol=1e-10, maxLinearIterations=20000, verbosity=True, saver=None):
+def geomechanics(problemData, rtol=1e-10, maxLinearIterations=20000, verbosity=True, saver=None, preconditioner="auto"):
     """Returns dict(u=..., p=..., iterations=[...], saver=...) after the reference's stopping rule
     (geomechanics.py:279-282)."""
     grid = problemData.grid
@@ -32,6 +32,9 @@ def geomechanics(problemData, rtol=1e-10, maxLinearIterations=20000, verbosity=T
     timeStep = problemData.timeStep
     saver = saver or Saver(grid, problemData.outputFilePath, problemData.libraryPath)
     system = DeviceSystem(grid, d + 1)
+    if preconditioner == "auto":          # block multigrid for BiCGStab from 50 000 rows up, the diagonal below
+        preconditioner = "amg" if system.rows >= 50000 else "jacobi"
+    system.set_preconditioner(preconditioner)
     names = ["u_x", "u_y", "u_z"][:d]
     old = np.concatenate([np.asarray(problemData.initialValues[v], dtype=np.float64) for v in names] +
                          [np.asarray(problemData.initialValues["p"], dtype=np.float64)])

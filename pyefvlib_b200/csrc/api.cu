@@ -219,6 +219,7 @@ int efv_system_set_values(efv_system *s, const double *data) {
 void efv_system_destroy(efv_system *s) {
   if (!s) return;
   if (s->amg) efv::amg_free(s->amg);
+  if (s->bprec) efv::block_prec_free(s->bprec);
   efv::krylov_free(s);
   efv::halo_release(s->halo);
   if (s->dl_stream) { cudaStreamSynchronize(s->dl_stream); cudaStreamDestroy(s->dl_stream); cudaEventDestroy(s->dl_ready); cudaEventDestroy(s->dl_done); }

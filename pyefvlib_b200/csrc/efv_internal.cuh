@@ -76,6 +76,7 @@ struct efv_mesh {
 namespace efv {
 struct KrylovWork;
 struct AmgHierarchy;
+struct BlockPrec;
 // owned/ghost exchange lists of a vertex-block partition
 struct Halo {
   bool active = false;
@@ -131,6 +132,7 @@ struct efv_system {
   // Krylov workspace
   efv::KrylovWork *kw = nullptr;
   efv::AmgHierarchy *amg = nullptr;    // aggregation multigrid hierarchy (built at the first preconditioned solve)
+  efv::BlockPrec *bprec = nullptr;     // coupled Biot systems: multigrid on the displacement and pressure blocks (BiCGStab)
   int precond = 0;                     // 0: Jacobi, 1: aggregation multigrid (efv_system_set_preconditioner)
   int lattice[3] = {0, 0, 0};          // owned vertices are numbered i + nx (j + ny k) on an nx x ny x nz lattice (0: unknown)
   double t_assemble_ms = 0, t_solve_ms = 0, t_spmv_ms = 0;
@@ -180,6 +182,9 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
 void spmv(efv_system *s, const double *x, double *y);
 void solve_pcg_amg(efv_system *s, double rtol, int maxit, int negate, int *iters, double *relres);
 void amg_free(AmgHierarchy *H);
+void block_prec_free(BlockPrec *b);
+void block_prec_prepare(efv_system *s);
+void block_prec_apply(efv_system *s, const double *w, const double *dinv, double *z, const int *done);
 void amg_level_export(efv_system *s, int level, int64_t *gptr, int32_t *gcol, double *vals, int32_t *agg);
 int amg_info(efv_system *s, int64_t *rows, int64_t *nnz, double *lmax, int cap, double *numeric_ms);
 double max_abs_diff(efv_system *s);

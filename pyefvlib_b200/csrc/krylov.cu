@@ -1262,9 +1262,10 @@ __global__ void __launch_bounds__(kBlock) k_bi_tt(int64_t n, const double *__res
   if (threadIdx.x == 0) partial[blockIdx.x] = tt;
 }
 // omega = (t,s)/(t,t); x += alpha p + omega s; r = s - omega t; partials (rhat,r), (r,r)
+// px / sx: the vectors that update x (p and s, or M^-1 p and M^-1 s under right preconditioning)
 __global__ void __launch_bounds__(kBlock) k_bi_xr(int64_t n, const double *__restrict__ sc, const double *__restrict__ ts_partial,
-                                                  const double *__restrict__ tt_partial, int G, const double *__restrict__ p,
-                                                  const double *__restrict__ sv, const double *__restrict__ t,
+                                                  const double *__restrict__ tt_partial, int G, const double *__restrict__ px,
+                                                  const double *__restrict__ sv, const double *__restrict__ sx, const double *__restrict__ t,
                                                   const double *__restrict__ rhat, double *__restrict__ x,
                                                   double *__restrict__ r, double *__restrict__ partial,
                                                   const int *__restrict__ flags) {
@@ -1276,7 +1277,7 @@ __global__ void __launch_bounds__(kBlock) k_bi_xr(int64_t n, const double *__res
   double alpha = sc[7];
   double hr = 0, rr = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    x[i] += alpha * p[i] + omega * sv[i];
+    x[i] += alpha * px[i] + omega * sx[i];
     double ri = sv[i] - omega * t[i];
     r[i] = ri;
     hr += rhat[i] * ri; rr += ri * ri;
@@ -1320,12 +1321,16 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
   const int64_t nalloc = s->rows;
   if (!w->r.n) { w->r.alloc(nalloc); w->p.alloc(nalloc); w->Ap.alloc(nalloc); w->dinv.alloc(nalloc); }
   if (!w->rhat.n) { w->rhat.alloc(nalloc); w->v.alloc(nalloc); w->sv.alloc(nalloc); w->t.alloc(nalloc); }
+  // coupled Biot operator with the multigrid preconditioner selected: block-diagonal V-cycles (amg.cu: BlockPrec)
+  const bool blockp = s->precond == 1 && s->physics == 2 && s->ndof >= 3;
+  if (blockp && !w->phat.n) { w->phat.alloc(nalloc); w->shat.alloc(nalloc); w->phat.zero(); w->shat.zero(); }
   const int G = w->grid;
   double *P = w->partial.p;
   auto global_sums = [&](double *part, int narr) { if (is_dist(s)) comm_allreduce_partials_inplace(part, G, narr); };
   EFV_CUDA(cudaEventRecord(w->e0, stream()));
   sell_prepare(s, w);
   EFV_LAUNCH(k_jacobi, grid_for(n, 256), 256, 0, s->n_owned, s->ndof, s->diag_slot.p, s->vals.p, 1.0, w->dinv.p);
+  if (blockp) block_prec_prepare(s);
   EFV_CUDA(cudaMemsetAsync(w->flags.p, 0, 4 * sizeof(int), stream()));
   halo_exchange(s, s->x.p);
   launch_spmv(s, G, s->x.p, plain_epi(w->Ap.p, 1.0, w->dinv.p, nullptr), nullptr, nullptr);
@@ -1340,15 +1345,19 @@ void solve_bicgstab(efv_system *s, double rtol, int maxit, int *iters, double *r
     for (; it < batch_end; ++it) {
       EFV_LAUNCH(k_bi_p, G, kBlock, 0, n, w->sc.p, w->r.p, w->v.p, w->p.p, w->rhat.p, w->flags.p);
       EFV_LAUNCH(k_bi_clear_restart, 1, 1, 0, w->flags.p);
-      halo_exchange(s, w->p.p);
-      launch_spmv(s, G, w->p.p, plain_epi(w->v.p, 1.0, w->dinv.p, w->rhat.p), P + 2 * G, w->flags.p);          // v = D^-1 A p, (rhat,v)
+      // right preconditioning: the products take M^-1 p and M^-1 s, and so does the update of x
+      double *pin = w->p.p, *sin = w->sv.p;
+      if (blockp) { block_prec_apply(s, w->p.p, w->dinv.p, w->phat.p, w->flags.p); pin = w->phat.p; }
+      halo_exchange(s, pin);
+      launch_spmv(s, G, pin, plain_epi(w->v.p, 1.0, w->dinv.p, w->rhat.p), P + 2 * G, w->flags.p);            // v = D^-1 A M^-1 p, (rhat,v)
       global_sums(P + 2 * G, 1);
       EFV_LAUNCH(k_bi_s, G, kBlock, 0, n, w->sc.p, P + 2 * G, G, w->r.p, w->v.p, w->sv.p, w->flags.p);
-      halo_exchange(s, w->sv.p);
-      launch_spmv(s, G, w->sv.p, plain_epi(w->t.p, 1.0, w->dinv.p, w->sv.p), P + 2 * G, w->flags.p);           // t = D^-1 A s, (t,s)
+      if (blockp) { block_prec_apply(s, w->sv.p, w->dinv.p, w->shat.p, w->flags.p); sin = w->shat.p; }
+      halo_exchange(s, sin);
+      launch_spmv(s, G, sin, plain_epi(w->t.p, 1.0, w->dinv.p, w->sv.p), P + 2 * G, w->flags.p);              // t = D^-1 A M^-1 s, (t,s)
       EFV_LAUNCH(k_bi_tt, G, kBlock, 0, n, w->t.p, P + 3 * G, w->flags.p);
       global_sums(P + 2 * G, 2);                                                                    // (t,s) and (t,t)
-      EFV_LAUNCH(k_bi_xr, G, kBlock, 0, n, w->sc.p, P + 2 * G, P + 3 * G, G, w->p.p, w->sv.p, w->t.p, w->rhat.p, s->x.p,
+      EFV_LAUNCH(k_bi_xr, G, kBlock, 0, n, w->sc.p, P + 2 * G, P + 3 * G, G, pin, w->sv.p, sin, w->t.p, w->rhat.p, s->x.p,
                  w->r.p, P, w->flags.p);
       global_sums(P, 2);                                                                            // (rhat,r) and (r,r)
       EFV_LAUNCH(k_bi_scalars, 1, kBlock, 0, it, G, P, P + 2 * G, P + 3 * G, w->sc.p, w->flags.p);

@@ -62,3 +62,30 @@ def test_matrix_rhs_solution(tag):
         assert util.rel_l2(x[:d * nV], xe[:d * nV]) <= 1e-8, (iters, relres)      # displacements
         assert util.rel_l2(x[d * nV:], xe[d * nV:]) <= 1e-8, (iters, relres)      # pressure
         xold = z["x"][k]                                       # feed the reference's own fields forward
+
+
+@pytest.mark.parametrize("tag", ["Hexas3x3x3", "eight_sphere", "Square"])
+def test_biot_block_multigrid_preconditioner(tag):
+    """BiCGStab right-preconditioned by multigrid V-cycles on the displacement and the pressure block (csrc/amg.cu: BlockPrec):
+    same fields as the equilibrated direct solve, in fewer iterations than with the diagonal."""
+    z = util.load("biot_" + tag)
+    c = BIOT_CASES[tag]
+    grid = util.product_grid(z)
+    d, nV = grid.dimension, grid.numberOfVertices
+    s = D.DeviceSystem(grid, d + 1)
+    send_bcs(s, grid, c["bcs"])
+    s.assemble_dirichlet_mode(D.DIRICHLET_ROWS)
+    s.biot_assemble(props_array(grid, c["props"]), c["dt"])
+    xold = np.zeros(s.rows)
+    s.upload(D.VEC_XOLD, xold)
+    s.build_rhs(True)
+    s.upload(D.VEC_X, xold)
+    itj, rrj = s.solve_bicgstab(1e-10, 5000)
+    s.set_preconditioner("amg")
+    s.upload(D.VEC_X, xold)
+    it, rr = s.solve_bicgstab(1e-10, 500)
+    assert rr <= 1e-10 and it <= itj, (it, itj, rr)
+    x = s.download(D.VEC_X)
+    xe = z["x_equilibrated"][0]
+    assert util.rel_l2(x[:d * nV], xe[:d * nV]) <= 1e-8, (it, rr)
+    assert util.rel_l2(x[d * nV:], xe[d * nV:]) <= 1e-8, (it, rr)
