@@ -68,6 +68,7 @@ def test_matrix_rhs_solution(tag):
 def test_biot_block_multigrid_preconditioner(tag):
     """BiCGStab right-preconditioned by multigrid V-cycles on the displacement and the pressure block (csrc/amg.cu: BlockPrec):
     same fields as the equilibrated direct solve, in fewer iterations than with the diagonal."""
+    import pyefvlib_b200.device as D
     z = util.load("biot_" + tag)
     c = BIOT_CASES[tag]
     grid = util.product_grid(z)
