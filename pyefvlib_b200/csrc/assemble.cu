@@ -756,8 +756,318 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
   }
 }
 
+// ---- elasticity: pair-centric tile kernel (round 2; k_elasticity_rows above remains the fall-back) ----------------------------
+// Same scheme as k_heat_tiles with an NDOF x NDOF block per (pair, column): a block owns a tile of R consecutive rows,
+// buckets the tile's (element, local vertex) pairs by (shape, local vertex), and ONE THREAD computes the whole row l of
+// the local block matrix of its pair -- J^-1 and s of the faces that touch l in registers, the shape-table entries as
+// immediates (statically unrolled for that l; the row-group kernel re-reads them and the staged operands from shared
+// memory for every (row, pair, column): 80 % L1 throughput at 12 % occupancy, profiles/r02_ncu_details_k_elasticity_rows.txt).
+// The blocks wait in a shared-memory slab; the row phase then sums them in ascending (local vertex, element) order
+// through the byte slot map, every entry owned by one lane: no float atomics, bit-reproducible.
+struct BTileSmem {
+  int rowacc, slab, posb, pks, order, krank, pkey, total;
+  __host__ __device__ BTileSmem(int R, int max_row_len, int cap, int mmax, int B) {
+    rowacc = 0;
+    slab = rowacc + R * max_row_len * B * 8;
+    posb = slab + (mmax * B + 1) * cap * 8;
+    pks = posb + cap * 8;
+    order = pks + cap * 4;
+    krank = order + (cap + 2048) * 2;
+    pkey = krank + cap * 2;
+    total = (pkey + cap + 15) & ~15;
+  }
+};
+template <class Tab, int L, int NDOF>
+__device__ __forceinline__ void elas_pair_row(const MeshView &m, const GeomView &g, const SysView &s, const double *__restrict__ props,
+                                              int64_t e, bool uniform, int idx, int cap, int slab_off, int posb_off, int mmax) {
+  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE, B = NDOF * NDOF;
+  static_assert(D == NDOF, "elasticity: one displacement component per space dimension");
+  const int64_t gi = uniform ? e : m.group_index(e);
+  int64_t n = g.n[CODE];
+  asm volatile("" : "+l"(n));                       // keep the SoA plane offsets out of loop-invariant hoisting
+  const double *pr = props + 3 * m.region[e];
+  const double lam = pr[0], mu = pr[1];
+  const double *Ji = g.Jinv[CODE] + gi, *Sv = g.S[CODE] + gi;
+  double J[NVF][D][D], sv[NVF][D];
+#pragma unroll
+  for (int k = 0; k < NVF; ++k) {
+    const int enc = Tab::vface_c(L, k);
+    const int f = enc < 0 ? 0 : enc >> 1;
+    const double sg = (enc & 1) ? -1.0 : 1.0;       // this vertex is the forward one of the face: -M (stress_equilibrium.py:105-117)
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int a = 0; a < D; ++a) J[k][i][a] = (enc >= 0) ? Ji[(int64_t)(f * D * D + i * D + a) * n] : 0.0;
+      sv[k][i] = (enc >= 0) ? sg * Sv[(int64_t)(f * 3 + i) * n] : 0.0;
+    }
+  }
+  const uint8_t *sp = s.slotpos + (uniform ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
+  unsigned long long pb;
+  if (uniform && M == 8) pb = *reinterpret_cast<const unsigned long long *>(sp);
+  else if (uniform && M == 4) pb = *reinterpret_cast<const unsigned int *>(sp);
+  else {
+    pb = 0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
+  }
+  const double vol = g.vol[CODE][(int64_t)L * n + gi];
+  *reinterpret_cast<unsigned long long *>(tile_smem + posb_off + idx * 8) = pb;
+  double *out = reinterpret_cast<double *>(tile_smem + slab_off) + idx;
+  out[(size_t)mmax * B * cap] = vol * pr[2];
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    double Mb[NDOF][NDOF];
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) Mb[i][c] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NVF; ++k) {
+      const int enc = Tab::vface_c(L, k);
+      const int f = enc < 0 ? 0 : enc >> 1;
+      if (enc >= 0) {
+        double gv[NDOF];
+        double gs = 0.0;
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i) {
+          double acc = 0.0;
+#pragma unroll
+          for (int a = 0; a < D; ++a)
+            if (Tab::ifD_c(f, j, a) != 0.0) acc += J[k][i][a] * Tab::ifD_c(f, j, a);       // g_i = sum_a Jinv[i][a] D[j][a]
+          gv[i] = acc;
+          gs += acc * sv[k][i];
+        }
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+          for (int c = 0; c < NDOF; ++c)
+            Mb[i][c] += lam * sv[k][i] * gv[c] + mu * (sv[k][c] * gv[i] + ((i == c) ? gs : 0.0));   // At.Ce.Bv in closed form
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+      for (int c = 0; c < NDOF; ++c) out[(size_t)(j * B + i * NDOF + c) * cap] = Mb[i][c];
+  }
+}
+template <class Tab, int UCODE, int NDOF>
+__device__ __forceinline__ void elas_pair_shape(int l, const MeshView &m, const GeomView &g, const SysView &s,
+                                                const double *__restrict__ props, int64_t e, int idx, int cap, int slab_off,
+                                                int posb_off, int mmax) {
+  if constexpr ((UCODE < 0 || UCODE == Tab::CODE) && Tab::DIM == NDOF) {
+    constexpr bool U = UCODE >= 0;
+    switch (l) {
+#define EFV_EPAIR_CASE(LL) \
+  case LL: if constexpr (Tab::M > LL) elas_pair_row<Tab, LL, NDOF>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
+      EFV_EPAIR_CASE(0) EFV_EPAIR_CASE(1) EFV_EPAIR_CASE(2) EFV_EPAIR_CASE(3)
+      EFV_EPAIR_CASE(4) EFV_EPAIR_CASE(5) EFV_EPAIR_CASE(6) EFV_EPAIR_CASE(7)
+#undef EFV_EPAIR_CASE
+      default: break;
+    }
+  }
+}
+
+template <int UCODE, int NDOF, int TT>
+__global__ void __launch_bounds__(TT, 2) k_elas_tiles(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
+                                                      const __grid_constant__ SysView s, const double *__restrict__ props,
+                                                      int gravity, int max_row_len, int R, int cap, int mmax, int dir_mode,
+                                                      const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
+                                                      double *__restrict__ gen_out, double *__restrict__ elim_out) {
+  constexpr int B = NDOF * NDOF;
+  const BTileSmem off(R, max_row_len, cap, mmax, B);
+#define T_ROWACC reinterpret_cast<double *>(tile_smem + off.rowacc)
+#define T_SLAB reinterpret_cast<double *>(tile_smem + off.slab)
+#define T_POSB reinterpret_cast<unsigned long long *>(tile_smem + off.posb)
+#define T_PKS reinterpret_cast<uint32_t *>(tile_smem + off.pks)
+#define T_ORDER reinterpret_cast<uint16_t *>(tile_smem + off.order)
+#define T_KRANK reinterpret_cast<uint16_t *>(tile_smem + off.krank)
+#define T_PKEY (tile_smem + off.pkey)
+  __shared__ int cnt[64], base[65], cbase[64], rp[33];
+  __shared__ uint8_t okey[(2048 + 2048) / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  // row phase: 8-lane groups; a row is shared by nsub groups that own disjoint block components
+  const int ngroups = TT / kAsmGroup, nsub = ngroups / R;
+  const int grp = tid / kAsmGroup, gl = tid % kAsmGroup;
+  const int rrow = grp % R, sub = grp / R;
+  const unsigned gmask = 0xffu << ((tid & 31) / kAsmGroup * kAsmGroup);
+  const int64_t ntiles = (s.nV + R - 1) / R;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t v0 = tile * R;
+    const int rows = (int)min((int64_t)R, s.nV - v0);
+    const int64_t P0 = m.inc_ptr[v0];
+    const int np = (int)(m.inc_ptr[v0 + rows] - P0);
+    if (tid <= rows) rp[tid] = (int)(m.inc_ptr[v0 + tid] - P0);
+    if (tid < 64) cnt[tid] = 0;
+    for (int i = tid; i < rows * max_row_len * B; i += TT) T_ROWACC[i] = 0.0;
+    __syncthreads();
+    // ---- bucket the tile's pairs by (shape, local vertex) ------------------------------------------------------------
+    for (int i = tid; i < np; i += TT) {
+      const uint32_t pk = m.inc[P0 + i];
+      const int code = (UCODE >= 0) ? UCODE : m.code(inc_elem(pk));
+      const int key = code * 8 + inc_local(pk);
+      const int rank = atomicAdd(&cnt[key], 1);          // decides only which thread computes the pair, never a summation order
+      T_PKS[i] = pk;
+      T_PKEY[i] = (uint8_t)key;
+      T_KRANK[i] = (uint16_t)rank;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
+      const int p0 = (c0 + 31) & ~31, p1 = (c1 + 31) & ~31;
+      int incl = p0 + p1, cincl = c0 + c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o), cup = __shfl_up_sync(0xffffffffu, cincl, o);
+        if (lane >= o) { incl += up; cincl += cup; }
+      }
+      const int b0 = incl - p0 - p1, cb0 = cincl - c0 - c1;
+      base[2 * tid] = b0;
+      base[2 * tid + 1] = b0 + p0;
+      cbase[2 * tid] = cb0;
+      cbase[2 * tid + 1] = cb0 + c0;
+      if (tid == 31) base[64] = incl;
+      for (int q = b0 + c0; q < b0 + p0; ++q) T_ORDER[q] = 0xffffu;
+      for (int q = b0 + p0 + c1; q < b0 + p0 + p1; ++q) T_ORDER[q] = 0xffffu;
+      for (int q = b0; q < b0 + p0; q += 32) okey[q >> 5] = (uint8_t)(2 * tid);
+      for (int q = b0 + p0; q < b0 + p0 + p1; q += 32) okey[q >> 5] = (uint8_t)(2 * tid + 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < np; i += TT) {
+      const int key = T_PKEY[i], rank = T_KRANK[i];
+      T_ORDER[base[key] + rank] = (uint16_t)i;
+      T_KRANK[i] = (uint16_t)(cbase[key] + rank);
+    }
+    __syncthreads();
+    // ---- pair phase ----------------------------------------------------------------------------------------------------
+    const int nslots = base[64];
+    for (int slot = tid; slot < nslots; slot += TT) {
+      const int pair = T_ORDER[slot];
+      if (pair == 0xffff) continue;
+      const int key = okey[slot >> 5];
+      const int64_t e = inc_elem(T_PKS[pair]);
+      const int l = key & 7;
+      const int idx = cbase[key] + (slot - base[key]);
+      switch (key >> 3) {
+        case 0: elas_pair_shape<TriangleTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 1: elas_pair_shape<QuadrilateralTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 2: elas_pair_shape<TetrahedronTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 3: elas_pair_shape<HexahedronTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        case 4: elas_pair_shape<PrismTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+        default: elas_pair_shape<PyramidTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
+      }
+    }
+    __syncthreads();
+    // ---- row phase: pairs in ascending (local vertex, element) order; sub-group `sub` owns components sub, sub + nsub, ... ---------
+    if (rrow < rows) {
+      const int64_t v = v0 + rrow;
+      double *row = T_ROWACC + (size_t)rrow * max_row_len * B;
+      double grav = 0.0;
+      for (int q = rp[rrow]; q < rp[rrow + 1]; ++q) {
+        const int mm = (UCODE >= 0) ? shape_m(UCODE) : shape_m(T_PKEY[q] >> 3);
+        const int c = T_KRANK[q];
+        if (gl < mm) {
+          const int pos = (int)((T_POSB[c] >> (8 * gl)) & 0xff);
+          for (int cc = sub; cc < B; cc += nsub) row[pos * B + cc] += T_SLAB[(size_t)(gl * B + cc) * cap + c];
+        }
+        if (gl == 0 && sub == 0) grav += T_SLAB[(size_t)mmax * B * cap + c];
+      }
+      if (gl == 0 && sub == 0) {
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i) gen_out[v * NDOF + i] = (gravity && i == 1) ? grav : 0.0;   // y component only (:81-90)
+      }
+    }
+    __syncthreads();
+    // ---- epilogue: Dirichlet treatment + store, one 8-lane group per row (sub-group 0) ---------------------------------------
+    if (rrow < rows && sub == 0) {
+      const int64_t v = v0 + rrow;
+      const int64_t r0 = s.gptr[v];
+      const int len = (int)(s.gptr[v + 1] - r0);
+      const double *row = T_ROWACC + (size_t)rrow * max_row_len * B;
+      bool rowd[NDOF];
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) rowd[i] = (dir_mode >= 0) ? dflag[v * NDOF + i] : false;
+      double el[NDOF];
+#pragma unroll
+      for (int i = 0; i < NDOF; ++i) el[i] = 0.0;
+      for (int t = gl; t < len; t += kAsmGroup) {
+        const int64_t c = s.gcol[r0 + t];
+        const double *blk = row + t * B;
+        double *out = s.vals + (r0 + t) * B;
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i)
+#pragma unroll
+          for (int j = 0; j < NDOF; ++j) {
+            double a = blk[i * NDOF + j];
+            if (rowd[i]) a = (c == v && i == j) ? 1.0 : 0.0;
+            else if (dir_mode == 1 && dflag[c * NDOF + j]) { el[i] -= a * dval[c * NDOF + j]; a = 0.0; }
+            out[i * NDOF + j] = a;
+          }
+      }
+      if (dir_mode == 1) {
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i) {
+          double tot = el[i];
+#pragma unroll
+          for (int o = kAsmGroup / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(gmask, tot, o);
+          if (gl == 0) elim_out[v * NDOF + i] = rowd[i] ? 0.0 : tot;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#undef T_ROWACC
+#undef T_SLAB
+#undef T_POSB
+#undef T_PKS
+#undef T_ORDER
+#undef T_KRANK
+#undef T_PKEY
+}
+// rows per tile / pair capacity / threads for the block tile kernel; false when nothing fits
+static bool elas_tile_shape(const efv_system *s, int B, int *R, int *cap, int *mmax, int *threads, size_t *smem) {
+  const efv_mesh *m = s->mesh;
+  *mmax = m->uniform_code >= 0 ? shape_m(m->uniform_code) : (m->dim == 3 ? 8 : 4);
+  for (int r = 32; r >= 4; r >>= 1) {
+    const int64_t pairs = (int64_t)r * m->max_incidence;
+    if (pairs > 2047) continue;
+    const int c = (int)((pairs + 15) & ~(int64_t)15) + 1;
+    const size_t bytes = (size_t)BTileSmem(r, s->max_row_len, c, *mmax, B).total;
+    if (bytes > 100 * 1024 && r > 4) continue;                     // at least two blocks per SM
+    if (bytes > 200 * 1024) return false;
+    *R = r; *cap = c; *smem = bytes;
+    *threads = pairs >= 160 ? 256 : 128;
+    if ((*threads / kAsmGroup) < r) *threads = 256;                // one 8-lane group per row at least
+    return (*threads / kAsmGroup) % r == 0;
+  }
+  return false;
+}
+template <int UCODE, int NDOF>
+static bool launch_elas_tiles(efv_system *s, const double *dprops, int gravity) {
+  const char *mode = getenv("EFV_ASSEMBLY");
+  if (mode && strcmp(mode, "rows") == 0) return false;
+  int R, cap, mmax, threads;
+  size_t smem;
+  if (!elas_tile_shape(s, NDOF * NDOF, &R, &cap, &mmax, &threads, &smem)) return false;
+  efv_mesh *m = s->mesh;
+  MeshView mv = view_of(m);
+  GeomView gv = geom_of(m);
+  SysView sv = sys_view(s);
+  const int64_t ntiles = div_up(s->n_owned, R);
+  if (threads == 256) {
+    EFV_CUDA(cudaFuncSetAttribute((k_elas_tiles<UCODE, NDOF, 256>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFV_LAUNCH((k_elas_tiles<UCODE, NDOF, 256>), grid_for(ntiles * 256, 256, 4), 256, smem, mv, gv, sv, dprops, gravity, s->max_row_len, R, cap,
+               mmax, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->elim.p);
+  } else {
+    EFV_CUDA(cudaFuncSetAttribute((k_elas_tiles<UCODE, NDOF, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EFV_LAUNCH((k_elas_tiles<UCODE, NDOF, 128>), grid_for(ntiles * 128, 128, 8), 128, smem, mv, gv, sv, dprops, gravity, s->max_row_len, R, cap,
+               mmax, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->elim.p);
+  }
+  return true;
+}
+
 template <int UCODE, int NDOF>
 static void launch_elasticity_rows(efv_system *s, const double *dprops, int gravity) {
+  if (launch_elas_tiles<UCODE, NDOF>(s, dprops, gravity)) return;       // default: pair-centric tile kernel
   efv_mesh *m = s->mesh;
   size_t smem = ((size_t)kElRows * s->max_row_len * NDOF * NDOF + (size_t)kElRows * kAsmGroup * 12 * kMaxVF) * sizeof(double);
   EFV_CUDA(cudaFuncSetAttribute((k_elasticity_rows<UCODE, NDOF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
