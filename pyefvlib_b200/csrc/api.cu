@@ -120,7 +120,7 @@ int efv_geometry_build(efv_mesh *m) {
 int efv_geometry_release(efv_mesh *m) {
   EFV_API_BEGIN
   EFV_REQUIRE(m, "null mesh");
-  for (int c = 0; c < efv::kNumShapes; ++c) { m->groups[c].Jinv.release(); m->groups[c].S.release(); m->groups[c].vol.release(); m->groups[c].St.release(); }
+  for (int c = 0; c < efv::kNumShapes; ++c) { m->groups[c].Jinv.release(); m->groups[c].S.release(); m->groups[c].vol.release(); m->groups[c].St.release(); m->groups[c].Frec.release(); }
   m->vertex_volume.release();
   m->has_geometry = false;
   EFV_API_END

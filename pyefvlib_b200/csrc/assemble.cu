@@ -764,6 +764,31 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
 // memory for every (row, pair, column): 80 % L1 throughput at 12 % occupancy, profiles/r02_ncu_details_k_elasticity_rows.txt).
 // The blocks wait in a shared-memory slab; the row phase then sums them in ascending (local vertex, element) order
 // through the byte slot map, every entry owned by one lane: no float atomics, bit-reproducible.
+// Geometry in the layout this kernel wants.  The SoA planes of geometry.cu are coalesced when consecutive lanes hold
+// consecutive elements; here a warp holds the pairs of ONE local vertex of a few rows, i.e. scattered elements, and every
+// 8-byte read would pull its own 32-byte sector (measured: 37 ms at C3 against 49 ms for the row-group kernel).  The
+// face records put [J^-1 | s] of an (element, face) into 96 contiguous bytes = three full sectors.
+__global__ void k_face_records(int64_t n, int NF, int D, const double *__restrict__ Jinv, const double *__restrict__ S,
+                               double *__restrict__ rec) {
+  const int RF = D * D + D;
+  const int64_t total = n * NF;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(t / n);               // face-major over the threads: coalesced reads of the SoA planes
+    const int64_t k = t % n;
+    double *out = rec + ((size_t)k * NF + f) * RF;
+    for (int a = 0; a < D * D; ++a) out[a] = Jinv[(int64_t)(f * D * D + a) * n + k];
+    for (int a = 0; a < D; ++a) out[D * D + a] = S[(int64_t)(f * 3 + a) * n + k];
+  }
+}
+static void ensure_face_records(efv_mesh *m) {
+  for (int code = 0; code < kNumShapes; ++code) {
+    ShapeGroup &g = m->groups[code];
+    if (!g.n || g.Frec.n) continue;
+    const int d = shape_dim(code), nf = shape_nf(code);
+    g.Frec.alloc((size_t)g.n * nf * (d * d + d));
+    EFV_LAUNCH(k_face_records, grid_for(g.n * nf, 256), 256, 0, g.n, nf, d, g.Jinv.p, g.S.p, g.Frec.p);
+  }
+}
 struct BTileSmem {
   int rowacc, slab, posb, pks, order, krank, pkey, total;
   __host__ __device__ BTileSmem(int R, int max_row_len, int cap, int mmax, int B) {
@@ -787,18 +812,25 @@ __device__ __forceinline__ void elas_pair_row(const MeshView &m, const GeomView 
   asm volatile("" : "+l"(n));                       // keep the SoA plane offsets out of loop-invariant hoisting
   const double *pr = props + 3 * m.region[e];
   const double lam = pr[0], mu = pr[1];
-  const double *Ji = g.Jinv[CODE] + gi, *Sv = g.S[CODE] + gi;
+  constexpr int RF = D * D + D, NF = Tab::NF;
+  const double2 *rec = reinterpret_cast<const double2 *>(g.Frec[CODE] + (size_t)gi * NF * RF);     // 16-byte aligned: RF is even
   double J[NVF][D][D], sv[NVF][D];
 #pragma unroll
   for (int k = 0; k < NVF; ++k) {
     const int enc = Tab::vface_c(L, k);
     const int f = enc < 0 ? 0 : enc >> 1;
     const double sg = (enc & 1) ? -1.0 : 1.0;       // this vertex is the forward one of the face: -M (stress_equilibrium.py:105-117)
+    double buf[RF];
+#pragma unroll
+    for (int q = 0; q < RF / 2; ++q) {
+      const double2 t2 = (enc >= 0) ? __ldg(rec + (f * RF) / 2 + q) : make_double2(0.0, 0.0);
+      buf[2 * q] = t2.x; buf[2 * q + 1] = t2.y;
+    }
 #pragma unroll
     for (int i = 0; i < D; ++i) {
 #pragma unroll
-      for (int a = 0; a < D; ++a) J[k][i][a] = (enc >= 0) ? Ji[(int64_t)(f * D * D + i * D + a) * n] : 0.0;
-      sv[k][i] = (enc >= 0) ? sg * Sv[(int64_t)(f * 3 + i) * n] : 0.0;
+      for (int a = 0; a < D; ++a) J[k][i][a] = buf[i * D + a];
+      sv[k][i] = sg * buf[D * D + i];
     }
   }
   const uint8_t *sp = s.slotpos + (uniform ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
@@ -1049,6 +1081,7 @@ static bool launch_elas_tiles(efv_system *s, const double *dprops, int gravity) 
   size_t smem;
   if (!elas_tile_shape(s, NDOF * NDOF, &R, &cap, &mmax, &threads, &smem)) return false;
   efv_mesh *m = s->mesh;
+  ensure_face_records(m);
   MeshView mv = view_of(m);
   GeomView gv = geom_of(m);
   SysView sv = sys_view(s);

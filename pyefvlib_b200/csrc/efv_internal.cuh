@@ -25,6 +25,8 @@ struct ShapeGroup {
   // SoA geometry (efv_geometry_build)
   DBuf<double> Jinv, S, vol;
   DBuf<double> St;          // per face  J^-T s  (NF*d components): all the heat operator needs
+  DBuf<double> Frec;        // AoS copy for the block assembly kernels: per (element, face) one record [J^-1 row-major | s] of
+                            // d*d + d doubles (96 B in 3-D = three full sectors), built on first use
 };
 
 struct Boundaries {

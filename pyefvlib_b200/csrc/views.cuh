@@ -68,6 +68,7 @@ struct GeomView {
   const double *S[kNumShapes];
   const double *vol[kNumShapes];
   const double *St[kNumShapes];
+  const double *Frec[kNumShapes];
   int64_t n[kNumShapes];
 };
 inline GeomView geom_of(const efv_mesh *m) {
@@ -77,6 +78,7 @@ inline GeomView geom_of(const efv_mesh *m) {
     g.S[c] = m->groups[c].S.p;
     g.vol[c] = m->groups[c].vol.p;
     g.St[c] = m->groups[c].St.p;
+    g.Frec[c] = m->groups[c].Frec.p;
     g.n[c] = m->groups[c].n;
   }
   return g;

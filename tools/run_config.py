@@ -36,13 +36,15 @@ if which == "c3":
     s.set_preconditioner(os.environ.get("PRECOND", "amg"))
     s.assemble_dirichlet_mode(DIRICHLET_SYMMETRIC)
     s.elasticity_assemble(np.array([[6.0e6, 0.4, 1800.0, 0.0]]), False)
+    first_assemble_ms = s.timings()["assemble_ms"]        # includes the one-time face records of the block tile kernel
+    s.elasticity_assemble(np.array([[6.0e6, 0.4, 1800.0, 0.0]]), False)
     s.build_rhs(False)
     s.upload(VEC_X, np.zeros(s.rows))
     it, rr = s.solve_pcg(1e-10, 100000, negate=True)
     tm = s.timings()
     x = s.download(VEC_X)
     out = dict(config="C3 elasticity tets", n=n, vertices=nV, elements=grid.numberOfElements, rows=s.rows, nnz=s.nnz,
-               pcg_iterations=it, relres=rr, assemble_ms=tm["assemble_ms"], solve_ms=tm["solve_ms"], setup_s=setup_s,
+               pcg_iterations=it, relres=rr, assemble_ms=tm["assemble_ms"], first_assemble_ms=first_assemble_ms, solve_ms=tm["solve_ms"], setup_s=setup_s,
                host_mesh_s=host_s, v_min=float(x[nV:2 * nV].min()), true_relres=s.true_residual(negate=True),
                preconditioner=os.environ.get("PRECOND", "amg"), amg=(s.amg_info() if os.environ.get("PRECOND", "amg") == "amg" else None), dof_per_s=s.rows / (1e-3 * (tm["assemble_ms"] + tm["solve_ms"])),
                iteration_GBs=(s.graph_nnz * (72 + 4) + s.rows * 112) * it / (tm["solve_ms"] * 1e-3) / 1e9)
