@@ -771,13 +771,12 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
 __global__ void k_face_records(int64_t n, int NF, int D, const double *__restrict__ Jinv, const double *__restrict__ S,
                                double *__restrict__ rec) {
   const int RF = D * D + D;
-  const int64_t total = n * NF;
+  const int64_t total = n * NF * RF;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int f = (int)(t / n);               // face-major over the threads: coalesced reads of the SoA planes
-    const int64_t k = t % n;
-    double *out = rec + ((size_t)k * NF + f) * RF;
-    for (int a = 0; a < D * D; ++a) out[a] = Jinv[(int64_t)(f * D * D + a) * n + k];
-    for (int a = 0; a < D; ++a) out[D * D + a] = S[(int64_t)(f * 3 + a) * n + k];
+    const int a = (int)(t % RF);              // output order: coalesced stores (one-time pass; the strided reads hit L2)
+    const int f = (int)((t / RF) % NF);
+    const int64_t k = t / ((int64_t)RF * NF);
+    rec[t] = (a < D * D) ? Jinv[(int64_t)(f * D * D + a) * n + k] : S[(int64_t)(f * 3 + (a - D * D)) * n + k];
   }
 }
 static void ensure_face_records(efv_mesh *m) {
@@ -786,7 +785,7 @@ static void ensure_face_records(efv_mesh *m) {
     if (!g.n || g.Frec.n) continue;
     const int d = shape_dim(code), nf = shape_nf(code);
     g.Frec.alloc((size_t)g.n * nf * (d * d + d));
-    EFV_LAUNCH(k_face_records, grid_for(g.n * nf, 256), 256, 0, g.n, nf, d, g.Jinv.p, g.S.p, g.Frec.p);
+    EFV_LAUNCH(k_face_records, grid_for(g.n * nf * (d * d + d), 256), 256, 0, g.n, nf, d, g.Jinv.p, g.S.p, g.Frec.p);
   }
 }
 struct BTileSmem {
@@ -813,24 +812,39 @@ __device__ __forceinline__ void elas_pair_row(const MeshView &m, const GeomView 
   const double *pr = props + 3 * m.region[e];
   const double lam = pr[0], mu = pr[1];
   constexpr int RF = D * D + D, NF = Tab::NF;
+  // simplices (triangle, tetrahedron): J^-1 and the shape derivatives are the same on every inner face, so the three faces
+  // of this vertex collapse into ONE with the signed sum of their area vectors (M is linear in s)
+  constexpr bool SIMPLEX = (CODE == 0 || CODE == 2);
+  constexpr int NK = SIMPLEX ? 1 : NVF;
   const double2 *rec = reinterpret_cast<const double2 *>(g.Frec[CODE] + (size_t)gi * NF * RF);     // 16-byte aligned: RF is even
-  double J[NVF][D][D], sv[NVF][D];
+  double J[NK][D][D], ls[NK][D], ms[NK][D];        // lambda * s and mu * s (signed)
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int i = 0; i < D; ++i) { ls[k][i] = 0.0; ms[k][i] = 0.0; }
 #pragma unroll
   for (int k = 0; k < NVF; ++k) {
     const int enc = Tab::vface_c(L, k);
     const int f = enc < 0 ? 0 : enc >> 1;
     const double sg = (enc & 1) ? -1.0 : 1.0;       // this vertex is the forward one of the face: -M (stress_equilibrium.py:105-117)
+    const int kk = SIMPLEX ? 0 : k;
     double buf[RF];
 #pragma unroll
     for (int q = 0; q < RF / 2; ++q) {
-      const double2 t2 = (enc >= 0) ? __ldg(rec + (f * RF) / 2 + q) : make_double2(0.0, 0.0);
+      double2 t2 = make_double2(0.0, 0.0);
+      if (enc >= 0 && (!SIMPLEX || k == 0 || 2 * q + 1 >= D * D)) t2 = __ldg(rec + (f * RF) / 2 + q);   // simplex: J from the first face only
       buf[2 * q] = t2.x; buf[2 * q + 1] = t2.y;
+    }
+    if (!SIMPLEX || k == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int a = 0; a < D; ++a) J[kk][i][a] = buf[i * D + a];
     }
 #pragma unroll
     for (int i = 0; i < D; ++i) {
-#pragma unroll
-      for (int a = 0; a < D; ++a) J[k][i][a] = buf[i * D + a];
-      sv[k][i] = sg * buf[D * D + i];
+      ls[kk][i] += lam * (sg * buf[D * D + i]);
+      ms[kk][i] += mu * (sg * buf[D * D + i]);
     }
   }
   const uint8_t *sp = s.slotpos + (uniform ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
@@ -854,12 +868,12 @@ __device__ __forceinline__ void elas_pair_row(const MeshView &m, const GeomView 
 #pragma unroll
       for (int c = 0; c < NDOF; ++c) Mb[i][c] = 0.0;
 #pragma unroll
-    for (int k = 0; k < NVF; ++k) {
+    for (int k = 0; k < NK; ++k) {
       const int enc = Tab::vface_c(L, k);
       const int f = enc < 0 ? 0 : enc >> 1;
       if (enc >= 0) {
         double gv[NDOF];
-        double gs = 0.0;
+        double mgs = 0.0;
 #pragma unroll
         for (int i = 0; i < NDOF; ++i) {
           double acc = 0.0;
@@ -867,13 +881,13 @@ __device__ __forceinline__ void elas_pair_row(const MeshView &m, const GeomView 
           for (int a = 0; a < D; ++a)
             if (Tab::ifD_c(f, j, a) != 0.0) acc += J[k][i][a] * Tab::ifD_c(f, j, a);       // g_i = sum_a Jinv[i][a] D[j][a]
           gv[i] = acc;
-          gs += acc * sv[k][i];
+          mgs += acc * ms[k][i];                                                            // mu (s . g)
         }
 #pragma unroll
         for (int i = 0; i < NDOF; ++i)
 #pragma unroll
           for (int c = 0; c < NDOF; ++c)
-            Mb[i][c] += lam * sv[k][i] * gv[c] + mu * (sv[k][c] * gv[i] + ((i == c) ? gs : 0.0));   // At.Ce.Bv in closed form
+            Mb[i][c] += ls[k][i] * gv[c] + ms[k][c] * gv[i] + ((i == c) ? mgs : 0.0);       // At.Ce.Bv in closed form
       }
     }
 #pragma unroll
@@ -997,9 +1011,11 @@ __global__ void __launch_bounds__(TT, 2) k_elas_tiles(const __grid_constant__ Me
       for (int q = rp[rrow]; q < rp[rrow + 1]; ++q) {
         const int mm = (UCODE >= 0) ? shape_m(UCODE) : shape_m(T_PKEY[q] >> 3);
         const int c = T_KRANK[q];
-        if (gl < mm) {
-          const int pos = (int)((T_POSB[c] >> (8 * gl)) & 0xff);
-          for (int cc = sub; cc < B; cc += nsub) row[pos * B + cc] += T_SLAB[(size_t)(gl * B + cc) * cap + c];
+        const unsigned long long pbits = T_POSB[c];
+        for (int item = sub * kAsmGroup + gl; item < mm * B; item += nsub * kAsmGroup) {   // item = (column, block component)
+          const int j = item / B, cc = item - j * B;
+          const int pos = (int)((pbits >> (8 * j)) & 0xff);
+          row[pos * B + cc] += T_SLAB[(size_t)item * cap + c];
         }
         if (gl == 0 && sub == 0) grav += T_SLAB[(size_t)mmax * B * cap + c];
       }
