@@ -1012,10 +1012,14 @@ __global__ void __launch_bounds__(TT, 2) k_elas_tiles(const __grid_constant__ Me
         const int mm = (UCODE >= 0) ? shape_m(UCODE) : shape_m(T_PKEY[q] >> 3);
         const int c = T_KRANK[q];
         const unsigned long long pbits = T_POSB[c];
-        for (int item = sub * kAsmGroup + gl; item < mm * B; item += nsub * kAsmGroup) {   // item = (column, block component)
-          const int j = item / B, cc = item - j * B;
+        // Every block component cc is owned by ONE 8-lane group for all pairs of the row (cc = sub, sub + nsub, ...), so that
+        // the contributions of different pairs to an entry are added by lanes of one warp, in pair order; the group's
+        // lanes share its (column, component) items.
+        const int ncomp = (B - sub + nsub - 1) / nsub;
+        for (int item = gl; item < mm * ncomp; item += kAsmGroup) {
+          const int j = item % mm, cc = sub + (item / mm) * nsub;
           const int pos = (int)((pbits >> (8 * j)) & 0xff);
-          row[pos * B + cc] += T_SLAB[(size_t)item * cap + c];
+          row[pos * B + cc] += T_SLAB[(size_t)(j * B + cc) * cap + c];
         }
         if (gl == 0 && sub == 0) grav += T_SLAB[(size_t)mmax * B * cap + c];
       }
