@@ -421,7 +421,13 @@ def run_gpu(args):
     asm_bytes = {"compulsory (coords + connectivity + region in, values + rhs out)": 24.0 * nV + 36.0 * nE + 8.0 * nnz + 8.0 * rows,
                  "kernel_streams (3 reduced face vectors k J^-T s, sub-volumes, byte slot map, incidence, values)":
                      (288.0 + 64.0 + 64.0 + 32.0) * nE + 8.0 * nnz + 16.0 * rows}
-    assembly_roofline = {"kernel": "k_heat_tiles<3>", "ms": asm_s * 1e3, "peak": peak, "unit": "GB/s",
+    # bytes the kernel MOVES: ncu dram__bytes_read + dram__bytes_write of one k_heat_lanes<3> launch at n = 216
+    # (profiles/r02_assembly_lanes.json); scaled with the element count at other sizes
+    asm_moved = 7.45e9 * nE / 9938375.0
+    assembly_roofline = {"kernel": "k_heat_lanes<3> (lane-per-row assembly, cp.async operand ring, fused Dirichlet + lumped terms)",
+                         "ms": asm_s * 1e3, "peak": peak, "unit": "GB/s", "bound": "hbm",
+                         "moved_bytes_per_launch_ncu": asm_moved, "moved_gbs": asm_moved / asm_s / 1e9,
+                         "moved_frac": asm_moved / asm_s / 1e9 / peak,
                          "achieved": {k: v / asm_s / 1e9 for k, v in asm_bytes.items()},
                          "frac": {k: v / asm_s / 1e9 / peak for k, v in asm_bytes.items()}}
 
@@ -448,7 +454,7 @@ def run_gpu(args):
         "same_config_as_cpu_baseline": same,
         "c5_steady": c5,
         "e2e": {"value": e2e_value, "unit": "DOF/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": float(np.mean(e2e_ms)), "what": "HeatTransferSolver(problemData).solve(), one time step, host arrays in / host field out"},
+                "ms_per_step": float(np.mean(e2e_ms)), "ms_runs": [float(x) for x in e2e_ms], "what": "HeatTransferSolver(problemData).solve(), one time step, host arrays in / host field out"},
         "gpu_launches": int(launches2 - launches1),
         "clocks": clocks,
     }

@@ -553,6 +553,433 @@ static bool launch_heat_tiles(efv_system *s, const double *dprops, int transient
   return true;
 }
 
+// ---- lane-per-row kernel (default heat assembly, round 2) --------------------------------------------------------------
+// k_heat_tiles still spends ~7 500 warp instructions per 32-row tile (bucketing, slab traffic, 8-lane row walks, three
+// block barriers per tile).  k_heat_lanes has no block-level phase at all: a WARP owns a tile of 32 consecutive rows and
+// LANE r owns row r.
+//  * pair schedule (mesh-level, built once: ensure_pair_schedule): the tile's (element, local vertex) pairs are stored
+//    [step][lane]; one step holds, for every lane, its next pair of ONE (shape, local vertex) key or a "none" marker.  The
+//    key is warp-uniform, so the pair arithmetic is statically unrolled per local vertex with the table entries as
+//    immediates and nothing diverges; descriptors are read with coalesced loads.  Per row the order stays ascending
+//    (local vertex, shape, element): every entry is summed by one lane in a fixed order -- no atomics, bit-reproducible,
+//    and for single-shape meshes bit-identical to k_heat_tiles / the partitioned runs.
+//  * operands travel global -> shared memory with per-lane asynchronous copies (cp.async, SASS LDGSTS): no registers are
+//    held while they are in flight; every warp keeps a ring of S = kLaneStages operand stages -- the 3 face vectors
+//    J^-T s, the sub-volume and the slot bytes of the steps i+1 .. i+S-1, and the descriptors of the steps up to i+2S-1,
+//    are in flight while step i computes.  A lane only ever reads what it copied itself: no barrier anywhere in the pipeline.
+//  * accumulator: a warp-private shared-memory image of the tile's CSR value segment (rows of a tile are contiguous in the
+//    CSR array); lane r adds coefficient j at  row_start(r) + slotpos[j].  The write-back is then a flat, fully
+//    coalesced streaming copy of that image; rows with a Dirichlet neighbour are fixed up in shared memory first.
+constexpr int kLaneWarps = 2;               // warps per block (they never synchronise with each other)
+constexpr int kLaneStages = 2;              // operand ring depth S
+// descriptor word: local vertex << 29 | last step of its tile << 28 | [mixed meshes: shape code << 25] | element
+constexpr int kPdLocalShift = 29, kPdLastBit = 28, kPdCodeShift = 25;
+__host__ __device__ constexpr uint32_t pd_elem_mask(bool mixed) { return (1u << (mixed ? kPdCodeShift : kPdLastBit)) - 1u; }
+__device__ __forceinline__ bool pd_none(uint32_t pk, bool mixed) { return (pk & pd_elem_mask(mixed)) == pd_elem_mask(mixed); }
+__device__ __forceinline__ bool pd_last(uint32_t pk) { return (pk >> kPdLastBit) & 1u; }
+__device__ __forceinline__ int pd_key(uint32_t pk, bool mixed) {                    // shape code * 8 + local vertex
+  return mixed ? (int)(((pk >> kPdCodeShift) & 7u) * 8u + (pk >> kPdLocalShift)) : (int)(pk >> kPdLocalShift);
+}
+
+// ---- pair schedule ---------------------------------------------------------------------------------------------------
+// one warp per tile, lane = vertex.  The incidence list of a vertex is ascending in (local vertex, element); for mixed
+// meshes the pairs of one local vertex are visited shape by shape.  FILL = false: steps of the tile; true: write them.
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_sched_build(MeshView m, int64_t ntiles, int32_t *__restrict__ tile_steps,
+                                                     const int64_t *__restrict__ off, uint32_t *__restrict__ spk) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (tile >= ntiles) return;
+  const int64_t v = (tile << 5) + lane;
+  int64_t p = 0, p1 = 0;
+  if (v < m.nV) { p = m.inc_ptr[v]; p1 = m.inc_ptr[v + 1]; }
+  const bool mixed = m.uniform_code < 0;
+  const uint32_t emask = pd_elem_mask(mixed);
+  int64_t st = 0, st_end = 0;
+  if (FILL) { st = off[tile]; st_end = off[tile + 1]; }
+  int steps = 0;
+  for (int l = 0; l < kMaxM; ++l) {
+    int64_t q = p;                                               // [p, q): this vertex's pairs with local vertex l
+    while (q < p1 && inc_local(m.inc[q]) == l) ++q;
+    for (int code = mixed ? 0 : m.uniform_code; code < (mixed ? kNumShapes : m.uniform_code + 1); ++code) {
+      int cnt = 0;
+      if (!mixed) cnt = (int)(q - p);
+      else for (int64_t t = p; t < q; ++t) cnt += m.code(inc_elem(m.inc[t])) == code;
+      const int nst = __reduce_max_sync(0xffffffffu, cnt);
+      if (FILL) {
+        int64_t t = p;
+        for (int i = 0; i < nst; ++i) {
+          uint32_t pk = emask;                                   // no pair for this lane in this step
+          if (i < cnt) {
+            if (mixed) while (m.code(inc_elem(m.inc[t])) != code) ++t;
+            pk = (uint32_t)inc_elem(m.inc[t++]);
+          }
+          pk |= (uint32_t)l << kPdLocalShift;
+          if (mixed) pk |= (uint32_t)code << kPdCodeShift;
+          if (st + i + 1 == st_end) pk |= 1u << kPdLastBit;
+          spk[(st + i) * 32 + lane] = pk;
+        }
+        st += nst;
+      }
+      steps += nst;
+    }
+    p = q;
+  }
+  if (steps == 0) {                                              // vertices without elements: one empty step keeps the pipeline uniform
+    if (FILL) spk[st * 32 + lane] = emask | (1u << kPdLastBit);
+    steps = 1;
+  }
+  if (!FILL && lane == 0) tile_steps[tile] = steps;
+}
+static bool ensure_pair_schedule(efv_mesh *m) {
+  if (m->sched_off.n) return true;
+  if (m->nE >= (int64_t)pd_elem_mask(m->uniform_code < 0)) return false;     // element ids must fit below the "none" marker
+  const int64_t ntiles = div_up(m->nV, 32);
+  MeshView mv = view_of(m);
+  DBuf<int32_t> cnt(ntiles);
+  EFV_LAUNCH(k_sched_build<false>, (unsigned)div_up(ntiles * 32, 128), 128, 0, mv, ntiles, cnt.p, (const int64_t *)nullptr,
+             (uint32_t *)nullptr);
+  m->sched_off.alloc(ntiles + 1);
+  m->sched_steps = exclusive_scan_i32_to_i64(cnt.p, m->sched_off.p, ntiles);
+  m->sched_pk.alloc((size_t)m->sched_steps * 32);
+  EFV_LAUNCH(k_sched_build<true>, (unsigned)div_up(ntiles * 32, 128), 128, 0, mv, ntiles, (int32_t *)nullptr, m->sched_off.p,
+             m->sched_pk.p);
+  return true;
+}
+
+// Operand stage layout [slot][lane] (8 B slots): slots 0 .. NVF*D-1 face vectors J^-T s, then the sub-volume, then the
+// slot bytes of the m columns (14 slots for the pyramid apex = the mixed-mesh size).
+__host__ __device__ constexpr int lane_slots(int ucode) { return ucode < 0 ? 14 : shape_nvf(ucode) * shape_dim(ucode) + 2; }
+__device__ __forceinline__ void cp_async8(unsigned dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(unsigned dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// issue the copies of one pair (element e, local vertex L) into the lane's column of a stage (stg = shared address of
+// slot 0 of this lane); nb = bytes per SoA plane of this shape group
+template <class Tab, int L, bool U>
+__device__ __forceinline__ void heat_lane_issue(unsigned stg, uint32_t pk, const MeshView &m, const GeomView &g, const SysView &s) {
+  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE;
+  if (pd_none(pk, !U)) return;
+  const int64_t e = (int64_t)(pk & pd_elem_mask(!U));
+  const int64_t gi = U ? e : m.group_index(e);
+  unsigned nb = (unsigned)g.n[CODE] * 8u;                         // < 2^28 elements: plane offsets = 32 x 32 -> 64-bit products
+  asm volatile("" : "+r"(nb));                                    // one IMAD.WIDE per address instead of hoisted 64-bit offsets
+  const char *St = reinterpret_cast<const char *>(g.St[CODE] + gi);
+#pragma unroll
+  for (int k = 0; k < NVF; ++k) {
+    const int f = Tab::vface_c(L, k) >> 1;
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+      if (Tab::vface_c(L, k) >= 0) cp_async8(stg + (k * D + a) * 256, St + (uint64_t)(unsigned)(f < 0 ? 0 : f * D + a) * nb);
+  }
+  cp_async8(stg + NVF * D * 256, reinterpret_cast<const char *>(g.vol[CODE] + gi) + (uint64_t)(unsigned)L * nb);
+  const uint8_t *sp = s.slotpos + (U ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
+  if (U && M == 8) cp_async8(stg + (NVF * D + 1) * 256, sp);
+  else if (U && M == 4) cp_async4(stg + (NVF * D + 1) * 256, sp);
+  else {                                                          // odd sizes / mixed meshes: bytes through registers
+    unsigned long long pb = 0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
+    asm volatile("st.shared.b64 [%0], %1;" ::"r"(stg + (NVF * D + 1) * 256), "l"(pb) : "memory");
+  }
+}
+// consume a stage: the whole local-matrix row L of the pair in registers, added into the lane's row of the tile image.
+// pc = {conductivity, rho cp / dt, heat generation} of the element's region
+template <class Tab, int L, bool U>
+__device__ __forceinline__ void heat_lane_compute(const double *__restrict__ stg, uint32_t pk, double cond, double pr1, double pr2,
+                                                  double *__restrict__ row, double &gen, double &accv) {
+  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF;
+  if (pd_none(pk, !U)) return;
+  const double vol = stg[NVF * D * 32];
+  const uint2 sb = *reinterpret_cast<const uint2 *>(stg + (NVF * D + 1) * 32);
+  gen += __dmul_rn(vol, pr2);                                     // products rounded first: the same bits as the tile kernel
+  accv += __dmul_rn(vol, pr1);
+  double t[NVF][D];
+#pragma unroll
+  for (int k = 0; k < NVF; ++k) {
+    const double sg = (Tab::vface_c(L, k) & 1) ? cond : -cond;    // forward vertex +flux, backward -flux (heat_transfer.py:52-54)
+#pragma unroll
+    for (int a = 0; a < D; ++a) t[k][a] = (Tab::vface_c(L, k) >= 0) ? stg[(k * D + a) * 32] * sg : 0.0;
+  }
+  // coefficient of column j:  k * G^T s  (heat_transfer.py:47); the m columns of one element are distinct positions of
+  // the row, so the read-modify-writes are issued four at a time (no false dependences between them)
+#pragma unroll
+  for (int j0 = 0; j0 < M; j0 += 4) {
+    double w[4], a_[4];
+    int pos[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      if (j < M) {
+        pos[jj] = (int)(((j < 4 ? sb.x : sb.y) >> (8 * (j & 3))) & 0xffu);
+        a_[jj] = row[pos[jj]];
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      if (j < M) {
+        double wj = 0.0;
+#pragma unroll
+        for (int k = 0; k < NVF; ++k) {
+          const int f = Tab::vface_c(L, k) >> 1;
+#pragma unroll
+          for (int a = 0; a < D; ++a)
+            if (Tab::vface_c(L, k) >= 0 && Tab::ifD_c(f < 0 ? 0 : f, j, a) != 0.0)
+              wj += Tab::ifD_c(f < 0 ? 0 : f, j, a) * t[k][a];
+        }
+        w[jj] = wj;
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (j0 + jj < M) row[pos[jj]] = a_[jj] + w[jj];
+  }
+}
+// key = shape code * 8 + local vertex (warp-uniform); UCODE >= 0 instantiates the 8 cases of one shape only (key = local vertex)
+#define EFV_LANE_KEYS(Tab, B, OP)                                                              \
+  case B + 0: if constexpr (Tab::M > 0) { OP(Tab, 0); } break;                                 \
+  case B + 1: if constexpr (Tab::M > 1) { OP(Tab, 1); } break;                                 \
+  case B + 2: if constexpr (Tab::M > 2) { OP(Tab, 2); } break;                                 \
+  case B + 3: if constexpr (Tab::M > 3) { OP(Tab, 3); } break;                                 \
+  case B + 4: if constexpr (Tab::M > 4) { OP(Tab, 4); } break;                                 \
+  case B + 5: if constexpr (Tab::M > 5) { OP(Tab, 5); } break;                                 \
+  case B + 6: if constexpr (Tab::M > 6) { OP(Tab, 6); } break;                                 \
+  case B + 7: if constexpr (Tab::M > 7) { OP(Tab, 7); } break;
+#define EFV_LANE_DISPATCH(UCODE, key, OP)                                                                      \
+  do {                                                                                                         \
+    if constexpr (UCODE == 0) { switch (key) { EFV_LANE_KEYS(TriangleTab, 0, OP) default: break; } }           \
+    else if constexpr (UCODE == 1) { switch (key) { EFV_LANE_KEYS(QuadrilateralTab, 0, OP) default: break; } } \
+    else if constexpr (UCODE == 2) { switch (key) { EFV_LANE_KEYS(TetrahedronTab, 0, OP) default: break; } }   \
+    else if constexpr (UCODE == 3) { switch (key) { EFV_LANE_KEYS(HexahedronTab, 0, OP) default: break; } }    \
+    else if constexpr (UCODE == 4) { switch (key) { EFV_LANE_KEYS(PrismTab, 0, OP) default: break; } }         \
+    else if constexpr (UCODE == 5) { switch (key) { EFV_LANE_KEYS(PyramidTab, 0, OP) default: break; } }       \
+    else {                                                                                                     \
+      switch (key) {                                                                                           \
+        EFV_LANE_KEYS(TriangleTab, 0, OP) EFV_LANE_KEYS(QuadrilateralTab, 8, OP) EFV_LANE_KEYS(TetrahedronTab, 16, OP) \
+        EFV_LANE_KEYS(HexahedronTab, 24, OP) EFV_LANE_KEYS(PrismTab, 32, OP) EFV_LANE_KEYS(PyramidTab, 40, OP) \
+        default: break;                                                                                        \
+      }                                                                                                        \
+    }                                                                                                          \
+  } while (0)
+
+extern __shared__ __align__(16) double lane_smem[];
+// shared memory of one warp, in doubles: tile image | S operand stages | 2S descriptor rows (128 B each)
+__host__ __device__ constexpr int lane_warp_doubles(int ucode, int acc_cap, int S) {
+  return acc_cap + S * lane_slots(ucode) * 32 + 2 * S * 16;
+}
+template <int UCODE, int S>
+__global__ void __launch_bounds__(kLaneWarps * 32) k_heat_lanes(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
+                                                                const __grid_constant__ SysView s, const double *__restrict__ props,
+                                                                const uint32_t *__restrict__ spk, const int64_t *__restrict__ soff,
+                                                                int transient, int acc_cap, int dir_mode, int single_region_i,
+                                                                const uint8_t *__restrict__ dflag, const uint8_t *__restrict__ rmark,
+                                                                const double *__restrict__ dval,
+                                                                double *__restrict__ gen_out, double *__restrict__ acc_out,
+                                                                double *__restrict__ elim_out) {
+  constexpr int R = 2 * S;
+  constexpr bool U = UCODE >= 0;
+  constexpr int kStageBytes = lane_slots(UCODE) * 256;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double *accw = lane_smem + (size_t)wib * lane_warp_doubles(UCODE, acc_cap, S);   // this warp's image of a tile's CSR value segment
+  const unsigned accw_sa = (unsigned)__cvta_generic_to_shared(accw);
+  const unsigned ring_sa = accw_sa + (unsigned)acc_cap * 8u + (unsigned)lane * 8u;   // this lane's column of the operand stages
+  const unsigned pkring_sa = accw_sa + (unsigned)acc_cap * 8u + S * kStageBytes + (unsigned)lane * 4u;   // ... of the descriptor rows
+  const bool single_region = single_region_i != 0;
+  const int ntiles = (int)((s.nV + 31) >> 5);
+  const int W = (int)(blockDim.x >> 5);
+  const int stride = (int)gridDim.x * W;
+  int tile = (int)blockIdx.x * W + wib;                          // tile of the step being computed
+  if (tile >= ntiles) return;
+  const int tail_rows = (int)(s.nV - ((int64_t)(ntiles - 1) << 5));       // rows of the last tile (owned block of a partition)
+  double cond = props[0], pr1 = props[1], pr2 = props[2];                 // one region: properties stay in registers
+  // row data of a tile, RAW loaded values: requested a whole tile ahead, not touched before the tile starts (any use of a
+  // loaded value waits for the load on the spot)
+  struct RowRaw { int64_t g0, g1; int dslot; uint8_t mark; };
+  auto load_rows = [&](int t) {
+    RowRaw rr{0, 0, 0, 0};
+    const int64_t v = ((int64_t)t << 5) + lane;
+    if (v < s.nV) {
+      rr.g0 = s.gptr[v];
+      rr.g1 = s.gptr[v + 1];
+      rr.dslot = s.diag_slot[v];
+      if (dir_mode >= 0) rr.mark = rmark[v];
+    } else {
+      rr.g0 = rr.g1 = s.gptr[s.nV];                                       // inactive lanes: empty row at the end of the segment
+    }
+    return rr;
+  };
+  // descriptor fetch: 2S-1 steps ahead of the compute; running pointer inside a tile, the step range of the fetch side's
+  // NEXT tile requested one tile ahead.  Past the end of the warp's tiles it stores "none" markers.
+  int tF = tile;
+  int64_t f0 = soff[tF], f1 = soff[tF + 1];
+  const uint32_t *pF = spk + f0 * 32 + lane;
+  int remF = (int)(f1 - f0);                                              // steps left in the fetch side's tile
+  int64_t nxt0 = 0, nxt1 = 0;
+  if (tF + stride < ntiles) { nxt0 = soff[tF + stride]; nxt1 = soff[tF + stride + 1]; }
+  bool okF = tF < ntiles - 1 || lane < tail_rows;                         // rows past the owned block have no pairs
+  auto fetch_desc = [&](int slot) {
+    const unsigned dst = pkring_sa + (unsigned)slot * 128u;
+    if (remF > 0 && okF) {
+      cp_async4(dst, pF);
+    } else {
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(pd_elem_mask(!U) | (remF == 1 ? 1u << kPdLastBit : 0u)) : "memory");
+    }
+    if (remF > 0) {
+      pF += 32;
+      if (--remF == 0) {
+        tF += stride;
+        if (tF < ntiles) {
+          pF = spk + nxt0 * 32 + lane;
+          remF = (int)(nxt1 - nxt0);
+          okF = tF < ntiles - 1 || lane < tail_rows;
+          if (tF + stride < ntiles) { nxt0 = soff[tF + stride]; nxt1 = soff[tF + stride + 1]; }
+        }
+      }
+    }
+  };
+#define EFV_ISSUE_OP(Tab, LL) heat_lane_issue<Tab, LL, U>(stg_sa, pkI, m, g, s)
+#define EFV_COMP_OP(Tab, LL) heat_lane_compute<Tab, LL, U>(stg, pkA, cond, pr1, pr2, row, gen, accv)
+  auto issue = [&](int stage, int drow) {                                 // operand copies of the step whose descriptor sits in row drow
+    uint32_t pkI;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pkI) : "r"(pkring_sa + (unsigned)drow * 128u) : "memory");
+    const unsigned stg_sa = ring_sa + (unsigned)stage * kStageBytes;
+    EFV_LANE_DISPATCH(UCODE, pd_key(pkI, !U), EFV_ISSUE_OP);
+  };
+  // prologue: descriptors of steps 0 .. 2S-2, then the operands of steps 0 .. S-2
+#pragma unroll 1
+  for (int j = 0; j < 2 * S - 1; ++j) fetch_desc(j);
+  cp_async_commit();
+  RowRaw rr = load_rows(tile), rrn = rr;
+  cp_async_wait<0>();
+#pragma unroll 1
+  for (int j = 0; j < S - 1; ++j) { issue(j, j); cp_async_commit(); }
+  int slotA = 0, dA = 0;                                                  // stage / descriptor row of the step being computed
+  bool first = true;
+  double gen = 0.0, accv = 0.0;
+  double *row = accw;
+  int64_t base0 = 0;
+  int total = 0, len = 0;
+  bool marked = false;
+  while (true) {
+    // step i computes; the descriptor of step i+2S-1 and the operands of step i+S-1 go out first
+    {
+      const int dF = dA == 0 ? R - 1 : dA - 1;                            // (i + 2S - 1) mod 2S
+      int dI = dA + S - 1;                                                // (i + S - 1) mod 2S
+      if (dI >= R) dI -= R;
+      const int sI = slotA == 0 ? S - 1 : slotA - 1;                      // (i + S - 1) mod S
+      fetch_desc(dF);
+      issue(sI, dI);
+      cp_async_commit();
+    }
+    if (first) {                                                          // first step of a tile: clear the image
+      if (tile + stride < ntiles) rrn = load_rows(tile + stride);         // and request the row data of the next tile
+      base0 = __shfl_sync(0xffffffffu, rr.g0, 0);
+      total = (int)(__shfl_sync(0xffffffffu, rr.g1, 31) - base0);
+      len = (int)(rr.g1 - rr.g0);
+      marked = rr.mark != 0;
+      for (int i = lane; i < total; i += 32) accw[i] = 0.0;
+      row = accw + (int)(rr.g0 - base0);
+      gen = 0.0; accv = 0.0;
+      first = false;
+      __syncwarp();
+    }
+    cp_async_wait<S - 1>();                                               // this step's operands have landed (own copies: no barrier)
+    uint32_t pkA;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pkA) : "r"(pkring_sa + (unsigned)dA * 128u) : "memory");
+    {
+      const double *stg = accw + acc_cap + lane + slotA * (kStageBytes / 8);
+      if (!single_region && !pd_none(pkA, !U)) {
+        const double *pr = props + 3 * m.region[pkA & pd_elem_mask(!U)];
+        cond = pr[0]; pr1 = pr[1]; pr2 = pr[2];
+      }
+      EFV_LANE_DISPATCH(UCODE, pd_key(pkA, !U), EFV_COMP_OP);
+    }
+    if (++slotA == S) slotA = 0;
+    if (++dA == R) dA = 0;
+    if (pd_last(pkA)) {
+      // ---- tile epilogue ----------------------------------------------------------------------------------------------
+      const int64_t v = ((int64_t)tile << 5) + lane;
+      if (v < s.nV) {
+        if (transient) row[(int)((int64_t)rr.dslot - rr.g0)] += accv;     // heat_transfer.py:62-67
+        gen_out[v] = gen;
+        acc_out[v] = accv;
+        if (dir_mode == 1 && !marked) elim_out[v] = 0.0;
+      }
+      __syncwarp();
+      unsigned mm = __ballot_sync(0xffffffffu, marked);
+      while (mm) {                                                        // rows with a Dirichlet DOF among their columns
+        const int r = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int rrel = (int)(__shfl_sync(0xffffffffu, rr.g0, r) - base0);
+        const int rlen = __shfl_sync(0xffffffffu, len, r);
+        const int64_t vr = ((int64_t)tile << 5) + r;
+        const bool rowd = dflag[vr];
+        double el = 0.0;
+        for (int t = lane; t < rlen; t += 32) {
+          const int c = s.gcol[base0 + rrel + t];
+          double a = accw[rrel + t];
+          if (rowd) a = (c == vr) ? 1.0 : 0.0;                            // heat_transfer.py:70-76
+          else if (dir_mode == 1 && dflag[c]) { el -= a * dval[c]; a = 0.0; }
+          accw[rrel + t] = a;
+        }
+        if (dir_mode == 1) {
+          el = warp_sum(el);
+          if (lane == 0) elim_out[vr] = rowd ? 0.0 : el;
+        }
+      }
+      __syncwarp();
+      double *dst = s.vals + base0;
+      for (int i = lane; i < total; i += 32) __stcs(dst + i, accw[i]);    // flat, coalesced, streaming copy of the segment
+      __syncwarp();
+      if (tile + stride >= ntiles) break;
+      tile += stride;
+      rr = rrn;
+      first = true;
+    }
+  }
+  cp_async_wait<0>();
+#undef EFV_ISSUE_OP
+#undef EFV_COMP_OP
+}
+// launch; false when the image of one tile does not fit in shared memory (very long rows) or the element ids do not fit
+// in a descriptor
+// launch; false when the image of one tile does not fit in shared memory (very long rows) or the element ids do not fit
+// in a descriptor.  Shared memory is deliberately NOT filled: the copies in flight live in L1 lines until they land, and
+// with the 228 KB carve-out (28 KB of L1) the kernel runs at 3.0 ms instead of 1.8 ms at C2 (profiles/r02_assembly_lanes.json).
+// 2 stages x 12 warps per SM under the 164 KB carve-out measured best (the ring is short because 12 independent warps
+// already cover a step's latency); deeper rings with fewer warps were equal or slower.
+constexpr int kLaneSmemBudget = 160 * 1024;   // per SM, leaves >= 92 KB of L1
+template <int UCODE>
+static bool launch_heat_lanes(efv_system *s, const double *dprops, int transient) {
+  constexpr int S = kLaneStages, W = kLaneWarps;
+  const int acc_cap = 32 * s->max_row_len;
+  const size_t smem = (size_t)W * lane_warp_doubles(UCODE, acc_cap, S) * sizeof(double);
+  if (smem + 1024 > (size_t)kLaneSmemBudget) return false;
+  efv_mesh *m = s->mesh;
+  if (!ensure_pair_schedule(m)) return false;
+  MeshView mv = view_of(m);
+  GeomView gv = geom_of(m);
+  SysView sv = sys_view(s);
+  EFV_CUDA(cudaFuncSetAttribute(k_heat_lanes<UCODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EFV_CUDA(cudaFuncSetAttribute(k_heat_lanes<UCODE, S>, cudaFuncAttributePreferredSharedMemoryCarveout, 70));
+  int per_sm = 0;
+  EFV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_heat_lanes<UCODE, S>, W * 32, smem));
+  per_sm = std::min<int>(per_sm, (int)(kLaneSmemBudget / (smem + 1024)));
+  if (per_sm < 1) return false;
+  const int64_t ntiles = div_up(s->n_owned, 32);
+  const int64_t blocks = std::min<int64_t>(div_up(ntiles, W), (int64_t)num_sms() * per_sm);
+  EFV_LAUNCH((k_heat_lanes<UCODE, S>), (int)std::max<int64_t>(blocks, 1), W * 32, smem, mv, gv, sv, dprops, m->sched_pk.p,
+             m->sched_off.p, transient, acc_cap, s->fuse_mode, m->n_regions == 1 ? 1 : 0, s->dir_flag.p,
+             s->row_mark.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
+  return true;
+}
+
 void heat_assemble(efv_system *s, const double *props_host, double dt, int transient) {
   efv_mesh *m = s->mesh;
   EFV_REQUIRE(s->ndof == 1, "heat needs a 1-DOF system");
@@ -574,21 +1001,24 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
     s->marks_valid = true;
   }
   EFV_CUDA(cudaEventRecord(s->ev0, stream()));
-  // default: the pair-centric tile kernel (k_heat_tiles); EFV_ASSEMBLY=rows, and meshes whose tiles do not fit in shared
-  // memory, take the row-group kernel (k_heat_rows).  (A two-phase element-batch formulation -- local matrices to a scratch
-  // array + segmented reduction through a transposed slot map -- was measured slower on every mesh type in round 1,
-  // profiles/r01_assembly_variants.json, and is gone.)
+  // default: the lane-per-row kernel (k_heat_lanes); EFV_ASSEMBLY=tiles selects the pair-centric tile kernel (k_heat_tiles,
+  // round 1), EFV_ASSEMBLY=rows the row-group kernel (k_heat_rows), which is also the fall-back for rows too long for the
+  // shared-memory accumulators.  All three sum every entry in the same order: bit-identical values.
   const char *mode = getenv("EFV_ASSEMBLY");
-  if (!(mode && strcmp(mode, "rows") == 0) &&
-             (m->uniform_code == 0   ? launch_heat_tiles<0>(s, s->props_dev.p, transient)
-              : m->uniform_code == 1 ? launch_heat_tiles<1>(s, s->props_dev.p, transient)
-              : m->uniform_code == 2 ? launch_heat_tiles<2>(s, s->props_dev.p, transient)
-              : m->uniform_code == 3 ? launch_heat_tiles<3>(s, s->props_dev.p, transient)
-              : m->uniform_code == 4 ? launch_heat_tiles<4>(s, s->props_dev.p, transient)
-              : m->uniform_code == 5 ? launch_heat_tiles<5>(s, s->props_dev.p, transient)
-                                     : launch_heat_tiles<-1>(s, s->props_dev.p, transient))) {
-    // default: pair-centric tile kernel
-  } else {
+  const bool want_rows = mode && strcmp(mode, "rows") == 0, want_tiles = mode && strcmp(mode, "tiles") == 0;
+  bool done = false;
+#define EFV_HEAT_BY_CODE(fn)                                                                  \
+  (m->uniform_code == 0   ? fn<0>(s, s->props_dev.p, transient)                               \
+   : m->uniform_code == 1 ? fn<1>(s, s->props_dev.p, transient)                               \
+   : m->uniform_code == 2 ? fn<2>(s, s->props_dev.p, transient)                               \
+   : m->uniform_code == 3 ? fn<3>(s, s->props_dev.p, transient)                               \
+   : m->uniform_code == 4 ? fn<4>(s, s->props_dev.p, transient)                               \
+   : m->uniform_code == 5 ? fn<5>(s, s->props_dev.p, transient)                               \
+                          : fn<-1>(s, s->props_dev.p, transient))
+  if (!want_rows && !want_tiles) done = EFV_HEAT_BY_CODE(launch_heat_lanes);
+  if (!done && !want_rows) done = EFV_HEAT_BY_CODE(launch_heat_tiles);
+#undef EFV_HEAT_BY_CODE
+  if (!done) {
     switch (m->uniform_code) {
       case 0: launch_heat_rows<0>(s, s->props_dev.p, transient); break;
       case 1: launch_heat_rows<1>(s, s->props_dev.p, transient); break;

@@ -70,6 +70,13 @@ struct efv_mesh {
   efv::DBuf<uint32_t> inc;
   efv::DBuf<int64_t> slot_ptr;   // per element offset into slot-map-sized arrays (sum of m*m); empty if uniform
   efv::DBuf<double> vertex_volume;
+  // pair schedule of the lane-per-row assembly (assemble.cu: k_heat_lanes), built on first use: tiles of 32 consecutive
+  // vertices; a tile's (element, local vertex) pairs laid out [step][lane] so that a step holds, for every lane (= row),
+  // the next pair of ONE (shape, local vertex) key (0xffffffff: none) -- coalesced, warp-uniform key, order per row
+  // ascending (local vertex, shape, element)
+  efv::DBuf<uint32_t> sched_pk;     // [steps][32]  local vertex | last step of the tile | [shape] | element (assemble.cu: kPd*)
+  efv::DBuf<int64_t> sched_off;     // [tiles + 1] first step of a tile
+  int64_t sched_steps = 0;
   efv::ShapeGroup groups[efv::kNumShapes];
   efv::Boundaries bnd;
   bool has_geometry = false;
