@@ -475,7 +475,9 @@ def main():
     ap.add_argument("--c5-n", type=int, default=368, help="vertices per side of the nested C5 case")
     ap.add_argument("--steady", action="store_true", help="(N>1 leg) steady problem instead of one transient step")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2: configs[1] (N>1: weak scaling, one C2 block per GPU); c5: configs[4] 368^3 strong scaling")
+                    help="c2: configs[1] (N>1: weak scaling at the per-GPU size of C2); c5: configs[4] 368^3 strong scaling")
+    ap.add_argument("--weak-family", default="cube", choices=["cube", "stack"],
+                    help="N>1 weak scaling: cube = the C2 cube refined to n N^(1/3) vertices per side; stack = one n^3 block per GPU in a row")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -436,8 +436,12 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     stream = torch.cuda.ExternalStream(L.efv_get_stream())
     transient = not getattr(args, "steady", False)
     strong = args.workload == "c5"
-    n = args.c5_n if strong else args.n
-    nz = n if strong else n * world
+    # weak scaling: the C2 cube refined isotropically so that every rank keeps the per-GPU size of the N = 1 run
+    # (216^3 -> 272^3 -> 343^3 -> 432^3 vertices on 1, 2, 4, 8 GPUs; z-slabs of n^2 planes), or, with --weak-family stack,
+    # one n^3 block per rank stacked into an n x n x (n N) box (the round-1 family, whose aspect ratio grows with N)
+    stack = getattr(args, "weak_family", "cube") == "stack"
+    n = args.c5_n if strong else (args.n if stack else int(round(args.n * world ** (1.0 / 3.0))))
+    nz = n if (strong or not stack) else n * world
     res, system, part = run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, args.steps, args.warmup, args.precond, stream)
     nV = res["vertices"]
     ms_per_step = res["ms_per_step"]
@@ -480,8 +484,10 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": (f"C5 strong scaling: 3D heat conduction, structured hex mesh {n}^3 vertices cut into {world} "
                                     "vertex-block slabs" if strong else
-                                    f"C2 weak scaling: each of the {world} ranks owns a {n}x{n}x{n}-vertex block of an {n}x{n}x{nz} hex box "
-                                    "(same spacing, same per-GPU work as the N=1 C2 run)") +
+                                    (f"C2 weak scaling: each of the {world} ranks owns a {n}x{n}x{n}-vertex block of an {n}x{n}x{nz} hex box "
+                                     "(same spacing, same per-GPU work as the N=1 C2 run)" if stack else
+                                     f"C2 weak scaling: the C2 cube refined to {n}^3 vertices ({nV / world / 1e6:.2f} M per GPU, N=1: 216^3 = 10.08 M), "
+                                     f"cut into {world} z-slabs")) +
                                    (f", dt=1e-2, 3-D BC set, PCG({args.precond}) rtol 1e-10, 1 time step per step from T0 = 0" if transient else
                                     f", STEADY, 3-D BC set, PCG({args.precond}) rtol 1e-10 from x0 = 0, one full assemble + solve per step"),
                        "vertices": nV, "pcg_iterations_per_step": res["iterations"], "warmup_iterations": res["warmup_iterations"],
