@@ -584,13 +584,17 @@ __device__ __forceinline__ int pd_key(uint32_t pk, bool mixed) {                
 // ---- pair schedule ---------------------------------------------------------------------------------------------------
 // one warp per tile, lane = vertex.  The incidence list of a vertex is ascending in (local vertex, element); for mixed
 // meshes the pairs of one local vertex are visited shape by shape.  FILL = false: steps of the tile; true: write them.
-template <bool FILL>
+template <bool FILL, int R>
 __global__ void __launch_bounds__(128) k_sched_build(MeshView m, int64_t ntiles, int32_t *__restrict__ tile_steps,
                                                      const int64_t *__restrict__ off, uint32_t *__restrict__ spk) {
+  // R rows per tile (R divides 32): a warp builds 32 / R tiles, one group of R lanes each
   const int lane = threadIdx.x & 31;
-  const int64_t tile = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t tile = gt / R;
+  const int r = (int)(gt % R);
   if (tile >= ntiles) return;
-  const int64_t v = (tile << 5) + lane;
+  const unsigned gmask = (R == 32) ? 0xffffffffu : (((1u << (R & 31)) - 1u) << (lane & ~(R - 1)));
+  const int64_t v = tile * R + r;
   int64_t p = 0, p1 = 0;
   if (v < m.nV) { p = m.inc_ptr[v]; p1 = m.inc_ptr[v + 1]; }
   const bool mixed = m.uniform_code < 0;
@@ -605,11 +609,11 @@ __global__ void __launch_bounds__(128) k_sched_build(MeshView m, int64_t ntiles,
       int cnt = 0;
       if (!mixed) cnt = (int)(q - p);
       else for (int64_t t = p; t < q; ++t) cnt += m.code(inc_elem(m.inc[t])) == code;
-      const int nst = __reduce_max_sync(0xffffffffu, cnt);
+      const int nst = __reduce_max_sync(gmask, cnt);
       if (FILL) {
         int64_t t = p;
         for (int i = 0; i < nst; ++i) {
-          uint32_t pk = emask;                                   // no pair for this lane in this step
+          uint32_t pk = emask;                                   // no pair for this row in this step
           if (i < cnt) {
             if (mixed) while (m.code(inc_elem(m.inc[t])) != code) ++t;
             pk = (uint32_t)inc_elem(m.inc[t++]);
@@ -617,7 +621,7 @@ __global__ void __launch_bounds__(128) k_sched_build(MeshView m, int64_t ntiles,
           pk |= (uint32_t)l << kPdLocalShift;
           if (mixed) pk |= (uint32_t)code << kPdCodeShift;
           if (st + i + 1 == st_end) pk |= 1u << kPdLastBit;
-          spk[(st + i) * 32 + lane] = pk;
+          spk[(st + i) * R + r] = pk;
         }
         st += nst;
       }
@@ -626,26 +630,29 @@ __global__ void __launch_bounds__(128) k_sched_build(MeshView m, int64_t ntiles,
     p = q;
   }
   if (steps == 0) {                                              // vertices without elements: one empty step keeps the pipeline uniform
-    if (FILL) spk[st * 32 + lane] = emask | (1u << kPdLastBit);
+    if (FILL) spk[st * R + r] = emask | (1u << kPdLastBit);
     steps = 1;
   }
-  if (!FILL && lane == 0) tile_steps[tile] = steps;
+  if (!FILL && r == 0) tile_steps[tile] = steps;
 }
-static bool ensure_pair_schedule(efv_mesh *m) {
-  if (m->sched_off.n) return true;
+template <int R>
+static bool build_pair_schedule(efv_mesh *m, DBuf<uint32_t> &pk, DBuf<int64_t> &off, int64_t &steps) {
+  if (off.n) return true;
   if (m->nE >= (int64_t)pd_elem_mask(m->uniform_code < 0)) return false;     // element ids must fit below the "none" marker
-  const int64_t ntiles = div_up(m->nV, 32);
+  const int64_t ntiles = div_up(m->nV, R);
   MeshView mv = view_of(m);
   DBuf<int32_t> cnt(ntiles);
-  EFV_LAUNCH(k_sched_build<false>, (unsigned)div_up(ntiles * 32, 128), 128, 0, mv, ntiles, cnt.p, (const int64_t *)nullptr,
+  EFV_LAUNCH((k_sched_build<false, R>), (unsigned)div_up(ntiles * R, 128), 128, 0, mv, ntiles, cnt.p, (const int64_t *)nullptr,
              (uint32_t *)nullptr);
-  m->sched_off.alloc(ntiles + 1);
-  m->sched_steps = exclusive_scan_i32_to_i64(cnt.p, m->sched_off.p, ntiles);
-  m->sched_pk.alloc((size_t)m->sched_steps * 32);
-  EFV_LAUNCH(k_sched_build<true>, (unsigned)div_up(ntiles * 32, 128), 128, 0, mv, ntiles, (int32_t *)nullptr, m->sched_off.p,
-             m->sched_pk.p);
+  off.alloc(ntiles + 1);
+  steps = exclusive_scan_i32_to_i64(cnt.p, off.p, ntiles);
+  pk.alloc((size_t)steps * R);
+  EFV_LAUNCH((k_sched_build<true, R>), (unsigned)div_up(ntiles * R, 128), 128, 0, mv, ntiles, (int32_t *)nullptr, off.p, pk.p);
   return true;
 }
+static bool ensure_pair_schedule(efv_mesh *m) { return build_pair_schedule<32>(m, m->sched_pk, m->sched_off, m->sched_steps); }
+// tiles of 8 rows: the block (ndof x ndof) assembly gives every row 4 lanes
+static bool ensure_pair_schedule8(efv_mesh *m) { return build_pair_schedule<8>(m, m->sched8_pk, m->sched8_off, m->sched8_steps); }
 
 // Operand stage layout [slot][lane] (8 B slots): slots 0 .. NVF*D-1 face vectors J^-T s, then the sub-volume, then the
 // slot bytes of the m columns (14 slots for the pyramid apex = the mixed-mesh size).
@@ -973,7 +980,8 @@ static bool launch_heat_lanes(efv_system *s, const double *dprops, int transient
   per_sm = std::min<int>(per_sm, (int)(kLaneSmemBudget / (smem + 1024)));
   if (per_sm < 1) return false;
   const int64_t ntiles = div_up(s->n_owned, 32);
-  const int64_t blocks = std::min<int64_t>(div_up(ntiles, W), (int64_t)num_sms() * per_sm);
+  int64_t blocks = std::min<int64_t>(div_up(ntiles, W), (int64_t)num_sms() * per_sm);
+  if (const char *e = getenv("EFV_LANE_GRID")) blocks = std::min<int64_t>(blocks, std::max(1, atoi(e)));   // tests: many tiles per warp
   EFV_LAUNCH((k_heat_lanes<UCODE, S>), (int)std::max<int64_t>(blocks, 1), W * 32, smem, mv, gv, sv, dprops, m->sched_pk.p,
              m->sched_off.p, transient, acc_cap, s->fuse_mode, m->n_regions == 1 ? 1 : 0, s->dir_flag.p,
              s->row_mark.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
@@ -1548,9 +1556,390 @@ static bool launch_elas_tiles(efv_system *s, const double *dprops, int gravity) 
   return true;
 }
 
+// ---- lane kernel for the block (elasticity) assembly ---------------------------------------------------------------------
+// The scheme of k_heat_lanes with an ndof x ndof block per graph entry: a warp owns a tile of 8 consecutive vertices, every
+// vertex gets 4 lanes, lane q < ndof owns component q of the vertex's block row (the three scalar rows of a vertex never
+// touch the same value).  A step of the pair schedule (tiles of 8, ensure_pair_schedule8) holds one (element, local vertex)
+// pair per vertex with a warp-uniform (shape, local vertex) key; the 4 lanes of a vertex split the asynchronous copies of
+// the pair's face records [J^-1 | s] (16-byte cp.async) into the stage of their vertex and, after the group has landed
+// and a __syncwarp, every compute lane reads all of it back (broadcast reads) and evaluates ITS row of
+//   M = lambda s g^T + mu (g s^T + (s.g) I)          (stress_equilibrium.py:50-67, :100)
+// for every column of the element.  Simplices collapse their faces as in elas_pair_row.  The accumulator is the shared-
+// memory image of the tile's BSR value segment; Dirichlet rows / columns are fixed up there and the segment leaves with a
+// flat coalesced streaming copy.  Per scalar row the summation order is ascending (local vertex, shape, element).
+constexpr int kBlkRows = 8, kBlkStages = 2, kBlkWarps = 2;
+// doubles per vertex and stage: NVF face records + sub-volume + slot bytes, padded to an ODD number of 16-byte units so that
+// the 8 vertices of a tile read their records from 8 different bank groups
+__host__ __device__ constexpr int blk_row_stride(int ucode, int dim) {
+  const int rf = dim * dim + dim;
+  const int slots = (ucode < 0 ? (dim == 3 ? 4 : 2) : shape_nvf(ucode)) * rf + 2;
+  const int units = (slots + 1) / 2;
+  return 2 * (units | 1);
+}
+__host__ __device__ constexpr int blk_warp_doubles(int ucode, int dim, int acc_cap) {
+  return acc_cap + kBlkStages * kBlkRows * blk_row_stride(ucode, dim) + 2 * kBlkStages * 16;
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// copies of one pair into the stage row of its vertex (stg = shared address of that row); lane q of the vertex's 4 lanes
+// takes every 4th 16-byte chunk, lane 0 also the sub-volume, lane 1 the slot bytes
+template <class Tab, int L, bool U>
+__device__ __forceinline__ void elas_lane_issue(unsigned stg, uint32_t pk, bool mx, int q, const MeshView &m, const GeomView &g,
+                                                const SysView &s) {
+  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE, RF = D * D + D, NF = Tab::NF;
+  constexpr bool SIMPLEX = (CODE == 0 || CODE == 2);
+  if (pd_none(pk, mx)) return;
+  const int64_t e = (int64_t)(pk & pd_elem_mask(mx));
+  const int64_t gi = U ? e : m.group_index(e);
+  const double2 *rec = reinterpret_cast<const double2 *>(g.Frec[CODE] + (size_t)gi * NF * RF);     // 16-byte aligned: RF is even
+#pragma unroll
+  for (int k = 0; k < NVF; ++k) {
+    const int enc = Tab::vface_c(L, k);
+    const int f = enc < 0 ? 0 : enc >> 1;
+#pragma unroll
+    for (int p = 0; p < RF / 2; ++p) {
+      constexpr int dummy = 0; (void)dummy;
+      const int c = k * (RF / 2) + p;
+      // simplices: J^-1 is the same on every face, only the first record is read in full, of the others only s
+      if (enc >= 0 && (!SIMPLEX || k == 0 || 2 * p + 1 >= D * D) && q == (c & 3)) cp_async16(stg + c * 16, rec + (f * RF) / 2 + p);
+    }
+  }
+  if (q == 0) {
+    unsigned nb = (unsigned)g.n[CODE] * 8u;
+    cp_async8(stg + NVF * RF * 8, reinterpret_cast<const char *>(g.vol[CODE] + gi) + (uint64_t)(unsigned)L * nb);
+  }
+  if (q == 1) {
+    const uint8_t *sp = s.slotpos + (U ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
+    if (U && M == 8) cp_async8(stg + (NVF * RF + 1) * 8, sp);
+    else if (U && M == 4) cp_async4(stg + (NVF * RF + 1) * 8, sp);
+    else {
+      unsigned long long pb = 0;
+#pragma unroll
+      for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
+      asm volatile("st.shared.b64 [%0], %1;" ::"r"(stg + (NVF * RF + 1) * 8), "l"(pb) : "memory");
+    }
+  }
+}
+// row q of every column block of the pair, added into the image (row = image of the vertex's block row, blocks row-major)
+template <class Tab, int L, int NDOF, bool U>
+__device__ __forceinline__ void elas_lane_compute(const double *__restrict__ stg, uint32_t pk, bool mx, int q, const double *__restrict__ pr,
+                                                  double *__restrict__ row, double &grav) {
+  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE, RF = D * D + D, B = NDOF * NDOF;
+  static_assert(D == NDOF, "elasticity: one displacement component per space dimension");
+  constexpr bool SIMPLEX = (CODE == 0 || CODE == 2);
+  constexpr int NK = SIMPLEX ? 1 : NVF;
+  if (pd_none(pk, mx) || q >= NDOF) return;
+  const double lam = pr[0], mu = pr[1];
+  double J[NK][D][D], ls[NK][D], ms[NK][D];        // lambda * s and mu * s (signed)
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+#pragma unroll
+    for (int i = 0; i < D; ++i) { ls[k][i] = 0.0; ms[k][i] = 0.0; }
+  const double2 *st2 = reinterpret_cast<const double2 *>(stg);
+#pragma unroll
+  for (int k = 0; k < NVF; ++k) {
+    const int enc = Tab::vface_c(L, k);
+    const double sg = (enc & 1) ? -1.0 : 1.0;       // this vertex is the forward one of the face: -M (stress_equilibrium.py:105-117)
+    const int kk = SIMPLEX ? 0 : k;
+    double buf[RF];
+#pragma unroll
+    for (int p = 0; p < RF / 2; ++p) {
+      double2 t2 = make_double2(0.0, 0.0);
+      if (enc >= 0 && (!SIMPLEX || k == 0 || 2 * p + 1 >= D * D)) t2 = st2[k * (RF / 2) + p];
+      buf[2 * p] = t2.x; buf[2 * p + 1] = t2.y;
+    }
+    if (!SIMPLEX || k == 0) {
+#pragma unroll
+      for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int a = 0; a < D; ++a) J[kk][i][a] = buf[i * D + a];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      ls[kk][i] += lam * (sg * buf[D * D + i]);
+      ms[kk][i] += mu * (sg * buf[D * D + i]);
+    }
+  }
+  const double vol = stg[NVF * RF];
+  const uint2 sb = *reinterpret_cast<const uint2 *>(stg + NVF * RF + 1);
+  grav += __dmul_rn(vol, pr[2]);
+  double lsq[NK], dq[NDOF];                         // lambda s_q of every face; unit vector of this lane's component
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    lsq[k] = ls[k][0];
+#pragma unroll
+    for (int i = 1; i < D; ++i) lsq[k] = (q == i) ? ls[k][i] : lsq[k];
+  }
+#pragma unroll
+  for (int c = 0; c < NDOF; ++c) dq[c] = (q == c) ? 1.0 : 0.0;
+  double *rowq = row + q * NDOF;
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    double Mq[NDOF];
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) Mq[c] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int enc = Tab::vface_c(L, k);
+      const int f = enc < 0 ? 0 : enc >> 1;
+      if (enc >= 0) {
+        double gv[NDOF];
+        double mgs = 0.0;
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i) {
+          double acc = 0.0;
+#pragma unroll
+          for (int a = 0; a < D; ++a)
+            if (Tab::ifD_c(f, j, a) != 0.0) acc += J[k][i][a] * Tab::ifD_c(f, j, a);       // g_i = sum_a Jinv[i][a] D[j][a]
+          gv[i] = acc;
+          mgs += acc * ms[k][i];                                                            // mu (s . g)
+        }
+        double gq = gv[0];
+#pragma unroll
+        for (int i = 1; i < NDOF; ++i) gq = (q == i) ? gv[i] : gq;
+#pragma unroll
+        for (int c = 0; c < NDOF; ++c) Mq[c] += lsq[k] * gv[c] + ms[k][c] * gq + dq[c] * mgs;   // row q of At.Ce.Bv in closed form
+      }
+    }
+    const int pos = (int)(((j < 4 ? sb.x : sb.y) >> (8 * (j & 3))) & 0xffu);
+    double *blk = rowq + pos * B;
+#pragma unroll
+    for (int c = 0; c < NDOF; ++c) blk[c] += Mq[c];
+  }
+}
+template <int UCODE, int NDOF>
+__global__ void __launch_bounds__(kBlkWarps * 32) k_elas_lanes(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
+                                                               const __grid_constant__ SysView s, const double *__restrict__ props,
+                                                               const uint32_t *__restrict__ spk, const int64_t *__restrict__ soff,
+                                                               int gravity, int acc_cap, int dir_mode,
+                                                               const uint8_t *__restrict__ dflag, const uint8_t *__restrict__ vmark,
+                                                               const double *__restrict__ dval,
+                                                               double *__restrict__ gen_out, double *__restrict__ elim_out) {
+  constexpr int S = kBlkStages, RR = 2 * kBlkStages, R = kBlkRows, B = NDOF * NDOF;
+  constexpr bool U = UCODE >= 0;
+  // the generic instantiation also serves single-shape meshes without an instantiation of their own (prisms, pyramids):
+  // the descriptor format follows the MESH (shape bits only when it is mixed)
+  const bool MX = !U && m.uniform_code < 0;
+  auto keyof = [&](uint32_t pk) { return MX ? pd_key(pk, true) : (U ? pd_key(pk, false) : m.uniform_code * 8 + pd_key(pk, false)); };
+  constexpr int kRowStride = blk_row_stride(UCODE, NDOF), kStageBytes = R * kRowStride * 8;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = lane >> 2, q = lane & 3;                                  // vertex of the tile, component / copy lane
+  double *accw = lane_smem + (size_t)wib * blk_warp_doubles(UCODE, NDOF, acc_cap);   // image of the tile's BSR value segment
+  const unsigned accw_sa = (unsigned)__cvta_generic_to_shared(accw);
+  const unsigned ring_sa = accw_sa + (unsigned)acc_cap * 8u + (unsigned)(r * kRowStride) * 8u;   // this vertex's row of the stages
+  const unsigned pkring_sa = accw_sa + (unsigned)acc_cap * 8u + S * kStageBytes + (unsigned)lane * 4u;
+  const int ntiles = (int)((s.nV + R - 1) / R);
+  const int stride = (int)gridDim.x * kBlkWarps;
+  int tile = (int)blockIdx.x * kBlkWarps + wib;
+  if (tile >= ntiles) return;
+  const int tail_rows = (int)(s.nV - (int64_t)(ntiles - 1) * R);
+  struct RowRaw { int64_t g0, g1; uint8_t mark; };
+  auto load_rows = [&](int t) {
+    RowRaw rr{0, 0, 0};
+    const int64_t v = (int64_t)t * R + r;
+    if (v < s.nV) {
+      rr.g0 = s.gptr[v];
+      rr.g1 = s.gptr[v + 1];
+      if (dir_mode >= 0) rr.mark = vmark[v];
+    } else {
+      rr.g0 = rr.g1 = s.gptr[s.nV];
+    }
+    return rr;
+  };
+  int tF = tile;
+  int64_t f0 = soff[tF], f1 = soff[tF + 1];
+  const uint32_t *pF = spk + f0 * R + r;
+  int remF = (int)(f1 - f0);
+  int64_t nxt0 = 0, nxt1 = 0;
+  if (tF + stride < ntiles) { nxt0 = soff[tF + stride]; nxt1 = soff[tF + stride + 1]; }
+  bool okF = tF < ntiles - 1 || r < tail_rows;
+  auto fetch_desc = [&](int slot) {
+    const unsigned dst = pkring_sa + (unsigned)slot * 128u;
+    if (remF > 0 && okF) {
+      cp_async4(dst, pF);
+    } else {
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(pd_elem_mask(MX) | (remF == 1 ? 1u << kPdLastBit : 0u)) : "memory");
+    }
+    if (remF > 0) {
+      pF += R;
+      if (--remF == 0) {
+        tF += stride;
+        if (tF < ntiles) {
+          pF = spk + nxt0 * R + r;
+          remF = (int)(nxt1 - nxt0);
+          okF = tF < ntiles - 1 || r < tail_rows;
+          if (tF + stride < ntiles) { nxt0 = soff[tF + stride]; nxt1 = soff[tF + stride + 1]; }
+        }
+      }
+    }
+  };
+  // the key of a step is warp-uniform but a vertex without a pair carries only the local vertex of ITS marker: take the key
+  // from the word itself (markers keep the step's local vertex and shape bits)
+#define EFV_BISSUE_OP(Tab, LL) if constexpr (Tab::DIM == NDOF) elas_lane_issue<Tab, LL, U>(stg_sa, pkI, MX, q, m, g, s)
+#define EFV_BCOMP_OP(Tab, LL) if constexpr (Tab::DIM == NDOF) elas_lane_compute<Tab, LL, NDOF, U>(stg, pkA, MX, q, pr, row, grav)
+  auto issue = [&](int stage, int drow) {
+    uint32_t pkI;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pkI) : "r"(pkring_sa + (unsigned)drow * 128u) : "memory");
+    const unsigned stg_sa = ring_sa + (unsigned)stage * kStageBytes;
+    EFV_LANE_DISPATCH(UCODE, keyof(pkI), EFV_BISSUE_OP);
+  };
+#pragma unroll 1
+  for (int j = 0; j < 2 * S - 1; ++j) fetch_desc(j);
+  cp_async_commit();
+  RowRaw rr = load_rows(tile), rrn = rr;
+  cp_async_wait<0>();
+#pragma unroll 1
+  for (int j = 0; j < S - 1; ++j) { issue(j, j); cp_async_commit(); }
+  int slotA = 0, dA = 0;
+  bool first = true;
+  double grav = 0.0;
+  double *row = accw;
+  int64_t base0 = 0;
+  int total = 0, len = 0;
+  bool marked = false;
+  while (true) {
+    {
+      const int dF = dA == 0 ? RR - 1 : dA - 1;
+      int dI = dA + S - 1;
+      if (dI >= RR) dI -= RR;
+      const int sI = slotA == 0 ? S - 1 : slotA - 1;
+      fetch_desc(dF);
+      issue(sI, dI);
+      cp_async_commit();
+    }
+    if (first) {
+      if (tile + stride < ntiles) rrn = load_rows(tile + stride);
+      base0 = __shfl_sync(0xffffffffu, rr.g0, 0);                         // in blocks
+      total = (int)(__shfl_sync(0xffffffffu, rr.g1, 31) - base0) * B;     // scalars of the segment
+      len = (int)(rr.g1 - rr.g0);
+      marked = rr.mark != 0;
+      for (int i = lane; i < total; i += 32) accw[i] = 0.0;
+      row = accw + (int)(rr.g0 - base0) * B;
+      grav = 0.0;
+      first = false;
+    }
+    cp_async_wait<S - 1>();
+    __syncwarp();                                                         // the 4 lanes of a vertex read each other's copies
+    uint32_t pkA;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pkA) : "r"(pkring_sa + (unsigned)dA * 128u) : "memory");
+    {
+      const double *stg = accw + acc_cap + slotA * (kStageBytes / 8) + r * kRowStride;
+      const double *pr = props;
+      if (!pd_none(pkA, MX)) pr += 3 * m.region[pkA & pd_elem_mask(MX)];
+      EFV_LANE_DISPATCH(UCODE, keyof(pkA), EFV_BCOMP_OP);
+    }
+    __syncwarp();                                                         // stage may be overwritten by the next issue
+    if (++slotA == S) slotA = 0;
+    if (++dA == RR) dA = 0;
+    if (pd_last(pkA)) {
+      // ---- tile epilogue ----------------------------------------------------------------------------------------------
+      const int64_t v = (int64_t)tile * R + r;
+      if (v < s.nV && q < NDOF) {
+        gen_out[v * NDOF + q] = (gravity && q == 1) ? grav : 0.0;         // y component only (stress_equilibrium.py:81-90)
+        if (dir_mode == 1 && !marked) elim_out[v * NDOF + q] = 0.0;
+      }
+      __syncwarp();
+      unsigned mm = __ballot_sync(0xffffffffu, marked && q == 0);
+      while (mm) {                                                        // vertices with a Dirichlet DOF among their columns
+        const int ln = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int rrel = (int)(__shfl_sync(0xffffffffu, rr.g0, ln) - base0);
+        const int rlen = __shfl_sync(0xffffffffu, len, ln);
+        const int64_t vr = (int64_t)tile * R + (ln >> 2);
+        double el[NDOF];
+#pragma unroll
+        for (int i = 0; i < NDOF; ++i) el[i] = 0.0;
+        for (int u = lane; u < rlen * B; u += 32) {
+          const int t = u / B, ij = u - t * B, i = ij / NDOF, j = ij - i * NDOF;
+          const int64_t c = s.gcol[base0 + rrel + t];
+          double a = accw[rrel * B + u];
+          if (dflag[vr * NDOF + i]) a = (c == vr && i == j) ? 1.0 : 0.0;
+          else if (dir_mode == 1 && dflag[c * NDOF + j]) {
+            const double d = a * dval[c * NDOF + j];
+#pragma unroll
+            for (int ii = 0; ii < NDOF; ++ii) el[ii] -= (ii == i) ? d : 0.0;
+            a = 0.0;
+          }
+          accw[rrel * B + u] = a;
+        }
+        if (dir_mode == 1) {
+#pragma unroll
+          for (int i = 0; i < NDOF; ++i) {
+            const double tot = warp_sum(el[i]);
+            if (lane == 0) elim_out[vr * NDOF + i] = dflag[vr * NDOF + i] ? 0.0 : tot;
+          }
+        }
+      }
+      __syncwarp();
+      double *dst = s.vals + base0 * B;
+      for (int i = lane; i < total; i += 32) __stcs(dst + i, accw[i]);
+      __syncwarp();
+      if (tile + stride >= ntiles) break;
+      tile += stride;
+      rr = rrn;
+      first = true;
+    }
+  }
+  cp_async_wait<0>();
+#undef EFV_BISSUE_OP
+#undef EFV_BCOMP_OP
+}
+// vertices with a Dirichlet DOF (any component) among the columns of their block row, themselves included
+__global__ void k_mark_vertices(int64_t nrows, int ndof, const int64_t *__restrict__ gptr, const int32_t *__restrict__ gcol,
+                                const uint8_t *__restrict__ flag, uint8_t *__restrict__ mark) {
+  const int lane = threadIdx.x & 7;
+  const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~7);
+  const int64_t groups = ((int64_t)gridDim.x * blockDim.x) >> 3;
+  const int64_t rounds = (nrows + groups - 1) / groups;
+  for (int64_t it = 0; it < rounds; ++it) {
+    const int64_t v = it * groups + ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3);
+    int any = 0;
+    if (v < nrows)
+      for (int64_t t = gptr[v] + lane; t < gptr[v + 1]; t += 8) {
+        const int64_t c = gcol[t];
+        for (int j = 0; j < ndof; ++j) any |= flag[c * ndof + j];
+      }
+    any = __any_sync(gmask, any);
+    if (v < nrows && lane == 0) mark[v] = (uint8_t)(any != 0);
+  }
+}
+template <int UCODE, int NDOF>
+static bool launch_elas_lanes(efv_system *s, const double *dprops, int gravity) {
+  const char *mode = getenv("EFV_ASSEMBLY");
+  if (mode && (strcmp(mode, "rows") == 0 || strcmp(mode, "tiles") == 0)) return false;
+  constexpr int B = NDOF * NDOF;
+  const int acc_cap = kBlkRows * s->max_row_len * B;
+  const size_t smem = (size_t)kBlkWarps * blk_warp_doubles(UCODE, NDOF, acc_cap) * sizeof(double);
+  if (smem + 1024 > (size_t)kLaneSmemBudget) return false;
+  efv_mesh *m = s->mesh;
+  if (!ensure_pair_schedule8(m)) return false;
+  ensure_face_records(m);
+  if (s->fuse_mode >= 0) {
+    if (s->row_mark.n < (size_t)s->nV) s->row_mark.alloc(s->nV);
+    EFV_LAUNCH(k_mark_vertices, grid_for(s->n_owned * 8, 256), 256, 0, s->n_owned, NDOF, s->gptr.p, s->gcol.p, s->dir_flag.p, s->row_mark.p);
+  }
+  MeshView mv = view_of(m);
+  GeomView gv = geom_of(m);
+  SysView sv = sys_view(s);
+  EFV_CUDA(cudaFuncSetAttribute((k_elas_lanes<UCODE, NDOF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EFV_CUDA(cudaFuncSetAttribute((k_elas_lanes<UCODE, NDOF>), cudaFuncAttributePreferredSharedMemoryCarveout, 70));
+  int per_sm = 0;
+  EFV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k_elas_lanes<UCODE, NDOF>), kBlkWarps * 32, smem));
+  per_sm = std::min<int>(per_sm, (int)(kLaneSmemBudget / (smem + 1024)));
+  if (per_sm < 1) return false;
+  const int64_t ntiles = div_up(s->n_owned, kBlkRows);
+  int64_t blocks = std::min<int64_t>(div_up(ntiles, kBlkWarps), (int64_t)num_sms() * per_sm);
+  if (const char *e = getenv("EFV_LANE_GRID")) blocks = std::min<int64_t>(blocks, std::max(1, atoi(e)));   // tests: many tiles per warp
+  EFV_LAUNCH((k_elas_lanes<UCODE, NDOF>), (int)std::max<int64_t>(blocks, 1), kBlkWarps * 32, smem, mv, gv, sv, dprops, m->sched8_pk.p,
+             m->sched8_off.p, gravity, acc_cap, s->fuse_mode, s->dir_flag.p, s->row_mark.p, s->dir_value.p, s->gen.p, s->elim.p);
+  return true;
+}
+
 template <int UCODE, int NDOF>
 static void launch_elasticity_rows(efv_system *s, const double *dprops, int gravity) {
-  if (launch_elas_tiles<UCODE, NDOF>(s, dprops, gravity)) return;       // default: pair-centric tile kernel
+  if (launch_elas_lanes<UCODE, NDOF>(s, dprops, gravity)) return;       // default: lane kernel (4 lanes per vertex)
+  if (launch_elas_tiles<UCODE, NDOF>(s, dprops, gravity)) return;       // EFV_ASSEMBLY=tiles: pair-centric tile kernel
   efv_mesh *m = s->mesh;
   size_t smem = ((size_t)kElRows * s->max_row_len * NDOF * NDOF + (size_t)kElRows * kAsmGroup * 12 * kMaxVF) * sizeof(double);
   EFV_CUDA(cudaFuncSetAttribute((k_elasticity_rows<UCODE, NDOF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2347,3 +2736,4 @@ void vec_download(const efv_system *s, const DBuf<double> &src, double *host) {
 }
 
 }  // namespace efv
+

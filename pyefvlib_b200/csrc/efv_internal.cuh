@@ -77,6 +77,9 @@ struct efv_mesh {
   efv::DBuf<uint32_t> sched_pk;     // [steps][32]  local vertex | last step of the tile | [shape] | element (assemble.cu: kPd*)
   efv::DBuf<int64_t> sched_off;     // [tiles + 1] first step of a tile
   int64_t sched_steps = 0;
+  efv::DBuf<uint32_t> sched8_pk;    // the same with tiles of 8 vertices, [steps][8] (block assembly: 4 lanes per row)
+  efv::DBuf<int64_t> sched8_off;
+  int64_t sched8_steps = 0;
   efv::ShapeGroup groups[efv::kNumShapes];
   efv::Boundaries bnd;
   bool has_geometry = false;
