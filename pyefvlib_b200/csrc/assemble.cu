@@ -1217,10 +1217,34 @@ __global__ void k_face_records(int64_t n, int NF, int D, const double *__restric
     rec[t] = (a < D * D) ? Jinv[(int64_t)(f * D * D + a) * n + k] : S[(int64_t)(f * 3 + (a - D * D)) * n + k];
   }
 }
-static void ensure_face_records(efv_mesh *m) {
+// simplex records: [s_f (d doubles) for every inner face | J^-1 of the element (the first face's copy) | pad]
+__host__ __device__ constexpr int simplex_rec_doubles(int code) { return code == 0 ? 10 : 28; }
+__global__ void k_simplex_records(int64_t n, int NF, int D, int RS, const double *__restrict__ Jinv, const double *__restrict__ S,
+                                  double *__restrict__ rec) {
+  const int64_t total = n * RS;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int a = (int)(t % RS);
+    const int64_t k = t / RS;
+    double v = 0.0;
+    if (a < NF * D) v = S[(int64_t)((a / D) * 3 + (a % D)) * n + k];
+    else if (a < NF * D + D * D) v = Jinv[(int64_t)(a - NF * D) * n + k];
+    rec[t] = v;
+  }
+}
+static void ensure_simplex_records(efv_mesh *m) {
+  for (int code = 0; code <= 2; code += 2) {
+    ShapeGroup &g = m->groups[code];
+    if (!g.n || g.Srec.n) continue;
+    const int d = shape_dim(code), nf = shape_nf(code), rs = simplex_rec_doubles(code);
+    g.Srec.alloc((size_t)g.n * rs);
+    EFV_LAUNCH(k_simplex_records, grid_for(g.n * rs, 256), 256, 0, g.n, nf, d, rs, g.Jinv.p, g.S.p, g.Srec.p);
+  }
+}
+static void ensure_face_records(efv_mesh *m, bool skip_simplices = false) {
   for (int code = 0; code < kNumShapes; ++code) {
     ShapeGroup &g = m->groups[code];
     if (!g.n || g.Frec.n) continue;
+    if (skip_simplices && (code == 0 || code == 2)) continue;
     const int d = shape_dim(code), nf = shape_nf(code);
     g.Frec.alloc((size_t)g.n * nf * (d * d + d));
     EFV_LAUNCH(k_face_records, grid_for(g.n * nf * (d * d + d), 256), 256, 0, g.n, nf, d, g.Jinv.p, g.S.p, g.Frec.p);
@@ -1570,9 +1594,12 @@ static bool launch_elas_tiles(efv_system *s, const double *dprops, int gravity) 
 constexpr int kBlkRows = 8, kBlkStages = 2, kBlkWarps = 2;
 // doubles per vertex and stage: NVF face records + sub-volume + slot bytes, padded to an ODD number of 16-byte units so that
 // the 8 vertices of a tile read their records from 8 different bank groups
+// simplices: [s of the NVF faces, d doubles each | pad to even | J^-1 | sub-volume | slot bytes]
+__host__ __device__ constexpr int blk_simplex_jbase(int dim) { return ((dim == 3 ? 3 : 2) * dim + 1) & ~1; }
 __host__ __device__ constexpr int blk_row_stride(int ucode, int dim) {
   const int rf = dim * dim + dim;
-  const int slots = (ucode < 0 ? (dim == 3 ? 4 : 2) : shape_nvf(ucode)) * rf + 2;
+  const int slots = (ucode == 0 || ucode == 2) ? blk_simplex_jbase(dim) + dim * dim + 2
+                                               : (ucode < 0 ? (dim == 3 ? 4 : 2) : shape_nvf(ucode)) * rf + 2;
   const int units = (slots + 1) / 2;
   return 2 * (units | 1);
 }
@@ -1592,32 +1619,49 @@ __device__ __forceinline__ void elas_lane_issue(unsigned stg, uint32_t pk, bool 
   if (pd_none(pk, mx)) return;
   const int64_t e = (int64_t)(pk & pd_elem_mask(mx));
   const int64_t gi = U ? e : m.group_index(e);
-  const double2 *rec = reinterpret_cast<const double2 *>(g.Frec[CODE] + (size_t)gi * NF * RF);     // 16-byte aligned: RF is even
+  constexpr int VOFF = SIMPLEX ? blk_simplex_jbase(D) + D * D : NVF * RF;      // sub-volume, then the slot bytes
+  if constexpr (SIMPLEX) {
+    // one compact record per element: the area vectors of the 3 (2) faces of this vertex, 8 bytes at a time (they start
+    // at odd doubles in 3-D), and J^-1 in 16-byte chunks
+    constexpr int RS = simplex_rec_doubles(CODE), JB = blk_simplex_jbase(D);
+    const double *rec = g.Srec[CODE] + (size_t)gi * RS;
 #pragma unroll
-  for (int k = 0; k < NVF; ++k) {
-    const int enc = Tab::vface_c(L, k);
-    const int f = enc < 0 ? 0 : enc >> 1;
+    for (int k = 0; k < NVF; ++k) {
+      const int f = Tab::vface_c(L, k) >> 1;
 #pragma unroll
-    for (int p = 0; p < RF / 2; ++p) {
-      constexpr int dummy = 0; (void)dummy;
-      const int c = k * (RF / 2) + p;
-      // simplices: J^-1 is the same on every face, only the first record is read in full, of the others only s
-      if (enc >= 0 && (!SIMPLEX || k == 0 || 2 * p + 1 >= D * D) && q == (c & 3)) cp_async16(stg + c * 16, rec + (f * RF) / 2 + p);
+      for (int a = 0; a < D; ++a)
+        if (q == ((k * D + a) & 3)) cp_async8(stg + (k * D + a) * 8, rec + f * D + a);
+    }
+#pragma unroll
+    for (int p = 0; p < (D * D) / 2; ++p)
+      if (q == (p & 3)) cp_async16(stg + (JB + 2 * p) * 8, rec + NF * D + 2 * p);
+    if ((D * D) & 1) { if (q == 3) cp_async8(stg + (JB + D * D - 1) * 8, rec + NF * D + D * D - 1); }
+  } else {
+    const double2 *rec = reinterpret_cast<const double2 *>(g.Frec[CODE] + (size_t)gi * NF * RF);   // 16-byte aligned: RF is even
+#pragma unroll
+    for (int k = 0; k < NVF; ++k) {
+      const int enc = Tab::vface_c(L, k);
+      const int f = enc < 0 ? 0 : enc >> 1;
+#pragma unroll
+      for (int p = 0; p < RF / 2; ++p) {
+        const int c = k * (RF / 2) + p;
+        if (enc >= 0 && q == (c & 3)) cp_async16(stg + c * 16, rec + (f * RF) / 2 + p);
+      }
     }
   }
   if (q == 0) {
     unsigned nb = (unsigned)g.n[CODE] * 8u;
-    cp_async8(stg + NVF * RF * 8, reinterpret_cast<const char *>(g.vol[CODE] + gi) + (uint64_t)(unsigned)L * nb);
+    cp_async8(stg + VOFF * 8, reinterpret_cast<const char *>(g.vol[CODE] + gi) + (uint64_t)(unsigned)L * nb);
   }
   if (q == 1) {
     const uint8_t *sp = s.slotpos + (U ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
-    if (U && M == 8) cp_async8(stg + (NVF * RF + 1) * 8, sp);
-    else if (U && M == 4) cp_async4(stg + (NVF * RF + 1) * 8, sp);
+    if (U && M == 8) cp_async8(stg + (VOFF + 1) * 8, sp);
+    else if (U && M == 4) cp_async4(stg + (VOFF + 1) * 8, sp);
     else {
       unsigned long long pb = 0;
 #pragma unroll
       for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
-      asm volatile("st.shared.b64 [%0], %1;" ::"r"(stg + (NVF * RF + 1) * 8), "l"(pb) : "memory");
+      asm volatile("st.shared.b64 [%0], %1;" ::"r"(stg + (VOFF + 1) * 8), "l"(pb) : "memory");
     }
   }
 }
@@ -1636,33 +1680,49 @@ __device__ __forceinline__ void elas_lane_compute(const double *__restrict__ stg
   for (int k = 0; k < NK; ++k)
 #pragma unroll
     for (int i = 0; i < D; ++i) { ls[k][i] = 0.0; ms[k][i] = 0.0; }
-  const double2 *st2 = reinterpret_cast<const double2 *>(stg);
+  constexpr int VOFF = SIMPLEX ? blk_simplex_jbase(D) + D * D : NVF * RF;
+  if constexpr (SIMPLEX) {
+    constexpr int JB = blk_simplex_jbase(D);
 #pragma unroll
-  for (int k = 0; k < NVF; ++k) {
-    const int enc = Tab::vface_c(L, k);
-    const double sg = (enc & 1) ? -1.0 : 1.0;       // this vertex is the forward one of the face: -M (stress_equilibrium.py:105-117)
-    const int kk = SIMPLEX ? 0 : k;
-    double buf[RF];
+    for (int i = 0; i < D; ++i)
 #pragma unroll
-    for (int p = 0; p < RF / 2; ++p) {
-      double2 t2 = make_double2(0.0, 0.0);
-      if (enc >= 0 && (!SIMPLEX || k == 0 || 2 * p + 1 >= D * D)) t2 = st2[k * (RF / 2) + p];
-      buf[2 * p] = t2.x; buf[2 * p + 1] = t2.y;
+      for (int a = 0; a < D; ++a) J[0][i][a] = stg[JB + i * D + a];
+#pragma unroll
+    for (int k = 0; k < NVF; ++k) {
+      const double sg = (Tab::vface_c(L, k) & 1) ? -1.0 : 1.0;
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        const double sv = stg[k * D + i];
+        ls[0][i] += lam * (sg * sv);
+        ms[0][i] += mu * (sg * sv);
+      }
     }
-    if (!SIMPLEX || k == 0) {
+  } else {
+    const double2 *st2 = reinterpret_cast<const double2 *>(stg);
+#pragma unroll
+    for (int k = 0; k < NVF; ++k) {
+      const int enc = Tab::vface_c(L, k);
+      const double sg = (enc & 1) ? -1.0 : 1.0;     // this vertex is the forward one of the face: -M (stress_equilibrium.py:105-117)
+      double buf[RF];
+#pragma unroll
+      for (int p = 0; p < RF / 2; ++p) {
+        double2 t2 = make_double2(0.0, 0.0);
+        if (enc >= 0) t2 = st2[k * (RF / 2) + p];
+        buf[2 * p] = t2.x; buf[2 * p + 1] = t2.y;
+      }
 #pragma unroll
       for (int i = 0; i < D; ++i)
 #pragma unroll
-        for (int a = 0; a < D; ++a) J[kk][i][a] = buf[i * D + a];
-    }
+        for (int a = 0; a < D; ++a) J[k][i][a] = buf[i * D + a];
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      ls[kk][i] += lam * (sg * buf[D * D + i]);
-      ms[kk][i] += mu * (sg * buf[D * D + i]);
+      for (int i = 0; i < D; ++i) {
+        ls[k][i] += lam * (sg * buf[D * D + i]);
+        ms[k][i] += mu * (sg * buf[D * D + i]);
+      }
     }
   }
-  const double vol = stg[NVF * RF];
-  const uint2 sb = *reinterpret_cast<const uint2 *>(stg + NVF * RF + 1);
+  const double vol = stg[VOFF];
+  const uint2 sb = *reinterpret_cast<const uint2 *>(stg + VOFF + 1);
   grav += __dmul_rn(vol, pr[2]);
   double lsq[NK], dq[NDOF];                         // lambda s_q of every face; unit vector of this lane's component
 #pragma unroll
@@ -1712,7 +1772,7 @@ template <int UCODE, int NDOF>
 __global__ void __launch_bounds__(kBlkWarps * 32) k_elas_lanes(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
                                                                const __grid_constant__ SysView s, const double *__restrict__ props,
                                                                const uint32_t *__restrict__ spk, const int64_t *__restrict__ soff,
-                                                               int gravity, int acc_cap, int dir_mode,
+                                                               int gravity, int acc_cap, int dir_mode, int single_region_i,
                                                                const uint8_t *__restrict__ dflag, const uint8_t *__restrict__ vmark,
                                                                const double *__restrict__ dval,
                                                                double *__restrict__ gen_out, double *__restrict__ elim_out) {
@@ -1725,6 +1785,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_elas_lanes(const __grid_cons
   constexpr int kRowStride = blk_row_stride(UCODE, NDOF), kStageBytes = R * kRowStride * 8;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int r = lane >> 2, q = lane & 3;                                  // vertex of the tile, component / copy lane
+  const bool single_region = single_region_i != 0;
   double *accw = lane_smem + (size_t)wib * blk_warp_doubles(UCODE, NDOF, acc_cap);   // image of the tile's BSR value segment
   const unsigned accw_sa = (unsigned)__cvta_generic_to_shared(accw);
   const unsigned ring_sa = accw_sa + (unsigned)acc_cap * 8u + (unsigned)(r * kRowStride) * 8u;   // this vertex's row of the stages
@@ -1826,7 +1887,7 @@ __global__ void __launch_bounds__(kBlkWarps * 32) k_elas_lanes(const __grid_cons
     {
       const double *stg = accw + acc_cap + slotA * (kStageBytes / 8) + r * kRowStride;
       const double *pr = props;
-      if (!pd_none(pkA, MX)) pr += 3 * m.region[pkA & pd_elem_mask(MX)];
+      if (!single_region && !pd_none(pkA, MX)) pr += 3 * m.region[pkA & pd_elem_mask(MX)];
       EFV_LANE_DISPATCH(UCODE, keyof(pkA), EFV_BCOMP_OP);
     }
     __syncwarp();                                                         // stage may be overwritten by the next issue
@@ -1914,7 +1975,8 @@ static bool launch_elas_lanes(efv_system *s, const double *dprops, int gravity) 
   if (smem + 1024 > (size_t)kLaneSmemBudget) return false;
   efv_mesh *m = s->mesh;
   if (!ensure_pair_schedule8(m)) return false;
-  ensure_face_records(m);
+  ensure_simplex_records(m);
+  ensure_face_records(m, true);
   if (s->fuse_mode >= 0) {
     if (s->row_mark.n < (size_t)s->nV) s->row_mark.alloc(s->nV);
     EFV_LAUNCH(k_mark_vertices, grid_for(s->n_owned * 8, 256), 256, 0, s->n_owned, NDOF, s->gptr.p, s->gcol.p, s->dir_flag.p, s->row_mark.p);
@@ -1932,7 +1994,8 @@ static bool launch_elas_lanes(efv_system *s, const double *dprops, int gravity) 
   int64_t blocks = std::min<int64_t>(div_up(ntiles, kBlkWarps), (int64_t)num_sms() * per_sm);
   if (const char *e = getenv("EFV_LANE_GRID")) blocks = std::min<int64_t>(blocks, std::max(1, atoi(e)));   // tests: many tiles per warp
   EFV_LAUNCH((k_elas_lanes<UCODE, NDOF>), (int)std::max<int64_t>(blocks, 1), kBlkWarps * 32, smem, mv, gv, sv, dprops, m->sched8_pk.p,
-             m->sched8_off.p, gravity, acc_cap, s->fuse_mode, s->dir_flag.p, s->row_mark.p, s->dir_value.p, s->gen.p, s->elim.p);
+             m->sched8_off.p, gravity, acc_cap, s->fuse_mode, m->n_regions == 1 ? 1 : 0, s->dir_flag.p, s->row_mark.p, s->dir_value.p,
+             s->gen.p, s->elim.p);
   return true;
 }
 

@@ -27,6 +27,8 @@ struct ShapeGroup {
   DBuf<double> St;          // per face  J^-T s  (NF*d components): all the heat operator needs
   DBuf<double> Frec;        // AoS copy for the block assembly kernels: per (element, face) one record [J^-1 row-major | s] of
                             // d*d + d doubles (96 B in 3-D = three full sectors), built on first use
+  DBuf<double> Srec;        // simplices only (J^-1 is the same on every face): per element [s of every face | J^-1], padded
+                            // to an even number of doubles (tetrahedron 28, triangle 10) -- 2.6x smaller than Frec
 };
 
 struct Boundaries {

@@ -69,6 +69,7 @@ struct GeomView {
   const double *vol[kNumShapes];
   const double *St[kNumShapes];
   const double *Frec[kNumShapes];
+  const double *Srec[kNumShapes];
   int64_t n[kNumShapes];
 };
 inline GeomView geom_of(const efv_mesh *m) {
@@ -79,6 +80,7 @@ inline GeomView geom_of(const efv_mesh *m) {
     g.vol[c] = m->groups[c].vol.p;
     g.St[c] = m->groups[c].St.p;
     g.Frec[c] = m->groups[c].Frec.p;
+    g.Srec[c] = m->groups[c].Srec.p;
     g.n[c] = m->groups[c].n;
   }
   return g;
