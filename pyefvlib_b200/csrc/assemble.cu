@@ -1,12 +1,14 @@
 // assemble.cu -- north_star kernels 3 and 4: fused FP64 assembly with a deterministic row-wise reduction,
 // Dirichlet row replacement / symmetric elimination, Neumann facet terms, right-hand sides.
 //
-// Assembly is ROW-CENTRIC: a group of GROUP lanes owns one graph row (vertex v).  It walks the incidence list
-// of v in ascending element order; for each incident (element e, local vertex l) it evaluates the inner faces
-// that touch l from the SoA geometry (Jacobian inverse + area vector per face), lane j producing the
-// coefficient of column conn[e][j], and adds it into a shared-memory copy of the row at the position given by
-// the byte slot map.  Every CSR entry is therefore summed by exactly one lane group in a fixed order: no float
-// atomics, bit-reproducible, values written with coalesced stores.  (apps/heat_transfer.py:41-68)
+// Assembly is ROW-CENTRIC: one owner per graph row (vertex v) walks the (element e, local vertex l) pairs of v in
+// ascending (local vertex, element) order, evaluates the inner faces that touch l from the stored geometry, and adds
+// the coefficient of every column conn[e][j] into a shared-memory copy of the row at the position given by the byte
+// slot map.  Every CSR entry is therefore summed by exactly one owner in a fixed order: no float atomics,
+// bit-reproducible, values written with coalesced stores.  (apps/heat_transfer.py:41-68)
+// The owner is a LANE in the default kernels (k_heat_lanes: a warp = 32 rows; k_elas_lanes: a warp = 8 vertices x 4 lanes)
+// and an 8-lane group in the round-1 row-group kernels (k_heat_rows, k_elasticity_rows, k_biot_rows), which remain the
+// fall-back and the Biot path.
 #include "views.cuh"
 #include <cstdlib>
 #include <cstring>
@@ -247,331 +249,29 @@ __global__ void k_mark_rows(int64_t nrows, const int64_t *__restrict__ gptr, con
   }
 }
 
-// ---- tile kernel (default heat assembly) ---------------------------------------------------------------------------------
-// k_heat_rows spends its time in the load/store unit: every lane of a row group re-reads the 9 staged face components
-// and 9 table entries from shared memory for every (row, element) pair.  k_heat_tiles keeps the row ownership (one
-// 8-lane group sums a row in ascending (local vertex, element) order: no float atomics, bit-reproducible)
-// but computes the pair contributions PAIR-centric: a block owns a tile of R consecutive rows, buckets the tile's
-// (element, local vertex) pairs by (shape, local vertex) so that every warp works on one local vertex l, and a thread
-// computes the whole local-matrix row l of its pair in registers with the table entries as constant-bank operands
-// (statically unrolled for that l).  The m coefficients go to a shared-memory slab indexed by the pair's position in
-// the row-major incidence order, from which the row groups then accumulate them through the byte slot map.
-constexpr int kTileThreads = 256;
-// byte offsets of the tile kernel's shared-memory arrays (32-bit shared addressing instead of seven generic pointers)
-struct TileSmem {
-  int rowacc, slab, posb, pks, order, krank, pkey, total;
-  __host__ __device__ TileSmem(int R, int max_row_len, int cap, int mmax) {
-    rowacc = 0;
-    slab = rowacc + R * max_row_len * 8;
-    posb = slab + (mmax + 2) * cap * 8;
-    pks = posb + cap * 8;
-    order = pks + cap * 4;                  // cap + 2048 work-list slots (64 buckets padded to warp multiples)
-    krank = order + (cap + 2048) * 2;
-    pkey = krank + cap * 2;
-    total = (pkey + cap + 15) & ~15;
-  }
-};
-extern __shared__ __align__(16) unsigned char tile_smem[];
-template <class Tab, int L>
-__device__ __forceinline__ void heat_pair_row(const MeshView &m, const GeomView &g, const SysView &s, const double *__restrict__ props,
-                                              int64_t e, bool uniform, int idx, int cap, int slab_off, int posb_off, int mmax,
-                                              bool single_region) {
-  // idx = compact position of the pair inside its (shape, local vertex) bucket: consecutive over the lanes of a warp
-  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE;
-  const int64_t gi = uniform ? e : m.group_index(e);
-  int64_t n = g.n[CODE];
-  // keep the SoA strides out of loop-invariant hoisting: 36 precomputed 64-bit plane offsets would not fit in registers
-  asm volatile("" : "+l"(n));
-  const double *pr = single_region ? props : props + 3 * m.region[e];     // one region: no dependent load before the props
-  const double cond = pr[0];
-  const double *St = g.St[CODE] + gi;
-  double t[NVF][D];
-#pragma unroll
-  for (int k = 0; k < NVF; ++k) {
-    const int f = Tab::vface_c(L, k) >> 1;
-#pragma unroll
-    for (int a = 0; a < D; ++a) t[k][a] = (Tab::vface_c(L, k) >= 0) ? St[(int64_t)(f * D + a) * n] : 0.0;   // -1: no such face
-  }
-  const uint8_t *sp = s.slotpos + (uniform ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
-  unsigned long long pb;
-  if (uniform && M == 8) pb = *reinterpret_cast<const unsigned long long *>(sp);
-  else if (uniform && M == 4) pb = *reinterpret_cast<const unsigned int *>(sp);
-  else {
-    pb = 0;
-#pragma unroll
-    for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
-  }
-  const double vol = g.vol[CODE][(int64_t)L * n + gi];
-  *reinterpret_cast<unsigned long long *>(tile_smem + posb_off + idx * 8) = pb;
-  double *out = reinterpret_cast<double *>(tile_smem + slab_off) + idx;
-  out[mmax * cap] = vol * pr[2];
-  out[(mmax + 1) * cap] = vol * pr[1];
-#pragma unroll
-  for (int k = 0; k < NVF; ++k) {
-    const double sg = (Tab::vface_c(L, k) & 1) ? cond : -cond;    // forward vertex +flux, backward -flux (heat_transfer.py:52-54)
-#pragma unroll
-    for (int a = 0; a < D; ++a) t[k][a] *= sg;
-  }
-#pragma unroll
-  for (int j = 0; j < M; ++j) {
-    double w = 0.0;
-#pragma unroll
-    for (int k = 0; k < NVF; ++k) {
-      const int f = Tab::vface_c(L, k) >> 1;
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-        if (Tab::vface_c(L, k) >= 0 && Tab::ifD_c(f < 0 ? 0 : f, j, a) != 0.0)
-          w += Tab::ifD_c(f < 0 ? 0 : f, j, a) * t[k][a];                         // k * G^T s (heat_transfer.py:47)
-    }
-    out[j * cap] = w;
-  }
-}
-template <class Tab, int UCODE>
-__device__ __forceinline__ void heat_pair_shape(int l, const MeshView &m, const GeomView &g, const SysView &s,
-                                                const double *__restrict__ props, int64_t e, int idx, int cap, int slab_off,
-                                                int posb_off, int mmax, bool single_region) {
-  if constexpr (UCODE < 0 || UCODE == Tab::CODE) {
-    constexpr bool U = UCODE >= 0;
-    switch (l) {
-#define EFV_PAIR_CASE(LL) \
-  case LL: if constexpr (Tab::M > LL) heat_pair_row<Tab, LL>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax, single_region); break;
-      EFV_PAIR_CASE(0) EFV_PAIR_CASE(1) EFV_PAIR_CASE(2) EFV_PAIR_CASE(3)
-      EFV_PAIR_CASE(4) EFV_PAIR_CASE(5) EFV_PAIR_CASE(6) EFV_PAIR_CASE(7)
-#undef EFV_PAIR_CASE
-      default: break;
-    }
-  }
-}
-
-template <int UCODE>
-__global__ void __launch_bounds__(kTileThreads, 5) k_heat_tiles(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
-                                                                const __grid_constant__ SysView s, const double *__restrict__ props,
-                                                                int transient, int max_row_len, int R, int cap, int mmax, int dir_mode,
-                                                                int single_region_i,
-                                                                const uint8_t *__restrict__ dflag, const uint8_t *__restrict__ rmark,
-                                                                const double *__restrict__ dval,
-                                                                double *__restrict__ gen_out, double *__restrict__ acc_out,
-                                                                double *__restrict__ elim_out) {
-  const TileSmem off(R, max_row_len, cap, mmax);
-#define T_ROWACC reinterpret_cast<double *>(tile_smem + off.rowacc)
-#define T_SLAB reinterpret_cast<double *>(tile_smem + off.slab)
-#define T_POSB reinterpret_cast<unsigned long long *>(tile_smem + off.posb)
-#define T_PKS reinterpret_cast<uint32_t *>(tile_smem + off.pks)
-#define T_ORDER reinterpret_cast<uint16_t *>(tile_smem + off.order)
-#define T_KRANK reinterpret_cast<uint16_t *>(tile_smem + off.krank)
-#define T_PKEY (tile_smem + off.pkey)
-  __shared__ int cnt[64], base[65], cbase[64], rp[33];           // buckets: shape code * 8 + local vertex
-  __shared__ uint8_t okey[(2048 + 2048) / 32];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int grp = tid / kAsmGroup, gl = tid % kAsmGroup;
-  const unsigned gmask = 0xffu << ((tid & 31) / kAsmGroup * kAsmGroup);
-  const int64_t ntiles = (s.nV + R - 1) / R;
-  const bool single_region = single_region_i != 0;
-  // The per-tile chain of dependent global loads (row range -> incidence entries -> geometry -> row pointers) is what
-  // the kernel waits on, so the head of the chain is fetched one tile ahead: while a tile is in its pair / row phases,
-  // the incidence boundaries and the first 256 packed pairs of the block's NEXT tile are already in flight.
-  int64_t cP0 = 0, cP1 = 0, c_rp = 0;
-  uint32_t c_pk = 0;
-  if ((int64_t)blockIdx.x < ntiles) {
-    const int64_t v0 = (int64_t)blockIdx.x * R;
-    const int rows = (int)min((int64_t)R, s.nV - v0);
-    cP0 = m.inc_ptr[v0];
-    cP1 = m.inc_ptr[v0 + rows];
-    if (tid <= rows) c_rp = m.inc_ptr[v0 + tid];
-    if (tid < cP1 - cP0) c_pk = m.inc[cP0 + tid];
-  }
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t v0 = tile * R;
-    const int rows = (int)min((int64_t)R, s.nV - v0);
-    const int64_t P0 = cP0;
-    const int np = (int)(cP1 - cP0);
-    // next tile of this block: boundaries now, packed pairs before the row phase (they need nP0)
-    const int64_t ntile = tile + gridDim.x;
-    int64_t nP0 = 0, nP1 = 0, n_rp = 0;
-    if (ntile < ntiles) {
-      const int64_t v0n = ntile * R;
-      const int rowsn = (int)min((int64_t)R, s.nV - v0n);
-      nP0 = m.inc_ptr[v0n];
-      nP1 = m.inc_ptr[v0n + rowsn];
-      if (tid <= rowsn) n_rp = m.inc_ptr[v0n + tid];
-    }
-    // row-phase operands of this tile: requested now, consumed after the pair phase
-    int64_t r0 = 0;
-    int len = 0, dslot = 0;
-    bool marked = false;
-    if (grp < rows) {
-      r0 = s.gptr[v0 + grp];
-      len = (int)(s.gptr[v0 + grp + 1] - r0);
-      dslot = s.diag_slot[v0 + grp];
-      marked = dir_mode >= 0 && rmark[v0 + grp];
-    }
-    if (tid <= rows) rp[tid] = (int)(c_rp - P0);
-    if (tid < 64) cnt[tid] = 0;
-    for (int i = tid; i < rows * max_row_len; i += kTileThreads) T_ROWACC[i] = 0.0;
-    __syncthreads();
-    // ---- bucket the tile's pairs by (shape, local vertex) ------------------------------------------------------------
-    for (int i = tid; i < np; i += kTileThreads) {
-      const uint32_t pk = (i < kTileThreads) ? c_pk : m.inc[P0 + i];
-      const int code = (UCODE >= 0) ? UCODE : m.code(inc_elem(pk));
-      const int key = code * 8 + inc_local(pk);
-      const int rank = atomicAdd(&cnt[key], 1);          // the rank only decides which thread computes the pair and where
-                                                         // in the slab its coefficients wait; the sums do not depend on it
-      T_PKS[i] = pk;
-      T_PKEY[i] = (uint8_t)key;
-      T_KRANK[i] = (uint16_t)rank;
-    }
-    __syncthreads();
-    if (tid < 32) {                                      // lane t scans buckets 2t and 2t+1
-      const int c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
-      const int p0 = (c0 + 31) & ~31, p1 = (c1 + 31) & ~31;
-      int incl = p0 + p1, cincl = c0 + c1;               // padded prefix: work-list slots; unpadded: compact slab positions
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, o), cup = __shfl_up_sync(0xffffffffu, cincl, o);
-        if (lane >= o) { incl += up; cincl += cup; }
-      }
-      const int b0 = incl - p0 - p1, cb0 = cincl - c0 - c1;
-      base[2 * tid] = b0;
-      base[2 * tid + 1] = b0 + p0;
-      cbase[2 * tid] = cb0;
-      cbase[2 * tid + 1] = cb0 + c0;
-      if (tid == 31) base[64] = incl;
-      for (int q = b0 + c0; q < b0 + p0; ++q) T_ORDER[q] = 0xffffu;
-      for (int q = b0 + p0 + c1; q < b0 + p0 + p1; ++q) T_ORDER[q] = 0xffffu;
-      for (int q = b0; q < b0 + p0; q += 32) okey[q >> 5] = (uint8_t)(2 * tid);
-      for (int q = b0 + p0; q < b0 + p0 + p1; q += 32) okey[q >> 5] = (uint8_t)(2 * tid + 1);
-    }
-    __syncthreads();
-    for (int i = tid; i < np; i += kTileThreads) {
-      const int key = T_PKEY[i], rank = T_KRANK[i];
-      T_ORDER[base[key] + rank] = (uint16_t)i;
-      T_KRANK[i] = (uint16_t)(cbase[key] + rank);         // from here on: pair -> compact slab position
-    }
-    __syncthreads();
-    // ---- pair phase: one thread = one (element, local vertex) pair, a warp = one (shape, local vertex) ---------------
-    const int nslots = base[64];
-    for (int slot = tid; slot < nslots; slot += kTileThreads) {
-      const int pair = T_ORDER[slot];
-      if (pair == 0xffff) continue;
-      const int key = okey[slot >> 5];
-      const int64_t e = inc_elem(T_PKS[pair]);
-      const int l = key & 7;
-      const int idx = cbase[key] + (slot - base[key]);
-      switch (key >> 3) {
-        case 0: heat_pair_shape<TriangleTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
-        case 1: heat_pair_shape<QuadrilateralTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
-        case 2: heat_pair_shape<TetrahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
-        case 3: heat_pair_shape<HexahedronTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
-        case 4: heat_pair_shape<PrismTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
-        default: heat_pair_shape<PyramidTab, UCODE>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax, single_region); break;
-      }
-    }
-    __syncthreads();
-    // ---- row phase: 8-lane group per row, pairs in ascending (local vertex, element) order ----------------------------
-    uint32_t n_pk = 0;
-    if (tid < nP1 - nP0) n_pk = m.inc[nP0 + tid];          // next tile's pairs: in flight during the row phase
-    if (grp < rows) {
-      const int64_t v = v0 + grp;
-      double *row = T_ROWACC + grp * max_row_len;
-      double gen = 0.0, accv = 0.0;
-      for (int q = rp[grp]; q < rp[grp + 1]; ++q) {
-        const int mm = (UCODE >= 0) ? shape_m(UCODE) : shape_m(T_PKEY[q] >> 3);
-        const int c = T_KRANK[q];
-        if (gl < mm) {
-          const int pos = (int)((T_POSB[c] >> (8 * gl)) & 0xff);
-          row[pos] += T_SLAB[gl * cap + c];
-        }
-        if (gl == 0) { gen += T_SLAB[mmax * cap + c]; accv += T_SLAB[(mmax + 1) * cap + c]; }
-      }
-      if (gl == 0) {
-        if (transient) row[dslot - r0] += accv;                // heat_transfer.py:62-67
-        gen_out[v] = gen;
-        acc_out[v] = accv;
-      }
-      __syncwarp(gmask);
-      if (!marked) {                                             // no Dirichlet DOF among the columns: plain copy
-        for (int t = gl; t < len; t += kAsmGroup) s.vals[r0 + t] = row[t];
-        if (dir_mode == 1 && gl == 0) elim_out[v] = 0.0;
-      } else {
-        const bool rowd = dflag[v];
-        double el = 0.0;
-        for (int t = gl; t < len; t += kAsmGroup) {
-          const int c = s.gcol[r0 + t];
-          double a = row[t];
-          if (rowd) a = (c == v) ? 1.0 : 0.0;                    // heat_transfer.py:70-76
-          else if (dir_mode == 1 && dflag[c]) { el -= a * dval[c]; a = 0.0; }
-          s.vals[r0 + t] = a;
-        }
-        if (dir_mode == 1) {
-#pragma unroll
-          for (int o = kAsmGroup / 2; o > 0; o >>= 1) el += __shfl_xor_sync(gmask, el, o);
-          if (gl == 0) elim_out[v] = rowd ? 0.0 : el;
-        }
-      }
-    }
-    __syncthreads();
-    cP0 = nP0; cP1 = nP1; c_rp = n_rp; c_pk = n_pk;
-  }
-#undef T_ROWACC
-#undef T_SLAB
-#undef T_POSB
-#undef T_PKS
-#undef T_ORDER
-#undef T_KRANK
-#undef T_PKEY
-}
-// rows per tile and pair capacity for a mesh; false when even 8-row tiles do not fit
-static bool heat_tile_shape(const efv_system *s, int *R, int *cap, int *mmax, size_t *smem) {
-  const efv_mesh *m = s->mesh;
-  *mmax = m->uniform_code >= 0 ? shape_m(m->uniform_code) : (m->dim == 3 ? 8 : 4);
-  for (int r = 32; r >= 8; r >>= 1) {
-    const int64_t pairs = (int64_t)r * m->max_incidence;
-    if (pairs > 2047) continue;                                   // 11-bit ranks, 16-bit work-list entries
-    const int c = (int)((pairs + 15) & ~(int64_t)15) + 1;          // = 1 (mod 16): the slab planes start in different banks
-    const size_t bytes = (size_t)TileSmem(r, s->max_row_len, c, *mmax).total;
-    if (bytes > 64 * 1024 && r > 8) continue;                      // keep several blocks per SM
-    if (bytes > 200 * 1024) return false;
-    *R = r; *cap = c; *smem = bytes;
-    return true;
-  }
-  return false;
-}
-template <int UCODE>
-static bool launch_heat_tiles(efv_system *s, const double *dprops, int transient) {
-  int R, cap, mmax;
-  size_t smem;
-  if (!heat_tile_shape(s, &R, &cap, &mmax, &smem)) return false;
-  efv_mesh *m = s->mesh;
-  MeshView mv = view_of(m);
-  GeomView gv = geom_of(m);
-  SysView sv = sys_view(s);
-  EFV_CUDA(cudaFuncSetAttribute(k_heat_tiles<UCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t ntiles = div_up(s->n_owned, R);
-  EFV_LAUNCH(k_heat_tiles<UCODE>, grid_for(ntiles * kTileThreads, kTileThreads, 8), kTileThreads, smem, mv, gv, sv, dprops,
-             transient, s->max_row_len, R, cap, mmax, s->fuse_mode, m->n_regions == 1 ? 1 : 0, s->dir_flag.p, s->row_mark.p,
-             s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
-  return true;
-}
-
 // ---- lane-per-row kernel (default heat assembly, round 2) --------------------------------------------------------------
-// k_heat_tiles still spends ~7 500 warp instructions per 32-row tile (bucketing, slab traffic, 8-lane row walks, three
-// block barriers per tile).  k_heat_lanes has no block-level phase at all: a WARP owns a tile of 32 consecutive rows and
-// LANE r owns row r.
+// k_heat_rows spends its time in the load/store unit (every lane of a row group re-reads staged operands and table entries
+// from shared memory for every (row, element) pair; the round-1 tile kernel that replaced it still needed ~7 500 warp
+// instructions per 32 rows for bucketing, slab traffic and three block barriers: 4.25 ms at C2).  k_heat_lanes has no
+// block-level phase at all: a WARP owns a tile of 32 consecutive rows and LANE r owns row r.
 //  * pair schedule (mesh-level, built once: ensure_pair_schedule): the tile's (element, local vertex) pairs are stored
 //    [step][lane]; one step holds, for every lane, its next pair of ONE (shape, local vertex) key or a "none" marker.  The
 //    key is warp-uniform, so the pair arithmetic is statically unrolled per local vertex with the table entries as
 //    immediates and nothing diverges; descriptors are read with coalesced loads.  Per row the order stays ascending
 //    (local vertex, shape, element): every entry is summed by one lane in a fixed order -- no atomics, bit-reproducible,
-//    and for single-shape meshes bit-identical to k_heat_tiles / the partitioned runs.
-//  * operands travel global -> shared memory with per-lane asynchronous copies (cp.async, SASS LDGSTS): no registers are
-//    held while they are in flight; every warp keeps a ring of S = kLaneStages operand stages -- the 3 face vectors
-//    J^-T s, the sub-volume and the slot bytes of the steps i+1 .. i+S-1, and the descriptors of the steps up to i+2S-1,
-//    are in flight while step i computes.  A lane only ever reads what it copied itself: no barrier anywhere in the pipeline.
+//    and for single-shape meshes the same order as the row-group kernel and the partitioned runs.
+//  * software pipeline over the warp's steps (across tile boundaries): the operands of step i+1 (3 face vectors J^-T s,
+//    sub-volume, slot bytes: 11 independent loads per lane) are requested into registers while step i computes -- the
+//    scaled face vectors of step i are taken out of the operand registers first, so one set is enough -- and the
+//    descriptors run 3 steps ahead through a small cp.async ring in shared memory; the row data of the next tile is
+//    requested a whole tile ahead.  Loaded values are never touched before the step that consumes them (any use would
+//    wait for the load on the spot: the first cut lost 35 % of its time in one such SEL).
 //  * accumulator: a warp-private shared-memory image of the tile's CSR value segment (rows of a tile are contiguous in the
 //    CSR array); lane r adds coefficient j at  row_start(r) + slotpos[j].  The write-back is then a flat, fully
 //    coalesced streaming copy of that image; rows with a Dirichlet neighbour are fixed up in shared memory first.
-constexpr int kLaneWarps = 2;               // warps per block (they never synchronise with each other)
-constexpr int kLaneStages = 2;              // operand ring depth S
+// A variant that staged the operands in shared memory with per-lane cp.async (deeper pipeline, fewer registers) measured
+// 1.73 ms against 1.62 ms: a cp.async lands one 32-byte sector per shared-memory wavefront, so its 11 copies per step cost
+// ~90 wavefronts where 11 register loads cost 22 (LSU data pipe 75 % busy, profiles/r02_assembly_lanes.json).
 // descriptor word: local vertex << 29 | last step of its tile << 28 | [mixed meshes: shape code << 25] | element
 constexpr int kPdLocalShift = 29, kPdLastBit = 28, kPdCodeShift = 25;
 __host__ __device__ constexpr uint32_t pd_elem_mask(bool mixed) { return (1u << (mixed ? kPdCodeShift : kPdLastBit)) - 1u; }
@@ -654,9 +354,6 @@ static bool ensure_pair_schedule(efv_mesh *m) { return build_pair_schedule<32>(m
 // tiles of 8 rows: the block (ndof x ndof) assembly gives every row 4 lanes
 static bool ensure_pair_schedule8(efv_mesh *m) { return build_pair_schedule<8>(m, m->sched8_pk, m->sched8_off, m->sched8_steps); }
 
-// Operand stage layout [slot][lane] (8 B slots): slots 0 .. NVF*D-1 face vectors J^-T s, then the sub-volume, then the
-// slot bytes of the m columns (14 slots for the pyramid apex = the mixed-mesh size).
-__host__ __device__ constexpr int lane_slots(int ucode) { return ucode < 0 ? 14 : shape_nvf(ucode) * shape_dim(ucode) + 2; }
 __device__ __forceinline__ void cp_async8(unsigned dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -666,88 +363,6 @@ __device__ __forceinline__ void cp_async4(unsigned dst, const void *src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// issue the copies of one pair (element e, local vertex L) into the lane's column of a stage (stg = shared address of
-// slot 0 of this lane); nb = bytes per SoA plane of this shape group
-template <class Tab, int L, bool U>
-__device__ __forceinline__ void heat_lane_issue(unsigned stg, uint32_t pk, const MeshView &m, const GeomView &g, const SysView &s) {
-  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE;
-  if (pd_none(pk, !U)) return;
-  const int64_t e = (int64_t)(pk & pd_elem_mask(!U));
-  const int64_t gi = U ? e : m.group_index(e);
-  unsigned nb = (unsigned)g.n[CODE] * 8u;                         // < 2^28 elements: plane offsets = 32 x 32 -> 64-bit products
-  asm volatile("" : "+r"(nb));                                    // one IMAD.WIDE per address instead of hoisted 64-bit offsets
-  const char *St = reinterpret_cast<const char *>(g.St[CODE] + gi);
-#pragma unroll
-  for (int k = 0; k < NVF; ++k) {
-    const int f = Tab::vface_c(L, k) >> 1;
-#pragma unroll
-    for (int a = 0; a < D; ++a)
-      if (Tab::vface_c(L, k) >= 0) cp_async8(stg + (k * D + a) * 256, St + (uint64_t)(unsigned)(f < 0 ? 0 : f * D + a) * nb);
-  }
-  cp_async8(stg + NVF * D * 256, reinterpret_cast<const char *>(g.vol[CODE] + gi) + (uint64_t)(unsigned)L * nb);
-  const uint8_t *sp = s.slotpos + (U ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
-  if (U && M == 8) cp_async8(stg + (NVF * D + 1) * 256, sp);
-  else if (U && M == 4) cp_async4(stg + (NVF * D + 1) * 256, sp);
-  else {                                                          // odd sizes / mixed meshes: bytes through registers
-    unsigned long long pb = 0;
-#pragma unroll
-    for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
-    asm volatile("st.shared.b64 [%0], %1;" ::"r"(stg + (NVF * D + 1) * 256), "l"(pb) : "memory");
-  }
-}
-// consume a stage: the whole local-matrix row L of the pair in registers, added into the lane's row of the tile image.
-// pc = {conductivity, rho cp / dt, heat generation} of the element's region
-template <class Tab, int L, bool U>
-__device__ __forceinline__ void heat_lane_compute(const double *__restrict__ stg, uint32_t pk, double cond, double pr1, double pr2,
-                                                  double *__restrict__ row, double &gen, double &accv) {
-  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF;
-  if (pd_none(pk, !U)) return;
-  const double vol = stg[NVF * D * 32];
-  const uint2 sb = *reinterpret_cast<const uint2 *>(stg + (NVF * D + 1) * 32);
-  gen += __dmul_rn(vol, pr2);                                     // products rounded first: the same bits as the tile kernel
-  accv += __dmul_rn(vol, pr1);
-  double t[NVF][D];
-#pragma unroll
-  for (int k = 0; k < NVF; ++k) {
-    const double sg = (Tab::vface_c(L, k) & 1) ? cond : -cond;    // forward vertex +flux, backward -flux (heat_transfer.py:52-54)
-#pragma unroll
-    for (int a = 0; a < D; ++a) t[k][a] = (Tab::vface_c(L, k) >= 0) ? stg[(k * D + a) * 32] * sg : 0.0;
-  }
-  // coefficient of column j:  k * G^T s  (heat_transfer.py:47); the m columns of one element are distinct positions of
-  // the row, so the read-modify-writes are issued four at a time (no false dependences between them)
-#pragma unroll
-  for (int j0 = 0; j0 < M; j0 += 4) {
-    double w[4], a_[4];
-    int pos[4];
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = j0 + jj;
-      if (j < M) {
-        pos[jj] = (int)(((j < 4 ? sb.x : sb.y) >> (8 * (j & 3))) & 0xffu);
-        a_[jj] = row[pos[jj]];
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = j0 + jj;
-      if (j < M) {
-        double wj = 0.0;
-#pragma unroll
-        for (int k = 0; k < NVF; ++k) {
-          const int f = Tab::vface_c(L, k) >> 1;
-#pragma unroll
-          for (int a = 0; a < D; ++a)
-            if (Tab::vface_c(L, k) >= 0 && Tab::ifD_c(f < 0 ? 0 : f, j, a) != 0.0)
-              wj += Tab::ifD_c(f < 0 ? 0 : f, j, a) * t[k][a];
-        }
-        w[jj] = wj;
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-      if (j0 + jj < M) row[pos[jj]] = a_[jj] + w[jj];
-  }
-}
 // key = shape code * 8 + local vertex (warp-uniform); UCODE >= 0 instantiates the 8 cases of one shape only (key = local vertex)
 #define EFV_LANE_KEYS(Tab, B, OP)                                                              \
   case B + 0: if constexpr (Tab::M > 0) { OP(Tab, 0); } break;                                 \
@@ -776,37 +391,103 @@ __device__ __forceinline__ void heat_lane_compute(const double *__restrict__ stg
   } while (0)
 
 extern __shared__ __align__(16) double lane_smem[];
-// shared memory of one warp, in doubles: tile image | S operand stages | 2S descriptor rows (128 B each)
-__host__ __device__ constexpr int lane_warp_doubles(int ucode, int acc_cap, int S) {
-  return acc_cap + S * lane_slots(ucode) * 32 + 2 * S * 16;
+constexpr int kLaneSmemBudget = 160 * 1024;   // shared memory per SM the lane kernels may fill: the copies / loads in flight live in L1
+                                              // lines until they land, and with the 228 KB carve-out (28 KB of L1) they run 1.7x slower
+// operands of one pair step (per lane): loaded for step i+1 while step i computes
+struct LaneOps { double t[12]; double vol; unsigned lo, hi; };
+template <class Tab, int L, bool U>
+__device__ __forceinline__ void heat_reg_load(LaneOps &o, uint32_t pk, const MeshView &m, const GeomView &g, const SysView &s) {
+  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE;
+  if (pd_none(pk, !U)) return;
+  const int64_t e = (int64_t)(pk & pd_elem_mask(!U));
+  const int64_t gi = U ? e : m.group_index(e);
+  unsigned nb = (unsigned)g.n[CODE] * 8u;                         // < 2^28 elements: plane offsets = 32 x 32 -> 64-bit products
+  asm volatile("" : "+r"(nb));                                    // one IMAD.WIDE per address instead of hoisted 64-bit offsets
+  const char *St = reinterpret_cast<const char *>(g.St[CODE] + gi);
+#pragma unroll
+  for (int k = 0; k < NVF; ++k) {
+    const int f = Tab::vface_c(L, k) >> 1;
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+      o.t[k * D + a] = (Tab::vface_c(L, k) >= 0)
+                           ? __ldg(reinterpret_cast<const double *>(St + (uint64_t)(unsigned)(f < 0 ? 0 : f * D + a) * nb)) : 0.0;
+  }
+  o.vol = __ldg(reinterpret_cast<const double *>(reinterpret_cast<const char *>(g.vol[CODE] + gi) + (uint64_t)(unsigned)L * nb));
+  const uint8_t *sp = s.slotpos + (U ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
+  if (U && M == 8) {
+    const uint2 w = __ldg(reinterpret_cast<const uint2 *>(sp));
+    o.lo = w.x; o.hi = w.y;
+  } else if (U && M == 4) {
+    o.lo = __ldg(reinterpret_cast<const unsigned *>(sp)); o.hi = 0;
+  } else {
+    unsigned long long pb = 0;
+#pragma unroll
+    for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
+    o.lo = (unsigned)pb; o.hi = (unsigned)(pb >> 32);
+  }
 }
-template <int UCODE, int S>
-__global__ void __launch_bounds__(kLaneWarps * 32) k_heat_lanes(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
-                                                                const __grid_constant__ SysView s, const double *__restrict__ props,
-                                                                const uint32_t *__restrict__ spk, const int64_t *__restrict__ soff,
-                                                                int transient, int acc_cap, int dir_mode, int single_region_i,
-                                                                const uint8_t *__restrict__ dflag, const uint8_t *__restrict__ rmark,
-                                                                const double *__restrict__ dval,
-                                                                double *__restrict__ gen_out, double *__restrict__ acc_out,
-                                                                double *__restrict__ elim_out) {
-  constexpr int R = 2 * S;
+// tc = the step's face vectors already multiplied by the conductivity; the forward / backward sign of a face is folded into
+// the table entries (exact: (-D) t = -(D t))
+template <class Tab, int L, bool U>
+__device__ __forceinline__ void heat_reg_compute(const double (&tc)[12], unsigned lo, unsigned hi, uint32_t pk, double *__restrict__ row) {
+  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF;
+  if (pd_none(pk, !U)) return;
+#pragma unroll
+  for (int j0 = 0; j0 < M; j0 += 4) {
+    double w[4], a_[4];
+    int pos[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      if (j < M) {
+        pos[jj] = (int)(((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xffu);
+        a_[jj] = row[pos[jj]];
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = j0 + jj;
+      if (j < M) {
+        double wj = 0.0;
+#pragma unroll
+        for (int k = 0; k < NVF; ++k) {
+          const int f = Tab::vface_c(L, k) >> 1;
+#pragma unroll
+          for (int a = 0; a < D; ++a)
+            if (Tab::vface_c(L, k) >= 0 && Tab::ifD_c(f < 0 ? 0 : f, j, a) != 0.0)
+              wj += ((Tab::vface_c(L, k) & 1) ? Tab::ifD_c(f < 0 ? 0 : f, j, a) : -Tab::ifD_c(f < 0 ? 0 : f, j, a)) * tc[k * D + a];
+        }
+        w[jj] = wj;
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      if (j0 + jj < M) row[pos[jj]] = a_[jj] + w[jj];
+  }
+}
+constexpr int kLaneWarps = 4;               // warps per block (they never synchronise with each other)
+template <int UCODE>
+__global__ void __launch_bounds__(kLaneWarps * 32, 5) k_heat_lanes(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
+                                                                   const __grid_constant__ SysView s, const double *__restrict__ props,
+                                                                   const uint32_t *__restrict__ spk, const int64_t *__restrict__ soff,
+                                                                   int transient, int acc_cap, int dir_mode, int single_region_i,
+                                                                   const uint8_t *__restrict__ dflag, const uint8_t *__restrict__ rmark,
+                                                                   const double *__restrict__ dval,
+                                                                   double *__restrict__ gen_out, double *__restrict__ acc_out,
+                                                                   double *__restrict__ elim_out) {
+  constexpr int RR = 4;                                                   // descriptor ring: steps i .. i+3
   constexpr bool U = UCODE >= 0;
-  constexpr int kStageBytes = lane_slots(UCODE) * 256;
+  constexpr int NT = U ? shape_nvf(UCODE < 0 ? 0 : UCODE) * shape_dim(UCODE < 0 ? 0 : UCODE) : 12;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  double *accw = lane_smem + (size_t)wib * lane_warp_doubles(UCODE, acc_cap, S);   // this warp's image of a tile's CSR value segment
-  const unsigned accw_sa = (unsigned)__cvta_generic_to_shared(accw);
-  const unsigned ring_sa = accw_sa + (unsigned)acc_cap * 8u + (unsigned)lane * 8u;   // this lane's column of the operand stages
-  const unsigned pkring_sa = accw_sa + (unsigned)acc_cap * 8u + S * kStageBytes + (unsigned)lane * 4u;   // ... of the descriptor rows
+  double *accw = lane_smem + (size_t)wib * (acc_cap + RR * 16);           // image of a tile's CSR value segment | descriptor ring
+  const unsigned pkring_sa = (unsigned)__cvta_generic_to_shared(accw + acc_cap) + (unsigned)lane * 4u;
   const bool single_region = single_region_i != 0;
   const int ntiles = (int)((s.nV + 31) >> 5);
-  const int W = (int)(blockDim.x >> 5);
-  const int stride = (int)gridDim.x * W;
-  int tile = (int)blockIdx.x * W + wib;                          // tile of the step being computed
+  const int stride = (int)gridDim.x * kLaneWarps;
+  int tile = (int)blockIdx.x * kLaneWarps + wib;
   if (tile >= ntiles) return;
-  const int tail_rows = (int)(s.nV - ((int64_t)(ntiles - 1) << 5));       // rows of the last tile (owned block of a partition)
-  double cond = props[0], pr1 = props[1], pr2 = props[2];                 // one region: properties stay in registers
-  // row data of a tile, RAW loaded values: requested a whole tile ahead, not touched before the tile starts (any use of a
-  // loaded value waits for the load on the spot)
+  const int tail_rows = (int)(s.nV - ((int64_t)(ntiles - 1) << 5));
+  double cond = props[0], pr1 = props[1], pr2 = props[2];
   struct RowRaw { int64_t g0, g1; int dslot; uint8_t mark; };
   auto load_rows = [&](int t) {
     RowRaw rr{0, 0, 0, 0};
@@ -817,19 +498,17 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_heat_lanes(const __grid_con
       rr.dslot = s.diag_slot[v];
       if (dir_mode >= 0) rr.mark = rmark[v];
     } else {
-      rr.g0 = rr.g1 = s.gptr[s.nV];                                       // inactive lanes: empty row at the end of the segment
+      rr.g0 = rr.g1 = s.gptr[s.nV];
     }
     return rr;
   };
-  // descriptor fetch: 2S-1 steps ahead of the compute; running pointer inside a tile, the step range of the fetch side's
-  // NEXT tile requested one tile ahead.  Past the end of the warp's tiles it stores "none" markers.
   int tF = tile;
   int64_t f0 = soff[tF], f1 = soff[tF + 1];
   const uint32_t *pF = spk + f0 * 32 + lane;
-  int remF = (int)(f1 - f0);                                              // steps left in the fetch side's tile
+  int remF = (int)(f1 - f0);
   int64_t nxt0 = 0, nxt1 = 0;
   if (tF + stride < ntiles) { nxt0 = soff[tF + stride]; nxt1 = soff[tF + stride + 1]; }
-  bool okF = tF < ntiles - 1 || lane < tail_rows;                         // rows past the owned block have no pairs
+  bool okF = tF < ntiles - 1 || lane < tail_rows;
   auto fetch_desc = [&](int slot) {
     const unsigned dst = pkring_sa + (unsigned)slot * 128u;
     if (remF > 0 && okF) {
@@ -850,45 +529,39 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_heat_lanes(const __grid_con
       }
     }
   };
-#define EFV_ISSUE_OP(Tab, LL) heat_lane_issue<Tab, LL, U>(stg_sa, pkI, m, g, s)
-#define EFV_COMP_OP(Tab, LL) heat_lane_compute<Tab, LL, U>(stg, pkA, cond, pr1, pr2, row, gen, accv)
-  auto issue = [&](int stage, int drow) {                                 // operand copies of the step whose descriptor sits in row drow
-    uint32_t pkI;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pkI) : "r"(pkring_sa + (unsigned)drow * 128u) : "memory");
-    const unsigned stg_sa = ring_sa + (unsigned)stage * kStageBytes;
-    EFV_LANE_DISPATCH(UCODE, pd_key(pkI, !U), EFV_ISSUE_OP);
+  auto desc = [&](int slot) {
+    uint32_t pk;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pk) : "r"(pkring_sa + (unsigned)slot * 128u) : "memory");
+    return pk;
   };
-  // prologue: descriptors of steps 0 .. 2S-2, then the operands of steps 0 .. S-2
-#pragma unroll 1
-  for (int j = 0; j < 2 * S - 1; ++j) fetch_desc(j);
+#define EFV_RLOAD_OP(Tab, LL) heat_reg_load<Tab, LL, U>(ops, pkN, m, g, s)
+#define EFV_RCOMP_OP(Tab, LL) heat_reg_compute<Tab, LL, U>(tc, lo, hi, pkA, row)
+  LaneOps ops;
+#pragma unroll
+  for (int n = 0; n < 12; ++n) ops.t[n] = 0.0;
+  ops.vol = 0.0; ops.lo = ops.hi = 0;
+  // prologue: descriptors of steps 0 .. 2, operands of step 0
+  fetch_desc(0); fetch_desc(1); fetch_desc(2);
   cp_async_commit();
   RowRaw rr = load_rows(tile), rrn = rr;
   cp_async_wait<0>();
-#pragma unroll 1
-  for (int j = 0; j < S - 1; ++j) { issue(j, j); cp_async_commit(); }
-  int slotA = 0, dA = 0;                                                  // stage / descriptor row of the step being computed
+  uint32_t pkA = desc(0);
+  {
+    const uint32_t pkN = pkA;
+    EFV_LANE_DISPATCH(UCODE, pd_key(pkN, !U), EFV_RLOAD_OP);
+  }
+  int dA = 0;
   bool first = true;
   double gen = 0.0, accv = 0.0;
   double *row = accw;
   int64_t base0 = 0;
-  int total = 0, len = 0;
+  int total = 0;
   bool marked = false;
   while (true) {
-    // step i computes; the descriptor of step i+2S-1 and the operands of step i+S-1 go out first
-    {
-      const int dF = dA == 0 ? R - 1 : dA - 1;                            // (i + 2S - 1) mod 2S
-      int dI = dA + S - 1;                                                // (i + S - 1) mod 2S
-      if (dI >= R) dI -= R;
-      const int sI = slotA == 0 ? S - 1 : slotA - 1;                      // (i + S - 1) mod S
-      fetch_desc(dF);
-      issue(sI, dI);
-      cp_async_commit();
-    }
     if (first) {                                                          // first step of a tile: clear the image
       if (tile + stride < ntiles) rrn = load_rows(tile + stride);         // and request the row data of the next tile
       base0 = __shfl_sync(0xffffffffu, rr.g0, 0);
       total = (int)(__shfl_sync(0xffffffffu, rr.g1, 31) - base0);
-      len = (int)(rr.g1 - rr.g0);
       marked = rr.mark != 0;
       for (int i = lane; i < total; i += 32) accw[i] = 0.0;
       row = accw + (int)(rr.g0 - base0);
@@ -896,22 +569,36 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_heat_lanes(const __grid_con
       first = false;
       __syncwarp();
     }
-    cp_async_wait<S - 1>();                                               // this step's operands have landed (own copies: no barrier)
-    uint32_t pkA;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(pkA) : "r"(pkring_sa + (unsigned)dA * 128u) : "memory");
-    {
-      const double *stg = accw + acc_cap + lane + slotA * (kStageBytes / 8);
-      if (!single_region && !pd_none(pkA, !U)) {
-        const double *pr = props + 3 * m.region[pkA & pd_elem_mask(!U)];
-        cond = pr[0]; pr1 = pr[1]; pr2 = pr[2];
-      }
-      EFV_LANE_DISPATCH(UCODE, pd_key(pkA, !U), EFV_COMP_OP);
+    // take step i out of the operand registers
+    if (!single_region && !pd_none(pkA, !U)) {
+      const double *pr = props + 3 * m.region[pkA & pd_elem_mask(!U)];
+      cond = pr[0]; pr1 = pr[1]; pr2 = pr[2];
     }
-    if (++slotA == S) slotA = 0;
-    if (++dA == R) dA = 0;
-    if (pd_last(pkA)) {
+    double tc[12];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) tc[n] = ops.t[n] * cond;
+    if (!pd_none(pkA, !U)) {
+      gen += __dmul_rn(ops.vol, pr2);                                     // products rounded first: the same bits as the tile kernel
+      accv += __dmul_rn(ops.vol, pr1);
+    }
+    const unsigned lo = ops.lo, hi = ops.hi;
+    // descriptor of step i+3, operands of step i+1
+    int dN = dA + 1; if (dN == RR) dN = 0;
+    int dF = dA + 3; if (dF >= RR) dF -= RR;
+    fetch_desc(dF);
+    cp_async_commit();
+    cp_async_wait<1>();                                                   // descriptors up to step i+2 have landed
+    const uint32_t pkN = desc(dN);
+    EFV_LANE_DISPATCH(UCODE, pd_key(pkN, !U), EFV_RLOAD_OP);
+    // compute step i
+    EFV_LANE_DISPATCH(UCODE, pd_key(pkA, !U), EFV_RCOMP_OP);
+    const bool last = pd_last(pkA);
+    pkA = pkN;
+    dA = dN;
+    if (last) {
       // ---- tile epilogue ----------------------------------------------------------------------------------------------
       const int64_t v = ((int64_t)tile << 5) + lane;
+      const int len = (int)(rr.g1 - rr.g0);
       if (v < s.nV) {
         if (transient) row[(int)((int64_t)rr.dslot - rr.g0)] += accv;     // heat_transfer.py:62-67
         gen_out[v] = gen;
@@ -951,38 +638,29 @@ __global__ void __launch_bounds__(kLaneWarps * 32) k_heat_lanes(const __grid_con
     }
   }
   cp_async_wait<0>();
-#undef EFV_ISSUE_OP
-#undef EFV_COMP_OP
+#undef EFV_RLOAD_OP
+#undef EFV_RCOMP_OP
 }
-// launch; false when the image of one tile does not fit in shared memory (very long rows) or the element ids do not fit
-// in a descriptor
-// launch; false when the image of one tile does not fit in shared memory (very long rows) or the element ids do not fit
-// in a descriptor.  Shared memory is deliberately NOT filled: the copies in flight live in L1 lines until they land, and
-// with the 228 KB carve-out (28 KB of L1) the kernel runs at 3.0 ms instead of 1.8 ms at C2 (profiles/r02_assembly_lanes.json).
-// 2 stages x 12 warps per SM under the 164 KB carve-out measured best (the ring is short because 12 independent warps
-// already cover a step's latency); deeper rings with fewer warps were equal or slower.
-constexpr int kLaneSmemBudget = 160 * 1024;   // per SM, leaves >= 92 KB of L1
 template <int UCODE>
 static bool launch_heat_lanes(efv_system *s, const double *dprops, int transient) {
-  constexpr int S = kLaneStages, W = kLaneWarps;
+  constexpr int W = kLaneWarps;
   const int acc_cap = 32 * s->max_row_len;
-  const size_t smem = (size_t)W * lane_warp_doubles(UCODE, acc_cap, S) * sizeof(double);
+  const size_t smem = (size_t)W * (acc_cap + 4 * 16) * sizeof(double);
   if (smem + 1024 > (size_t)kLaneSmemBudget) return false;
   efv_mesh *m = s->mesh;
   if (!ensure_pair_schedule(m)) return false;
   MeshView mv = view_of(m);
   GeomView gv = geom_of(m);
   SysView sv = sys_view(s);
-  EFV_CUDA(cudaFuncSetAttribute(k_heat_lanes<UCODE, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  EFV_CUDA(cudaFuncSetAttribute(k_heat_lanes<UCODE, S>, cudaFuncAttributePreferredSharedMemoryCarveout, 70));
+  EFV_CUDA(cudaFuncSetAttribute(k_heat_lanes<UCODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  EFV_CUDA(cudaFuncSetAttribute(k_heat_lanes<UCODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 58));   // 132 KB: room for L1
   int per_sm = 0;
-  EFV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_heat_lanes<UCODE, S>, W * 32, smem));
-  per_sm = std::min<int>(per_sm, (int)(kLaneSmemBudget / (smem + 1024)));
+  EFV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_heat_lanes<UCODE>, W * 32, smem));
   if (per_sm < 1) return false;
   const int64_t ntiles = div_up(s->n_owned, 32);
   int64_t blocks = std::min<int64_t>(div_up(ntiles, W), (int64_t)num_sms() * per_sm);
   if (const char *e = getenv("EFV_LANE_GRID")) blocks = std::min<int64_t>(blocks, std::max(1, atoi(e)));   // tests: many tiles per warp
-  EFV_LAUNCH((k_heat_lanes<UCODE, S>), (int)std::max<int64_t>(blocks, 1), W * 32, smem, mv, gv, sv, dprops, m->sched_pk.p,
+  EFV_LAUNCH((k_heat_lanes<UCODE>), (int)std::max<int64_t>(blocks, 1), W * 32, smem, mv, gv, sv, dprops, m->sched_pk.p,
              m->sched_off.p, transient, acc_cap, s->fuse_mode, m->n_regions == 1 ? 1 : 0, s->dir_flag.p,
              s->row_mark.p, s->dir_value.p, s->gen.p, s->acc.p, s->elim.p);
   return true;
@@ -1009,11 +687,11 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
     s->marks_valid = true;
   }
   EFV_CUDA(cudaEventRecord(s->ev0, stream()));
-  // default: the lane-per-row kernel (k_heat_lanes); EFV_ASSEMBLY=tiles selects the pair-centric tile kernel (k_heat_tiles,
-  // round 1), EFV_ASSEMBLY=rows the row-group kernel (k_heat_rows), which is also the fall-back for rows too long for the
-  // shared-memory accumulators.  All three sum every entry in the same order: bit-identical values.
+  // default: the lane-per-row kernel (k_heat_lanes); EFV_ASSEMBLY=rows selects the row-group kernel (k_heat_rows), which is
+  // also the fall-back for rows too long for the shared-memory image and for element ids that do not fit in a descriptor.
+  // Both sum every entry in the same order.
   const char *mode = getenv("EFV_ASSEMBLY");
-  const bool want_rows = mode && strcmp(mode, "rows") == 0, want_tiles = mode && strcmp(mode, "tiles") == 0;
+  const bool want_rows = mode && strcmp(mode, "rows") == 0;
   bool done = false;
 #define EFV_HEAT_BY_CODE(fn)                                                                  \
   (m->uniform_code == 0   ? fn<0>(s, s->props_dev.p, transient)                               \
@@ -1023,8 +701,7 @@ void heat_assemble(efv_system *s, const double *props_host, double dt, int trans
    : m->uniform_code == 4 ? fn<4>(s, s->props_dev.p, transient)                               \
    : m->uniform_code == 5 ? fn<5>(s, s->props_dev.p, transient)                               \
                           : fn<-1>(s, s->props_dev.p, transient))
-  if (!want_rows && !want_tiles) done = EFV_HEAT_BY_CODE(launch_heat_lanes);
-  if (!done && !want_rows) done = EFV_HEAT_BY_CODE(launch_heat_tiles);
+  if (!want_rows) done = EFV_HEAT_BY_CODE(launch_heat_lanes);
 #undef EFV_HEAT_BY_CODE
   if (!done) {
     switch (m->uniform_code) {
@@ -1194,18 +871,11 @@ __global__ void __launch_bounds__(128) k_elasticity_rows(MeshView m, GeomView g,
   }
 }
 
-// ---- elasticity: pair-centric tile kernel (round 2; k_elasticity_rows above remains the fall-back) ----------------------------
-// Same scheme as k_heat_tiles with an NDOF x NDOF block per (pair, column): a block owns a tile of R consecutive rows,
-// buckets the tile's (element, local vertex) pairs by (shape, local vertex), and ONE THREAD computes the whole row l of
-// the local block matrix of its pair -- J^-1 and s of the faces that touch l in registers, the shape-table entries as
-// immediates (statically unrolled for that l; the row-group kernel re-reads them and the staged operands from shared
-// memory for every (row, pair, column): 80 % L1 throughput at 12 % occupancy, profiles/r02_ncu_details_k_elasticity_rows.txt).
-// The blocks wait in a shared-memory slab; the row phase then sums them in ascending (local vertex, element) order
-// through the byte slot map, every entry owned by one lane: no float atomics, bit-reproducible.
-// Geometry in the layout this kernel wants.  The SoA planes of geometry.cu are coalesced when consecutive lanes hold
-// consecutive elements; here a warp holds the pairs of ONE local vertex of a few rows, i.e. scattered elements, and every
-// 8-byte read would pull its own 32-byte sector (measured: 37 ms at C3 against 49 ms for the row-group kernel).  The
-// face records put [J^-1 | s] of an (element, face) into 96 contiguous bytes = three full sectors.
+// ---- geometry records of the block (elasticity) lane kernel ------------------------------------------------------------
+// The SoA planes of geometry.cu are coalesced when consecutive lanes hold consecutive elements; the block kernel gives a
+// vertex 4 lanes that fetch ONE pair together, i.e. a warp touches 8 scattered elements, and every 8-byte read of a plane
+// would pull its own 32-byte sector.  The face records put [J^-1 | s] of an (element, face) into 96 contiguous bytes = three
+// full sectors; simplices get one compact record per element (below).
 __global__ void k_face_records(int64_t n, int NF, int D, const double *__restrict__ Jinv, const double *__restrict__ S,
                                double *__restrict__ rec) {
   const int RF = D * D + D;
@@ -1250,336 +920,6 @@ static void ensure_face_records(efv_mesh *m, bool skip_simplices = false) {
     EFV_LAUNCH(k_face_records, grid_for(g.n * nf * (d * d + d), 256), 256, 0, g.n, nf, d, g.Jinv.p, g.S.p, g.Frec.p);
   }
 }
-struct BTileSmem {
-  int rowacc, slab, posb, pks, order, krank, pkey, total;
-  __host__ __device__ BTileSmem(int R, int max_row_len, int cap, int mmax, int B) {
-    rowacc = 0;
-    slab = rowacc + R * max_row_len * B * 8;
-    posb = slab + (mmax * B + 1) * cap * 8;
-    pks = posb + cap * 8;
-    order = pks + cap * 4;
-    krank = order + (cap + 2048) * 2;
-    pkey = krank + cap * 2;
-    total = (pkey + cap + 15) & ~15;
-  }
-};
-template <class Tab, int L, int NDOF>
-__device__ __forceinline__ void elas_pair_row(const MeshView &m, const GeomView &g, const SysView &s, const double *__restrict__ props,
-                                              int64_t e, bool uniform, int idx, int cap, int slab_off, int posb_off, int mmax) {
-  constexpr int M = Tab::M, D = Tab::DIM, NVF = Tab::NVF, CODE = Tab::CODE, B = NDOF * NDOF;
-  static_assert(D == NDOF, "elasticity: one displacement component per space dimension");
-  const int64_t gi = uniform ? e : m.group_index(e);
-  int64_t n = g.n[CODE];
-  asm volatile("" : "+l"(n));                       // keep the SoA plane offsets out of loop-invariant hoisting
-  const double *pr = props + 3 * m.region[e];
-  const double lam = pr[0], mu = pr[1];
-  constexpr int RF = D * D + D, NF = Tab::NF;
-  // simplices (triangle, tetrahedron): J^-1 and the shape derivatives are the same on every inner face, so the three faces
-  // of this vertex collapse into ONE with the signed sum of their area vectors (M is linear in s)
-  constexpr bool SIMPLEX = (CODE == 0 || CODE == 2);
-  constexpr int NK = SIMPLEX ? 1 : NVF;
-  const double2 *rec = reinterpret_cast<const double2 *>(g.Frec[CODE] + (size_t)gi * NF * RF);     // 16-byte aligned: RF is even
-  double J[NK][D][D], ls[NK][D], ms[NK][D];        // lambda * s and mu * s (signed)
-#pragma unroll
-  for (int k = 0; k < NK; ++k)
-#pragma unroll
-    for (int i = 0; i < D; ++i) { ls[k][i] = 0.0; ms[k][i] = 0.0; }
-#pragma unroll
-  for (int k = 0; k < NVF; ++k) {
-    const int enc = Tab::vface_c(L, k);
-    const int f = enc < 0 ? 0 : enc >> 1;
-    const double sg = (enc & 1) ? -1.0 : 1.0;       // this vertex is the forward one of the face: -M (stress_equilibrium.py:105-117)
-    const int kk = SIMPLEX ? 0 : k;
-    double buf[RF];
-#pragma unroll
-    for (int q = 0; q < RF / 2; ++q) {
-      double2 t2 = make_double2(0.0, 0.0);
-      if (enc >= 0 && (!SIMPLEX || k == 0 || 2 * q + 1 >= D * D)) t2 = __ldg(rec + (f * RF) / 2 + q);   // simplex: J from the first face only
-      buf[2 * q] = t2.x; buf[2 * q + 1] = t2.y;
-    }
-    if (!SIMPLEX || k == 0) {
-#pragma unroll
-      for (int i = 0; i < D; ++i)
-#pragma unroll
-        for (int a = 0; a < D; ++a) J[kk][i][a] = buf[i * D + a];
-    }
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      ls[kk][i] += lam * (sg * buf[D * D + i]);
-      ms[kk][i] += mu * (sg * buf[D * D + i]);
-    }
-  }
-  const uint8_t *sp = s.slotpos + (uniform ? e * (int64_t)(M * M) : m.slot_begin(e)) + L * M;
-  unsigned long long pb;
-  if (uniform && M == 8) pb = *reinterpret_cast<const unsigned long long *>(sp);
-  else if (uniform && M == 4) pb = *reinterpret_cast<const unsigned int *>(sp);
-  else {
-    pb = 0;
-#pragma unroll
-    for (int j = 0; j < M; ++j) pb |= (unsigned long long)sp[j] << (8 * j);
-  }
-  const double vol = g.vol[CODE][(int64_t)L * n + gi];
-  *reinterpret_cast<unsigned long long *>(tile_smem + posb_off + idx * 8) = pb;
-  double *out = reinterpret_cast<double *>(tile_smem + slab_off) + idx;
-  out[(size_t)mmax * B * cap] = vol * pr[2];
-#pragma unroll
-  for (int j = 0; j < M; ++j) {
-    double Mb[NDOF][NDOF];
-#pragma unroll
-    for (int i = 0; i < NDOF; ++i)
-#pragma unroll
-      for (int c = 0; c < NDOF; ++c) Mb[i][c] = 0.0;
-#pragma unroll
-    for (int k = 0; k < NK; ++k) {
-      const int enc = Tab::vface_c(L, k);
-      const int f = enc < 0 ? 0 : enc >> 1;
-      if (enc >= 0) {
-        double gv[NDOF];
-        double mgs = 0.0;
-#pragma unroll
-        for (int i = 0; i < NDOF; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int a = 0; a < D; ++a)
-            if (Tab::ifD_c(f, j, a) != 0.0) acc += J[k][i][a] * Tab::ifD_c(f, j, a);       // g_i = sum_a Jinv[i][a] D[j][a]
-          gv[i] = acc;
-          mgs += acc * ms[k][i];                                                            // mu (s . g)
-        }
-#pragma unroll
-        for (int i = 0; i < NDOF; ++i)
-#pragma unroll
-          for (int c = 0; c < NDOF; ++c)
-            Mb[i][c] += ls[k][i] * gv[c] + ms[k][c] * gv[i] + ((i == c) ? mgs : 0.0);       // At.Ce.Bv in closed form
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NDOF; ++i)
-#pragma unroll
-      for (int c = 0; c < NDOF; ++c) out[(size_t)(j * B + i * NDOF + c) * cap] = Mb[i][c];
-  }
-}
-template <class Tab, int UCODE, int NDOF>
-__device__ __forceinline__ void elas_pair_shape(int l, const MeshView &m, const GeomView &g, const SysView &s,
-                                                const double *__restrict__ props, int64_t e, int idx, int cap, int slab_off,
-                                                int posb_off, int mmax) {
-  if constexpr ((UCODE < 0 || UCODE == Tab::CODE) && Tab::DIM == NDOF) {
-    constexpr bool U = UCODE >= 0;
-    switch (l) {
-#define EFV_EPAIR_CASE(LL) \
-  case LL: if constexpr (Tab::M > LL) elas_pair_row<Tab, LL, NDOF>(m, g, s, props, e, U, idx, cap, slab_off, posb_off, mmax); break;
-      EFV_EPAIR_CASE(0) EFV_EPAIR_CASE(1) EFV_EPAIR_CASE(2) EFV_EPAIR_CASE(3)
-      EFV_EPAIR_CASE(4) EFV_EPAIR_CASE(5) EFV_EPAIR_CASE(6) EFV_EPAIR_CASE(7)
-#undef EFV_EPAIR_CASE
-      default: break;
-    }
-  }
-}
-
-template <int UCODE, int NDOF, int TT>
-__global__ void __launch_bounds__(TT, 2) k_elas_tiles(const __grid_constant__ MeshView m, const __grid_constant__ GeomView g,
-                                                      const __grid_constant__ SysView s, const double *__restrict__ props,
-                                                      int gravity, int max_row_len, int R, int cap, int mmax, int dir_mode,
-                                                      const uint8_t *__restrict__ dflag, const double *__restrict__ dval,
-                                                      double *__restrict__ gen_out, double *__restrict__ elim_out) {
-  constexpr int B = NDOF * NDOF;
-  const BTileSmem off(R, max_row_len, cap, mmax, B);
-#define T_ROWACC reinterpret_cast<double *>(tile_smem + off.rowacc)
-#define T_SLAB reinterpret_cast<double *>(tile_smem + off.slab)
-#define T_POSB reinterpret_cast<unsigned long long *>(tile_smem + off.posb)
-#define T_PKS reinterpret_cast<uint32_t *>(tile_smem + off.pks)
-#define T_ORDER reinterpret_cast<uint16_t *>(tile_smem + off.order)
-#define T_KRANK reinterpret_cast<uint16_t *>(tile_smem + off.krank)
-#define T_PKEY (tile_smem + off.pkey)
-  __shared__ int cnt[64], base[65], cbase[64], rp[33];
-  __shared__ uint8_t okey[(2048 + 2048) / 32];
-  const int tid = threadIdx.x, lane = tid & 31;
-  // row phase: 8-lane groups; a row is shared by nsub groups that own disjoint block components
-  const int ngroups = TT / kAsmGroup, nsub = ngroups / R;
-  const int grp = tid / kAsmGroup, gl = tid % kAsmGroup;
-  const int rrow = grp % R, sub = grp / R;
-  const unsigned gmask = 0xffu << ((tid & 31) / kAsmGroup * kAsmGroup);
-  const int64_t ntiles = (s.nV + R - 1) / R;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t v0 = tile * R;
-    const int rows = (int)min((int64_t)R, s.nV - v0);
-    const int64_t P0 = m.inc_ptr[v0];
-    const int np = (int)(m.inc_ptr[v0 + rows] - P0);
-    if (tid <= rows) rp[tid] = (int)(m.inc_ptr[v0 + tid] - P0);
-    if (tid < 64) cnt[tid] = 0;
-    for (int i = tid; i < rows * max_row_len * B; i += TT) T_ROWACC[i] = 0.0;
-    __syncthreads();
-    // ---- bucket the tile's pairs by (shape, local vertex) ------------------------------------------------------------
-    for (int i = tid; i < np; i += TT) {
-      const uint32_t pk = m.inc[P0 + i];
-      const int code = (UCODE >= 0) ? UCODE : m.code(inc_elem(pk));
-      const int key = code * 8 + inc_local(pk);
-      const int rank = atomicAdd(&cnt[key], 1);          // decides only which thread computes the pair, never a summation order
-      T_PKS[i] = pk;
-      T_PKEY[i] = (uint8_t)key;
-      T_KRANK[i] = (uint16_t)rank;
-    }
-    __syncthreads();
-    if (tid < 32) {
-      const int c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
-      const int p0 = (c0 + 31) & ~31, p1 = (c1 + 31) & ~31;
-      int incl = p0 + p1, cincl = c0 + c1;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, o), cup = __shfl_up_sync(0xffffffffu, cincl, o);
-        if (lane >= o) { incl += up; cincl += cup; }
-      }
-      const int b0 = incl - p0 - p1, cb0 = cincl - c0 - c1;
-      base[2 * tid] = b0;
-      base[2 * tid + 1] = b0 + p0;
-      cbase[2 * tid] = cb0;
-      cbase[2 * tid + 1] = cb0 + c0;
-      if (tid == 31) base[64] = incl;
-      for (int q = b0 + c0; q < b0 + p0; ++q) T_ORDER[q] = 0xffffu;
-      for (int q = b0 + p0 + c1; q < b0 + p0 + p1; ++q) T_ORDER[q] = 0xffffu;
-      for (int q = b0; q < b0 + p0; q += 32) okey[q >> 5] = (uint8_t)(2 * tid);
-      for (int q = b0 + p0; q < b0 + p0 + p1; q += 32) okey[q >> 5] = (uint8_t)(2 * tid + 1);
-    }
-    __syncthreads();
-    for (int i = tid; i < np; i += TT) {
-      const int key = T_PKEY[i], rank = T_KRANK[i];
-      T_ORDER[base[key] + rank] = (uint16_t)i;
-      T_KRANK[i] = (uint16_t)(cbase[key] + rank);
-    }
-    __syncthreads();
-    // ---- pair phase ----------------------------------------------------------------------------------------------------
-    const int nslots = base[64];
-    for (int slot = tid; slot < nslots; slot += TT) {
-      const int pair = T_ORDER[slot];
-      if (pair == 0xffff) continue;
-      const int key = okey[slot >> 5];
-      const int64_t e = inc_elem(T_PKS[pair]);
-      const int l = key & 7;
-      const int idx = cbase[key] + (slot - base[key]);
-      switch (key >> 3) {
-        case 0: elas_pair_shape<TriangleTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        case 1: elas_pair_shape<QuadrilateralTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        case 2: elas_pair_shape<TetrahedronTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        case 3: elas_pair_shape<HexahedronTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        case 4: elas_pair_shape<PrismTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-        default: elas_pair_shape<PyramidTab, UCODE, NDOF>(l, m, g, s, props, e, idx, cap, off.slab, off.posb, mmax); break;
-      }
-    }
-    __syncthreads();
-    // ---- row phase: pairs in ascending (local vertex, element) order; sub-group `sub` owns components sub, sub + nsub, ... ---------
-    if (rrow < rows) {
-      const int64_t v = v0 + rrow;
-      double *row = T_ROWACC + (size_t)rrow * max_row_len * B;
-      double grav = 0.0;
-      for (int q = rp[rrow]; q < rp[rrow + 1]; ++q) {
-        const int mm = (UCODE >= 0) ? shape_m(UCODE) : shape_m(T_PKEY[q] >> 3);
-        const int c = T_KRANK[q];
-        const unsigned long long pbits = T_POSB[c];
-        // Every block component cc is owned by ONE 8-lane group for all pairs of the row (cc = sub, sub + nsub, ...), so that
-        // the contributions of different pairs to an entry are added by lanes of one warp, in pair order; the group's
-        // lanes share its (column, component) items.
-        const int ncomp = (B - sub + nsub - 1) / nsub;
-        for (int item = gl; item < mm * ncomp; item += kAsmGroup) {
-          const int j = item % mm, cc = sub + (item / mm) * nsub;
-          const int pos = (int)((pbits >> (8 * j)) & 0xff);
-          row[pos * B + cc] += T_SLAB[(size_t)(j * B + cc) * cap + c];
-        }
-        if (gl == 0 && sub == 0) grav += T_SLAB[(size_t)mmax * B * cap + c];
-      }
-      if (gl == 0 && sub == 0) {
-#pragma unroll
-        for (int i = 0; i < NDOF; ++i) gen_out[v * NDOF + i] = (gravity && i == 1) ? grav : 0.0;   // y component only (:81-90)
-      }
-    }
-    __syncthreads();
-    // ---- epilogue: Dirichlet treatment + store, one 8-lane group per row (sub-group 0) ---------------------------------------
-    if (rrow < rows && sub == 0) {
-      const int64_t v = v0 + rrow;
-      const int64_t r0 = s.gptr[v];
-      const int len = (int)(s.gptr[v + 1] - r0);
-      const double *row = T_ROWACC + (size_t)rrow * max_row_len * B;
-      bool rowd[NDOF];
-#pragma unroll
-      for (int i = 0; i < NDOF; ++i) rowd[i] = (dir_mode >= 0) ? dflag[v * NDOF + i] : false;
-      double el[NDOF];
-#pragma unroll
-      for (int i = 0; i < NDOF; ++i) el[i] = 0.0;
-      for (int t = gl; t < len; t += kAsmGroup) {
-        const int64_t c = s.gcol[r0 + t];
-        const double *blk = row + t * B;
-        double *out = s.vals + (r0 + t) * B;
-#pragma unroll
-        for (int i = 0; i < NDOF; ++i)
-#pragma unroll
-          for (int j = 0; j < NDOF; ++j) {
-            double a = blk[i * NDOF + j];
-            if (rowd[i]) a = (c == v && i == j) ? 1.0 : 0.0;
-            else if (dir_mode == 1 && dflag[c * NDOF + j]) { el[i] -= a * dval[c * NDOF + j]; a = 0.0; }
-            out[i * NDOF + j] = a;
-          }
-      }
-      if (dir_mode == 1) {
-#pragma unroll
-        for (int i = 0; i < NDOF; ++i) {
-          double tot = el[i];
-#pragma unroll
-          for (int o = kAsmGroup / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(gmask, tot, o);
-          if (gl == 0) elim_out[v * NDOF + i] = rowd[i] ? 0.0 : tot;
-        }
-      }
-    }
-    __syncthreads();
-  }
-#undef T_ROWACC
-#undef T_SLAB
-#undef T_POSB
-#undef T_PKS
-#undef T_ORDER
-#undef T_KRANK
-#undef T_PKEY
-}
-// rows per tile / pair capacity / threads for the block tile kernel; false when nothing fits
-static bool elas_tile_shape(const efv_system *s, int B, int *R, int *cap, int *mmax, int *threads, size_t *smem) {
-  const efv_mesh *m = s->mesh;
-  *mmax = m->uniform_code >= 0 ? shape_m(m->uniform_code) : (m->dim == 3 ? 8 : 4);
-  for (int r = 32; r >= 4; r >>= 1) {
-    const int64_t pairs = (int64_t)r * m->max_incidence;
-    if (pairs > 2047) continue;
-    const int c = (int)((pairs + 15) & ~(int64_t)15) + 1;
-    const size_t bytes = (size_t)BTileSmem(r, s->max_row_len, c, *mmax, B).total;
-    if (bytes > 100 * 1024 && r > 4) continue;                     // at least two blocks per SM
-    if (bytes > 200 * 1024) return false;
-    *R = r; *cap = c; *smem = bytes;
-    *threads = pairs >= 160 ? 256 : 128;
-    if ((*threads / kAsmGroup) < r) *threads = 256;                // one 8-lane group per row at least
-    return (*threads / kAsmGroup) % r == 0;
-  }
-  return false;
-}
-template <int UCODE, int NDOF>
-static bool launch_elas_tiles(efv_system *s, const double *dprops, int gravity) {
-  const char *mode = getenv("EFV_ASSEMBLY");
-  if (mode && strcmp(mode, "rows") == 0) return false;
-  int R, cap, mmax, threads;
-  size_t smem;
-  if (!elas_tile_shape(s, NDOF * NDOF, &R, &cap, &mmax, &threads, &smem)) return false;
-  efv_mesh *m = s->mesh;
-  ensure_face_records(m);
-  MeshView mv = view_of(m);
-  GeomView gv = geom_of(m);
-  SysView sv = sys_view(s);
-  const int64_t ntiles = div_up(s->n_owned, R);
-  if (threads == 256) {
-    EFV_CUDA(cudaFuncSetAttribute((k_elas_tiles<UCODE, NDOF, 256>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EFV_LAUNCH((k_elas_tiles<UCODE, NDOF, 256>), grid_for(ntiles * 256, 256, 4), 256, smem, mv, gv, sv, dprops, gravity, s->max_row_len, R, cap,
-               mmax, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->elim.p);
-  } else {
-    EFV_CUDA(cudaFuncSetAttribute((k_elas_tiles<UCODE, NDOF, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EFV_LAUNCH((k_elas_tiles<UCODE, NDOF, 128>), grid_for(ntiles * 128, 128, 8), 128, smem, mv, gv, sv, dprops, gravity, s->max_row_len, R, cap,
-               mmax, s->fuse_mode, s->dir_flag.p, s->dir_value.p, s->gen.p, s->elim.p);
-  }
-  return true;
-}
-
 // ---- lane kernel for the block (elasticity) assembly ---------------------------------------------------------------------
 // The scheme of k_heat_lanes with an ndof x ndof block per graph entry: a warp owns a tile of 8 consecutive vertices, every
 // vertex gets 4 lanes, lane q < ndof owns component q of the vertex's block row (the three scalar rows of a vertex never
@@ -1588,7 +928,8 @@ static bool launch_elas_tiles(efv_system *s, const double *dprops, int gravity) 
 // the pair's face records [J^-1 | s] (16-byte cp.async) into the stage of their vertex and, after the group has landed
 // and a __syncwarp, every compute lane reads all of it back (broadcast reads) and evaluates ITS row of
 //   M = lambda s g^T + mu (g s^T + (s.g) I)          (stress_equilibrium.py:50-67, :100)
-// for every column of the element.  Simplices collapse their faces as in elas_pair_row.  The accumulator is the shared-
+// for every column of the element.  Simplices (J^-1 and the shape derivatives are the same on every inner face) collapse
+// their faces into ONE with the signed sum of the area vectors (M is linear in s).  The accumulator is the shared-
 // memory image of the tile's BSR value segment; Dirichlet rows / columns are fixed up there and the segment leaves with a
 // flat coalesced streaming copy.  Per scalar row the summation order is ascending (local vertex, shape, element).
 constexpr int kBlkRows = 8, kBlkStages = 2, kBlkWarps = 2;
@@ -1968,7 +1309,7 @@ __global__ void k_mark_vertices(int64_t nrows, int ndof, const int64_t *__restri
 template <int UCODE, int NDOF>
 static bool launch_elas_lanes(efv_system *s, const double *dprops, int gravity) {
   const char *mode = getenv("EFV_ASSEMBLY");
-  if (mode && (strcmp(mode, "rows") == 0 || strcmp(mode, "tiles") == 0)) return false;
+  if (mode && strcmp(mode, "rows") == 0) return false;
   constexpr int B = NDOF * NDOF;
   const int acc_cap = kBlkRows * s->max_row_len * B;
   const size_t smem = (size_t)kBlkWarps * blk_warp_doubles(UCODE, NDOF, acc_cap) * sizeof(double);
@@ -2001,8 +1342,7 @@ static bool launch_elas_lanes(efv_system *s, const double *dprops, int gravity) 
 
 template <int UCODE, int NDOF>
 static void launch_elasticity_rows(efv_system *s, const double *dprops, int gravity) {
-  if (launch_elas_lanes<UCODE, NDOF>(s, dprops, gravity)) return;       // default: lane kernel (4 lanes per vertex)
-  if (launch_elas_tiles<UCODE, NDOF>(s, dprops, gravity)) return;       // EFV_ASSEMBLY=tiles: pair-centric tile kernel
+  if (launch_elas_lanes<UCODE, NDOF>(s, dprops, gravity)) return;       // default: lane kernel (4 lanes per vertex); EFV_ASSEMBLY=rows: below
   efv_mesh *m = s->mesh;
   size_t smem = ((size_t)kElRows * s->max_row_len * NDOF * NDOF + (size_t)kElRows * kAsmGroup * 12 * kMaxVF) * sizeof(double);
   EFV_CUDA(cudaFuncSetAttribute((k_elasticity_rows<UCODE, NDOF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

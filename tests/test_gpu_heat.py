@@ -180,15 +180,14 @@ def test_structured_against_oracle(n, kind, perturb):
 @pytest.mark.parametrize("tag", ["Hexas6x6x6_we", "eight_sphere", "Prisms_3d", "Pyrams_3d", "test_mixed", "Square"])
 @pytest.mark.parametrize("mode", ["rows", "symmetric", "none"])
 def test_assembly_kernels_agree(tag, mode, monkeypatch):
-    """The lane-per-row kernel (default), the pair-centric tile kernel and the row-group kernel sum every entry in a fixed
-    order: values, lumped vectors and the elimination vector agree to rounding, and lanes == tiles bit for bit on
-    single-shape meshes (same arithmetic, same order).  Covers the fused Dirichlet epilogue of all three."""
+    """The lane-per-row kernel (default) and the row-group kernel (EFV_ASSEMBLY=rows) sum every entry in a fixed order:
+    values, lumped vectors and the elimination vector agree to rounding.  Covers the fused Dirichlet epilogue of both."""
     import pyefvlib_b200.device as D
     z = util.load("heat_" + tag)
     grid = util.product_grid(z)
     case = HEAT_CASES[tag]
     out = {}
-    for kernel in ("lanes", "tiles", "rows"):
+    for kernel in ("lanes", "rows"):
         monkeypatch.setenv("EFV_ASSEMBLY", kernel)
         s = D.DeviceSystem(grid, 1)
         apply_bcs(s, grid, case["bcs"])
@@ -199,28 +198,27 @@ def test_assembly_kernels_agree(tag, mode, monkeypatch):
         s.build_rhs(True)
         out[kernel] = (s.values(), s.download(D.VEC_B))
     scale = np.abs(out["rows"][0]).max()
-    for kernel in ("lanes", "tiles"):
-        assert np.abs(out[kernel][0] - out["rows"][0]).max() <= 1e-14 * scale
-        assert util.rel_max(out[kernel][1], out["rows"][1]) <= 1e-13
-    if tag != "test_mixed":                        # mixed meshes: the schedule orders a row's pairs (local vertex, shape, element)
-        assert np.array_equal(out["lanes"][0], out["tiles"][0])
+    assert np.abs(out["lanes"][0] - out["rows"][0]).max() <= 1e-14 * scale
+    assert util.rel_max(out["lanes"][1], out["rows"][1]) <= 1e-13
 
 
-@pytest.mark.parametrize("n", [40])
-def test_lane_assembly_many_tiles_per_warp(n, monkeypatch):
-    """n = 40: 2 000 tiles over ~1 800 resident warps is still one tile per warp; a capped grid makes every warp walk
-    dozens of tiles through the operand ring (tile changes, row-data prefetch, tail tile)."""
+@pytest.mark.parametrize("kind", ["hex", "tet"])
+def test_lane_assembly_many_tiles_per_warp(kind, monkeypatch):
+    """A capped grid (EFV_LANE_GRID) makes every warp walk dozens of tiles through the software pipeline (tile changes,
+    row-data prefetch, tail tile): same bits as the full grid, same values as the row-group kernel."""
     import pyefvlib_b200 as P
     import pyefvlib_b200.device as D
     from tests.cases import BC3D, HEAT_PROPS
-    grid = P.Grid(P.structured_grid_data(n, "hex", 0.1))
+    grid = P.Grid(P.structured_grid_data(40 if kind == "hex" else 22, kind, 0.1))
     vals = {}
-    for kernel in ("lanes", "tiles"):
+    for label, kernel, cap in (("full", "lanes", None), ("capped", "lanes", "3"), ("rows", "rows", None)):
         monkeypatch.setenv("EFV_ASSEMBLY", kernel)
-        monkeypatch.setenv("EFV_LANE_GRID", "7")
+        if cap: monkeypatch.setenv("EFV_LANE_GRID", cap)
+        else: monkeypatch.delenv("EFV_LANE_GRID", raising=False)
         s = D.DeviceSystem(grid, 1)
         apply_bcs(s, grid, BC3D)
         s.assemble_dirichlet_mode(D.DIRICHLET_SYMMETRIC)
         s.heat_assemble(props_array(grid, HEAT_PROPS), 1e-2, True)
-        vals[kernel] = s.values()
-    assert np.array_equal(vals["lanes"], vals["tiles"])
+        vals[label] = s.values()
+    assert np.array_equal(vals["full"], vals["capped"])
+    assert np.abs(vals["full"] - vals["rows"]).max() <= 1e-14 * np.abs(vals["rows"]).max()

@@ -141,7 +141,7 @@ def test_block_spmv_tets_elasticity(blocks):
 
 @pytest.mark.parametrize("n", [64, 96])
 def test_heat_matrix_and_solution_vs_oracle_large(n):
-    """Assembly through many tiles per block (k_heat_tiles' prefetch loop) and the solve, against the ORACLE's matrix
+    """Assembly through many tiles per warp (software pipeline of k_heat_lanes) and the solve, against the ORACLE's matrix
     and scipy's solution of it (rtol 1e-13): values <= 1e-12 row-relative, solution <= 1e-8 relative L2."""
     from oracle import efv_oracle as O
     og = O.OracleGrid(O.structured_grid_data(n, "hex"))
