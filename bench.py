@@ -423,8 +423,8 @@ def run_gpu(args):
                      (288.0 + 64.0 + 64.0 + 32.0) * nE + 8.0 * nnz + 16.0 * rows}
     # bytes the kernel MOVES: ncu dram__bytes_read + dram__bytes_write of one k_heat_lanes<3> launch at n = 216
     # (profiles/r02_assembly_lanes.json); scaled with the element count at other sizes
-    asm_moved = 7.45e9 * nE / 9938375.0
-    assembly_roofline = {"kernel": "k_heat_lanes<3> (lane-per-row assembly, cp.async operand ring, fused Dirichlet + lumped terms)",
+    asm_moved = 7.74e9 * nE / 9938375.0
+    assembly_roofline = {"kernel": "k_heat_lanes<3> (lane-per-row assembly on the pair schedule, operands one step ahead in registers, fused Dirichlet + lumped terms)",
                          "ms": asm_s * 1e3, "peak": peak, "unit": "GB/s", "bound": "hbm",
                          "moved_bytes_per_launch_ncu": asm_moved, "moved_gbs": asm_moved / asm_s / 1e9,
                          "moved_frac": asm_moved / asm_s / 1e9 / peak,
