@@ -467,7 +467,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=216, help="vertices per side of the structured mesh (216 = C2)")
+    ap.add_argument("--n", "--mesh-n", dest="n", type=int, default=216, help="vertices per side of the structured mesh (216 = C2)")
     ap.add_argument("--cpu-n", type=int, default=0, help="vertices per side of the bounded CPU sample (0: chosen from the time budget)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--precond", default="amg", choices=["amg", "jacobi"], help="preconditioner of the CG solve")
