@@ -935,11 +935,10 @@ static void ensure_face_records(efv_mesh *m, bool skip_simplices = false) {
 constexpr int kBlkRows = 8, kBlkStages = 2, kBlkWarps = 2;
 // doubles per vertex and stage: NVF face records + sub-volume + slot bytes, padded to an ODD number of 16-byte units so that
 // the 8 vertices of a tile read their records from 8 different bank groups
-// simplices: [s of the NVF faces, d doubles each | pad to even | J^-1 | sub-volume | slot bytes]
-__host__ __device__ constexpr int blk_simplex_jbase(int dim) { return ((dim == 3 ? 3 : 2) * dim + 1) & ~1; }
+// simplices: the element's whole compact record [s of every face | J^-1 | pad], then sub-volume and slot bytes
 __host__ __device__ constexpr int blk_row_stride(int ucode, int dim) {
   const int rf = dim * dim + dim;
-  const int slots = (ucode == 0 || ucode == 2) ? blk_simplex_jbase(dim) + dim * dim + 2
+  const int slots = (ucode == 0 || ucode == 2) ? simplex_rec_doubles(ucode) + 2
                                                : (ucode < 0 ? (dim == 3 ? 4 : 2) : shape_nvf(ucode)) * rf + 2;
   const int units = (slots + 1) / 2;
   return 2 * (units | 1);
@@ -960,34 +959,24 @@ __device__ __forceinline__ void elas_lane_issue(unsigned stg, uint32_t pk, bool 
   if (pd_none(pk, mx)) return;
   const int64_t e = (int64_t)(pk & pd_elem_mask(mx));
   const int64_t gi = U ? e : m.group_index(e);
-  constexpr int VOFF = SIMPLEX ? blk_simplex_jbase(D) + D * D : NVF * RF;      // sub-volume, then the slot bytes
+  constexpr int VOFF = SIMPLEX ? simplex_rec_doubles(CODE) : NVF * RF;         // sub-volume, then the slot bytes
+  // The 4 lanes of a vertex copy 4 CONSECUTIVE doubles per instruction = one 32-byte sector (records are sector-aligned): a
+  // cp.async costs one shared-memory wavefront per sector it brings, whatever the lanes do with it.
   if constexpr (SIMPLEX) {
-    // one compact record per element: the area vectors of the 3 (2) faces of this vertex, 8 bytes at a time (they start
-    // at odd doubles in 3-D), and J^-1 in 16-byte chunks
-    constexpr int RS = simplex_rec_doubles(CODE), JB = blk_simplex_jbase(D);
+    constexpr int RS = simplex_rec_doubles(CODE);                              // the element's whole record [s of every face | J^-1 | pad]
     const double *rec = g.Srec[CODE] + (size_t)gi * RS;
 #pragma unroll
-    for (int k = 0; k < NVF; ++k) {
-      const int f = Tab::vface_c(L, k) >> 1;
-#pragma unroll
-      for (int a = 0; a < D; ++a)
-        if (q == ((k * D + a) & 3)) cp_async8(stg + (k * D + a) * 8, rec + f * D + a);
-    }
-#pragma unroll
-    for (int p = 0; p < (D * D) / 2; ++p)
-      if (q == (p & 3)) cp_async16(stg + (JB + 2 * p) * 8, rec + NF * D + 2 * p);
-    if ((D * D) & 1) { if (q == 3) cp_async8(stg + (JB + D * D - 1) * 8, rec + NF * D + D * D - 1); }
+    for (int i0 = 0; i0 < RS; i0 += 4)
+      if (i0 + 3 < RS || q < RS - i0) cp_async8(stg + (i0 + q) * 8, rec + i0 + q);
   } else {
-    const double2 *rec = reinterpret_cast<const double2 *>(g.Frec[CODE] + (size_t)gi * NF * RF);   // 16-byte aligned: RF is even
+    const double *rec = g.Frec[CODE] + (size_t)gi * NF * RF;
 #pragma unroll
     for (int k = 0; k < NVF; ++k) {
       const int enc = Tab::vface_c(L, k);
       const int f = enc < 0 ? 0 : enc >> 1;
 #pragma unroll
-      for (int p = 0; p < RF / 2; ++p) {
-        const int c = k * (RF / 2) + p;
-        if (enc >= 0 && q == (c & 3)) cp_async16(stg + c * 16, rec + (f * RF) / 2 + p);
-      }
+      for (int i0 = 0; i0 < RF; i0 += 4)
+        if (enc >= 0 && (i0 + 3 < RF || q < RF - i0)) cp_async8(stg + (k * RF + i0 + q) * 8, rec + f * RF + i0 + q);
     }
   }
   if (q == 0) {
@@ -1021,9 +1010,9 @@ __device__ __forceinline__ void elas_lane_compute(const double *__restrict__ stg
   for (int k = 0; k < NK; ++k)
 #pragma unroll
     for (int i = 0; i < D; ++i) { ls[k][i] = 0.0; ms[k][i] = 0.0; }
-  constexpr int VOFF = SIMPLEX ? blk_simplex_jbase(D) + D * D : NVF * RF;
+  constexpr int VOFF = SIMPLEX ? simplex_rec_doubles(CODE) : NVF * RF;
   if constexpr (SIMPLEX) {
-    constexpr int JB = blk_simplex_jbase(D);
+    constexpr int JB = Tab::NF * D;                 // record = [s of every face | J^-1 | pad]
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -1031,9 +1020,10 @@ __device__ __forceinline__ void elas_lane_compute(const double *__restrict__ stg
 #pragma unroll
     for (int k = 0; k < NVF; ++k) {
       const double sg = (Tab::vface_c(L, k) & 1) ? -1.0 : 1.0;
+      const int f = Tab::vface_c(L, k) >> 1;
 #pragma unroll
       for (int i = 0; i < D; ++i) {
-        const double sv = stg[k * D + i];
+        const double sv = stg[f * D + i];
         ls[0][i] += lam * (sg * sv);
         ms[0][i] += mu * (sg * sv);
       }
