@@ -164,3 +164,29 @@ def test_bad_connectivity_is_rejected():
     gd.elementsConnectivities[0, 0] = 10 ** 6
     with pytest.raises(_lib.EfvError, match="outside"):
         P.Grid(gd).device
+
+
+@pytest.mark.parametrize("tag", ["Hexas4x4x4", "Prisms", "Pyrams", "eight_sphere", "10x10_gravity"])
+@pytest.mark.parametrize("mode", ["rows", "symmetric"])
+def test_assembly_kernels_agree(tag, mode, monkeypatch):
+    """Lane kernel (default; with a capped grid: many tiles per warp through the cp.async ring) against the round-1 row-group
+    kernel (EFV_ASSEMBLY=rows): block values, gravity vector and elimination vector, both fused Dirichlet modes."""
+    import pyefvlib_b200.device as D
+    z = util.load("stress_" + tag)
+    c = STRESS_CASES[tag]
+    grid = util.product_grid(z)
+    out = {}
+    for label, kernel, cap in (("lanes", "lanes", None), ("capped", "lanes", "2"), ("rows", "rows", None)):
+        monkeypatch.setenv("EFV_ASSEMBLY", kernel)
+        if cap: monkeypatch.setenv("EFV_LANE_GRID", cap)
+        else: monkeypatch.delenv("EFV_LANE_GRID", raising=False)
+        s = D.DeviceSystem(grid, grid.dimension)
+        send_bcs(s, grid, c["bcs"])
+        s.assemble_dirichlet_mode(D.DIRICHLET_ROWS if mode == "rows" else D.DIRICHLET_SYMMETRIC)
+        s.elasticity_assemble(props_array(grid, c["props"]), c["gravity"])
+        s.build_rhs(False)
+        out[label] = (s.values(), s.download(D.VEC_B))
+    assert np.array_equal(out["lanes"][0], out["capped"][0]) and np.array_equal(out["lanes"][1], out["capped"][1])
+    scale = np.abs(out["rows"][0]).max()
+    assert np.abs(out["lanes"][0] - out["rows"][0]).max() <= 1e-13 * scale
+    assert util.rel_max(out["lanes"][1], out["rows"][1]) <= 1e-12
