@@ -131,7 +131,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -240,6 +240,7 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         from pyefvlib_b200 import distributed as efd
+        args.clock_sampler = ClockSampler          # rank 0 samples its GPU's clocks / throttle reasons during the run
         return efd.bench_multi_gpu(args, BC3D, PROPS, DT, RTOL)
     torch.cuda.set_device(local_rank)
     L = _lib.load()
@@ -280,13 +281,15 @@ def run_gpu(args):
 
     # ---- value: K time steps with resident inputs ------------------------------------------------------------------
     iters_log = []
+    # clocks / throttle reasons under this load: nvidia-smi needs ~0.1 s to deliver its first sample and the timed region is
+    # ~0.3 s long, so the sampler (every 50 ms) already runs through the warm-up steps, which are the same work
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         iters_log.append(hot_path_step(system, grid, props)[0])
     # the timed steps are time steps 1..K of the configuration (from T0 = 0), not a later sub-window
     system.upload(VEC_XOLD, np.zeros(rows))
     system.upload(VEC_X, np.zeros(rows))
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     torch.cuda.synchronize()
     launches1 = L.efv_kernel_launch_count()
     s0, s1 = ev(), ev()

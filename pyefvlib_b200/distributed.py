@@ -299,7 +299,7 @@ def _allreduce_max(value, world):
     return float(t.item())
 
 
-def run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, steps, warmup, precond, stream):
+def run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, steps, warmup, precond, stream, sampler=None):
     """The hot path on the n x n x nz structured hexahedral mesh cut into `world` vertex-block slabs (world = 1: the whole
     mesh on one GPU): slab generation on the host, upload + geometry + CSR (setup), then `warmup` + `steps` passes of
     assembly + BCs + RHS + PCG solve (+ advance).  Transient runs restart from T0 = 0 after the warm-up; steady runs
@@ -341,6 +341,8 @@ def run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, s
         it, rr = system.solve_pcg(RTOL, 20000)
         system.advance()
         return it, rr
+    if sampler:
+        sampler.start()                          # clocks under load: warm-up + timed steps (not the host-side slab generation)
     warm = [step()[0] for _ in range(warmup)]
     if transient:
         system.upload(VEC_XOLD, zeros); system.upload(VEC_X, zeros)      # timed steps = time steps 1..K from T0
@@ -357,6 +359,7 @@ def run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, s
     barrier()
     launches2 = L.efv_kernel_launch_count()
     total_ms = _allreduce_max(e0.elapsed_time(e1), world)
+    clocks = sampler.stop() if sampler else None
     true_relres = system.true_residual()                     # b - A x with one extra SpMV, all-reduced
     assert true_relres <= 2e-10, f"true residual {true_relres:.3e} exceeds 2e-10"
     sums = system.vec_sums(VEC_X)
@@ -364,7 +367,7 @@ def run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, s
                solve_ms=float(np.mean(solve_ms)), assemble_ms=float(np.mean(asm_ms)), setup_ms=setup_ms, host_slab_generation_s=host_s,
                true_relres=true_relres, field_sum=sums[0], field_sum_of_squares=sums[1], launches=int(launches2 - launches1),
                iterations_total=int(np.sum(iters)), ms_per_iteration=float(np.sum(solve_ms)) / max(1, int(np.sum(iters))),
-               n_owned=part.n_owned)
+               n_owned=part.n_owned, clocks=clocks)
     if precond == "amg":
         out["amg"] = system.amg_info()
     return out, system, part
@@ -442,7 +445,10 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     stack = getattr(args, "weak_family", "cube") == "stack"
     n = args.c5_n if strong else (args.n if stack else int(round(args.n * world ** (1.0 / 3.0))))
     nz = n if (strong or not stack) else n * world
-    res, system, part = run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, args.steps, args.warmup, args.precond, stream)
+    sampler = args.clock_sampler(local_rank) if (rank == 0 and getattr(args, "clock_sampler", None)) else None
+    res, system, part = run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, args.steps, args.warmup, args.precond, stream,
+                                             sampler=sampler)
+    clocks = res.get("clocks")
     nV = res["vertices"]
     ms_per_step = res["ms_per_step"]
     # e2e: slab upload + setup + one step + owned field download through the same Python API, host arrays in / host field out
@@ -509,6 +515,7 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
                     "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": 1e3 * e2e_s,
                     "what": "per-rank slab upload + setup + assembly + one solve + owned field download"},
             "gpu_launches": res["launches"],
+            "clocks": clocks,
         }
         line.update(nested)
         print(json.dumps(line))
