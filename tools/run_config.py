@@ -69,6 +69,8 @@ else:
     s.set_preconditioner(os.environ.get("PRECOND", "amg"))
     s.assemble_dirichlet_mode(DIRICHLET_ROWS)
     s.biot_assemble(props, 20.0)
+    first_asm = s.timings()["assemble_ms"]                  # includes the one-time pair schedule and face records
+    s.biot_assemble(props, 20.0)
     asm = s.timings()["assemble_ms"]
     s.upload(VEC_XOLD, np.zeros(s.rows)); s.upload(VEC_X, np.zeros(s.rows))
     its, ms = [], []
@@ -80,7 +82,7 @@ else:
         s.advance()
     x = s.download(VEC_X)
     out = dict(config="C4 Biot hex", n=n, vertices=nV, elements=grid.numberOfElements, rows=s.rows, nnz=s.nnz, bicgstab_iterations=its,
-               assemble_ms=asm, solve_ms_per_step=ms, setup_s=setup_s, host_mesh_s=host_s, p_max=float(x[3 * nV:].max()),
+               assemble_ms=asm, first_assemble_ms=first_asm, solve_ms_per_step=ms, setup_s=setup_s, host_mesh_s=host_s, p_max=float(x[3 * nV:].max()),
                uy_min=float(x[nV:2 * nV].min()), dof_per_s=s.rows * 5 / (1e-3 * (asm + sum(ms))), true_relres=s.true_residual(),
                preconditioner=os.environ.get("PRECOND", "amg"))
 print(json.dumps(out))
