@@ -440,10 +440,13 @@ def bench_multi_gpu(args, BC3D, PROPS, DT, RTOL):
     transient = not getattr(args, "steady", False)
     strong = args.workload == "c5"
     # weak scaling: the C2 cube refined isotropically so that every rank keeps the per-GPU size of the N = 1 run
-    # (216^3 -> 272^3 -> 343^3 -> 432^3 vertices on 1, 2, 4, 8 GPUs; z-slabs of n^2 planes), or, with --weak-family stack,
-    # one n^3 block per rank stacked into an n x n x (n N) box (the round-1 family, whose aspect ratio grows with N)
+    # (216^3 -> 273^3 -> 343^3 -> 433^3 vertices on 1, 2, 4, 8 GPUs; z-slabs of n^2 planes), or, with --weak-family stack,
+    # one n^3 block per rank stacked into an n x n x (n N) box (the round-1 family, whose aspect ratio grows with N).
+    # The refined sizes are made ODD: the SpMV gathers x from 9 lines that are n and n^2 entries apart, and line strides
+    # that are multiples of 128 B alias in the caches (same rows, one GPU: 65 ns per 1 000 rows at n = 432, 53 at n = 433;
+    # tools/spmv_shape_probe.py, profiles/r02_spmv_vs_plane_size.json)
     stack = getattr(args, "weak_family", "cube") == "stack"
-    n = args.c5_n if strong else (args.n if stack else int(round(args.n * world ** (1.0 / 3.0))))
+    n = args.c5_n if strong else (args.n if stack else int(round(args.n * world ** (1.0 / 3.0))) | 1)
     nz = n if (strong or not stack) else n * world
     sampler = args.clock_sampler(local_rank) if (rank == 0 and getattr(args, "clock_sampler", None)) else None
     res, system, part = run_partitioned_case(n, nz, rank, world, BC3D, PROPS, DT, RTOL, transient, args.steps, args.warmup, args.precond, stream,
