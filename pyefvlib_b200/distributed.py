@@ -126,7 +126,8 @@ def structured_part(n, kind, rank, world, perturb=0.0, nz=None):
     ranges = block_ranges(n2 * nz, world, align=n2)
     k0, k1 = int(ranges[rank] // n2), int(ranges[rank + 1] // n2)           # owned planes [k0, k1)
     lo, hi = max(k0 - 1, 0), min(k1 + 1, nz)                                # local planes [lo, hi)
-    arr = _grid.structured_arrays(n, kind, layer_lo=lo, layer_hi=min(hi - 1, nz - 1), nz=nz)
+    arr = _grid.structured_arrays(n, kind, layer_lo=lo, layer_hi=min(hi - 1, nz - 1), nz=nz,
+                                  conn_dtype=np.int32 if n2 * nz < 2 ** 31 else np.int64)
     n_owned = (k1 - k0) * n2
     below = np.arange(lo * n2, k0 * n2, dtype=np.int64)
     above = np.arange(k1 * n2, hi * n2, dtype=np.int64)
@@ -138,7 +139,15 @@ def structured_part(n, kind, rank, world, perturb=0.0, nz=None):
         out = np.where(gid < k0 * n2, n_owned + (gid - lo * n2), out)
         out = np.where(gid >= k1 * n2, n_owned + len(below) + (gid - k1 * n2), out)
         return out
-    conn_local = to_local(arr["conn"]).astype(np.int32)
+    # connectivity: one affine pass (owned ids), then the general map on the two element layers that touch a ghost plane
+    # (2.2 s -> 0.3 s per 10 M-vertex slab)
+    conn_g = arr["conn"]
+    conn_local = (conn_g - conn_g.dtype.type(k0 * n2)).astype(np.int32, copy=False)
+    per_layer = (n - 1) * (n - 1) * (6 if kind == "tet" else 1)
+    if len(below):
+        conn_local[:per_layer] = to_local(conn_g[:per_layer])
+    if len(above):
+        conn_local[-per_layer:] = to_local(conn_g[-per_layer:])
     facets_local = []
     for name in _grid.BOUNDARY_NAMES_3D:
         f = arr["facets"][name]
@@ -146,8 +155,12 @@ def structured_part(n, kind, rank, world, perturb=0.0, nz=None):
             keep = ((f >= k0 * n2) & (f < k1 * n2)).any(axis=1)
             f = f[keep]
         facets_local.append(to_local(f).astype(np.int32).reshape(len(f), 4 if kind == "hex" else 3))
-    coords = _grid.structured_coords(n, l2g, perturb, nz)
-    I, J, K = l2g % n, (l2g // n) % n, l2g // n2
+    plane_ranges = [(k0, k1)] + ([(lo, k0)] if len(below) else []) + ([(k1, hi)] if len(above) else [])     # = l2g, plane by plane
+    coords = _grid.structured_coords(n, l2g, perturb, nz, planes=plane_ranges)
+    npl = len(l2g) // n2
+    I = np.broadcast_to(np.arange(n, dtype=np.int64)[None, None, :], (npl, n, n)).reshape(-1)
+    J = np.broadcast_to(np.arange(n, dtype=np.int64)[None, :, None], (npl, n, n)).reshape(-1)
+    K = np.repeat(np.concatenate([np.arange(a, b, dtype=np.int64) for a, b in plane_ranges]), n2)
     on = {"West": I == 0, "East": I == n - 1, "South": J == 0, "North": J == n - 1, "Bottom": K == 0, "Top": K == nz - 1}
     bverts = [np.nonzero(on[name])[0].astype(np.int64) for name in _grid.BOUNDARY_NAMES_3D]
     nbr, send_lists, recv = [], [], [0]

@@ -360,21 +360,23 @@ def _tet_face_uses_first_diagonal():
     return _tet_diag_cache
 
 
-def structured_arrays(n, kind="hex", layer_lo=0, layer_hi=None, nz=None):
+def structured_arrays(n, kind="hex", layer_lo=0, layer_hi=None, nz=None, conn_dtype=np.int64):
     """Global-id connectivity of the cube layers [layer_lo, layer_hi) (a layer = all cubes with the same z index) and
     the boundary facets attached to them: dict(conn, facets={name: array}).  Bottom / Top facets are included when
-    layer 0 / the last layer is.  nz vertex planes in z (default n)."""
+    layer 0 / the last layer is.  nz vertex planes in z (default n).  conn_dtype: np.int32 halves the time when the ids fit."""
     ne = n - 1
     nez = (nz or n) - 1
     layer_hi = nez if layer_hi is None else layer_hi
-    vid = lambda i, j, k: i + n * j + n * n * k
-    e = np.arange(layer_lo * ne * ne, layer_hi * ne * ne, dtype=np.int64)
-    i, j, k = e % ne, (e // ne) % ne, e // (ne * ne)
-    corner = lambda bits: vid(i + bits[0], j + bits[1], k + bits[2])
+    # first vertex of every cube, cubes ordered x fastest (element id = i + ne j + ne^2 k): broadcasting instead of
+    # div / mod passes over the element ids (3 s -> 0.5 s for the 10 M hexahedra of C2)
+    kk = np.arange(layer_lo, layer_hi, dtype=np.int64)
+    jj = np.arange(ne, dtype=np.int64)
+    v0 = (kk[:, None, None] * (n * n) + jj[None, :, None] * n + jj[None, None, :]).reshape(-1).astype(conn_dtype, copy=False)
+    off = lambda bits: bits[0] + n * bits[1] + n * n * bits[2]
     if kind == "hex":
-        conn = np.stack([corner(b) for b in _HEX_CORNERS], axis=1)
+        conn = v0[:, None] + np.array([off(b) for b in _HEX_CORNERS], dtype=conn_dtype)[None, :]
     elif kind == "tet":
-        conn = np.stack([np.stack([corner(b) for b in t], axis=1) for t in _TET_SPLIT], axis=1).reshape(-1, 4)
+        conn = (v0[:, None, None] + np.array([[off(b) for b in t] for t in _TET_SPLIT], dtype=conn_dtype)[None, :, :]).reshape(-1, 4)
     else:
         raise Exception("kind must be 'hex' or 'tet'")
     facets = {}
@@ -398,12 +400,27 @@ def structured_arrays(n, kind="hex", layer_lo=0, layer_hi=None, nz=None):
     return dict(conn=conn, facets=facets)
 
 
-def structured_coords(n, ids, perturb=0.0, nz=None):
-    """Coordinates of the global vertex ids `ids` of the n x n x nz lattice with spacing 1/(n-1) (unit cube if nz = n)."""
+def structured_coords(n, ids, perturb=0.0, nz=None, planes=None):
+    """Coordinates of the global vertex ids `ids` (None: all of them, in order) of the n x n x nz lattice with spacing
+    1/(n-1) (unit cube if nz = n).  planes = [(k_lo, k_hi), ...]: `ids` are these whole z planes, in this order (broadcast
+    instead of div / mod passes over the ids)."""
     ax = np.linspace(0.0, 1.0, n)
-    I, J, K = ids % n, (ids // n) % n, ids // (n * n)
     nz = nz or n
     az = ax if nz == n else np.arange(nz) * (1.0 / (n - 1))
+    if ids is None and planes is None:
+        planes = [(0, nz)]
+    if planes is not None and not perturb:
+        parts = []
+        for lo, hi in planes:
+            c = np.empty((hi - lo, n, n, 3))
+            c[..., 0] = ax[None, None, :]
+            c[..., 1] = ax[None, :, None]
+            c[..., 2] = az[lo:hi, None, None]
+            parts.append(c.reshape(-1, 3))
+        return parts[0] if len(parts) == 1 else np.concatenate(parts)
+    if ids is None:
+        ids = np.concatenate([np.arange(lo * n * n, hi * n * n, dtype=np.int64) for lo, hi in planes])
+    I, J, K = ids % n, (ids // n) % n, ids // (n * n)
     coords = np.stack([ax[I], ax[J], az[K]], axis=1)
     if perturb:
         h = 1.0 / (n - 1)
@@ -419,9 +436,9 @@ def structured_grid_data(n, kind="hex", perturb=0.0, nz=None):
     the bundled local order or the 6-tetrahedra-per-cube split of meshes/msh/3D/Tetras.msh, one region "Body",
     boundaries West East South North Bottom Top.  `perturb` moves interior vertices by a smooth deterministic
     perturb*h*sin(...) field to exercise non-affine hexahedra."""
-    arr = structured_arrays(n, kind, nz=nz)
-    coords = structured_coords(n, np.arange(n * n * (nz or n), dtype=np.int64), perturb, nz)
-    conn = arr["conn"].astype(np.int32)
+    arr = structured_arrays(n, kind, nz=nz, conn_dtype=np.int32 if n * n * (nz or n) < 2 ** 31 else np.int64)
+    coords = structured_coords(n, None, perturb, nz)
+    conn = arr["conn"].astype(np.int32, copy=False)
     sizes = [len(arr["facets"][nm]) for nm in BOUNDARY_NAMES_3D]
     starts = np.concatenate([[0], np.cumsum(sizes)])
     bconn = np.concatenate([arr["facets"][nm] for nm in BOUNDARY_NAMES_3D]).astype(np.int32)
