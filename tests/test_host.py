@@ -143,3 +143,24 @@ def test_structured_generator_matches_oracle_generator():
         assert np.array_equal(gd.elementsConnectivities, np.asarray(og.elementsConnectivities))
         assert np.array_equal(gd.boundariesConnectivities, np.asarray(og.boundariesConnectivities))
         assert gd.boundariesNames == og.boundariesNames
+
+
+def test_bench_clock_sampler_parses_nvidia_smi_lines():
+    """bench.py's clock record: median SM clock, maximum, throttle reasons from `nvidia-smi --query-gpu ... --format=csv`."""
+    import bench
+    s = bench.ClockSampler(0)
+    s.proc = type("P", (), {"terminate": lambda self: None, "wait": lambda self, timeout=None: 0, "kill": lambda self: None})()
+    s.lines = ["0, 1965, 1965, 612.3, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+               "0, 1890, 1965, 998.1, 0x0000000000000004, Not Active, Not Active, Not Active, Active",
+               "0, 1920, 1965, 950.0, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active",
+               "garbage line"]
+    out = s.stop()
+    assert out["sm_mhz"] == 1920.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"]
+
+
+def test_weak_scaling_sizes_are_odd_and_keep_the_per_gpu_size():
+    """bench.py --gpus N (weak): the C2 cube refined to round(216 N^(1/3)) | 1 vertices per side (pyefvlib_b200/distributed.py)."""
+    for world, expect in ((2, 273), (4, 343), (8, 433)):
+        n = int(round(216 * world ** (1.0 / 3.0))) | 1
+        assert n == expect and abs(n ** 3 / world / 216 ** 3 - 1.0) < 0.012
